@@ -1,0 +1,75 @@
+// Shared helpers for the qeb sm_100a kernels: error reporting, launch checks, warp primitives.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <math.h>
+
+#define QEB_OK 0
+#define QEB_ERR_INVALID -1   // bad shape / alignment / null pointer, nothing launched
+#define QEB_ERR_CUDA -2      // CUDA runtime / driver error at launch
+#define QEB_ERR_UNSUPPORTED -3
+
+#define QEB_API extern "C" __attribute__((visibility("default")))
+
+// thread-local last error message (qeb_last_error)
+void qeb_set_error(const char* fmt, ...);
+
+#define QEB_REQUIRE(cond, ...)            \
+  do {                                    \
+    if (!(cond)) {                        \
+      qeb_set_error(__VA_ARGS__);         \
+      return QEB_ERR_INVALID;             \
+    }                                     \
+  } while (0)
+
+#define QEB_CUDA(expr)                                                             \
+  do {                                                                             \
+    cudaError_t _e = (expr);                                                       \
+    if (_e != cudaSuccess) {                                                       \
+      qeb_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return QEB_ERR_CUDA;                                                         \
+    }                                                                              \
+  } while (0)
+
+#define QEB_LAUNCH_CHECK() QEB_CUDA(cudaGetLastError())
+
+static inline int qeb_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+constexpr int kNumSMs = 148;  // B200
+// grid for a grid-stride elementwise kernel: enough blocks to cover `total`, capped at a few waves of the 148 SMs
+static inline int qeb_grid(long long total, int threads, int blocks_per_sm = 8) {
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// launch-counter (bench.py reports gpu_launches from it)
+void qeb_count_launch(int n = 1);
+
+#ifdef __CUDACC__
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+#endif

@@ -1,0 +1,159 @@
+// Gaussian jitter and crop/pad of text strips. HBM-bound elementwise/gather kernels.
+//
+// Replaces
+//   AddGaussianNoice.__call__  transform_helper.py:33-45 (+ add_noise loops train_nn_patch.py:187-191,
+//                              train_nn_area.py:184-191): out = clamp(img - coef * N(mean, sigma_img), 0, 1)
+//   get_text_stack / padder    utils.py:118-141: crop each bbox of a (1,H,W) image, centre-pad with 1.0 to (h,w)
+//
+// Jitter: one sigma per image (the reference draws r_std per image on the host; that stays a host draw).
+// Noise is either supplied (exact restatement of the reference arithmetic on a given noise tensor) or generated
+// in-kernel with Philox4x32-10 + Box-Muller: counter = (group index within image, image index, 0, 0),
+// key = (seed_lo, seed_hi), each counter yields the 4 normals of 4 consecutive pixels (float4 load/store).
+#include "common.cuh"
+
+namespace {
+
+struct Philox {
+  static constexpr unsigned int M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __device__ static uint4 rand4(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const unsigned int hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+      const unsigned int hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+      c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+      k.x += W0;
+      k.y += W1;
+    }
+    return c;
+  }
+};
+
+__device__ __forceinline__ float2 box_muller(unsigned int a, unsigned int b) {
+  // u1 in (0,1], u2 in [0,1)
+  const float u1 = ((float)(a >> 8) + 1.0f) * (1.0f / 16777216.0f);
+  const float u2 = (float)(b >> 8) * (1.0f / 16777216.0f);
+  const float r = sqrtf(-2.0f * logf(u1));
+  float s, c;
+  sincospif(2.0f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+__device__ __forceinline__ float jitter1(float img, float noise, float coef) {
+  // img - coef*noise as two roundings (torch: mul then sub), then clamp
+  const float v = __fsub_rn(img, __fmul_rn(coef, noise));
+  return fminf(fmaxf(v, 0.f), 1.f);
+}
+
+// hw4 = pixels per image / 4
+__global__ void jitter_kernel(const float4* __restrict__ img, const float* __restrict__ sigma, float mean, float coef,
+                              const float4* __restrict__ noise_in, unsigned long long seed, long long n_img, int hw4,
+                              float4* __restrict__ out, float4* __restrict__ noise_out) {
+  const long long total = n_img * hw4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long im = i / hw4;
+    const unsigned int g = (unsigned int)(i - im * hw4);
+    float4 z;
+    if (noise_in) {
+      z = noise_in[i];
+    } else {
+      const uint4 r = Philox::rand4(make_uint4(g, (unsigned int)im, (unsigned int)(im >> 32), 0u),
+                                    make_uint2((unsigned int)seed, (unsigned int)(seed >> 32)));
+      const float2 n01 = box_muller(r.x, r.y), n23 = box_muller(r.z, r.w);
+      const float sg = sigma[im];
+      z = make_float4(__fadd_rn(mean, __fmul_rn(sg, n01.x)), __fadd_rn(mean, __fmul_rn(sg, n01.y)),
+                      __fadd_rn(mean, __fmul_rn(sg, n23.x)), __fadd_rn(mean, __fmul_rn(sg, n23.y)));
+    }
+    const float4 p = img[i];
+    out[i] = make_float4(jitter1(p.x, z.x, coef), jitter1(p.y, z.y, coef), jitter1(p.z, z.z, coef),
+                         jitter1(p.w, z.w, coef));
+    if (noise_out) noise_out[i] = z;
+  }
+}
+
+// boxes: (n,4) int32 x_min,y_min,x_max,y_max (python slice semantics, clipped to the image).
+// out[i,y,x] = crop_i[y - pad_top, x - pad_left] inside the crop, else 1.0 (negative pads crop, as ConstantPad2d does)
+__global__ void crop_pad_gather_kernel(const float* __restrict__ img, int H, int W, const int* __restrict__ boxes, int n,
+                                       int oh, int ow, float* __restrict__ out) {
+  const int per = oh * ow;
+  const long long total = (long long)n * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per), r = (int)(i - (long long)b * per);
+    const int y = r / ow, x = r - y * ow;
+    const int x0 = min(max(boxes[4 * b + 0], 0), W), y0 = min(max(boxes[4 * b + 1], 0), H);
+    const int x1 = min(max(boxes[4 * b + 2], x0), W), y1 = min(max(boxes[4 * b + 3], y0), H);
+    const int cw = x1 - x0, ch = y1 - y0;
+    // floor division like python's //
+    const int dl = ow - cw, dt = oh - ch;
+    const int pl = (dl >= 0) ? dl / 2 : -((-dl + 1) / 2);
+    const int pt = (dt >= 0) ? dt / 2 : -((-dt + 1) / 2);
+    const int cy = y - pt, cx = x - pl;
+    float v = 1.0f;
+    if (cy >= 0 && cy < ch && cx >= 0 && cx < cw) v = img[(long long)(y0 + cy) * W + (x0 + cx)];
+    out[i] = v;
+  }
+}
+
+// backward: scatter-add grad of the strips into the image gradient (boxes may overlap -> atomics)
+__global__ void crop_pad_scatter_kernel(const float* __restrict__ gout, int H, int W, const int* __restrict__ boxes,
+                                        int n, int oh, int ow, float* __restrict__ gimg) {
+  const int per = oh * ow;
+  const long long total = (long long)n * per;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / per), r = (int)(i - (long long)b * per);
+    const int y = r / ow, x = r - y * ow;
+    const int x0 = min(max(boxes[4 * b + 0], 0), W), y0 = min(max(boxes[4 * b + 1], 0), H);
+    const int x1 = min(max(boxes[4 * b + 2], x0), W), y1 = min(max(boxes[4 * b + 3], y0), H);
+    const int cw = x1 - x0, ch = y1 - y0;
+    const int dl = ow - cw, dt = oh - ch;
+    const int pl = (dl >= 0) ? dl / 2 : -((-dl + 1) / 2);
+    const int pt = (dt >= 0) ? dt / 2 : -((-dt + 1) / 2);
+    const int cy = y - pt, cx = x - pl;
+    if (cy >= 0 && cy < ch && cx >= 0 && cx < cw) atomicAdd(&gimg[(long long)(y0 + cy) * W + (x0 + cx)], gout[i]);
+  }
+}
+
+}  // namespace
+
+// img/out/noise: (n_img, hw) fp32 contiguous, hw % 4 == 0, 16-byte aligned. noise_in NULL => Philox noise from seed.
+QEB_API int qeb_gauss_jitter(const float* img, const float* sigma, float mean, float coef, const float* noise_in,
+                             unsigned long long seed, long long n_img, int hw, float* out, float* noise_out,
+                             void* stream) {
+  if (n_img == 0) return QEB_OK;
+  QEB_REQUIRE(img && out && n_img > 0 && hw > 0, "gauss_jitter: bad args");
+  QEB_REQUIRE(noise_in || sigma, "gauss_jitter: need sigma when noise is generated");
+  QEB_REQUIRE(hw % 4 == 0, "gauss_jitter: pixels per image (%d) must be a multiple of 4", hw);
+  QEB_REQUIRE(((uintptr_t)img | (uintptr_t)out | (uintptr_t)noise_in | (uintptr_t)noise_out) % 16 == 0,
+              "gauss_jitter: buffers must be 16-byte aligned");
+  const long long total = n_img * (hw / 4);
+  const int grid = qeb_grid(total, 256);
+  jitter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)img, sigma, mean, coef, (const float4*)noise_in,
+                                                        seed, n_img, hw / 4, (float4*)out, (float4*)noise_out);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+QEB_API int qeb_crop_pad_gather(const float* img, int H, int W, const int* boxes, int n, int oh, int ow, float* out,
+                                void* stream) {
+  if (n == 0) return QEB_OK;
+  QEB_REQUIRE(img && boxes && out && H > 0 && W > 0 && oh > 0 && ow > 0 && n > 0, "crop_pad_gather: bad args");
+  const long long total = (long long)n * oh * ow;
+  const int grid = qeb_grid(total, 256);
+  crop_pad_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, H, W, boxes, n, oh, ow, out);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+// gimg (H,W) must be zero-initialised (or hold a gradient to accumulate into)
+QEB_API int qeb_crop_pad_scatter(const float* gout, int H, int W, const int* boxes, int n, int oh, int ow, float* gimg,
+                                 void* stream) {
+  if (n == 0) return QEB_OK;
+  QEB_REQUIRE(gout && boxes && gimg && H > 0 && W > 0 && oh > 0 && ow > 0 && n > 0, "crop_pad_scatter: bad args");
+  const long long total = (long long)n * oh * ow;
+  const int grid = qeb_grid(total, 256);
+  crop_pad_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, H, W, boxes, n, oh, ow, gimg);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}

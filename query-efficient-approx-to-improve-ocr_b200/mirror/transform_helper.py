@@ -1,0 +1,83 @@
+"""AddGaussianNoice of the reference's transform_helper.py:26-45 on the device, plus the batched add_noise.
+
+Same constructor and call signature. Per image: r_std = randint(0, std+1)/100 (stochastic) or std/100, + 1e-13;
+out = clamp(image - noise_coef * N(mean, r_std), 0, 1). The per-image sigma draw stays on the host generator
+(torch.randint, as the reference); the normal deviates come from the in-kernel Philox stream (qeb_gauss_jitter),
+seeded from the host generator, so runs are reproducible under torch.manual_seed. The reference's own noise
+values (CPU mt19937 stream) are not reproduced - only their distribution; `apply_noise` restates the arithmetic
+bit-exactly on a given noise tensor.
+"""
+import torch
+
+from .. import _lib
+
+
+def _launch(img2d, sigma, mean, coef, noise_in, seed, want_noise):
+    n_img, hw = img2d.shape
+    out = torch.empty_like(img2d)
+    noise = torch.empty_like(img2d) if want_noise else None
+    _lib.call("qeb_gauss_jitter", img2d.data_ptr(), _lib.ptr(sigma), float(mean), float(coef), _lib.ptr(noise_in),
+              int(seed), n_img, hw, out.data_ptr(), _lib.ptr(noise), _lib.stream())
+    return out, noise
+
+
+def _check(images):
+    if not images.is_cuda or images.dtype != torch.float32:
+        raise _lib.QebError("qeb jitter needs CUDA fp32 images (no CPU fallback)")
+
+
+def apply_noise(images, noise, noise_coef=1):
+    """clamp(images - noise_coef*noise, 0, 1) on the device for a given noise tensor (transform_helper.py:40-41)."""
+    _check(images)
+    x = images.contiguous()
+    z = noise.to(x.device, torch.float32).contiguous()
+    out, _ = _launch(x.view(1, -1), None, 0.0, noise_coef, z.view(1, -1), 0, False)
+    return out.view_as(images)
+
+
+def jitter_batch(images, sigmas, mean=0.0, noise_coef=1, seed=None, return_noise=False):
+    """images (N,...) CUDA fp32; sigmas (N) per-image std (host or device). One launch for the whole batch -
+    the fused form of the add_noise loops at train_nn_patch.py:187-191 / train_nn_area.py:184-191."""
+    _check(images)
+    x = images.contiguous()
+    n = x.shape[0]
+    sg = torch.as_tensor(sigmas, dtype=torch.float32)
+    if not sg.is_cuda:
+        sg = sg.pin_memory().to(x.device, non_blocking=True)
+    if seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    out, noise = _launch(x.view(n, -1), sg.contiguous(), mean, noise_coef, None, seed, return_noise)
+    out = out.view_as(images)
+    return (out, noise.view_as(images)) if return_noise else out
+
+
+class AddGaussianNoice(object):
+    def __init__(self, std=5, mean=0, is_stochastic=False, return_noise=False):
+        self.std = std
+        self.mean = mean
+        self.is_stochastic = is_stochastic
+        self.return_noise = return_noise
+
+    def _sigmas(self, n):
+        if self.is_stochastic:
+            r = torch.randint(low=0, high=self.std + 1, size=(n,)).to(torch.float64) / 100.0
+        else:
+            r = torch.full((n,), self.std / 100.0, dtype=torch.float64)
+        return (r + 0.0000000000001).to(torch.float32)
+
+    def __call__(self, image, noise_coef=1):
+        """One image (C,H,W) like the reference call."""
+        out = jitter_batch(image.unsqueeze(0), self._sigmas(1), self.mean, noise_coef, return_noise=self.return_noise)
+        if self.return_noise:
+            return out[0].squeeze(0), out[1].squeeze(0)
+        return out.squeeze(0)
+
+    def batch(self, images, noise_coef=1):
+        """Whole batch (N,C,H,W), one sigma per image, one launch."""
+        return jitter_batch(images, self._sigmas(images.shape[0]), self.mean, noise_coef, return_noise=self.return_noise)
+
+
+def add_noise(imgs, noiser, noise_coef=1):
+    """TrainNNPrep.add_noise (train_nn_area.py:184-191 returns (imgs, noise); train_nn_patch.py:187-191 imgs only,
+    selected by noiser.return_noise)."""
+    return noiser.batch(imgs, noise_coef)
