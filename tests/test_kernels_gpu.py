@@ -256,8 +256,8 @@ def test_jitter_statistics_full_size(m):
     mu = noise.view(512, -1).mean(dim=1).cpu()
     assert torch.allclose(sd, sig, rtol=0.05, atol=1e-6) and mu.abs().max() < 0.004
     assert float(out.min()) >= 0 and float(out.max()) <= 1
-    z = noise[sig > 0.01].flatten()
-    z = (z / z.std()).cpu()
+    sel = sig > 0.01  # normalise per image: a mixture of different sigmas is not Gaussian (kurtosis > 3)
+    z = (noise[sel].view(int(sel.sum()), -1) / sig[sel].to(noise.device)[:, None]).flatten().cpu()
     assert abs(float((z ** 3).mean())) < 0.02 and abs(float((z ** 4).mean()) - 3) < 0.05
 
 
