@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one preprocessor-update training step (phase B of the reference's trainers,
+train_nn_area.py:277-287 / train_nn_patch.py:312-345): UNet (BatchNorm in train mode) -> CRNN surrogate (train(),
+BatchNorm frozen by set_bn_eval) -> CTC(mean) + 1.0 * MSE-to-white -> backward through both networks -> Adam step on
+the UNet. Batch 64 synthetic 32x128 patches per GPU (BASELINE.json configs[1]); metric = patches/sec.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (sm_100a kernels behind the mirror modules)
+  python bench.py --impl reference ...                      the reference's CPU path (torch CPU, all host threads)
+For N > 1 launch with torch.distributed.run (one rank per GPU); the batch is sharded 64/GPU (weak scaling) and the
+UNet gradients are all-reduced (AVG) over NCCL once per step.
+
+Prints ONE JSON line on rank 0. `value`: inputs resident in HBM, CUDA-event timing, max over ranks. `e2e`: the same
+step through the trainers' calling convention with HOST inputs (pinned image batch -> H2D, label strings encoded on
+the host -> int32 CPU targets -> H2D, loss read back -> D2H) inside the timed region. `roofline`: the kernel family
+with the largest share of the step, measured with CUDA events around every launch of the library in a separate
+profiled pass. `cpu_baseline`: the oracle port (oracle/nn_oracle.py + torch CPU CTC/MSE/Adam) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHAR_SET = ['`', ' ', '!', '"', '#', '$', '%', '&', "'", '(', ')', '*', '+', ',', '-', '.', '0', '1', '2', '3', '4',
+            '5', '6', '7', '8', '9', ':', ';', '<', '=', '>', '?', '@', 'A', 'B', 'C', 'D', 'E', 'F', 'G', 'H', 'I', 'J',
+            'K', 'L', 'M', 'N', 'O', 'P', 'Q', 'R', 'S', 'T', 'U', 'V', 'W', 'X', 'Y', 'Z', '[', ']', '^', 'a', 'b', 'c',
+            'd', 'e', 'f', 'g', 'h', 'i', 'j', 'k', 'l', 'm', 'n', 'o', 'p', 'q', 'r', 's', 't', 'u', 'v', 'w', 'x', 'y',
+            'z', '{', '|', '~', '€', '}', '\\', '/']
+BATCH = 64          # patches per GPU (BASELINE.json configs[1])
+H, W = 32, 128      # properties.input_size
+LR_PREP = 5e-5      # patch_cli.py / area_cli.py default
+SCALAR = 1.0        # weight of the MSE term (default --scalar 1)
+# algorithmic FLOPs per patch of this step: UNet fprop+dgrad+wgrad 3 x 1.504 + CRNN fprop+dgrad 2 x 1.778
+# (+ the CRNN weight gradients the reference also computes and discards: + 1.778)
+GFLOP_PER_PATCH = 3 * 1.504 + 3 * 1.778
+
+
+def synth_batch(n, seed):
+    """POS-shaped synthetic data: near-white background with darker strokes; labels 1..16 chars (mean ~4.8)."""
+    g = torch.Generator().manual_seed(seed)
+    x = 0.9 + 0.1 * torch.rand(n, 1, H, W, generator=g)
+    strokes = (torch.rand(n, 1, H // 4, W // 4, generator=g) < 0.18).float()
+    strokes = torch.nn.functional.interpolate(strokes, scale_factor=4, mode="nearest")
+    x = (x - 0.75 * strokes * torch.rand(n, 1, H, W, generator=g)).clamp_(0, 1)
+    rng = random.Random(seed)
+    labels = []
+    for _ in range(n):
+        ln = min(16, 1 + int(rng.expovariate(1 / 3.8)))
+        labels.append("".join(rng.choice(CHAR_SET[1:]) for _ in range(ln)))
+    return x, labels
+
+
+def encode(labels, char_to_index):
+    # TrainNNPrep._call_model: train_nn_area.py:163-171
+    y = torch.tensor([char_to_index[c] for l in labels for c in l], dtype=torch.int32)
+    y_size = torch.tensor([len(l) for l in labels], dtype=torch.int32)
+    return y, y_size
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nme, v in zip(names, r[4:8]):
+                if v == "Active":
+                    reasons.add(nme)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------ reference arm
+def cpu_step_factory(batch, seed=42):
+    """The oracle port of the same step on CPU: mirror modules as parameter containers, torch library ops."""
+    from oracle import nn_oracle
+    from qeb_b200.mirror.models.model_crnn import CRNN
+    from qeb_b200.mirror.models.model_unet import UNet
+    from qeb_b200.mirror.utils import set_bn_eval
+    torch.manual_seed(seed)
+    prep, crnn = UNet(), CRNN(len(CHAR_SET), False)
+    crnn.register_backward_hook(crnn.backward_hook)
+    ctc, mse = torch.nn.CTCLoss(), torch.nn.MSELoss()
+    opt = torch.optim.Adam(prep.parameters(), lr=LR_PREP, weight_decay=0)
+    c2i = {c: i for i, c in enumerate(CHAR_SET)}
+    x, labels = synth_batch(batch, 7)
+
+    def step():
+        prep.train(); crnn.train(); crnn.apply(set_bn_eval)
+        prep.zero_grad(); crnn.zero_grad()
+        img = nn_oracle.unet_forward(prep, x)
+        scores = nn_oracle.crnn_forward(crnn, img)
+        y, y_size = encode(labels, c2i)
+        pred_size = torch.tensor([scores.shape[0]] * batch, dtype=torch.int32)
+        loss = ctc(scores, y, pred_size, y_size) + SCALAR * mse(img, torch.ones(img.shape))
+        loss.backward()
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample = BATCH if args.steps + args.warmup <= 30 else 16
+    step = cpu_step_factory(sample)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {"impl": "reference", "metric": "patches/sec per train step (UNet+CRNN+CTC)", "value": value, "unit": "patches/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port",
+                             "sample": f"{args.steps} steps of {sample} patches, torch {torch.__version__} CPU fp32"},
+            "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "configs[1]: train_nn_area phase B step - UNet(train BN) + CRNN surrogate (BN frozen) fwd/bwd + CTC(mean) + "
+                        "1.0*MSE-to-white + Adam(lr 5e-5) on the UNet; 64 synthetic 32x128 patches per GPU, V=95, T=31",
+            "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "patch": [H, W], "parallelism": f"dp{n_gpus}",
+            "operand_precision": "tf32 tensor-core operands, fp32 accumulate/activations (reference: fp32)",
+            "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="qeb", choices=["qeb", "reference"])
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-profile", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "qeb" else max(args.warmup, 1)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    import qeb_b200
+    from qeb_b200 import _lib
+    from qeb_b200.mirror import ctc as qctc
+    from qeb_b200.mirror import train_ops
+    from qeb_b200.mirror.models.model_crnn import CRNN
+    from qeb_b200.mirror.models.model_unet import UNet
+    from qeb_b200.mirror.utils import set_bn_eval
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the qeb hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.load().qeb_check_device() == 0, _lib.load().qeb_last_error()
+
+    torch.manual_seed(42)
+    prep, crnn = UNet().to(dev), CRNN(len(CHAR_SET), False).to(dev)
+    crnn.register_backward_hook(crnn.backward_hook)          # train_nn_area.py:92
+    ctc_loss = qctc.CTCLoss()                                 # train_nn_area.py:146
+    opt = train_ops.Adam(prep.parameters(), lr=LR_PREP, weight_decay=0)  # train_nn_area.py:152-154
+    c2i = {c: i for i, c in enumerate(CHAR_SET)}
+    x_host, labels = synth_batch(BATCH, 7 + rank)
+    x_pin = x_host.pin_memory()
+    x_dev = x_host.to(dev)
+    y, y_size = encode(labels, c2i)
+    pred_size = torch.tensor([W // 4 - 1] * BATCH, dtype=torch.int32)
+    packed = qctc.pack_targets(y, pred_size, y_size, dev)
+    unet_params = [p for p in prep.parameters()]
+
+    def allreduce_grads():
+        if world == 1:
+            return
+        bases = {id(p.grad._base): p.grad._base for p in unet_params if p.grad is not None and p.grad._base is not None}
+        if len(bases) == 1 and all(p.grad is not None and p.grad._base is not None for p in unet_params):
+            dist.all_reduce(next(iter(bases.values())), op=dist.ReduceOp.AVG)   # one flat 31 MB buffer
+        else:
+            flat = torch.cat([p.grad.reshape(-1) for p in unet_params])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            off = 0
+            for p in unet_params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+
+    def step_device():
+        prep.train(); crnn.train(); crnn.apply(set_bn_eval)          # train_nn_area.py:277-279
+        prep.zero_grad(set_to_none=True); crnn.zero_grad(set_to_none=True)
+        img = prep(x_dev)                                             # :283
+        scores = crnn(img)                                            # :284 (_call_model)
+        loss = ctc_loss(scores, packed) + SCALAR * train_ops.mse_to_ones(img)   # :285 (_get_loss)
+        loss.backward()                                               # :286
+        allreduce_grads()
+        opt.step()                                                    # :287
+        return loss
+
+    def step_e2e():
+        prep.train(); crnn.train(); crnn.apply(set_bn_eval)
+        prep.zero_grad(set_to_none=True); crnn.zero_grad(set_to_none=True)
+        xv = x_pin.to(dev, non_blocking=True)                         # X_var = images.to(self.device)  :217
+        img = prep(xv)
+        scores = crnn(img)
+        yy, yy_size = encode(labels, c2i)                             # host-side label encoding, as _call_model
+        ps = torch.tensor([scores.shape[0]] * BATCH, dtype=torch.int32)
+        loss = ctc_loss(scores, yy, ps, yy_size) + SCALAR * train_ops.mse_to_ones(img)
+        loss.backward()
+        allreduce_grads()
+        opt.step()
+        return loss.item()                                            # D2H read of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, out
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    ms_step, last_loss = timed(step_device, args.steps)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    roofline, kernels = None, None
+    if not args.skip_profile:
+        _lib.prof_enable(True)
+        torch.cuda.synchronize()
+        _lib.prof_report()  # drop anything recorded so far
+        psteps = min(args.steps, 5)
+        for _ in range(psteps):
+            step_device()
+        torch.cuda.synchronize()
+        rep = _lib.prof_report()
+        _lib.prof_enable(False)
+        total = sum(v["ms"] for v in rep.values())
+        kernels = {k: {"launches_per_step": v["launches"] / psteps, "ms_per_step": v["ms"] / psteps, "share": v["ms"] / total,
+                       "tflops": v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0.0,
+                       "gbs": v["bytes"] / v["ms"] / 1e6 if v["ms"] > 0 else 0.0} for k, v in rep.items()}
+        top = max(rep, key=lambda k: rep[k]["ms"])
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(top)
+        except (OSError, ValueError):
+            pass
+        v = rep[top]
+        if top.startswith("tc_"):
+            peak = peaks.get("bf16_tflops", 1590.0)
+            ach = v["flops"] / v["ms"] / 1e9
+            roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                        "traffic": traffic, "peak_source": ("measured bf16 dense burst (MEASURED_PEAKS.json); the kernel is kind::tf32, "
+                                                            "nominally half the bf16 rate" if peaks else "fallback 1590 bf16")}
+        else:
+            peak = peaks.get("hbm_gbs", 6650.0)
+            ach = v["bytes"] / v["ms"] / 1e6
+            roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                        "traffic": traffic, "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6650"}
+        roofline["share_of_step"] = v["ms"] / total
+        roofline["launches_per_step"] = v["launches"] / psteps
+        roofline["avg_launch_ms"] = v["ms"] / v["launches"]
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        threads = os.cpu_count() or 1
+        torch.set_num_threads(threads)
+        cstep = cpu_step_factory(BATCH)
+        cstep()
+        t0, n = time.perf_counter(), 0
+        while n < 3 or (time.perf_counter() - t0 < 12 and n < 12):
+            cstep(); n += 1
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": BATCH * n / dt, "unit": "patches/s", "cores": threads, "kind": "port",
+                        "sample": f"{n} steps of {BATCH} patches ({dt:.1f} s), oracle/nn_oracle.py on torch {torch.__version__} CPU fp32"}
+
+    if rank == 0:
+        value = BATCH * world / (ms_step / 1e3)
+        e2e = BATCH * world / (ms_e2e / 1e3)
+        h2d = x_pin.numel() * 4 + (y.numel() + 3 * BATCH) * 4
+        line = {"metric": "patches/sec per train step (UNet+CRNN+CTC)", "value": value, "unit": "patches/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(world),
+                "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
+                "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": float(last_loss),
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

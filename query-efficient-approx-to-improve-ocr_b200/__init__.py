@@ -13,6 +13,6 @@ __all__ = ["QebError", "launch_count", "reset_launch_count", "build"]
 
 def build(verbose=False, force=False):
     """Compile csrc/*.cu for sm_100a into libqeb_sm100.so (in-tree)."""
-    from . import build as _build
+    from . import _build
 
     return _build.build(verbose=verbose, force=force)

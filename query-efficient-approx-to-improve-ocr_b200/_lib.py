@@ -31,6 +31,31 @@ SIGNATURES = {
     "qeb_gauss_jitter": (I, [P, P, F, F, P, ULL, LL, I, P, P, P]),
     "qeb_crop_pad_gather": (I, [P, I, I, P, I, I, I, P, P]),
     "qeb_crop_pad_scatter": (I, [P, I, I, P, I, I, I, P, P]),
+    "qeb_pack_weight": (I, [P, P, I, I, I, I, I, P]),
+    "qeb_nchw_to_nhwc": (I, [P, P, I, I, I, I, I, P]),
+    "qeb_nhwc_to_nchw": (I, [P, P, I, I, I, I, I, P]),
+    "qeb_conv_fprop_tc": (I, [P, I, I, I, I, I, P, I, I, I, I, I, P, P, I, P, I, I, P]),
+    "qeb_conv_wgrad_tc": (I, [P, I, I, I, I, P, I, I, I, I, I, I, I, P, P]),
+    "qeb_convT2x2_fprop_tc": (I, [P, I, I, I, I, I, P, P, I, P, I, P]),
+    "qeb_convT2x2_dgrad_tc": (I, [P, I, I, I, I, I, P, I, P, I, P]),
+    "qeb_convT2x2_wgrad_tc": (I, [P, I, I, I, I, P, I, I, I, P, P]),
+    "qeb_lstm_layer_fwd": (I, [P, P, P, P, P, I, I, P]),
+    "qeb_lstm_layer_bwd": (I, [P, P, P, P, P, I, I, P]),
+    "qeb_prof_enable": (None, [I]),
+    "qeb_prof_report": (I, [ctypes.c_char_p, I]),
+    "qeb_mse_ones_fwd": (I, [P, LL, P, P]),
+    "qeb_mse_ones_bwd": (I, [P, LL, P, P, P]),
+    "qeb_adam_table_entry_bytes": (I, []),
+    "qeb_adam_multi": (I, [P, I, LL, F, F, F, F, F, I, P]),
+    "qeb_crnn_workspace_bytes": (SZ, [I, I, I]),
+    "qeb_crnn_num_params": (I, []),
+    "qeb_crnn_forward": (I, [P, I, I, I, P, P, I, P, P, P]),
+    "qeb_crnn_backward": (I, [P, I, I, I, P, I, P, P, P, P, P]),
+    "qeb_unet_workspace_bytes": (SZ, [I, I, I]),
+    "qeb_unet_num_params": (I, []),
+    "qeb_unet_num_buffers": (I, []),
+    "qeb_unet_forward": (I, [P, I, I, I, P, P, I, P, P, P]),
+    "qeb_unet_backward": (I, [P, I, I, I, P, I, P, P, P, P, P, P]),
 }
 
 _lib = None
@@ -82,3 +107,16 @@ def launch_count():
 
 def reset_launch_count():
     load().qeb_reset_launch_count()
+
+
+def prof_enable(on=True):
+    load().qeb_prof_enable(1 if on else 0)
+
+
+def prof_report():
+    """Per-kernel-family totals recorded since prof_enable(True): {tag: {launches, ms, flops, bytes}}."""
+    import json
+
+    buf = ctypes.create_string_buffer(1 << 16)
+    call("qeb_prof_report", buf, len(buf))
+    return json.loads(buf.value.decode())

@@ -1,7 +1,11 @@
 // C-ABI plumbing shared by every entry point: thread-local error string, launch counter, device probe.
 #include "common.cuh"
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
 #include <string.h>
+#include <vector>
 
 static thread_local char g_err[1024] = "";
 static std::atomic<long long> g_launches{0};
@@ -33,5 +37,72 @@ QEB_API int qeb_check_device(void) {
     qeb_set_error("qeb kernels are built for sm_100a only; device %d is sm_%d%d (%s)", dev, p.major, p.minor, p.name);
     return QEB_ERR_UNSUPPORTED;
   }
+  return QEB_OK;
+}
+
+// ---- per-kernel profiling (bench.py's roofline leg): CUDA events around every launch of the library, recorded on the
+// launching stream, with the launch site's algorithmic FLOPs / bytes. Off by default (two event records per launch).
+namespace {
+struct ProfRec {
+  const char* tag;
+  cudaEvent_t e0, e1;
+  double flops, bytes;
+};
+std::atomic<int> g_prof{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_recs;
+}  // namespace
+
+int qeb_prof_on() { return g_prof.load(std::memory_order_relaxed); }
+
+int qeb_prof_begin(const char* tag, cudaStream_t st, double flops, double bytes) {
+  ProfRec r;
+  r.tag = tag; r.flops = flops; r.bytes = bytes;
+  if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
+  cudaEventRecord(r.e0, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_recs.push_back(r);
+  return (int)g_recs.size() - 1;
+}
+
+void qeb_prof_end(int idx, cudaStream_t st) {
+  if (idx < 0) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  cudaEventRecord(g_recs[idx].e1, st);
+}
+
+QEB_API void qeb_prof_enable(int on) { g_prof.store(on, std::memory_order_relaxed); }
+
+// Synchronises, aggregates the records per tag and writes a JSON object
+// {"tag": {"launches": n, "ms": total, "flops": total, "bytes": total}, ...} into buf; clears the records.
+QEB_API int qeb_prof_report(char* buf, int cap) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : g_recs) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.e1);
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    Agg& a = agg[r.tag];
+    a.n += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_recs.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  if ((int)out.size() + 1 > cap) {
+    qeb_set_error("prof_report: buffer too small (%d needed)", (int)out.size() + 1);
+    return QEB_ERR_INVALID;
+  }
+  memcpy(buf, out.c_str(), out.size() + 1);
   return QEB_OK;
 }

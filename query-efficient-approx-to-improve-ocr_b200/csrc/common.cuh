@@ -49,6 +49,21 @@ static inline int qeb_grid(long long total, int threads, int blocks_per_sm = 8) 
 // launch-counter (bench.py reports gpu_launches from it)
 void qeb_count_launch(int n = 1);
 
+// per-launch profiling scope (abi.cu): no-op unless qeb_prof_enable(1)
+int qeb_prof_on();
+int qeb_prof_begin(const char* tag, cudaStream_t st, double flops, double bytes);
+void qeb_prof_end(int idx, cudaStream_t st);
+struct ProfScope {
+  int idx = -1;
+  cudaStream_t st;
+  ProfScope(const char* tag, cudaStream_t s, double flops = 0.0, double bytes = 0.0) : st(s) {
+    if (qeb_prof_on()) idx = qeb_prof_begin(tag, s, flops, bytes);
+  }
+  ~ProfScope() {
+    if (idx >= 0) qeb_prof_end(idx, st);
+  }
+};
+
 #ifdef __CUDACC__
 constexpr unsigned FULL_MASK = 0xffffffffu;
 

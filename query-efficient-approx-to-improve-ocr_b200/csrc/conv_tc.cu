@@ -14,6 +14,7 @@
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (tcgen05.ld -> bias/ReLU ->
 // global). Pipelines: smem full/empty mbarriers (kStages deep), one TMEM-full barrier.
 #include "tc_common.cuh"
+#include "nn.cuh"
 
 namespace tc {
 
@@ -73,13 +74,22 @@ struct FpropParams {
   int kh, kw, ph, pw;
   int cin, kchunks;
   int n_total;        // GEMM N (all output channels)
-  const float* bias;  // per GEMM-N column, nullable
+  const float* bias;   // per GEMM-N column, nullable
+  const float* scale;  // per GEMM-N column, nullable: v = acc*scale + bias
   int relu;
   float* out;
-  long long out_pix_stride;  // elements between consecutive output pixels
+  long long osn, osh, osw;   // output strides (image, row, pixel) in elements
+  const float* mask;         // nullable: v = mask(n,h,w,c) > 0 ? v : 0
+  long long msn, msh, msw;
   int mode;                  // 0: plain NHWC store; 1: ConvTranspose 2x2 s2 pixel shuffle (N index = (dh*2+dw)*up_c + co)
   int up_c;
   int accumulate;            // 1: out += result (used when a gradient already holds a partial sum)
+  int vec_ok;                // 16-byte aligned rows: float4 stores allowed
+  int a_map_per_tap;         // 1: tap selects the A tensor map (ConvTranspose dgrad sub-lattices), no coordinate shift
+};
+
+struct TmapArray4 {
+  CUtensorMap m[4];
 };
 
 template <int BLOCK_N>
@@ -92,7 +102,7 @@ struct FpropCfg {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const FpropParams p) {
   using Cfg = FpropCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -109,7 +119,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int num_kb = p.kh * p.kw * p.kchunks;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_a);
+    for (int i = 0; i < (p.a_map_per_tap ? 4 : 1); ++i) prefetch_tmap(&tmaps_a.m[i]);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -136,7 +146,8 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          tma_load_4d(sa, &tmap_a, &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
+          if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
+          else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
           tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
@@ -182,22 +193,41 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       if (valid && ncol < p.n_total) {
         float* dst;
         if (p.mode == 0) {
-          dst = p.out + ((long long)(n * p.h_out + h) * p.w_out + w) * p.out_pix_stride + ncol;
+          dst = p.out + n * p.osn + h * p.osh + w * p.osw + ncol;
         } else {
           const int sub = ncol / p.up_c, co = ncol - sub * p.up_c;
-          const int oh = 2 * h + (sub >> 1), ow = 2 * w + (sub & 1);
-          dst = p.out + ((long long)(n * 2 * p.h_out + oh) * (2 * p.w_out) + ow) * p.out_pix_stride + co;
+          dst = p.out + n * p.osn + (2 * h + (sub >> 1)) * p.osh + (2 * w + (sub & 1)) * p.osw + co;
         }
         const int lim = min(32, p.n_total - ncol);
+        const int pcol = p.mode == 1 ? ncol % p.up_c : ncol;  // per-channel vectors are indexed by the output channel
+        if (p.scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= (j < lim) ? __ldg(p.scale + pcol + j) : 0.f;
+        }
         if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += (j < lim) ? __ldg(p.bias + ncol + j) : 0.f;
+          for (int j = 0; j < 32; ++j) v[j] += (j < lim) ? __ldg(p.bias + pcol + j) : 0.f;
         }
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
-        if (lim == 32) {
+        if (p.mask) {
+          const float* mk = p.mask + n * p.msn + h * p.msh + w * p.msw + ncol;
+          if (lim == 32 && p.vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 q4 = __ldg(reinterpret_cast<const float4*>(mk) + j);
+              v[4 * j] = q4.x > 0.f ? v[4 * j] : 0.f;
+              v[4 * j + 1] = q4.y > 0.f ? v[4 * j + 1] : 0.f;
+              v[4 * j + 2] = q4.z > 0.f ? v[4 * j + 2] : 0.f;
+              v[4 * j + 3] = q4.w > 0.f ? v[4 * j + 3] : 0.f;
+            }
+          } else {
+            for (int j = 0; j < lim; ++j) v[j] = mk[j] > 0.f ? v[j] : 0.f;
+          }
+        }
+        if (lim == 32 && p.vec_ok) {
           float4* d4 = reinterpret_cast<float4*>(dst);
           if (p.accumulate) {
 #pragma unroll
@@ -221,7 +251,7 @@ conv_fprop_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 }
 
 template <int BLOCK_N>
-int launch_fprop(const CUtensorMap& ta, const CUtensorMap& tb, const FpropParams& p, int m_tiles, int n_tiles,
+int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p, int m_tiles, int n_tiles,
                  cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N>;
   static bool attr = false;
@@ -229,6 +259,9 @@ int launch_fprop(const CUtensorMap& ta, const CUtensorMap& tb, const FpropParams
     QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr = true;
   }
+  ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
+                 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
+                 4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
   conv_fprop_tc_kernel<BLOCK_N><<<dim3(m_tiles, n_tiles), kThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -243,63 +276,50 @@ int pow2_ceil(int v) {
 
 }  // namespace
 
-// Convolution (stride 1) / GEMM, K-major operands.
-//   x: NHWC fp32 activations, n_img x h_in x w_in pixels, `cin` channels read at channel stride x_cstride
-//      (x already points at the first channel of the slice). cin % 32 == 0.
-//   wpacked: [n_total][kh*kw*cin] fp32 (K-major rows; a torch Linear weight is already in this form for kh=kw=1).
-//   out: NHWC fp32, n_img x h_out x w_out pixels, channel stride out_cstride, n_total channels written
-//        (mode 1: ConvTranspose2d 2x2 s2 pixel shuffle, n_total = 4*up_c, output image 2h_out x 2w_out, up_c channels).
-//   A plain GEMM C[M,N] = A[M,K] B[N,K]^T is n_img=1, h=1, w=M, cin=K, kh=kw=1.
-//   block_n: 0 = choose; else one of 32/64/128/256.
-QEB_API int qeb_conv_fprop_tc(const float* x, int n_img, int h_in, int w_in, int cin, int x_cstride, const float* wpacked,
-                              int n_total, int kh, int kw, int ph, int pw, int h_out, int w_out, const float* bias,
-                              int relu, float* out, int out_cstride, int mode, int up_c, int accumulate, int block_n,
-                              void* stream) {
-  QEB_REQUIRE(x && wpacked && out, "conv_fprop_tc: null pointer");
-  QEB_REQUIRE(n_img > 0 && h_in > 0 && w_in > 0 && h_out > 0 && w_out > 0, "conv_fprop_tc: bad spatial dims");
-  QEB_REQUIRE(cin > 0 && cin % 32 == 0, "conv_fprop_tc: cin=%d must be a positive multiple of 32", cin);
-  QEB_REQUIRE(x_cstride >= cin && x_cstride % 4 == 0 && out_cstride % 4 == 0, "conv_fprop_tc: channel strides must be multiples of 4");
-  QEB_REQUIRE(n_total > 0 && kh > 0 && kw > 0, "conv_fprop_tc: bad filter dims");
-  QEB_REQUIRE(((uintptr_t)out & 15) == 0, "conv_fprop_tc: out must be 16-byte aligned");
-  QEB_REQUIRE(mode == 0 || (mode == 1 && up_c > 0 && n_total == 4 * up_c && up_c % 32 == 0), "conv_fprop_tc: bad mode/up_c");
-  cudaStream_t st = (cudaStream_t)stream;
+namespace {
 
+int tmap_img(CUtensorMap* out, const Img& a, const float* base, int c, long long sn, long long sh, long long sw, int w,
+             int h, const uint32_t* box, int swz32) {
+  const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)a.n};
+  const uint64_t str[3] = {(uint64_t)sw * 4, (uint64_t)sh * 4, (uint64_t)sn * 4};
+  return make_tmap_f32(out, base, 4, dims, str, box, swz32);
+}
+
+// shared driver of the three K-major entry points. a_maps: number of A tensor maps already encoded in ta (1 or 4).
+int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const float* wpacked, int n_total, int kh,
+                 int kw, int ph, int pw, int cin, const Img& out, int h_out, int w_out, const TcEpilogue& ep, int mode,
+                 int up_c, const float* bias, cudaStream_t st) {
   FpropParams p;
-  p.n_img = n_img; p.h_out = h_out; p.w_out = w_out;
+  p.n_img = x_geom.n; p.h_out = h_out; p.w_out = w_out;
   p.wt = min(pow2_ceil(w_out), kBlockM);
   p.ht = min(pow2_ceil(h_out), kBlockM / p.wt);
   p.nt = kBlockM / (p.wt * p.ht);
   p.tiles_w = qeb_cdiv(w_out, p.wt);
   p.tiles_h = qeb_cdiv(h_out, p.ht);
-  const int tiles_n_img = qeb_cdiv(n_img, p.nt);
-  const int m_tiles = p.tiles_w * p.tiles_h * tiles_n_img;
+  const int m_tiles = p.tiles_w * p.tiles_h * qeb_cdiv(x_geom.n, p.nt);
   p.kh = kh; p.kw = kw; p.ph = ph; p.pw = pw;
   p.cin = cin; p.kchunks = cin / kBlockK;
   p.n_total = n_total;
-  p.bias = bias; p.relu = relu;
-  p.out = out; p.out_pix_stride = out_cstride;
-  p.mode = mode; p.up_c = up_c > 0 ? up_c : 1; p.accumulate = accumulate;
-
-  int bn = block_n;
-  if (bn == 0) {
-    // largest tile that still yields >= ~1 wave of CTAs; never wider than the (padded) problem
-    const int nmax = min(256, max(32, pow2_ceil(n_total)));
-    bn = nmax;
-    while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < kNumSMs) bn >>= 1;
-    if (mode == 1) while (bn > p.up_c) bn >>= 1;
+  p.bias = bias; p.scale = ep.scale; p.relu = ep.relu;
+  p.out = out.p; p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
+  p.mask = nullptr; p.msn = p.msh = p.msw = 0;
+  bool vec = ((uintptr_t)out.p & 15) == 0 && out.sn % 4 == 0 && out.sh % 4 == 0 && out.sw % 4 == 0;
+  if (ep.mask) {
+    p.mask = ep.mask->p; p.msn = ep.mask->sn; p.msh = ep.mask->sh; p.msw = ep.mask->sw;
+    vec = vec && ((uintptr_t)p.mask & 15) == 0 && p.msn % 4 == 0 && p.msh % 4 == 0 && p.msw % 4 == 0;
   }
-  QEB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv_fprop_tc: block_n %d", bn);
-  QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "conv_fprop_tc: block_n must divide up_c in pixel-shuffle mode");
+  p.vec_ok = vec;
+  p.mode = mode; p.up_c = up_c > 0 ? up_c : 1; p.accumulate = ep.accumulate;
+  p.a_map_per_tap = per_tap;
+
+  // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
+  int bn = min(256, max(32, pow2_ceil(n_total)));
+  while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < kNumSMs) bn >>= 1;
+  if (mode == 1) while (bn > p.up_c) bn >>= 1;
+  QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "tc fprop: tile width %d must divide the up-conv channels %d", bn, p.up_c);
   const int n_tiles = qeb_cdiv(n_total, bn);
 
-  CUtensorMap ta, tb;
-  {
-    const uint64_t dims[4] = {(uint64_t)cin, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n_img};
-    const uint64_t str[3] = {(uint64_t)x_cstride * 4, (uint64_t)w_in * x_cstride * 4, (uint64_t)h_in * w_in * x_cstride * 4};
-    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)p.wt, (uint32_t)p.ht, (uint32_t)p.nt};
-    int rc = make_tmap_f32(&ta, x, 4, dims, str, box);
-    if (rc) return rc;
-  }
+  CUtensorMap tb;
   {
     const uint64_t ktot = (uint64_t)kh * kw * cin;
     const uint64_t dims[2] = {ktot, (uint64_t)n_total};
@@ -309,11 +329,95 @@ QEB_API int qeb_conv_fprop_tc(const float* x, int n_img, int h_in, int w_in, int
     if (rc) return rc;
   }
   switch (bn) {
-    case 32: return launch_fprop<32>(ta, tb, p, m_tiles, n_tiles, st);
-    case 64: return launch_fprop<64>(ta, tb, p, m_tiles, n_tiles, st);
-    case 128: return launch_fprop<128>(ta, tb, p, m_tiles, n_tiles, st);
-    default: return launch_fprop<256>(ta, tb, p, m_tiles, n_tiles, st);
+    case 32: return launch_fprop<32>(ta_in, tb, p, m_tiles, n_tiles, st);
+    case 64: return launch_fprop<64>(ta_in, tb, p, m_tiles, n_tiles, st);
+    case 128: return launch_fprop<128>(ta_in, tb, p, m_tiles, n_tiles, st);
+    default: return launch_fprop<256>(ta_in, tb, p, m_tiles, n_tiles, st);
   }
+}
+
+void fprop_box(int h_out, int w_out, uint32_t* box) {
+  const int wt = min(pow2_ceil(w_out), kBlockM);
+  const int ht = min(pow2_ceil(h_out), kBlockM / wt);
+  box[0] = kBlockK; box[1] = wt; box[2] = ht; box[3] = kBlockM / (wt * ht);
+}
+
+bool strides_ok(const Img& a) { return ((uintptr_t)a.p & 15) == 0 && a.sn % 4 == 0 && a.sh % 4 == 0 && a.sw % 4 == 0; }
+
+}  // namespace
+
+int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
+                  const TcEpilogue& ep, cudaStream_t st) {
+  QEB_REQUIRE(x.p && wpacked && out.p, "tc_conv_fprop: null pointer");
+  QEB_REQUIRE(x.c > 0 && x.c % 32 == 0, "tc_conv_fprop: cin=%d must be a positive multiple of 32", x.c);
+  QEB_REQUIRE(strides_ok(x), "tc_conv_fprop: input must be 16-byte aligned with strides that are multiples of 4");
+  QEB_REQUIRE(out.n == x.n && out.h == x.h + 2 * ph - kh + 1 && out.w == x.w + 2 * pw - kw + 1,
+              "tc_conv_fprop: output geometry %dx%dx%d does not match input %dx%dx%d k%dx%d p%d,%d", out.n, out.h, out.w, x.n,
+              x.h, x.w, kh, kw, ph, pw);
+  QEB_REQUIRE(n_total > 0 && n_total <= out.c, "tc_conv_fprop: n_total %d vs out.c %d", n_total, out.c);
+  TmapArray4 ta;
+  uint32_t box[4];
+  fprop_box(out.h, out.w, box);
+  int rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
+  if (rc) return rc;
+  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st);
+}
+
+int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st) {
+  QEB_REQUIRE(x.p && wpacked && out.p, "tc_convT_fprop: null pointer");
+  QEB_REQUIRE(x.c % 32 == 0 && out.c % 32 == 0, "tc_convT_fprop: channels must be multiples of 32");
+  QEB_REQUIRE(strides_ok(x), "tc_convT_fprop: input alignment");
+  QEB_REQUIRE(out.n == x.n && out.h == 2 * x.h && out.w == 2 * x.w, "tc_convT_fprop: output must be 2x the input");
+  TmapArray4 ta;
+  uint32_t box[4];
+  fprop_box(x.h, x.w, box);
+  int rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
+  if (rc) return rc;
+  TcEpilogue ep;
+  return fprop_common(ta, false, x, wpacked, 4 * out.c, 1, 1, 0, 0, x.c, out, x.h, x.w, ep, 1, out.c, bias, st);
+}
+
+int tc_convT_dgrad(const Img& dy, const float* wpacked, const Img& dx, const TcEpilogue& ep, cudaStream_t st) {
+  QEB_REQUIRE(dy.p && wpacked && dx.p, "tc_convT_dgrad: null pointer");
+  QEB_REQUIRE(dy.c % 32 == 0, "tc_convT_dgrad: channels must be multiples of 32");
+  QEB_REQUIRE(strides_ok(dy), "tc_convT_dgrad: input alignment");
+  QEB_REQUIRE(dy.n == dx.n && dy.h == 2 * dx.h && dy.w == 2 * dx.w, "tc_convT_dgrad: dy must be 2x dx");
+  TmapArray4 ta;
+  uint32_t box[4];
+  fprop_box(dx.h, dx.w, box);
+  for (int t = 0; t < 4; ++t) {  // sub-lattice (dh,dw) of dy viewed as a dx-sized image
+    const int dh = t >> 1, dw = t & 1;
+    int rc = tmap_img(&ta.m[t], dy, dy.p + dh * dy.sh + dw * dy.sw, dy.c, dy.sn, 2 * dy.sh, 2 * dy.sw, dx.w, dx.h, box, 0);
+    if (rc) return rc;
+  }
+  return fprop_common(ta, true, dx, wpacked, dx.c, 2, 2, 0, 0, dy.c, dx, dx.h, dx.w, ep, 0, 0, ep.bias, st);
+}
+
+// C ABI (tests and external callers): contiguous NHWC with channel strides.
+QEB_API int qeb_conv_fprop_tc(const float* x, int n_img, int h_in, int w_in, int cin, int x_cstride, const float* wpacked,
+                              int n_total, int kh, int kw, int ph, int pw, const float* bias, const float* scale, int relu,
+                              float* out, int out_cstride, int accumulate, void* stream) {
+  QEB_REQUIRE(h_in + 2 * ph - kh + 1 > 0 && w_in + 2 * pw - kw + 1 > 0, "conv_fprop_tc: empty output");
+  Img xi = img_nhwc(const_cast<float*>(x), n_img, h_in, w_in, cin, x_cstride);
+  Img oi = img_nhwc(out, n_img, h_in + 2 * ph - kh + 1, w_in + 2 * pw - kw + 1, n_total, out_cstride);
+  TcEpilogue ep;
+  ep.bias = bias; ep.scale = scale; ep.relu = relu; ep.accumulate = accumulate;
+  return tc_conv_fprop(xi, wpacked, n_total, kh, kw, ph, pw, oi, ep, (cudaStream_t)stream);
+}
+
+QEB_API int qeb_convT2x2_fprop_tc(const float* x, int n_img, int h, int w, int cin, int x_cstride, const float* wpacked,
+                                  const float* bias, int cout, float* out, int out_cstride, void* stream) {
+  Img xi = img_nhwc(const_cast<float*>(x), n_img, h, w, cin, x_cstride);
+  Img oi = img_nhwc(out, n_img, 2 * h, 2 * w, cout, out_cstride);
+  return tc_convT_fprop(xi, wpacked, bias, oi, (cudaStream_t)stream);
+}
+
+QEB_API int qeb_convT2x2_dgrad_tc(const float* dy, int n_img, int h, int w, int cout, int dy_cstride, const float* wpacked,
+                                  int cin, float* dx, int dx_cstride, void* stream) {
+  Img di = img_nhwc(const_cast<float*>(dy), n_img, 2 * h, 2 * w, cout, dy_cstride);
+  Img xi = img_nhwc(dx, n_img, h, w, cin, dx_cstride);
+  TcEpilogue ep;
+  return tc_convT_dgrad(di, wpacked, xi, ep, (cudaStream_t)stream);
 }
 
 // =================================================================================================================
@@ -340,10 +444,6 @@ struct WgradParams {
   int a_map_per_tap;  // 1: tap selects the A tensor map (ConvTranspose sub-lattices), no coordinate shift
   float* out;
   long long s_rowc, s_kh, s_kw, s_col;  // element strides of the gradient tensor
-};
-
-struct TmapArray4 {
-  CUtensorMap m[4];
 };
 
 template <int BLOCK_N>
@@ -470,6 +570,8 @@ int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams&
     QEB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr = true;
   }
+  ProfScope prof("tc_conv_wgrad", st, 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.row_blocks * 32,
+                 4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.a_groups * 32 + p.n_total) + (double)p.n_total * p.row_blocks * 32));
   conv_wgrad_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -478,75 +580,16 @@ int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams&
 
 }  // namespace
 
-// Weight gradient of a stride-1 convolution / GEMM (mode 0) or of ConvTranspose2d 2x2 s2 (mode 1), accumulated with
-// atomics into `dw` (caller zero-fills it unless it wants accumulation).
-//  mode 0: a = layer input x (n_img,h_in,w_in,a_c @ a_cstride), b = dY (n_img,h_out,w_out,b_c @ b_cstride);
-//          dw[b_ch][a_ch][kh][kw] (torch Conv2d / Linear layout), dw[(co*a_c + ci)*kh*kw + tap].
-//  mode 1: a = dY of the transposed conv (n_img, 2h_out, 2w_out, a_c @ a_cstride), b = layer input x (n_img,h_out,w_out,b_c);
-//          dw[b_ch (Cin)][a_ch (Cout)][2][2] (torch ConvTranspose2d layout).
-QEB_API int qeb_conv_wgrad_tc(const float* a, int a_c, int a_cstride, int h_in, int w_in, const float* b, int b_c,
-                              int b_cstride, int n_img, int h_out, int w_out, int kh, int kw, int ph, int pw, float* dw,
-                              int mode, int block_n, void* stream) {
-  QEB_REQUIRE(a && b && dw, "conv_wgrad_tc: null pointer");
-  QEB_REQUIRE(a_c > 0 && a_c % 32 == 0 && b_c > 0 && b_c % 32 == 0, "conv_wgrad_tc: channels must be multiples of 32 (%d, %d)", a_c, b_c);
-  QEB_REQUIRE(a_cstride % 4 == 0 && b_cstride % 4 == 0, "conv_wgrad_tc: channel strides must be multiples of 4");
-  QEB_REQUIRE(mode == 0 || (mode == 1 && kh == 2 && kw == 2), "conv_wgrad_tc: bad mode");
-  cudaStream_t st = (cudaStream_t)stream;
-  WgradParams p;
-  p.n_img = n_img; p.h_out = h_out; p.w_out = w_out;
-  p.wt = min(pow2_ceil(w_out), kWgPix);
-  p.ht = min(pow2_ceil(h_out), kWgPix / p.wt);
-  p.nt = kWgPix / (p.wt * p.ht);
-  p.tiles_w = qeb_cdiv(w_out, p.wt);
-  p.tiles_h = qeb_cdiv(h_out, p.ht);
-  p.tiles_total = p.tiles_w * p.tiles_h * qeb_cdiv(n_img, p.nt);
-  p.kh = kh; p.kw = kw; p.ph = ph; p.pw = pw;
-  p.a_groups = a_c / 32;
-  p.row_blocks = kh * kw * p.a_groups;
-  p.n_total = b_c;
-  p.a_map_per_tap = mode;
-  p.out = dw;
-  if (mode == 0) {
-    p.s_rowc = (long long)kh * kw; p.s_kh = kw; p.s_kw = 1; p.s_col = (long long)a_c * kh * kw;
-  } else {
-    p.s_rowc = 4; p.s_kh = 2; p.s_kw = 1; p.s_col = (long long)a_c * 4;
-  }
-  int bn = block_n;
-  if (bn == 0) bn = min(256, max(32, pow2_ceil(b_c)));
-  QEB_REQUIRE(bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv_wgrad_tc: block_n %d", bn);
+namespace {
+
+int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, int a_c, int b_c, cudaStream_t st) {
+  int bn = min(256, max(32, pow2_ceil(b_c)));
   const int m_tiles = qeb_cdiv(p.row_blocks, 4), n_tiles = qeb_cdiv(b_c, bn);
   // split-K so that the grid covers the SMs a few times over, at least 8 pixel tiles per CTA
   int splits = qeb_cdiv(2 * kNumSMs, m_tiles * n_tiles);
   splits = max(1, min(splits, qeb_cdiv(p.tiles_total, 8)));
   p.per_split = qeb_cdiv(p.tiles_total, splits);
   splits = qeb_cdiv(p.tiles_total, p.per_split);
-
-  TmapArray4 ta;
-  CUtensorMap tb;
-  const uint32_t box[4] = {32u, (uint32_t)p.wt, (uint32_t)p.ht, (uint32_t)p.nt};
-  if (mode == 0) {
-    const uint64_t dims[4] = {(uint64_t)a_c, (uint64_t)w_in, (uint64_t)h_in, (uint64_t)n_img};
-    const uint64_t str[3] = {(uint64_t)a_cstride * 4, (uint64_t)w_in * a_cstride * 4, (uint64_t)h_in * w_in * a_cstride * 4};
-    int rc = make_tmap_f32(&ta.m[0], a, 4, dims, str, box, 1);
-    if (rc) return rc;
-    ta.m[1] = ta.m[2] = ta.m[3] = ta.m[0];
-  } else {
-    // four sub-lattices (dh,dw) of the 2h_out x 2w_out gradient image, each viewed as an h_out x w_out image
-    const int H2 = 2 * h_out, W2 = 2 * w_out;
-    for (int t = 0; t < 4; ++t) {
-      const int dh = t >> 1, dw_ = t & 1;
-      const uint64_t dims[4] = {(uint64_t)a_c, (uint64_t)w_out, (uint64_t)h_out, (uint64_t)n_img};
-      const uint64_t str[3] = {(uint64_t)2 * a_cstride * 4, (uint64_t)2 * W2 * a_cstride * 4, (uint64_t)H2 * W2 * a_cstride * 4};
-      int rc = make_tmap_f32(&ta.m[t], a + ((long long)dh * W2 + dw_) * a_cstride, 4, dims, str, box, 1);
-      if (rc) return rc;
-    }
-  }
-  {
-    const uint64_t dims[4] = {(uint64_t)b_c, (uint64_t)w_out, (uint64_t)h_out, (uint64_t)n_img};
-    const uint64_t str[3] = {(uint64_t)b_cstride * 4, (uint64_t)w_out * b_cstride * 4, (uint64_t)h_out * w_out * b_cstride * 4};
-    int rc = make_tmap_f32(&tb, b, 4, dims, str, box, 1);
-    if (rc) return rc;
-  }
   const dim3 grid(m_tiles, n_tiles, splits);
   switch (bn) {
     case 32: return launch_wgrad<32>(ta, tb, p, grid, st);
@@ -554,4 +597,86 @@ QEB_API int qeb_conv_wgrad_tc(const float* a, int a_c, int a_cstride, int h_in, 
     case 128: return launch_wgrad<128>(ta, tb, p, grid, st);
     default: return launch_wgrad<256>(ta, tb, p, grid, st);
   }
+}
+
+void wgrad_geometry(WgradParams& p, int n_img, int h_out, int w_out, uint32_t* box) {
+  p.n_img = n_img; p.h_out = h_out; p.w_out = w_out;
+  p.wt = min(pow2_ceil(w_out), kWgPix);
+  p.ht = min(pow2_ceil(h_out), kWgPix / p.wt);
+  p.nt = kWgPix / (p.wt * p.ht);
+  p.tiles_w = qeb_cdiv(w_out, p.wt);
+  p.tiles_h = qeb_cdiv(h_out, p.ht);
+  p.tiles_total = p.tiles_w * p.tiles_h * qeb_cdiv(n_img, p.nt);
+  box[0] = 32; box[1] = p.wt; box[2] = p.ht; box[3] = p.nt;
+}
+
+}  // namespace
+
+int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, float* dw, long long s_co, long long s_ci,
+                  long long s_kh, long long s_kw, cudaStream_t st) {
+  QEB_REQUIRE(x.p && dy.p && dw, "tc_conv_wgrad: null pointer");
+  QEB_REQUIRE(x.c > 0 && x.c % 32 == 0, "tc_conv_wgrad: input channels %d must be a multiple of 32", x.c);
+  QEB_REQUIRE(strides_ok(x) && strides_ok(dy), "tc_conv_wgrad: operands must be 16-byte aligned, strides multiples of 4");
+  QEB_REQUIRE(x.n == dy.n, "tc_conv_wgrad: batch mismatch");
+  WgradParams p;
+  uint32_t box[4];
+  wgrad_geometry(p, dy.n, dy.h, dy.w, box);
+  p.kh = kh; p.kw = kw; p.ph = ph; p.pw = pw;
+  p.a_groups = x.c / 32;
+  p.row_blocks = kh * kw * p.a_groups;
+  p.n_total = dy.c;
+  p.a_map_per_tap = 0;
+  p.out = dw;
+  p.s_rowc = s_ci; p.s_kh = s_kh; p.s_kw = s_kw; p.s_col = s_co;
+  TmapArray4 ta;
+  CUtensorMap tb;
+  int rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 1);
+  if (rc) return rc;
+  ta.m[1] = ta.m[2] = ta.m[3] = ta.m[0];
+  rc = tmap_img(&tb, dy, dy.p, dy.c, dy.sn, dy.sh, dy.sw, dy.w, dy.h, box, 1);
+  if (rc) return rc;
+  return wgrad_common(ta, tb, p, x.c, dy.c, st);
+}
+
+int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
+  QEB_REQUIRE(x.p && dy.p && dw, "tc_convT_wgrad: null pointer");
+  QEB_REQUIRE(x.c % 32 == 0 && dy.c % 32 == 0, "tc_convT_wgrad: channels must be multiples of 32");
+  QEB_REQUIRE(strides_ok(x) && strides_ok(dy), "tc_convT_wgrad: operand alignment");
+  QEB_REQUIRE(x.n == dy.n && dy.h == 2 * x.h && dy.w == 2 * x.w, "tc_convT_wgrad: dy must be 2x x");
+  // M side: (tap, co) from the four sub-lattices of dy; N side: ci. dw[ci][co][dh][dw].
+  WgradParams p;
+  uint32_t box[4];
+  wgrad_geometry(p, x.n, x.h, x.w, box);
+  p.kh = 2; p.kw = 2; p.ph = 0; p.pw = 0;
+  p.a_groups = dy.c / 32;
+  p.row_blocks = 4 * p.a_groups;
+  p.n_total = x.c;
+  p.a_map_per_tap = 1;
+  p.out = dw;
+  p.s_rowc = 4; p.s_kh = 2; p.s_kw = 1; p.s_col = (long long)dy.c * 4;
+  TmapArray4 ta;
+  CUtensorMap tb;
+  for (int t = 0; t < 4; ++t) {
+    const int dh = t >> 1, dwi = t & 1;
+    int rc = tmap_img(&ta.m[t], dy, dy.p + dh * dy.sh + dwi * dy.sw, dy.c, dy.sn, 2 * dy.sh, 2 * dy.sw, x.w, x.h, box, 1);
+    if (rc) return rc;
+  }
+  int rc = tmap_img(&tb, x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 1);
+  if (rc) return rc;
+  return wgrad_common(ta, tb, p, dy.c, x.c, st);
+}
+
+// C ABI: weight gradient of a stride-1 convolution / Linear in torch's layout dw[co][ci][kh][kw], accumulated.
+QEB_API int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, int w_in, const float* dy, int cout,
+                              int dy_cstride, int n_img, int kh, int kw, int ph, int pw, float* dw, void* stream) {
+  Img xi = img_nhwc(const_cast<float*>(x), n_img, h_in, w_in, cin, x_cstride);
+  Img di = img_nhwc(const_cast<float*>(dy), n_img, h_in + 2 * ph - kh + 1, w_in + 2 * pw - kw + 1, cout, dy_cstride);
+  return tc_conv_wgrad(xi, di, kh, kw, ph, pw, dw, (long long)cin * kh * kw, (long long)kh * kw, kw, 1, (cudaStream_t)stream);
+}
+
+QEB_API int qeb_convT2x2_wgrad_tc(const float* x, int cin, int x_cstride, int h, int w, const float* dy, int cout,
+                                  int dy_cstride, int n_img, float* dw, void* stream) {
+  Img xi = img_nhwc(const_cast<float*>(x), n_img, h, w, cin, x_cstride);
+  Img di = img_nhwc(const_cast<float*>(dy), n_img, 2 * h, 2 * w, cout, dy_cstride);
+  return tc_convT_wgrad(xi, di, dw, (cudaStream_t)stream);
 }

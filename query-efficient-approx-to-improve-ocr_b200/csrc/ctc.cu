@@ -330,6 +330,7 @@ QEB_API int qeb_ctc_fwd(const float* log_probs, long long st_t, long long st_b, 
   QEB_REQUIRE(max_target_len >= 0 && 2 * max_target_len + 1 <= 32 * kMaxSPL, "ctc_fwd: target length %d > 127 unsupported", max_target_len);
   QEB_REQUIRE(max_target_len == 0 || targets, "ctc_fwd: null targets");
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof("ctc_fwd", st, 0.0, 4.0 * B * T * V);
   CtcArgs a{log_probs, st_t, st_b, batch_index, targets, tgt_offsets, input_lengths, target_lengths,
             B, T, V, blank, 2 * max_target_len + 1, log_alpha, nll};
   const int grid = qeb_cdiv(B, kWarpsPerBlock);
@@ -362,6 +363,7 @@ QEB_API int qeb_ctc_bwd(const float* log_probs, long long st_t, long long st_b, 
   QEB_REQUIRE(B > 0 && T > 0 && V > 0, "ctc_bwd: bad sizes");
   QEB_REQUIRE(max_target_len >= 0 && 2 * max_target_len + 1 <= 32 * kMaxSPL, "ctc_bwd: target length %d > 127 unsupported", max_target_len);
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope prof("ctc_bwd", st, 0.0, 8.0 * B * T * V);
   CtcBwdArgs g;
   g.f = CtcArgs{log_probs, st_t, st_b, batch_index, targets, tgt_offsets, input_lengths, target_lengths,
                 B, T, V, blank, 2 * max_target_len + 1, const_cast<float*>(log_alpha), const_cast<float*>(nll)};
@@ -385,6 +387,7 @@ QEB_API int qeb_ctc_bwd(const float* log_probs, long long st_t, long long st_b, 
 
 QEB_API int qeb_log_softmax_fwd(const float* x, float* y, long long rows, int V, void* stream) {
   QEB_REQUIRE(x && y && rows > 0 && V > 0, "log_softmax_fwd: bad args");
+  ProfScope prof("log_softmax", (cudaStream_t)stream, 0.0, 8.0 * rows * V);
   log_softmax_fwd_kernel<<<qeb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, y, rows, V);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -393,6 +396,7 @@ QEB_API int qeb_log_softmax_fwd(const float* x, float* y, long long rows, int V,
 
 QEB_API int qeb_log_softmax_bwd(const float* y, const float* dy, float* dx, long long rows, int V, void* stream) {
   QEB_REQUIRE(y && dy && dx && rows > 0 && V > 0, "log_softmax_bwd: bad args");
+  ProfScope prof("log_softmax", (cudaStream_t)stream, 0.0, 12.0 * rows * V);
   log_softmax_bwd_kernel<<<qeb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, rows, V);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();

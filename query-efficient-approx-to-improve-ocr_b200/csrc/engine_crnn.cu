@@ -1,0 +1,355 @@
+// CRNN surrogate, forward and backward, as one host-side launch sequence over the sm_100a kernels.
+// Reference: models/model_crnn.py:5-56 (Convolutional.forward :47-56, CRNN.forward :16-21, map_to_sequence :23-28).
+//
+//   x (B,1,32,W) --conv1+ReLU--> pool 2x2 --conv2+ReLU--> pool 2x2 --conv3+ReLU--> conv4+ReLU --> pool (2,1)
+//     --conv5+BN1+ReLU--> conv6+BN2+ReLU --> pool (2,1) --conv7 (2x2, no pad)--> (T = W/4-1, B, 512)
+//     --BiLSTM x2 (hidden 256)--> Linear(512, V) --> logits (T,B,V)          [log_softmax is its own op, ctc.cu]
+//
+// Activations are NHWC fp32 in a caller-owned workspace (layout: CrnnPlan below); the module input (B,1,32,W) is
+// already NHWC because it has one channel. conv2..conv7, the LSTM input projections and the Linear layer run on
+// tcgen05 (conv_tc.cu); conv1, pooling, batch norm and the bias gradients are direct kernels (nn_ops.cu); the
+// recurrence is the cluster kernel of lstm.cu. BatchNorm follows the module mode: batch statistics + running-stat
+// update (phase A, train_nn_patch.py:226) or frozen running statistics folded into the conv epilogue (phase B after
+// set_bn_eval, utils.py:113-115).
+#include "nn.cuh"
+
+namespace {
+
+enum {  // parameter order of the C ABI (= state_dict order of the reference module)
+  P_C1W, P_C1B, P_C2W, P_C2B, P_C3W, P_C3B, P_C4W, P_C4B, P_C5W, P_C5B, P_BN1W, P_BN1B, P_C6W, P_C6B, P_BN2W, P_BN2B,
+  P_C7W, P_C7B, P_LSTM0,  // + (layer*2 + dir)*4 + {w_ih, w_hh, b_ih, b_hh}
+  P_LINW = P_LSTM0 + 16, P_LINB, P_COUNT
+};
+enum { B_BN1_MEAN, B_BN1_VAR, B_BN1_NBT, B_BN2_MEAN, B_BN2_VAR, B_BN2_NBT, B_COUNT };
+
+constexpr int kHid = 256;
+
+struct Arena {
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  float* take(size_t n_floats) {
+    float* p = reinterpret_cast<float*>(base + off);
+    off += (n_floats * sizeof(float) + 255) & ~size_t(255);
+    return p;
+  }
+};
+
+struct CrnnPlan {
+  int B, W, V, T, W2, W4;
+  // saved by the forward for the backward
+  float *a1f, *a1, *a2f, *a2, *a3, *a4f, *a4, *z5, *a5, *z6, *a6f, *a6, *x0, *g0, *c0, *y0, *g1, *c1, *y1;
+  float *scsh5, *scsh6;  // BN scale/shift/mean/invstd (4*512 each)
+  double* bnstats;       // 2 layers x 2*512
+  // packed weights
+  float *wp2, *wp3, *wp4, *wp5, *wp6, *wp7, *wih0, *wih1, *bias0, *bias1;
+  // backward scratch
+  float *dlp, *wlinT, *wihT, *wpd, *dy1, *dy0, *dx0, *d6, *d6f, *d5, *d4, *d4f, *d3, *d2, *d2f, *d1, *d1f;
+  double* bnred;
+  size_t bytes;
+};
+
+CrnnPlan make_plan(int B, int W, int V, void* base) {
+  CrnnPlan p;
+  p.B = B; p.W = W; p.V = V; p.W2 = W / 2; p.W4 = W / 4; p.T = W / 4 - 1;
+  Arena a(base);
+  const size_t px32 = (size_t)B * 32 * W, px16 = (size_t)B * 16 * p.W2, px8 = (size_t)B * 8 * p.W4, px4 = (size_t)B * 4 * p.W4,
+               px2 = (size_t)B * 2 * p.W4, tb = (size_t)p.T * B;
+  p.a1f = a.take(px32 * 64); p.a1 = a.take(px16 * 64);
+  p.a2f = a.take(px16 * 128); p.a2 = a.take(px8 * 128);
+  p.a3 = a.take(px8 * 256);
+  p.a4f = a.take(px8 * 256); p.a4 = a.take(px4 * 256);
+  p.z5 = a.take(px4 * 512); p.a5 = a.take(px4 * 512);
+  p.z6 = a.take(px4 * 512); p.a6f = a.take(px4 * 512); p.a6 = a.take(px2 * 512);
+  p.x0 = a.take(tb * 512);
+  p.g0 = a.take(tb * 2048); p.c0 = a.take(tb * 512); p.y0 = a.take(tb * 512);
+  p.g1 = a.take(tb * 2048); p.c1 = a.take(tb * 512); p.y1 = a.take(tb * 512);
+  p.scsh5 = a.take(4 * 512); p.scsh6 = a.take(4 * 512);
+  p.bnstats = reinterpret_cast<double*>(a.take(2 * 2 * 512 * 2));
+  p.wp2 = a.take((size_t)128 * 9 * 64); p.wp3 = a.take((size_t)256 * 9 * 128); p.wp4 = a.take((size_t)256 * 9 * 256);
+  p.wp5 = a.take((size_t)512 * 9 * 256); p.wp6 = a.take((size_t)512 * 9 * 512); p.wp7 = a.take((size_t)512 * 4 * 512);
+  p.wih0 = a.take((size_t)2048 * 512); p.wih1 = a.take((size_t)2048 * 512);
+  p.bias0 = a.take(2048); p.bias1 = a.take(2048);
+  p.dlp = a.take(tb * 96); p.wlinT = a.take((size_t)512 * 96); p.wihT = a.take((size_t)512 * 2048);
+  p.wpd = a.take((size_t)512 * 9 * 512);
+  p.dy1 = a.take(tb * 512); p.dy0 = a.take(tb * 512); p.dx0 = a.take(tb * 512);
+  p.d6 = a.take(px2 * 512); p.d6f = a.take(px4 * 512); p.d5 = a.take(px4 * 512);
+  p.d4 = a.take(px4 * 256); p.d4f = a.take(px8 * 256); p.d3 = a.take(px8 * 256);
+  p.d2 = a.take(px8 * 128); p.d2f = a.take(px16 * 128);
+  p.d1 = a.take(px16 * 64); p.d1f = a.take(px32 * 64);
+  p.bnred = reinterpret_cast<double*>(a.take(2 * 512 * 2));
+  p.bytes = a.off;
+  return p;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != QEB_OK) return _rc; \
+  } while (0)
+
+// torch Conv2d weight (Cout,Cin,kh,kw) -> fprop B operand [Cout][tap][Cin]
+int pack_fprop(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
+  return pack_3d(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin, st);
+}
+// -> dgrad B operand [Cin][flipped tap][Cout]
+int pack_dgrad(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
+  // dst[ci][ft][co] = w[co][ci][taps-1-ft]: walk the source taps backwards with a negative stride
+  return pack_3d(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout, st);
+}
+
+BnParams bn_of(const float* const* params, void* const* buffers, int pw, int pb, int bm) {
+  BnParams b;
+  b.gamma = params[pw]; b.beta = params[pb];
+  b.running_mean = static_cast<float*>(buffers[bm]);
+  b.running_var = static_cast<float*>(buffers[bm + 1]);
+  b.num_batches_tracked = static_cast<long long*>(buffers[bm + 2]);
+  b.eps = 1e-5f; b.momentum = 0.1f;
+  return b;
+}
+
+}  // namespace
+
+QEB_API size_t qeb_crnn_workspace_bytes(int B, int W, int V) {
+  if (B <= 0 || W < 8 || W % 4 != 0 || V <= 0 || V > 96) return 0;
+  return make_plan(B, W, V, nullptr).bytes;
+}
+
+QEB_API int qeb_crnn_num_params(void) { return P_COUNT; }
+
+// x: (B,1,32,W) fp32. params: P_COUNT device pointers in state_dict order; buffers: BN running_mean/var (fp32) and
+// num_batches_tracked (int64) for batchnorm1, batchnorm2. bn_train: 1 = batch statistics (+ running-stat update),
+// 0 = running statistics. logits: (T,B,V) dense. ws: qeb_crnn_workspace_bytes(), kept untouched until the backward.
+QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* const* params, void* const* buffers,
+                             int bn_train, void* ws, float* logits, void* stream) {
+  QEB_REQUIRE(x && params && buffers && ws && logits, "crnn_forward: null pointer");
+  QEB_REQUIRE(B > 0 && W >= 8 && W % 4 == 0 && V > 0 && V <= 96, "crnn_forward: B=%d W=%d V=%d unsupported", B, W, V);
+  QEB_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)x & 15) == 0, "crnn_forward: workspace/input alignment");
+  cudaStream_t st = (cudaStream_t)stream;
+  const CrnnPlan p = make_plan(B, W, V, ws);
+  const int T = p.T;
+  Img X = img_nhwc(const_cast<float*>(x), B, 32, W, 1);
+  Img A1f = img_nhwc(p.a1f, B, 32, W, 64), A1 = img_nhwc(p.a1, B, 16, p.W2, 64);
+  Img A2f = img_nhwc(p.a2f, B, 16, p.W2, 128), A2 = img_nhwc(p.a2, B, 8, p.W4, 128);
+  Img A3 = img_nhwc(p.a3, B, 8, p.W4, 256);
+  Img A4f = img_nhwc(p.a4f, B, 8, p.W4, 256), A4 = img_nhwc(p.a4, B, 4, p.W4, 256);
+  Img Z5 = img_nhwc(p.z5, B, 4, p.W4, 512), A5 = img_nhwc(p.a5, B, 4, p.W4, 512);
+  Img Z6 = img_nhwc(p.z6, B, 4, p.W4, 512), A6f = img_nhwc(p.a6f, B, 4, p.W4, 512), A6 = img_nhwc(p.a6, B, 2, p.W4, 512);
+
+  TRY(c1_conv_fwd(X, params[P_C1W], params[P_C1B], 1, A1f, st));
+  TRY(maxpool_fwd(A1f, 2, 2, A1, st));
+  TcEpilogue ep;
+  ep.relu = 1;
+  TRY(pack_fprop(params[P_C2W], p.wp2, 128, 64, 9, st));
+  ep.bias = params[P_C2B];
+  TRY(tc_conv_fprop(A1, p.wp2, 128, 3, 3, 1, 1, A2f, ep, st));
+  TRY(maxpool_fwd(A2f, 2, 2, A2, st));
+  TRY(pack_fprop(params[P_C3W], p.wp3, 256, 128, 9, st));
+  ep.bias = params[P_C3B];
+  TRY(tc_conv_fprop(A2, p.wp3, 256, 3, 3, 1, 1, A3, ep, st));
+  TRY(pack_fprop(params[P_C4W], p.wp4, 256, 256, 9, st));
+  ep.bias = params[P_C4B];
+  TRY(tc_conv_fprop(A3, p.wp4, 256, 3, 3, 1, 1, A4f, ep, st));
+  TRY(maxpool_fwd(A4f, 2, 1, A4, st));
+
+  TRY(pack_fprop(params[P_C5W], p.wp5, 512, 256, 9, st));
+  TRY(pack_fprop(params[P_C6W], p.wp6, 512, 512, 9, st));
+  const BnParams bn1 = bn_of(params, buffers, P_BN1W, P_BN1B, B_BN1_MEAN), bn2 = bn_of(params, buffers, P_BN2W, P_BN2B, B_BN2_MEAN);
+  if (bn_train) {
+    TRY(fill_zero(p.bnstats, 2 * 2 * 512 * sizeof(double), st));
+    TcEpilogue raw;
+    raw.bias = params[P_C5B];
+    TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, Z5, raw, st));
+    TRY(bn_train_stats(Z5, p.bnstats, st));
+    TRY(bn_train_finalize(p.bnstats, img_pixels(Z5), 512, bn1, p.scsh5, st));
+    TRY(bn_apply(Z5, p.scsh5, 1, A5, st));
+    raw.bias = params[P_C6B];
+    TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, Z6, raw, st));
+    TRY(bn_train_stats(Z6, p.bnstats + 1024, st));
+    TRY(bn_train_finalize(p.bnstats + 1024, img_pixels(Z6), 512, bn2, p.scsh6, st));
+    TRY(bn_apply(Z6, p.scsh6, 1, A6f, st));
+  } else {
+    // frozen statistics: y = relu(conv*scale + shift), shift folds the conv bias
+    TRY(bn_eval_scsh(512, bn1, params[P_C5B], p.scsh5, st));
+    TRY(bn_eval_scsh(512, bn2, params[P_C6B], p.scsh6, st));
+    TcEpilogue f;
+    f.relu = 1;
+    f.scale = p.scsh5; f.bias = p.scsh5 + 512;
+    TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, A5, f, st));
+    f.scale = p.scsh6; f.bias = p.scsh6 + 512;
+    TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, A6f, f, st));
+  }
+  TRY(maxpool_fwd(A6f, 2, 1, A6, st));
+
+  // conv7 writes the sequence-major (T,B,512) tensor directly (map_to_sequence fused)
+  TRY(pack_fprop(params[P_C7W], p.wp7, 512, 512, 4, st));
+  Img X0seq;
+  X0seq.p = p.x0; X0seq.n = B; X0seq.h = 1; X0seq.w = T; X0seq.c = 512; X0seq.sn = 512; X0seq.sh = 0; X0seq.sw = (long long)B * 512;
+  TcEpilogue e7;
+  e7.bias = params[P_C7B];
+  TRY(tc_conv_fprop(A6, p.wp7, 512, 2, 2, 0, 0, X0seq, e7, st));
+
+  // two bidirectional LSTM layers: input projection GEMM (both directions at once, N = 2048) + recurrence
+  const int TB = T * B;
+  float* xin = p.x0;
+  for (int l = 0; l < 2; ++l) {
+    const float* const* lp = params + P_LSTM0 + l * 8;
+    float* wih = l ? p.wih1 : p.wih0;
+    float* bias = l ? p.bias1 : p.bias0;
+    float* g = l ? p.g1 : p.g0;
+    float* c = l ? p.c1 : p.c0;
+    float* y = l ? p.y1 : p.y0;
+    for (int d = 0; d < 2; ++d) {
+      QEB_CUDA(cudaMemcpyAsync(wih + (size_t)d * 1024 * 512, lp[d * 4 + 0], (size_t)1024 * 512 * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+      TRY(vec_add(lp[d * 4 + 2], lp[d * 4 + 3], bias + d * 1024, 1024, st));
+    }
+    TcEpilogue eg;
+    eg.bias = bias;
+    TRY(tc_conv_fprop(img_nhwc(xin, 1, 1, TB, 512), wih, 2048, 1, 1, 0, 0, img_nhwc(g, 1, 1, TB, 2048), eg, st));
+    TRY(lstm_layer_fwd(g, lp[1], lp[5], c, y, T, B, st));
+    xin = y;
+  }
+  TcEpilogue el;
+  el.bias = params[P_LINB];
+  TRY(tc_conv_fprop(img_nhwc(p.y1, 1, 1, TB, 512), params[P_LINW], V, 1, 1, 0, 0, img_nhwc(logits, 1, 1, TB, V), el, st));
+  return QEB_OK;
+}
+
+// dlogits: (T,B,V) dense. grads: P_COUNT pointers (entries may be NULL, all NULL-able: that gradient is skipped);
+// every non-NULL gradient is ACCUMULATED into (zero it for a plain gradient). dx: (B,1,32,W) or NULL.
+// The workspace must be the one the forward filled, with the same B, W, V, params and bn_train.
+QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
+                              const float* dlogits, float* const* grads, float* dx, void* stream) {
+  QEB_REQUIRE(x && params && ws && dlogits && grads, "crnn_backward: null pointer");
+  QEB_REQUIRE(B > 0 && W >= 8 && W % 4 == 0 && V > 0 && V <= 96, "crnn_backward: B=%d W=%d V=%d unsupported", B, W, V);
+  cudaStream_t st = (cudaStream_t)stream;
+  const CrnnPlan p = make_plan(B, W, V, ws);
+  const int T = p.T, TB = T * B;
+  Img X = img_nhwc(const_cast<float*>(x), B, 32, W, 1);
+  Img A1f = img_nhwc(p.a1f, B, 32, W, 64), A1 = img_nhwc(p.a1, B, 16, p.W2, 64);
+  Img A2f = img_nhwc(p.a2f, B, 16, p.W2, 128), A2 = img_nhwc(p.a2, B, 8, p.W4, 128);
+  Img A3 = img_nhwc(p.a3, B, 8, p.W4, 256);
+  Img A4f = img_nhwc(p.a4f, B, 8, p.W4, 256), A4 = img_nhwc(p.a4, B, 4, p.W4, 256);
+  Img Z5 = img_nhwc(p.z5, B, 4, p.W4, 512), A5 = img_nhwc(p.a5, B, 4, p.W4, 512);
+  Img Z6 = img_nhwc(p.z6, B, 4, p.W4, 512), A6f = img_nhwc(p.a6f, B, 4, p.W4, 512), A6 = img_nhwc(p.a6, B, 2, p.W4, 512);
+  Img D1f = img_nhwc(p.d1f, B, 32, W, 64), D1 = img_nhwc(p.d1, B, 16, p.W2, 64);
+  Img D2f = img_nhwc(p.d2f, B, 16, p.W2, 128), D2 = img_nhwc(p.d2, B, 8, p.W4, 128);
+  Img D3 = img_nhwc(p.d3, B, 8, p.W4, 256);
+  Img D4f = img_nhwc(p.d4f, B, 8, p.W4, 256), D4 = img_nhwc(p.d4, B, 4, p.W4, 256);
+  Img D5 = img_nhwc(p.d5, B, 4, p.W4, 512), D6f = img_nhwc(p.d6f, B, 4, p.W4, 512), D6 = img_nhwc(p.d6, B, 2, p.W4, 512);
+  const TcEpilogue plain;
+
+  // ---- Linear
+  TRY(fill_zero(p.dlp, (size_t)TB * 96 * sizeof(float), st));
+  TRY(pack_3d(dlogits, p.dlp, 1, TB, V, 0, V, 1, 0, 96, st));
+  Img DLP = img_nhwc(p.dlp, 1, 1, TB, 96);
+  Img DLPv = img_nhwc(p.dlp, 1, 1, TB, V, 96);
+  Img Y1 = img_nhwc(p.y1, 1, 1, TB, 512), Y0 = img_nhwc(p.y0, 1, 1, TB, 512), X0 = img_nhwc(p.x0, 1, 1, TB, 512);
+  if (grads[P_LINW]) TRY(tc_conv_wgrad(Y1, DLPv, 1, 1, 0, 0, grads[P_LINW], 512, 1, 0, 0, st));
+  if (grads[P_LINB]) TRY(colsum_acc(DLPv, grads[P_LINB], st));
+  TRY(fill_zero(p.wlinT, (size_t)512 * 96 * sizeof(float), st));
+  TRY(pack_3d(params[P_LINW], p.wlinT, 1, 512, V, 0, 1, 512, 0, 96, st));  // wlinT[c][v] = W[v][c]
+  TRY(tc_conv_fprop(DLP, p.wlinT, 512, 1, 1, 0, 0, img_nhwc(p.dy1, 1, 1, TB, 512), plain, st));
+
+  // ---- LSTM layers, top down
+  for (int l = 1; l >= 0; --l) {
+    const float* const* lp = params + P_LSTM0 + l * 8;
+    float* const* lg = grads + P_LSTM0 + l * 8;
+    float* g = l ? p.g1 : p.g0;
+    const float* c = l ? p.c1 : p.c0;
+    float* y = l ? p.y1 : p.y0;
+    const float* dy = l ? p.dy1 : p.dy0;
+    const Img Xin = l ? Y0 : X0;
+    TRY(lstm_layer_bwd(g, c, dy, lp[1], lp[5], T, B, st));  // g now holds d(pre-activations), (T,B,2,1024)
+    for (int d = 0; d < 2; ++d) {
+      Img DG = img_nhwc(g + d * 1024, 1, 1, TB, 1024, 2048);
+      if (lg[d * 4 + 0]) TRY(tc_conv_wgrad(Xin, DG, 1, 1, 0, 0, lg[d * 4 + 0], 512, 1, 0, 0, st));
+      if (lg[d * 4 + 1]) {
+        // dW_hh = sum_t dG_t^T h_{t-1} (forward) / h_{t+1} (reverse): the h sequence shifted by one step, zero outside
+        Img Hs;
+        Hs.p = y + d * kHid; Hs.n = 1; Hs.h = T; Hs.w = B; Hs.c = kHid; Hs.sn = (long long)T * B * 512; Hs.sh = (long long)B * 512; Hs.sw = 512;
+        Img DGs;
+        DGs.p = g + d * 1024; DGs.n = 1; DGs.h = T; DGs.w = B; DGs.c = 1024; DGs.sn = (long long)T * B * 2048; DGs.sh = (long long)B * 2048; DGs.sw = 2048;
+        TRY(tc_conv_wgrad(Hs, DGs, 1, 1, d ? -1 : 1, 0, lg[d * 4 + 1], kHid, 1, 0, 0, st));
+      }
+      if (lg[d * 4 + 2]) TRY(colsum_acc(DG, lg[d * 4 + 2], st));
+      if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], st));
+    }
+    // d(input) = dG * [W_ih_fwd ; W_ih_rev]: B operand [512][2048], wihT[c][d*1024 + r] = W_ih_d[r][c]
+    for (int d = 0; d < 2; ++d) TRY(pack_3d(lp[d * 4 + 0], p.wihT + d * 1024, 1, 512, 1024, 0, 1, 512, 0, 2048, st));
+    TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), p.wihT, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512), plain, st));
+  }
+
+  // ---- conv7 (dz7 = dx0, sequence-major view of a (B,1,T,512) image)
+  Img DZ7;
+  DZ7.p = p.dx0; DZ7.n = B; DZ7.h = 1; DZ7.w = T; DZ7.c = 512; DZ7.sn = 512; DZ7.sh = 0; DZ7.sw = (long long)B * 512;
+  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, grads[P_C7W], 512 * 4, 4, 2, 1, st));
+  if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], st));
+  TRY(pack_dgrad(params[P_C7W], p.wpd, 512, 512, 4, st));
+  TRY(tc_conv_fprop(DZ7, p.wpd, 512, 2, 2, 1, 1, D6, plain, st));
+
+  // ---- conv6 + BN2 + ReLU + pool(2,1), conv5 + BN1 + ReLU
+  const bool bn_grads = grads[P_BN1W] || grads[P_BN2W];
+  if (bn_train || bn_grads) TRY(fill_zero(p.bnred, 2 * 512 * 2 * sizeof(double), st));
+  if (bn_train) {
+    TRY(maxpool_bwd(A6f, D6, 2, 1, 0, nullptr, nullptr, D6f, st));  // grad at relu(bn(z6)); the ReLU mask comes from z6
+    TRY(bn_bwd_reduce(Z6, D6f, p.scsh6, 1, p.bnred, st));
+    TRY(bn_bwd_apply_train(Z6, D6f, p.scsh6, 1, p.bnred, params[P_BN2W], D6f, grads[P_BN2W], grads[P_BN2B], st));
+  } else if (bn_grads) {
+    TRY(maxpool_bwd(A6f, D6, 2, 1, 1, nullptr, nullptr, D6f, st));  // g = routed grad * (a6f > 0)
+    TRY(bn_bwd_reduce(A6f, D6f, p.scsh6, 2, p.bnred, st));
+    TRY(bn_bwd_apply_eval(A6f, D6f, p.scsh6, 2, p.bnred, D6f, grads[P_BN2W], grads[P_BN2B], st));
+  } else {
+    TRY(maxpool_bwd(A6f, D6, 2, 1, 1, p.scsh6, nullptr, D6f, st));  // dz6 = routed grad * (a6f > 0) * scale, one pass
+  }
+  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, grads[P_C6W], 512 * 9, 9, 3, 1, st));
+  if (grads[P_C6B]) TRY(colsum_acc(D6f, grads[P_C6B], st));
+  TRY(pack_dgrad(params[P_C6W], p.wpd, 512, 512, 9, st));
+  if (bn_train) {
+    TRY(tc_conv_fprop(D6f, p.wpd, 512, 3, 3, 1, 1, D5, plain, st));
+    TRY(bn_bwd_reduce(Z5, D5, p.scsh5, 1, p.bnred + 1024, st));
+    TRY(bn_bwd_apply_train(Z5, D5, p.scsh5, 1, p.bnred + 1024, params[P_BN1W], D5, grads[P_BN1W], grads[P_BN1B], st));
+  } else if (bn_grads) {
+    TRY(tc_conv_fprop(D6f, p.wpd, 512, 3, 3, 1, 1, D5, plain, st));
+    TRY(bn_bwd_reduce(A5, D5, p.scsh5, 2, p.bnred + 1024, st));
+    TRY(bn_bwd_apply_eval(A5, D5, p.scsh5, 2, p.bnred + 1024, D5, grads[P_BN1W], grads[P_BN1B], st));
+  } else {
+    TcEpilogue e;
+    e.scale = p.scsh5; e.mask = &A5;  // dz5 = d(a5) * scale, zero where a5 == 0, fused into the dgrad epilogue
+    TRY(tc_conv_fprop(D6f, p.wpd, 512, 3, 3, 1, 1, D5, e, st));
+  }
+  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, grads[P_C5W], 256 * 9, 9, 3, 1, st));
+  if (grads[P_C5B]) TRY(colsum_acc(D5, grads[P_C5B], st));
+  TRY(pack_dgrad(params[P_C5W], p.wpd, 512, 256, 9, st));
+  TRY(tc_conv_fprop(D5, p.wpd, 256, 3, 3, 1, 1, D4, plain, st));
+
+  // ---- conv4 + ReLU + pool(2,1), conv3 + ReLU
+  TRY(maxpool_bwd(A4f, D4, 2, 1, 1, nullptr, nullptr, D4f, st));
+  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, grads[P_C4W], 256 * 9, 9, 3, 1, st));
+  if (grads[P_C4B]) TRY(colsum_acc(D4f, grads[P_C4B], st));
+  TRY(pack_dgrad(params[P_C4W], p.wpd, 256, 256, 9, st));
+  {
+    TcEpilogue e;
+    e.mask = &A3;  // ReLU of conv3 fused into the dgrad epilogue
+    TRY(tc_conv_fprop(D4f, p.wpd, 256, 3, 3, 1, 1, D3, e, st));
+  }
+  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, grads[P_C3W], 128 * 9, 9, 3, 1, st));
+  if (grads[P_C3B]) TRY(colsum_acc(D3, grads[P_C3B], st));
+  TRY(pack_dgrad(params[P_C3W], p.wpd, 256, 128, 9, st));
+  TRY(tc_conv_fprop(D3, p.wpd, 128, 3, 3, 1, 1, D2, plain, st));
+
+  // ---- conv2 + ReLU + pool, conv1 + ReLU + pool
+  TRY(maxpool_bwd(A2f, D2, 2, 2, 1, nullptr, nullptr, D2f, st));
+  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, grads[P_C2W], 64 * 9, 9, 3, 1, st));
+  if (grads[P_C2B]) TRY(colsum_acc(D2f, grads[P_C2B], st));
+  const bool need_d1 = grads[P_C1W] || grads[P_C1B] || dx;
+  if (need_d1) {
+    TRY(pack_dgrad(params[P_C2W], p.wpd, 128, 64, 9, st));
+    TRY(tc_conv_fprop(D2f, p.wpd, 64, 3, 3, 1, 1, D1, plain, st));
+    TRY(maxpool_bwd(A1f, D1, 2, 2, 1, nullptr, nullptr, D1f, st));
+    if (grads[P_C1W]) TRY(c1_conv_wgrad(X, D1f, grads[P_C1W], grads[P_C1B], st));
+    if (dx) TRY(c1_conv_dgrad(D1f, params[P_C1W], img_nhwc(dx, B, 32, W, 1), st));
+  }
+  return QEB_OK;
+}

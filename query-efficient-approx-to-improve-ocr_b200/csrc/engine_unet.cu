@@ -1,0 +1,289 @@
+// UNet preprocessor, forward and backward, as one host-side launch sequence over the sm_100a kernels.
+// Reference: models/model_unet.py:9-109 (forward :49-76, _block :78-109): features 32..512, 18 x (conv3x3 no bias +
+// BatchNorm + ReLU), 4 max-pools, 4 ConvTranspose2d(2, stride 2) with skip concats, 1x1 conv + sigmoid.
+//
+// Layout: NHWC fp32 in a caller-owned workspace. torch.cat((upconv, encoder), 1) costs nothing: the encoder writes
+// channels [C,2C) and the up-convolution channels [0,C) of one shared buffer per level, and the decoder's first
+// conv reads the 2C-channel buffer in place. All 3x3 convs except the first (one input channel, direct kernel) and
+// the up-convolutions run on tcgen05 (conv_tc.cu). BatchNorm uses batch statistics in train mode (per-channel
+// sums by a reduction kernel, normalise+ReLU by an elementwise kernel) and is folded into the conv epilogue in
+// eval mode.
+#include "nn.cuh"
+
+namespace {
+
+constexpr int kLevels = 5;   // enc1..enc4 + bottleneck
+constexpr int kUnits = 18;   // conv+BN+ReLU units
+// parameter order of the C ABI: 9 blocks (enc1..4, bottleneck, dec4..1) x {conv1.w, norm1.w, norm1.b, conv2.w, norm2.w,
+// norm2.b}, then upconv4..1 {w, b}, then conv {w, b}
+enum { P_BLOCKS = 0, P_UP = 54, P_CONVW = 62, P_CONVB = 63, P_COUNT = 64 };
+// buffers: per block {norm1.mean, norm1.var, norm1.nbt, norm2.mean, norm2.var, norm2.nbt}
+constexpr int B_COUNT = 54;
+
+struct Arena {
+  char* base;
+  size_t off = 0;
+  explicit Arena(void* b) : base(static_cast<char*>(b)) {}
+  float* take(size_t n_floats) {
+    float* p = reinterpret_cast<float*>(base + off);
+    off += (n_floats * sizeof(float) + 255) & ~size_t(255);
+    return p;
+  }
+};
+
+struct UnetPlan {
+  int B, H, W;
+  int C[kLevels], h[kLevels], w[kLevels];
+  size_t M[kLevels];
+  // encoder / bottleneck blocks (index = level) and decoder blocks (index = level 0..3)
+  float *ez1[kLevels], *ea1[kLevels], *ez2[kLevels], *pool[kLevels - 1], *bott;
+  float *cat[kLevels - 1];
+  float *dz1[kLevels - 1], *da1[kLevels - 1], *dz2[kLevels - 1], *dout[kLevels - 1];
+  float* scsh;      // kUnits x 4*512
+  double* bnstats;  // kUnits x 1024
+  float* wpack;     // one conv's packed weights at a time (largest: 512 x 9 x 512)
+  float *sA[kLevels], *sB[kLevels], *sC[kLevels];
+  double* bnred;    // kUnits x 1024
+  size_t bytes;
+};
+
+UnetPlan make_plan(int B, int H, int W, void* base) {
+  UnetPlan p;
+  p.B = B; p.H = H; p.W = W;
+  Arena a(base);
+  for (int i = 0; i < kLevels; ++i) {
+    p.C[i] = 32 << i; p.h[i] = H >> i; p.w[i] = W >> i;
+    p.M[i] = (size_t)B * p.h[i] * p.w[i];
+  }
+  for (int i = 0; i < kLevels; ++i) {
+    p.ez1[i] = a.take(p.M[i] * p.C[i]); p.ea1[i] = a.take(p.M[i] * p.C[i]); p.ez2[i] = a.take(p.M[i] * p.C[i]);
+  }
+  p.bott = a.take(p.M[4] * p.C[4]);
+  for (int i = 0; i < kLevels - 1; ++i) {
+    p.pool[i] = a.take(p.M[i + 1] * p.C[i]);
+    p.cat[i] = a.take(p.M[i] * 2 * p.C[i]);
+    p.dz1[i] = a.take(p.M[i] * p.C[i]); p.da1[i] = a.take(p.M[i] * p.C[i]); p.dz2[i] = a.take(p.M[i] * p.C[i]);
+    p.dout[i] = a.take(p.M[i] * p.C[i]);
+  }
+  p.scsh = a.take((size_t)kUnits * 4 * 512);
+  p.bnstats = reinterpret_cast<double*>(a.take((size_t)kUnits * 1024 * 2));
+  p.wpack = a.take((size_t)512 * 9 * 512);
+  for (int i = 0; i < kLevels; ++i) {
+    p.sA[i] = a.take(p.M[i] * 2 * p.C[i]); p.sB[i] = a.take(p.M[i] * p.C[i]); p.sC[i] = a.take(p.M[i] * p.C[i]);
+  }
+  p.bnred = reinterpret_cast<double*>(a.take((size_t)kUnits * 1024 * 2));
+  p.bytes = a.off;
+  return p;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != QEB_OK) return _rc; \
+  } while (0)
+
+int pack_fprop(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
+  return pack_3d(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin, st);
+}
+int pack_dgrad(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
+  return pack_3d(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout, st);
+}
+
+struct Ctx {
+  const float* const* params;
+  void* const* buffers;
+  float* const* grads;
+  const UnetPlan* p;
+  int bn_train;
+  cudaStream_t st;
+};
+
+BnParams bn_of(const Ctx& c, int block, int which) {
+  BnParams b;
+  b.gamma = c.params[block * 6 + which * 3 + 1];
+  b.beta = c.params[block * 6 + which * 3 + 2];
+  b.running_mean = static_cast<float*>(c.buffers[block * 6 + which * 3 + 0]);
+  b.running_var = static_cast<float*>(c.buffers[block * 6 + which * 3 + 1]);
+  b.num_batches_tracked = static_cast<long long*>(c.buffers[block * 6 + which * 3 + 2]);
+  b.eps = 1e-5f; b.momentum = 0.1f;
+  return b;
+}
+
+// one conv3x3 (no bias) + BN + ReLU unit. z: raw conv output (train mode only), out: activation.
+int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out) {
+  const int unit = block * 2 + which;
+  const float* w = c.params[block * 6 + which * 3];
+  float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
+  const BnParams bn = bn_of(c, block, which);
+  const int cout = out.c;
+  if (in.c == 1) {
+    TRY(c1_conv_fwd(in, w, nullptr, 0, z, c.st));
+    if (c.bn_train) {
+      TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
+      TRY(bn_train_finalize(c.p->bnstats + (size_t)unit * 1024, img_pixels(z), cout, bn, scsh, c.st));
+    } else {
+      TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
+    }
+    return bn_apply(z, scsh, 1, out, c.st);
+  }
+  TRY(pack_fprop(w, c.p->wpack, cout, in.c, 9, c.st));
+  if (c.bn_train) {
+    const TcEpilogue raw;
+    TRY(tc_conv_fprop(in, c.p->wpack, cout, 3, 3, 1, 1, z, raw, c.st));
+    TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
+    TRY(bn_train_finalize(c.p->bnstats + (size_t)unit * 1024, img_pixels(z), cout, bn, scsh, c.st));
+    return bn_apply(z, scsh, 1, out, c.st);
+  }
+  TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
+  TcEpilogue f;
+  f.relu = 1; f.scale = scsh; f.bias = scsh + cout;
+  return tc_conv_fprop(in, c.p->wpack, cout, 3, 3, 1, 1, out, f, c.st);
+}
+
+// backward of one unit. g: gradient at the unit's output (overwritten with the gradient at the conv output);
+// din: where the gradient at the unit's input goes (nullptr: not needed).
+int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const Img& g, const Img* din) {
+  const int unit = block * 2 + which;
+  const float* w = c.params[block * 6 + which * 3];
+  float* const* gr = c.grads + block * 6 + which * 3;
+  const float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
+  if (c.bn_train) {
+    double* red = c.p->bnred + (size_t)unit * 1024;
+    TRY(bn_bwd_reduce(z, g, scsh, 1, red, c.st));
+    TRY(bn_bwd_apply_train(z, g, scsh, 1, red, nullptr, g, gr[1], gr[2], c.st));
+  } else {  // frozen statistics: the mask and xhat come from the layer output
+    double* red = gr[1] ? c.p->bnred + (size_t)unit * 1024 : nullptr;
+    if (red) TRY(bn_bwd_reduce(out, g, scsh, 2, red, c.st));
+    TRY(bn_bwd_apply_eval(out, g, scsh, 2, red, g, gr[1], gr[2], c.st));
+  }
+  if (in.c == 1) {
+    if (gr[0]) TRY(c1_conv_wgrad(in, g, gr[0], nullptr, c.st));
+    if (din) TRY(c1_conv_dgrad(g, w, *din, c.st));
+    return QEB_OK;
+  }
+  if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, gr[0], (long long)in.c * 9, 9, 3, 1, c.st));
+  if (din) {
+    TRY(pack_dgrad(w, c.p->wpack, g.c, in.c, 9, c.st));
+    const TcEpilogue plain;
+    TRY(tc_conv_fprop(g, c.p->wpack, in.c, 3, 3, 1, 1, *din, plain, c.st));
+  }
+  return QEB_OK;
+}
+
+}  // namespace
+
+QEB_API size_t qeb_unet_workspace_bytes(int B, int H, int W) {
+  if (B <= 0 || H < 16 || W < 16 || H % 16 || W % 16) return 0;
+  return make_plan(B, H, W, nullptr).bytes;
+}
+
+QEB_API int qeb_unet_num_params(void) { return P_COUNT; }
+QEB_API int qeb_unet_num_buffers(void) { return B_COUNT; }
+
+// x: (B,1,H,W) fp32, H and W multiples of 16. y: (B,1,H,W) in (0,1). bn_train as in qeb_crnn_forward.
+QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* const* params, void* const* buffers,
+                             int bn_train, void* ws, float* y, void* stream) {
+  QEB_REQUIRE(x && params && buffers && ws && y, "unet_forward: null pointer");
+  QEB_REQUIRE(B > 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0, "unet_forward: B=%d H=%d W=%d unsupported", B, H, W);
+  QEB_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)x & 15) == 0, "unet_forward: workspace/input alignment");
+  const UnetPlan p = make_plan(B, H, W, ws);
+  Ctx c;
+  c.params = params; c.buffers = buffers; c.grads = nullptr; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
+  if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
+
+  Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
+  for (int i = 0; i < kLevels; ++i) {  // encoder blocks + bottleneck
+    const int C = p.C[i];
+    Img z1 = img_nhwc(p.ez1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.ea1[i], B, p.h[i], p.w[i], C);
+    Img z2 = img_nhwc(p.ez2[i], B, p.h[i], p.w[i], C);
+    Img out = i < 4 ? img_nhwc(p.cat[i] + C, B, p.h[i], p.w[i], C, 2 * C) : img_nhwc(p.bott, B, p.h[i], p.w[i], C);
+    TRY(unit_fwd(c, i, 0, in, z1, a1));
+    TRY(unit_fwd(c, i, 1, a1, z2, out));
+    if (i < 4) {
+      Img pl = img_nhwc(p.pool[i], B, p.h[i + 1], p.w[i + 1], C);
+      TRY(maxpool_fwd(out, 2, 2, pl, c.st));
+      in = pl;
+    }
+  }
+  Img below = img_nhwc(p.bott, B, p.h[4], p.w[4], p.C[4]);
+  for (int i = 3; i >= 0; --i) {  // decoder blocks: block index 5 + (3 - i), up-conv index (3 - i)
+    const int C = p.C[i], blk = 5 + (3 - i), up = 3 - i;
+    // ConvTranspose weight (2C, C, 2, 2) -> B operand [(dh*2+dw)*C + co][2C]
+    TRY(pack_3d(params[P_UP + up * 2], p.wpack, 4, C, 2 * C, 1, 4, (long long)C * 4, (long long)C * 2 * C, 2 * C, c.st));
+    Img upo = img_nhwc(p.cat[i], B, p.h[i], p.w[i], C, 2 * C);
+    TRY(tc_convT_fprop(below, p.wpack, params[P_UP + up * 2 + 1], upo, c.st));
+    Img cat = img_nhwc(p.cat[i], B, p.h[i], p.w[i], 2 * C);
+    Img z1 = img_nhwc(p.dz1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.da1[i], B, p.h[i], p.w[i], C);
+    Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
+    TRY(unit_fwd(c, blk, 0, cat, z1, a1));
+    TRY(unit_fwd(c, blk, 1, a1, z2, out));
+    below = out;
+  }
+  return o1_conv_sigmoid_fwd(below, params[P_CONVW], params[P_CONVB], y, c.st);
+}
+
+// dy: (B,1,H,W). grads: P_COUNT pointers, NULL = skip, non-NULL gradients are ACCUMULATED into. dx: (B,1,H,W) or NULL.
+// y must be the forward's output; ws the forward's workspace.
+QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
+                              const float* y, const float* dy, float* const* grads, float* dx, void* stream) {
+  QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
+  QEB_REQUIRE(B > 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0, "unet_backward: B=%d H=%d W=%d unsupported", B, H, W);
+  const UnetPlan p = make_plan(B, H, W, ws);
+  Ctx c;
+  c.params = params; c.buffers = nullptr; c.grads = grads; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
+  TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
+
+  // final 1x1 conv + sigmoid
+  Img d0 = img_nhwc(p.dout[0], B, H, W, 32), g0 = img_nhwc(p.sC[0], B, H, W, 32);
+  QEB_REQUIRE(grads[P_CONVW] && grads[P_CONVB], "unet_backward: the final conv's gradients are required");
+  TRY(o1_conv_sigmoid_bwd(d0, params[P_CONVW], y, dy, g0, grads[P_CONVW], grads[P_CONVB], c.st));
+
+  for (int i = 0; i <= 3; ++i) {  // decoder blocks, top (full resolution) first
+    const int C = p.C[i], blk = 5 + (3 - i), up = 3 - i;
+    Img cat = img_nhwc(p.cat[i], B, p.h[i], p.w[i], 2 * C);
+    Img z1 = img_nhwc(p.dz1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.da1[i], B, p.h[i], p.w[i], C);
+    Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
+    Img g = img_nhwc(p.sC[i], B, p.h[i], p.w[i], C), ga1 = img_nhwc(p.sB[i], B, p.h[i], p.w[i], C);
+    Img gcat = img_nhwc(p.sA[i], B, p.h[i], p.w[i], 2 * C);
+    TRY(unit_bwd(c, blk, 1, a1, z2, out, g, &ga1));
+    TRY(unit_bwd(c, blk, 0, cat, z1, a1, ga1, &gcat));
+    // up-convolution: dU = gcat[:, :C]
+    Img dU = img_slice(gcat, 0, C);
+    Img below = i < 3 ? img_nhwc(p.dout[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C) : img_nhwc(p.bott, B, p.h[4], p.w[4], 2 * C);
+    if (grads[P_UP + up * 2 + 1]) TRY(colsum_acc(dU, grads[P_UP + up * 2 + 1], c.st));
+    if (grads[P_UP + up * 2]) TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], c.st));
+    // dgrad B operand [2C][(dh*2+dw)*C + co] from the torch weight (2C, C, 2, 2)
+    TRY(pack_3d(params[P_UP + up * 2], p.wpack, 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C, c.st));
+    Img gbelow = img_nhwc(p.sC[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C);
+    const TcEpilogue plain;
+    TRY(tc_convT_dgrad(dU, p.wpack, gbelow, plain, c.st));
+  }
+  for (int i = 4; i >= 0; --i) {  // bottleneck, then encoder blocks
+    const int C = p.C[i];
+    Img z1 = img_nhwc(p.ez1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.ea1[i], B, p.h[i], p.w[i], C);
+    Img z2 = img_nhwc(p.ez2[i], B, p.h[i], p.w[i], C);
+    Img out = i < 4 ? img_nhwc(p.cat[i] + C, B, p.h[i], p.w[i], C, 2 * C) : img_nhwc(p.bott, B, p.h[i], p.w[i], C);
+    Img g = img_nhwc(p.sC[i], B, p.h[i], p.w[i], C), ga1 = img_nhwc(p.sB[i], B, p.h[i], p.w[i], C);
+    if (i < 4) {
+      // gradient at the encoder output = skip-connection part of the concat gradient + routed pooling gradient
+      Img gpool = img_nhwc(p.sA[i + 1], B, p.h[i + 1], p.w[i + 1], C);
+      Img skip = img_nhwc(p.sA[i] + C, B, p.h[i], p.w[i], C, 2 * C);
+      TRY(maxpool_bwd(out, gpool, 2, 2, 0, nullptr, &skip, g, c.st));
+    }
+    TRY(unit_bwd(c, i, 1, a1, z2, out, g, &ga1));
+    if (i > 0) {
+      Img in = img_nhwc(p.pool[i - 1], B, p.h[i], p.w[i], p.C[i - 1]);
+      Img gin = img_nhwc(p.sA[i], B, p.h[i], p.w[i], p.C[i - 1]);
+      TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, &gin));
+    } else {
+      Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
+      if (dx) {
+        Img gx = img_nhwc(dx, B, H, W, 1);
+        TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, &gx));
+      } else {
+        TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, nullptr));
+      }
+    }
+  }
+  return QEB_OK;
+}

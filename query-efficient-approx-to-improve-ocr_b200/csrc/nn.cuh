@@ -1,0 +1,111 @@
+// Internal (C++) interface between the network engines (engine_crnn.cu, engine_unet.cu) and the kernel files.
+// Activations are NHWC fp32 views with arbitrary pixel strides (channel stride 1), so that concat buffers,
+// sequence-major (T,B,C) tensors and channel slices are read and written in place.
+#pragma once
+#include "common.cuh"
+
+struct Img {
+  float* p;
+  int n, h, w, c;
+  long long sn, sh, sw;  // element strides of the image / row / pixel index
+};
+
+// contiguous NHWC image whose pixels are `cstride` floats apart (cstride >= c: a channel slice of a wider buffer)
+static inline Img img_nhwc(float* p, int n, int h, int w, int c, int cstride = 0) {
+  if (cstride == 0) cstride = c;
+  Img i;
+  i.p = p; i.n = n; i.h = h; i.w = w; i.c = c;
+  i.sw = cstride; i.sh = (long long)w * cstride; i.sn = (long long)h * w * cstride;
+  return i;
+}
+static inline Img img_slice(const Img& a, int c0, int c) {
+  Img i = a;
+  i.p = a.p + c0; i.c = c;
+  return i;
+}
+static inline long long img_pixels(const Img& a) { return (long long)a.n * a.h * a.w; }
+// true when pixel index (n,h,w) -> offset is a single stride (rows/images packed back to back)
+static inline bool img_flat(const Img& a) { return a.sh == a.sw * a.w && a.sn == a.sh * a.h; }
+
+// ---- tensor-core (tcgen05, kind::tf32) contractions, conv_tc.cu -------------------------------------------------
+struct TcEpilogue {
+  const float* bias = nullptr;   // per output channel
+  const float* scale = nullptr;  // per output channel, applied before bias: v = acc*scale + bias
+  int relu = 0;
+  const Img* mask = nullptr;     // v = (mask(n,h,w,c) > 0) ? v : 0   (ReLU backward of the layer below, fused)
+  int accumulate = 0;            // out += v
+};
+// stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
+int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
+                  const TcEpilogue& ep, cudaStream_t st);
+// ConvTranspose2d 2x2 stride 2: x (n,h,w,cin) -> out (n,2h,2w,cout). wpacked: [(dh*2+dw)*cout + co][cin]; bias (cout).
+int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st);
+// its input gradient: dy (n,2h,2w,cout) -> dx (n,h,w,cin). wpacked: [cin][(dh*2+dw)*cout + co].
+int tc_convT_dgrad(const Img& dy, const float* wpacked, const Img& dx, const TcEpilogue& ep, cudaStream_t st);
+// weight gradient, accumulated with atomics: dw[co*s_co + ci*s_ci + ky*s_kh + kx*s_kw] += sum_pix x(pix+tap, ci) dy(pix, co)
+int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, float* dw, long long s_co, long long s_ci,
+                  long long s_kh, long long s_kw, cudaStream_t st);
+// ConvTranspose2d 2x2 s2 weight gradient: dw[ci][co][dh][dw] (torch layout) += sum x(n,h,w,ci) dy(n,2h+dh,2w+dw,co)
+int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st);
+
+// ---- weight packing, layout.cu ------------------------------------------------------------------------------------
+// generic strided gather: dst[i0*d0 + i1*d1 + i2] = src[i0*s0 + i1*s1 + i2*s2] for i0<n0, i1<n1, i2<n2 (dst innermost
+// contiguous); entries of a padded destination are expected to be zero-filled by the caller.
+int pack_3d(const float* src, float* dst, int n0, int n1, int n2, long long s0, long long s1, long long s2, long long d0,
+            long long d1, cudaStream_t st);
+
+// ---- direct (SIMT) kernels, nn_ops.cu ---------------------------------------------------------------------------
+// 3x3 pad-1 convolution with ONE input channel: x (n,h,w,1) -> out (n,h,w,cout); w torch layout (cout,1,3,3).
+int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const Img& out, cudaStream_t st);
+int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStream_t st);  // accumulates
+int c1_conv_dgrad(const Img& dy, const float* w, const Img& dx, cudaStream_t st);          // overwrites dx
+// 1x1 convolution to ONE output channel + sigmoid: y = sigmoid(sum_c x*w[c] + b)
+int o1_conv_sigmoid_fwd(const Img& x, const float* w, const float* b, float* y, cudaStream_t st);
+// dz = dy*y*(1-y); dx = dz*w[c]; dw[c] += sum dz*x; db += sum dz
+int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const float* dy, const Img& dx, float* dw, float* db,
+                        cudaStream_t st);
+// max pooling (ph x pw window = stride), NHWC
+int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st);
+// dx = routed dy (first maximal element wins) * chan_scale[c] (if given), zeroed where x <= 0 when relu_mask, plus `add`
+// (same shape as x) if given
+int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
+                const Img& dx, cudaStream_t st);
+// batch norm over all pixels of z (train: batch statistics; eval: running statistics)
+struct BnParams {
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* num_batches_tracked;
+  float eps, momentum;
+};
+// stats: [0,c) sum, [c,2c) sumsq (double accumulators); scsh: [0,c) scale, [c,2c) shift, then train: [2c,3c) mean,
+// [3c,4c) invstd; eval: [2c,3c) beta, [3c,4c) 1/gamma (xhat is recovered from the layer output)
+int bn_train_stats(const Img& z, double* stats, cudaStream_t st);
+int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st);
+int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh, cudaStream_t st);
+// out = relu?(z*scale + shift)
+int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st);
+// backward through relu(bn(z)): red: [0,c) sum g, [c,2c) sum g*xhat (double), g = dy * (z*scale+shift > 0 if relu)
+int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, double* red, cudaStream_t st);
+// train: dz = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M); dgamma += sum_gx, dbeta += sum_g (when given)
+int bn_bwd_apply_train(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const float* gamma,
+                       const Img& dz, float* dgamma, float* dbeta, cudaStream_t st);
+// eval (frozen statistics): dz = g*scale; relu = 2: `z` is the layer's ReLU OUTPUT (the pre-activation is not kept)
+// red (from bn_bwd_reduce on the same tensors) is only needed for dgamma += sum g*xhat, dbeta += sum g.
+int bn_bwd_apply_eval(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const Img& dz,
+                      float* dgamma, float* dbeta, cudaStream_t st);
+// out[c] += sum over pixels of x(pix, c)   (bias gradients)
+int colsum_acc(const Img& x, float* out, cudaStream_t st);
+// dx = dy * (a > 0)
+int relu_bwd(const Img& a, const Img& dy, const Img& dx, cudaStream_t st);
+int fill_zero(void* p, size_t bytes, cudaStream_t st);
+// out = a + b (b may be null)
+int vec_add(const float* a, const float* b, float* out, int n, cudaStream_t st);
+
+// ---- LSTM recurrence, lstm.cu ------------------------------------------------------------------------------------
+// One bidirectional layer, hidden size 256. gates: (T,B,2,4*256) holding x*W_ih^T + b_ih + b_hh on entry (gate order
+// i,f,g,o as torch), overwritten with the ACTIVATED gates; w_hh[dir]: torch layout (1024,256); cells: (T,B,2,256) c_t;
+// y: (T,B,512) [forward | reverse].
+int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
+                   cudaStream_t st);
+// dy: (T,B,512). gates (activated) are overwritten with the gradients at the pre-activations (T,B,2,1024).
+int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
+                   int B, cudaStream_t st);

@@ -1,0 +1,784 @@
+// Direct (SIMT) kernels of the UNet / CRNN step: the HBM-bound layers that are not dense contractions.
+//   - 3x3 convolution with one input channel (CRNN conv1 models/model_crnn.py:37,48; UNet enc1conv1
+//     models/model_unet.py:78-92): K = 9, bandwidth-bound, fprop / wgrad / dgrad
+//   - final 1x1 convolution to one channel + sigmoid (models/model_unet.py:45-47,76) and its backward
+//   - max pooling 2x2 / (2,1) (models/model_crnn.py:48-54, models/model_unet.py:14-20) forward and backward,
+//     the backward fused with the ReLU mask and the skip-connection gradient add
+//   - BatchNorm2d in train mode (batch statistics, running-stat update) and eval mode, fused with ReLU, forward
+//     and backward (models/model_crnn.py:42-44,52-53; models/model_unet.py:93-106)
+//   - bias gradients (column sums), ReLU backward.
+// Layout: NHWC fp32 (nn.cuh Img). All kernels are grid-stride with float4 accesses along the channel dimension.
+#include "nn.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+struct Geo {  // pixel decomposition of an Img
+  int h, w;
+  long long sn, sh, sw;
+};
+__host__ __device__ inline Geo geo(const Img& a) {
+  Geo g;
+  g.h = a.h; g.w = a.w; g.sn = a.sn; g.sh = a.sh; g.sw = a.sw;
+  return g;
+}
+__device__ __forceinline__ long long pix_off(const Geo& g, long long pix) {
+  const int w = (int)(pix % g.w);
+  const long long t = pix / g.w;
+  const int h = (int)(t % g.h);
+  const long long n = t / g.h;
+  return n * g.sn + h * g.sh + w * g.sw;
+}
+
+bool vec4_ok(const Img& a) { return ((uintptr_t)a.p & 15) == 0 && a.sn % 4 == 0 && a.sh % 4 == 0 && a.sw % 4 == 0 && a.c % 4 == 0; }
+
+// ------------------------------------------------------------------------------------------------ conv, Cin = 1
+// thread = (pixel, 4 output channels); weights of the 4 channels live in registers
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) c1_fwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int relu, float* __restrict__ out,
+                                                          Geo go, long long n_pix) {
+  constexpr int CQ = COUT / 4;
+  const int cq = threadIdx.x % CQ;
+  float wr[4][9], br[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cq * 4 + j) * 9 + t);
+    br[j] = bias ? __ldg(bias + cq * 4 + j) : 0.f;
+  }
+  const long long stride = (long long)gridDim.x * (kThreads / CQ);
+  for (long long pix = (long long)blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ; pix < n_pix; pix += stride) {
+    const int wv = (int)(pix % gx.w);
+    const long long t = pix / gx.w;
+    const int hv = (int)(t % gx.h);
+    const long long n = t / gx.h;
+    const float* xb = x + n * gx.sn;
+    float xv[9];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int hh = hv + ky - 1, ww = wv + kx - 1;
+        xv[ky * 3 + kx] = (hh >= 0 && hh < gx.h && ww >= 0 && ww < gx.w) ? __ldg(xb + hh * gx.sh + ww * gx.sw) : 0.f;
+      }
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float a = br[j];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) a = fmaf(xv[k], wr[j][k], a);
+      acc[j] = relu ? fmaxf(a, 0.f) : a;
+    }
+    st4(out + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+  }
+}
+
+// dw[co][tap] += sum_pix dy[pix][co] * x[pix+tap]; dbias[co] += sum_pix dy[pix][co]
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) c1_wgrad_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
+                                                            Geo gd, float* __restrict__ dw, float* __restrict__ dbias,
+                                                            long long n_pix) {
+  constexpr int CQ = COUT / 4;
+  constexpr int PPB = kThreads / CQ;  // pixels per block iteration
+  const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
+  float acc[4][10];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int t = 0; t < 10; ++t) acc[j][t] = 0.f;
+  const long long stride = (long long)gridDim.x * PPB;
+  for (long long pix = (long long)blockIdx.x * PPB + pl; pix < n_pix; pix += stride) {
+    const int wv = (int)(pix % gx.w);
+    const long long t = pix / gx.w;
+    const int hv = (int)(t % gx.h);
+    const long long n = t / gx.h;
+    const float* xb = x + n * gx.sn;
+    const float4 g = ld4(dy + n * gd.sn + hv * gd.sh + wv * gd.sw + cq * 4);
+    const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int hh = hv + ky - 1, ww = wv + kx - 1;
+        const float xv = (hh >= 0 && hh < gx.h && ww >= 0 && ww < gx.w) ? __ldg(xb + hh * gx.sh + ww * gx.sw) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j][ky * 3 + kx] = fmaf(gv[j], xv, acc[j][ky * 3 + kx]);
+      }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j][9] += gv[j];
+  }
+  // reduce over the PPB pixel lanes of the block through shared memory, then one atomic per (channel, tap)
+  __shared__ float red[PPB][CQ * 4 + 1];
+  for (int t = 0; t < 10; ++t) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[pl][cq * 4 + j] = acc[j][t];
+    __syncthreads();
+    if (threadIdx.x < COUT) {
+      float s = 0.f;
+      for (int i = 0; i < PPB; ++i) s += red[i][threadIdx.x];
+      if (t < 9) atomicAdd(dw + threadIdx.x * 9 + t, s);
+      else if (dbias) atomicAdd(dbias + threadIdx.x, s);
+    }
+  }
+}
+
+// dx[h][w] = sum_{ky,kx,co} dy[h-ky+1][w-kx+1][co] * w[co][ky][kx];  CQ lanes per pixel, shuffle-reduced
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) c1_dgrad_kernel(const float* __restrict__ dy, Geo gd, const float* __restrict__ w,
+                                                            float* __restrict__ dx, Geo gx, long long n_pix) {
+  constexpr int CQ = COUT / 4;
+  const int cq = threadIdx.x % CQ;
+  float wr[4][9];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cq * 4 + j) * 9 + t);
+  const long long stride = (long long)gridDim.x * (kThreads / CQ);
+  const long long n_iter = (n_pix + stride - 1) / stride;
+  long long pix = (long long)blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ;
+  for (long long it = 0; it < n_iter; ++it, pix += stride) {  // uniform trip count: shuffles below need full warps
+    float a = 0.f;
+    int wv = 0, hv = 0;
+    long long n = 0;
+    const bool live = pix < n_pix;
+    if (live) {
+      wv = (int)(pix % gx.w);
+      const long long t = pix / gx.w;
+      hv = (int)(t % gx.h);
+      n = t / gx.h;
+      const float* db = dy + n * gd.sn + cq * 4;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int hh = hv - ky + 1, ww = wv - kx + 1;
+          if (hh >= 0 && hh < gd.h && ww >= 0 && ww < gd.w) {
+            const float4 g = ld4(db + hh * gd.sh + ww * gd.sw);
+            a = fmaf(g.x, wr[0][ky * 3 + kx], a);
+            a = fmaf(g.y, wr[1][ky * 3 + kx], a);
+            a = fmaf(g.z, wr[2][ky * 3 + kx], a);
+            a = fmaf(g.w, wr[3][ky * 3 + kx], a);
+          }
+        }
+    }
+#pragma unroll
+    for (int o = CQ / 2; o > 0; o >>= 1) a += __shfl_xor_sync(FULL_MASK, a, o);
+    if (live && cq == 0) dx[n * gx.sn + hv * gx.sh + wv * gx.sw] = a;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ 1x1 conv -> 1 ch + sigmoid
+template <int CIN>
+__global__ void __launch_bounds__(kThreads) o1_fwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ w,
+                                                          const float* __restrict__ b, float* __restrict__ y, long long n_pix) {
+  constexpr int CQ = CIN / 4;
+  const int cq = threadIdx.x % CQ;
+  const float4 wv = ld4(w + cq * 4);
+  const float bv = __ldg(b);
+  const long long stride = (long long)gridDim.x * (kThreads / CQ);
+  const long long n_iter = (n_pix + stride - 1) / stride;
+  long long pix = (long long)blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ;
+  for (long long it = 0; it < n_iter; ++it, pix += stride) {
+    float a = 0.f;
+    const bool live = pix < n_pix;
+    if (live) {
+      const float4 v = ld4(x + pix_off(gx, pix) + cq * 4);
+      a = v.x * wv.x + v.y * wv.y + v.z * wv.z + v.w * wv.w;
+    }
+#pragma unroll
+    for (int o = CQ / 2; o > 0; o >>= 1) a += __shfl_xor_sync(FULL_MASK, a, o);
+    if (live && cq == 0) y[pix] = 1.f / (1.f + expf(-(a + bv)));
+  }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(kThreads) o1_bwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ w,
+                                                          const float* __restrict__ y, const float* __restrict__ dy,
+                                                          float* __restrict__ dx, Geo gdx, float* __restrict__ dw,
+                                                          float* __restrict__ db, long long n_pix) {
+  constexpr int CQ = CIN / 4;
+  constexpr int PPB = kThreads / CQ;
+  const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
+  const float4 wv = ld4(w + cq * 4);
+  float4 aw = make_float4(0.f, 0.f, 0.f, 0.f);
+  float ab = 0.f;
+  const long long stride = (long long)gridDim.x * PPB;
+  for (long long pix = (long long)blockIdx.x * PPB + pl; pix < n_pix; pix += stride) {
+    const float yv = y[pix];
+    const float dz = dy[pix] * yv * (1.f - yv);
+    const float4 xv = ld4(x + pix_off(gx, pix) + cq * 4);
+    aw.x = fmaf(dz, xv.x, aw.x); aw.y = fmaf(dz, xv.y, aw.y); aw.z = fmaf(dz, xv.z, aw.z); aw.w = fmaf(dz, xv.w, aw.w);
+    ab += dz;
+    st4(dx + pix_off(gdx, pix) + cq * 4, make_float4(dz * wv.x, dz * wv.y, dz * wv.z, dz * wv.w));
+  }
+  __shared__ float red[PPB][CIN + 1];
+  __shared__ float redb[PPB];
+  red[pl][cq * 4] = aw.x; red[pl][cq * 4 + 1] = aw.y; red[pl][cq * 4 + 2] = aw.z; red[pl][cq * 4 + 3] = aw.w;
+  if (cq == 0) redb[pl] = ab;
+  __syncthreads();
+  if (threadIdx.x < CIN) {
+    float s = 0.f;
+    for (int i = 0; i < PPB; ++i) s += red[i][threadIdx.x];
+    atomicAdd(dw + threadIdx.x, s);
+  } else if (threadIdx.x == CIN) {
+    float s = 0.f;
+    for (int i = 0; i < PPB; ++i) s += redb[i];
+    atomicAdd(db, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ max pooling
+template <int PH, int PW>
+__global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, Geo gx, float* __restrict__ out,
+                                                               Geo go, int cq_n, long long total) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int cq = (int)(i % cq_n);
+    const long long pix = i / cq_n;
+    const int wv = (int)(pix % go.w);
+    const long long t = pix / go.w;
+    const int hv = (int)(t % go.h);
+    const long long n = t / go.h;
+    const float* xb = x + n * gx.sn + (long long)(hv * PH) * gx.sh + (long long)(wv * PW) * gx.sw + cq * 4;
+    float4 m = ld4(xb);
+#pragma unroll
+    for (int a = 0; a < PH; ++a)
+#pragma unroll
+      for (int b = 0; b < PW; ++b) {
+        if (a == 0 && b == 0) continue;
+        const float4 v = ld4(xb + a * gx.sh + b * gx.sw);
+        // NaN-propagating max like ATen (v > m || isnan(v))
+        m.x = (v.x > m.x || v.x != v.x) ? v.x : m.x;
+        m.y = (v.y > m.y || v.y != v.y) ? v.y : m.y;
+        m.z = (v.z > m.z || v.z != v.z) ? v.z : m.z;
+        m.w = (v.w > m.w || v.w != v.w) ? v.w : m.w;
+      }
+    st4(out + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, m);
+  }
+}
+
+template <int PH, int PW>
+__global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
+                                                               Geo gd, int relu_mask, const float* __restrict__ chan_scale,
+                                                               const float* __restrict__ add, Geo ga, float* __restrict__ dx,
+                                                               Geo gdx, int cq_n, long long total) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int cq = (int)(i % cq_n);
+    const long long pix = i / cq_n;
+    const int wv = (int)(pix % gd.w);
+    const long long t = pix / gd.w;
+    const int hv = (int)(t % gd.h);
+    const long long n = t / gd.h;
+    const float* xb = x + n * gx.sn + (long long)(hv * PH) * gx.sh + (long long)(wv * PW) * gx.sw + cq * 4;
+    float v[PH * PW][4];
+#pragma unroll
+    for (int a = 0; a < PH; ++a)
+#pragma unroll
+      for (int b = 0; b < PW; ++b) {
+        const float4 q = ld4(xb + a * gx.sh + b * gx.sw);
+        v[a * PW + b][0] = q.x; v[a * PW + b][1] = q.y; v[a * PW + b][2] = q.z; v[a * PW + b][3] = q.w;
+      }
+    float4 g4 = ld4(dy + n * gd.sn + hv * gd.sh + wv * gd.sw + cq * 4);
+    if (chan_scale) {
+      const float4 s4 = ld4(chan_scale + cq * 4);
+      g4.x *= s4.x; g4.y *= s4.y; g4.z *= s4.z; g4.w *= s4.w;
+    }
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+    int arg[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int best = 0;
+      float m = v[0][j];
+#pragma unroll
+      for (int k = 1; k < PH * PW; ++k)
+        if (v[k][j] > m || v[k][j] != v[k][j]) { m = v[k][j]; best = k; }
+      arg[j] = best;
+    }
+#pragma unroll
+    for (int a = 0; a < PH; ++a)
+#pragma unroll
+      for (int b = 0; b < PW; ++b) {
+        const int k = a * PW + b;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = (arg[j] == k && (!relu_mask || v[k][j] > 0.f)) ? g[j] : 0.f;
+        const long long off = n * gdx.sn + (long long)(hv * PH + a) * gdx.sh + (long long)(wv * PW + b) * gdx.sw + cq * 4;
+        if (add) {
+          const float4 q = ld4(add + n * ga.sn + (long long)(hv * PH + a) * ga.sh + (long long)(wv * PW + b) * ga.sw + cq * 4);
+          o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w;
+        }
+        st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ batch norm
+// z: [M][C] rows `zs` floats apart. thread = (row lane, channel quad).
+__global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restrict__ z, long long zs, long long M, int C,
+                                                            double* __restrict__ stats) {
+  const int cq_n = C / 4, rpb = kThreads / cq_n;
+  const int cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < rpb) {
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+      const float4 v = ld4(z + r * zs + cq * 4);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+  }
+  extern __shared__ float sm[];  // [2][rpb][C]
+  float* ss = sm;
+  float* sq = sm + rpb * C;
+  if (rl < rpb) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ss[rl * C + cq * 4 + j] = s[j]; sq[rl * C + cq * 4 + j] = q[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < rpb; ++i) { a += ss[i * C + c]; b += sq[i * C + c]; }
+    atomicAdd(stats + c, a);
+    atomicAdd(stats + C + c, b);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, long long count, int C, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* running_mean, float* running_var,
+                                   long long* nbt, float eps, float momentum, float* __restrict__ scsh) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && nbt) *nbt += 1;
+  if (c >= C) return;
+  const double mean = stats[c] / (double)count;
+  double var = stats[C + c] / (double)count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scsh[c] = sc;
+  scsh[C + c] = beta[c] - (float)mean * sc;
+  scsh[2 * C + c] = (float)mean;
+  scsh[3 * C + c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1 ? var * (double)count / (double)(count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+__global__ void bn_eval_scsh_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                    const float* __restrict__ conv_bias, float* __restrict__ scsh) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(rv[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scsh[c] = sc;
+  // conv_bias given: shift folds the convolution bias (the conv epilogue then applies scale/shift directly)
+  scsh[C + c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+  // frozen statistics: the backward only keeps the layer OUTPUT, from which xhat = (out - beta)/gamma where out > 0
+  scsh[2 * C + c] = beta[c];
+  scsh[3 * C + c] = gamma[c] != 0.f ? 1.f / gamma[c] : 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restrict__ z, long long zs, long long M, int C,
+                                                            const float* __restrict__ scsh, int relu, float* __restrict__ out,
+                                                            long long os) {
+  const int cq_n = C / 4;
+  const long long total = M * cq_n;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int cq = (int)(i % cq_n);
+    const long long r = i / cq_n;
+    const float4 v = ld4(z + r * zs + cq * 4);
+    const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
+    float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4(out + r * os + cq * 4, o);
+  }
+}
+
+// relu: 0 = none, 1 = mask recomputed from the pre-activation v (z*scale+shift > 0), 2 = v IS the ReLU output (v > 0)
+__device__ __forceinline__ float4 bn_masked_grad(const float4 v, const float4 g, const float4 sc, const float4 sh, int relu) {
+  if (!relu) return g;
+  if (relu == 2) return make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f);
+  return make_float4(fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f,
+                     fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f);
+}
+
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __restrict__ z, long long zs,
+                                                                 const float* __restrict__ dy, long long ds, long long M, int C,
+                                                                 const float* __restrict__ scsh, int relu,
+                                                                 double* __restrict__ red) {
+  const int cq_n = C / 4, rpb = kThreads / cq_n;
+  const int cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+  if (rl < rpb) {
+    const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
+    const float4 mu = ld4(scsh + 2 * C + cq * 4), is = ld4(scsh + 3 * C + cq * 4);
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+      const float4 v = ld4(z + r * zs + cq * 4);
+      const float4 g = bn_masked_grad(v, ld4(dy + r * ds + cq * 4), sc, sh, relu);
+      s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
+      q[0] = fmaf(g.x, (v.x - mu.x) * is.x, q[0]); q[1] = fmaf(g.y, (v.y - mu.y) * is.y, q[1]);
+      q[2] = fmaf(g.z, (v.z - mu.z) * is.z, q[2]); q[3] = fmaf(g.w, (v.w - mu.w) * is.w, q[3]);
+    }
+  }
+  extern __shared__ float sm[];
+  float* ss = sm;
+  float* sq = sm + rpb * C;
+  if (rl < rpb) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ss[rl * C + cq * 4 + j] = s[j]; sq[rl * C + cq * 4 + j] = q[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kThreads) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < rpb; ++i) { a += ss[i * C + c]; b += sq[i * C + c]; }
+    atomicAdd(red + c, a);
+    atomicAdd(red + C + c, b);
+  }
+}
+
+// mode 0 (train): dz = gamma*invstd*(g - mean_g - xhat*mean_gx); mode 1 (eval): dz = g*scale
+__global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __restrict__ z, long long zs,
+                                                                const float* __restrict__ dy, long long ds, long long M, int C,
+                                                                const float* __restrict__ scsh, int relu,
+                                                                const double* __restrict__ red, int mode,
+                                                                float* __restrict__ dz, long long dzs, float* __restrict__ dgamma,
+                                                                float* __restrict__ dbeta) {
+  const int cq_n = C / 4;
+  const long long total = M * cq_n;
+  if (blockIdx.x == 0 && dgamma) {
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      dgamma[c] += (float)red[C + c];
+      dbeta[c] += (float)red[c];
+    }
+  }
+  const float invM = 1.f / (float)M;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int cq = (int)(i % cq_n);
+    const long long r = i / cq_n;
+    const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
+    const float4 v = ld4(z + r * zs + cq * 4);
+    const float4 g = bn_masked_grad(v, ld4(dy + r * ds + cq * 4), sc, sh, relu);
+    float4 o;
+    if (mode == 1) {
+      o = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
+    } else {
+      const float4 mu = ld4(scsh + 2 * C + cq * 4), is = ld4(scsh + 3 * C + cq * 4);
+      const float mg[4] = {(float)red[cq * 4] * invM, (float)red[cq * 4 + 1] * invM, (float)red[cq * 4 + 2] * invM,
+                           (float)red[cq * 4 + 3] * invM};
+      const float mx[4] = {(float)red[C + cq * 4] * invM, (float)red[C + cq * 4 + 1] * invM, (float)red[C + cq * 4 + 2] * invM,
+                           (float)red[C + cq * 4 + 3] * invM};
+      o.x = sc.x * (g.x - mg[0] - (v.x - mu.x) * is.x * mx[0]);
+      o.y = sc.y * (g.y - mg[1] - (v.y - mu.y) * is.y * mx[1]);
+      o.z = sc.z * (g.z - mg[2] - (v.z - mu.z) * is.z * mx[2]);
+      o.w = sc.w * (g.w - mg[3] - (v.w - mu.w) * is.w * mx[3]);
+    }
+    st4(dz + r * dzs + cq * 4, o);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x, long long xs, long long M, int C,
+                                                          float* __restrict__ out) {
+  const int cq_n = (C + 3) / 4, rpb = max(1, kThreads / cq_n);
+  extern __shared__ float sm[];  // [rpb][cq_n*4]
+  const int Cp = cq_n * 4;
+  for (int cq0 = 0; cq0 < cq_n; cq0 += kThreads) {  // C up to 4*kThreads per pass
+    const int cq = cq0 + threadIdx.x % min(cq_n, kThreads), rl = threadIdx.x / min(cq_n, kThreads);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (rl < rpb && cq < cq_n) {
+      for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+        const float* p = x + r * xs + cq * 4;
+        if (cq * 4 + 3 < C) {
+          const float4 v = ld4(p);
+          s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        } else {
+          for (int j = 0; cq * 4 + j < C; ++j) s[j] += p[j];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sm[rl * Cp + cq * 4 + j] = s[j];
+    }
+    __syncthreads();
+    for (int c = cq0 * 4 + threadIdx.x; c < min(C, (cq0 + kThreads) * 4); c += kThreads) {
+      float a = 0.f;
+      for (int i = 0; i < rpb; ++i) a += sm[i * Cp + c];
+      atomicAdd(out + c, a);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const float* __restrict__ a, Geo ga, const float* __restrict__ dy,
+                                                            Geo gd, float* __restrict__ dx, Geo gx, int cq_n, long long total) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int cq = (int)(i % cq_n);
+    const long long pix = i / cq_n;
+    const float4 av = ld4(a + pix_off(ga, pix) + cq * 4);
+    const float4 g = ld4(dy + pix_off(gd, pix) + cq * 4);
+    st4(dx + pix_off(gx, pix) + cq * 4,
+        make_float4(av.x > 0.f ? g.x : 0.f, av.y > 0.f ? g.y : 0.f, av.z > 0.f ? g.z : 0.f, av.w > 0.f ? g.w : 0.f));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) pack3d_kernel(const float* __restrict__ src, float* __restrict__ dst, int n0, int n1,
+                                                          int n2, long long s0, long long s1, long long s2, long long d0,
+                                                          long long d1) {
+  const long long total = (long long)n0 * n1 * n2;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const int i2 = (int)(i % n2);
+    const long long t = i / n2;
+    const int i1 = (int)(t % n1);
+    const long long i0 = t / n1;
+    dst[i0 * d0 + i1 * d1 + i2] = src[i0 * s0 + i1 * s1 + (long long)i2 * s2];
+  }
+}
+
+__global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+#define REQ_FLAT(img, what) QEB_REQUIRE(img_flat(img) && vec4_ok(img), what ": tensor must be a packed NHWC view with 16-byte aligned rows")
+
+}  // namespace
+
+int fill_zero(void* p, size_t bytes, cudaStream_t st) {
+  ProfScope prof("memset", st, 0.0, (double)bytes);
+  QEB_CUDA(cudaMemsetAsync(p, 0, bytes, st));
+  return QEB_OK;
+}
+
+int pack_3d(const float* src, float* dst, int n0, int n1, int n2, long long s0, long long s1, long long s2, long long d0,
+            long long d1, cudaStream_t st) {
+  ProfScope prof("pack", st, 0.0, 8.0 * n0 * n1 * n2);
+  const long long total = (long long)n0 * n1 * n2;
+  if (total == 0) return QEB_OK;
+  pack3d_kernel<<<qeb_grid(total, kThreads), kThreads, 0, st>>>(src, dst, n0, n1, n2, s0, s1, s2, d0, d1);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const Img& out, cudaStream_t st) {
+  ProfScope prof("c1_conv_fwd", st, 18.0 * (double)img_pixels(x) * out.c, 4.0 * (double)img_pixels(x) * (1 + out.c));
+  QEB_REQUIRE(x.c == 1 && (out.c == 32 || out.c == 64), "c1_conv_fwd: 1 -> 32/64 channels only (got %d -> %d)", x.c, out.c);
+  QEB_REQUIRE(x.n == out.n && x.h == out.h && x.w == out.w && vec4_ok(out), "c1_conv_fwd: geometry/alignment");
+  const long long n_pix = img_pixels(x);
+  const int g = qeb_grid(n_pix * (out.c / 4), kThreads, 4);
+  if (out.c == 32) c1_fwd_kernel<32><<<g, kThreads, 0, st>>>(x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix);
+  else c1_fwd_kernel<64><<<g, kThreads, 0, st>>>(x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStream_t st) {
+  ProfScope prof("c1_conv_wgrad", st, 18.0 * (double)img_pixels(x) * dy.c, 4.0 * (double)img_pixels(x) * (1 + dy.c));
+  QEB_REQUIRE(x.c == 1 && (dy.c == 32 || dy.c == 64), "c1_conv_wgrad: 1 -> 32/64 channels only");
+  QEB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w && vec4_ok(dy), "c1_conv_wgrad: geometry/alignment");
+  const long long n_pix = img_pixels(x);
+  const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 2);
+  if (dy.c == 32) c1_wgrad_kernel<32><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix);
+  else c1_wgrad_kernel<64><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int c1_conv_dgrad(const Img& dy, const float* w, const Img& dx, cudaStream_t st) {
+  ProfScope prof("c1_conv_dgrad", st, 18.0 * (double)img_pixels(dx) * dy.c, 4.0 * (double)img_pixels(dx) * (1 + dy.c));
+  QEB_REQUIRE(dx.c == 1 && (dy.c == 32 || dy.c == 64), "c1_conv_dgrad: 1 <- 32/64 channels only");
+  QEB_REQUIRE(dx.n == dy.n && dx.h == dy.h && dx.w == dy.w && vec4_ok(dy), "c1_conv_dgrad: geometry/alignment");
+  const long long n_pix = img_pixels(dx);
+  const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 8);
+  if (dy.c == 32) c1_dgrad_kernel<32><<<g, kThreads, 0, st>>>(dy.p, geo(dy), w, dx.p, geo(dx), n_pix);
+  else c1_dgrad_kernel<64><<<g, kThreads, 0, st>>>(dy.p, geo(dy), w, dx.p, geo(dx), n_pix);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int o1_conv_sigmoid_fwd(const Img& x, const float* w, const float* b, float* y, cudaStream_t st) {
+  ProfScope prof("o1_conv_sigmoid_fwd", st, 2.0 * (double)img_pixels(x) * x.c, 4.0 * (double)img_pixels(x) * (1 + x.c));
+  QEB_REQUIRE(x.c == 32 && vec4_ok(x), "o1_conv_sigmoid_fwd: 32 input channels, aligned");
+  const long long n_pix = img_pixels(x);
+  o1_fwd_kernel<32><<<qeb_grid(n_pix * 8, kThreads, 8), kThreads, 0, st>>>(x.p, geo(x), w, b, y, n_pix);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const float* dy, const Img& dx, float* dw, float* db,
+                        cudaStream_t st) {
+  ProfScope prof("o1_conv_sigmoid_bwd", st, 4.0 * (double)img_pixels(x) * x.c, 4.0 * (double)img_pixels(x) * (2 + 2 * x.c));
+  QEB_REQUIRE(x.c == 32 && dx.c == 32 && vec4_ok(x) && vec4_ok(dx), "o1_conv_sigmoid_bwd: 32 channels, aligned");
+  const long long n_pix = img_pixels(x);
+  o1_bwd_kernel<32><<<qeb_grid(n_pix * 8, kThreads, 2), kThreads, 0, st>>>(x.p, geo(x), w, y, dy, dx.p, geo(dx), dw, db, n_pix);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st) {
+  ProfScope prof("maxpool_fwd", st, 0.0, 4.0 * x.c * ((double)img_pixels(x) + (double)img_pixels(out)));
+  QEB_REQUIRE(vec4_ok(x) && vec4_ok(out) && x.c == out.c, "maxpool_fwd: channel count / alignment");
+  QEB_REQUIRE(x.h == out.h * ph && x.w == out.w * pw && x.n == out.n, "maxpool_fwd: input must be a multiple of the window");
+  const int cq_n = x.c / 4;
+  const long long total = img_pixels(out) * cq_n;
+  const int g = qeb_grid(total, kThreads);
+  if (ph == 2 && pw == 2) maxpool_fwd_kernel<2, 2><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total);
+  else if (ph == 2 && pw == 1) maxpool_fwd_kernel<2, 1><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total);
+  else QEB_REQUIRE(false, "maxpool_fwd: window %dx%d not supported", ph, pw);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
+                const Img& dx, cudaStream_t st) {
+  ProfScope prof("maxpool_bwd", st, 0.0, 4.0 * x.c * (2 * (double)img_pixels(x) + (double)img_pixels(dy) + (add ? (double)img_pixels(x) : 0.0)));
+  QEB_REQUIRE(vec4_ok(x) && vec4_ok(dy) && vec4_ok(dx) && x.c == dy.c && x.c == dx.c, "maxpool_bwd: channel count / alignment");
+  QEB_REQUIRE(x.h == dy.h * ph && x.w == dy.w * pw && x.n == dy.n, "maxpool_bwd: input must be a multiple of the window");
+  QEB_REQUIRE(!add || (vec4_ok(*add) && add->c == x.c), "maxpool_bwd: add tensor");
+  const int cq_n = x.c / 4;
+  const long long total = img_pixels(dy) * cq_n;
+  const int g = qeb_grid(total, kThreads);
+  Geo ga = add ? geo(*add) : geo(x);
+  const float* ap = add ? add->p : nullptr;
+  if (ph == 2 && pw == 2)
+    maxpool_bwd_kernel<2, 2><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
+                                                     total);
+  else if (ph == 2 && pw == 1)
+    maxpool_bwd_kernel<2, 1><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
+                                                     total);
+  else QEB_REQUIRE(false, "maxpool_bwd: window %dx%d not supported", ph, pw);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+static int reduce_grid(long long M, int rpb) {
+  long long g = (M + rpb - 1) / rpb;
+  const long long cap = 4 * kNumSMs;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+int bn_train_stats(const Img& z, double* stats, cudaStream_t st) {
+  ProfScope prof("bn_stats", st, 0.0, 4.0 * z.c * (double)img_pixels(z));
+  REQ_FLAT(z, "bn_train_stats");
+  QEB_REQUIRE(z.c <= 1024, "bn_train_stats: at most 1024 channels");
+  const long long M = img_pixels(z);
+  const int rpb = kThreads / (z.c / 4);
+  bn_stats_kernel<<<reduce_grid(M, rpb), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, M, z.c, stats);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st) {
+  ProfScope prof("bn_finalize", st);
+  bn_finalize_kernel<<<qeb_cdiv(c, 128), 128, 0, st>>>(stats, count, c, bn.gamma, bn.beta, bn.running_mean, bn.running_var,
+                                                       bn.num_batches_tracked, bn.eps, bn.momentum, scsh);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh, cudaStream_t st) {
+  ProfScope prof("bn_finalize", st);
+  bn_eval_scsh_kernel<<<qeb_cdiv(c, 128), 128, 0, st>>>(c, bn.gamma, bn.beta, bn.running_mean, bn.running_var, bn.eps, conv_bias,
+                                                        scsh);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st) {
+  ProfScope prof("bn_apply", st, 0.0, 8.0 * z.c * (double)img_pixels(z));
+  REQ_FLAT(z, "bn_apply");
+  REQ_FLAT(out, "bn_apply");
+  QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_apply: shape mismatch");
+  const long long M = img_pixels(z);
+  bn_apply_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, double* red, cudaStream_t st) {
+  ProfScope prof("bn_bwd_reduce", st, 0.0, 8.0 * z.c * (double)img_pixels(z));
+  REQ_FLAT(z, "bn_bwd_reduce");
+  REQ_FLAT(dy, "bn_bwd_reduce");
+  QEB_REQUIRE(z.c == dy.c && img_pixels(z) == img_pixels(dy) && z.c <= 1024, "bn_bwd_reduce: shape mismatch");
+  const long long M = img_pixels(z);
+  const int rpb = kThreads / (z.c / 4);
+  bn_bwd_reduce_kernel<<<reduce_grid(M, rpb), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, dy.p, dy.sw, M, z.c, scsh,
+                                                                                           relu, red);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, int mode, const Img& dz,
+                        float* dgamma, float* dbeta, cudaStream_t st) {
+  ProfScope prof("bn_bwd_apply", st, 0.0, 12.0 * z.c * (double)img_pixels(z));
+  REQ_FLAT(z, "bn_bwd_apply");
+  REQ_FLAT(dy, "bn_bwd_apply");
+  REQ_FLAT(dz, "bn_bwd_apply");
+  QEB_REQUIRE(z.c == dy.c && z.c == dz.c && img_pixels(z) == img_pixels(dy) && img_pixels(z) == img_pixels(dz),
+              "bn_bwd_apply: shape mismatch");
+  const long long M = img_pixels(z);
+  bn_bwd_apply_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
+                                                                             dz.p, dz.sw, dgamma, dbeta);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_bwd_apply_train(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const float* gamma,
+                       const Img& dz, float* dgamma, float* dbeta, cudaStream_t st) {
+  (void)gamma;  // scale = gamma*invstd is already in scsh
+  return bn_bwd_apply(z, dy, scsh, relu, red, 0, dz, dgamma, dbeta, st);
+}
+
+int bn_bwd_apply_eval(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const Img& dz,
+                      float* dgamma, float* dbeta, cudaStream_t st) {
+  return bn_bwd_apply(z, dy, scsh, relu, red, 1, dz, red ? dgamma : nullptr, red ? dbeta : nullptr, st);
+}
+
+int colsum_acc(const Img& x, float* out, cudaStream_t st) {
+  ProfScope prof("colsum", st, 0.0, 4.0 * x.c * (double)img_pixels(x));
+  QEB_REQUIRE(img_flat(x) && ((uintptr_t)x.p & 15) == 0 && x.sw % 4 == 0, "colsum_acc: packed, 16-byte aligned rows");
+  const long long M = img_pixels(x);
+  const int cq_n = (x.c + 3) / 4;
+  const int rpb = max(1, kThreads / cq_n);
+  colsum_kernel<<<reduce_grid(M, rpb), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st>>>(x.p, x.sw, M, x.c, out);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int relu_bwd(const Img& a, const Img& dy, const Img& dx, cudaStream_t st) {
+  ProfScope prof("relu_bwd", st, 0.0, 12.0 * a.c * (double)img_pixels(a));
+  QEB_REQUIRE(vec4_ok(a) && vec4_ok(dy) && vec4_ok(dx) && a.c == dy.c && a.c == dx.c, "relu_bwd: channel count / alignment");
+  const int cq_n = a.c / 4;
+  const long long total = img_pixels(a) * cq_n;
+  relu_bwd_kernel<<<qeb_grid(total, kThreads), kThreads, 0, st>>>(a.p, geo(a), dy.p, geo(dy), dx.p, geo(dx), cq_n, total);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int vec_add(const float* a, const float* b, float* out, int n, cudaStream_t st) {
+  ProfScope prof("vec_add", st, 0.0, 12.0 * n);
+  vec_add_kernel<<<qeb_cdiv(n, 256), 256, 0, st>>>(a, b, out, n);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}

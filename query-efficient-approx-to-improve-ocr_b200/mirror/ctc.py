@@ -46,6 +46,19 @@ def _pack_int_args(targets, input_lengths, target_lengths, B, device):
     return dev[:n_pad], dev[n_pad:n_pad + B], dev[n_pad + B:n_pad + 2 * B], dev[n_pad + 2 * B:], max_len
 
 
+class PackedTargets:
+    """Targets / lengths already staged on the device (pack_targets): lets a caller that keeps its labels on the GPU
+    skip the per-call host staging + H2D copy that the reference's int32-CPU-tensor calling convention implies."""
+
+    def __init__(self, tg, offs, il, tl, max_len, B):
+        self.tg, self.offs, self.il, self.tl, self.max_len, self.B = tg, offs, il, tl, max_len, B
+
+
+def pack_targets(targets, input_lengths, target_lengths, device):
+    B = int(torch.as_tensor(target_lengths).numel())
+    return PackedTargets(*_pack_int_args(targets, input_lengths, target_lengths, B, torch.device(device)), B)
+
+
 class _CTC(torch.autograd.Function):
     @staticmethod
     def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, reduction, zero_infinity, batch_index):
@@ -61,7 +74,12 @@ class _CTC(torch.autograd.Function):
         if batch_index is not None:
             bidx = torch.as_tensor(batch_index, dtype=torch.int32).to(dev)
             B = bidx.numel()
-        tg, offs, il, tl, max_len = _pack_int_args(targets, input_lengths, target_lengths, B, dev)
+        if isinstance(targets, PackedTargets):
+            if targets.B != B:
+                raise RuntimeError(f"CTCLoss: packed targets hold {targets.B} samples, log_probs {B}")
+            tg, offs, il, tl, max_len = targets.tg, targets.offs, targets.il, targets.tl, targets.max_len
+        else:
+            tg, offs, il, tl, max_len = _pack_int_args(targets, input_lengths, target_lengths, B, dev)
         red = _RED[reduction]
         log_alpha = torch.empty(_lib.load().qeb_ctc_workspace_bytes(B, T, max_len) // 4, dtype=torch.float32, device=dev)
         nll = torch.empty(B, dtype=torch.float32, device=dev)
@@ -109,7 +127,7 @@ class CTCLoss(torch.nn.Module):
         self.reduction = reduction
         self.zero_infinity = zero_infinity
 
-    def forward(self, log_probs, targets, input_lengths, target_lengths):
+    def forward(self, log_probs, targets, input_lengths=None, target_lengths=None):
         return ctc_loss(log_probs, targets, input_lengths, target_lengths, self.blank, self.reduction, self.zero_infinity)
 
 

@@ -136,3 +136,68 @@ def test_oracle_matches_live_reference():
         mine = po.topk_query(v32, min(k, n))
         assert np.array_equal(np.sort(v32[mine]), np.sort(v32[tidx.numpy()]))
         assert np.array_equal(mine, torch.argsort(torch.tensor(vals), descending=True, stable=True)[:min(k, n)].numpy())
+
+
+# ------------------------------------------------------------------------------------------------ network oracle
+def _encode(labels):
+    c2i = {c: i for i, c in enumerate(CHAR_SET)}
+    y = torch.tensor([c2i[c] for l in labels for c in l], dtype=torch.int32)
+    return y, torch.tensor([len(l) for l in labels], dtype=torch.int32)
+
+
+def test_nn_oracle_crnn_matches_golden():
+    """The mirror CRNN's parameter containers initialise exactly like the reference under seed 42 (same state_dict
+    keys, same values), and the torch restatement of the graph reproduces the reference's scores, loss and
+    gradients (fixture written by oracle/gen_golden.py from the unmodified models/model_crnn.py)."""
+    from oracle import nn_oracle
+    from qeb_b200.mirror.models.model_crnn import CRNN
+    g = load_golden("crnn.npz")
+    dig = json.load(open(os.path.join(GOLDEN, "crnn_digest.json")))
+    torch.manual_seed(42)
+    m = CRNN(len(CHAR_SET), False)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(dig["param_digest_seed42"].keys())
+    for k, (s, a) in dig["param_digest_seed42"].items():
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * max(1, abs(s)) and abs(float(v.abs().sum()) - a) <= 1e-9 * max(1, a), k
+    m.register_backward_hook(m.backward_hook)
+    m.train()
+    x = torch.from_numpy(g["x"])
+    scores = nn_oracle.crnn_forward(m, x)
+    np.testing.assert_allclose(scores.detach().numpy(), g["scores_train"], atol=2e-5)
+    y, ylen = torch.from_numpy(g["targets"]), torch.from_numpy(g["target_lengths"])
+    il = torch.tensor([scores.shape[0]] * x.shape[0], dtype=torch.int)
+    loss = torch.nn.CTCLoss()(scores, y, il, ylen)
+    assert torch.isinf(loss) and np.isinf(g["loss_train"])
+    # the reference registers its NaN-scrubbing hook on the module; the restatement is a free function, so scrub here
+    scores.register_hook(lambda gr: torch.nan_to_num(gr, nan=0.0))
+    loss.backward()
+    np.testing.assert_allclose(m.convo.conv1.weight.grad.numpy(), g["grad_conv1_w"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(m.linear.bias.grad.numpy(), g["grad_linear_b"], rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(m.convo.batchnorm1.running_mean.numpy(), g["bn1_mean"], atol=1e-6)
+
+
+def test_nn_oracle_unet_matches_golden():
+    from oracle import nn_oracle
+    from qeb_b200.mirror.models.model_unet import UNet
+    g = load_golden("unet.npz")
+    dig = json.load(open(os.path.join(GOLDEN, "unet_digest.json")))
+    torch.manual_seed(42)
+    m = UNet()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(dig["param_digest_seed42"].keys())
+    for k, (s, a) in dig["param_digest_seed42"].items():
+        v = sd[k].double()
+        assert abs(float(v.sum()) - s) <= 1e-9 * max(1, abs(s)) and abs(float(v.abs().sum()) - a) <= 1e-9 * max(1, a), k
+    m.train()
+    x = torch.from_numpy(g["x"])
+    y = nn_oracle.unet_forward(m, x)
+    np.testing.assert_allclose(y.detach().numpy(), g["y_train"], atol=2e-6)
+    loss = torch.nn.MSELoss()(y, torch.ones_like(y))
+    np.testing.assert_allclose(float(loss), float(g["loss_train"]), rtol=1e-5)
+    loss.backward()
+    np.testing.assert_allclose(m.encoder1.enc1conv1.weight.grad.numpy(), g["grad_enc1conv1_w"], rtol=2e-3, atol=1e-7)
+    np.testing.assert_allclose(m.conv.weight.grad.numpy(), g["grad_conv_w"], rtol=2e-3, atol=1e-7)
+    m.eval()
+    with torch.no_grad():
+        np.testing.assert_allclose(nn_oracle.unet_forward(m, x).numpy(), g["y_eval"], atol=2e-6)
