@@ -96,12 +96,15 @@ template <int BLOCK_N>
 struct FpropCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  // several CTAs per SM (3 / 3 / 2 / 1 for BLOCK_N 32 / 64 / 128 / 256) so that one CTA's prologue and epilogue overlap
+  // another's main loop; the K loops here are short (9..144 stages), so a deep per-CTA ring buys less than occupancy
+  static constexpr int kCtasPerSm = (BLOCK_N >= 256) ? 1 : (BLOCK_N >= 128 ? 2 : 3);
+  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 3;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N>::kCtasPerSm)
 conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const FpropParams p) {
   using Cfg = FpropCfg<BLOCK_N>;
@@ -447,7 +450,7 @@ struct WgradParams {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N>::kCtasPerSm)
 conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const WgradParams p) {
   using Cfg = FpropCfg<BLOCK_N>;  // same stage geometry: 16 KB A side + BLOCK_N*128 B side

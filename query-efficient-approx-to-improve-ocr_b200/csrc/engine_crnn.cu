@@ -44,7 +44,7 @@ struct CrnnPlan {
   // packed weights
   float *wp2, *wp3, *wp4, *wp5, *wp6, *wp7, *wih0, *wih1, *bias0, *bias1;
   // backward scratch
-  float *dlp, *wlinT, *wihT, *wpd, *dy1, *dy0, *dx0, *d6, *d6f, *d5, *d4, *d4f, *d3, *d2, *d2f, *d1, *d1f;
+  float *dlp, *wlinT, *wihT0, *wihT1, *wpd2, *wpd3, *wpd4, *wpd5, *wpd6, *wpd7, *dy1, *dy0, *dx0, *d6, *d6f, *d5, *d4, *d4f, *d3, *d2, *d2f, *d1, *d1f;
   double* bnred;
   size_t bytes;
 };
@@ -70,14 +70,16 @@ CrnnPlan make_plan(int B, int W, int V, void* base) {
   p.wp5 = a.take((size_t)512 * 9 * 256); p.wp6 = a.take((size_t)512 * 9 * 512); p.wp7 = a.take((size_t)512 * 4 * 512);
   p.wih0 = a.take((size_t)2048 * 512); p.wih1 = a.take((size_t)2048 * 512);
   p.bias0 = a.take(2048); p.bias1 = a.take(2048);
-  p.dlp = a.take(tb * 96); p.wlinT = a.take((size_t)512 * 96); p.wihT = a.take((size_t)512 * 2048);
-  p.wpd = a.take((size_t)512 * 9 * 512);
+  p.dlp = a.take(tb * 96); p.wlinT = a.take((size_t)512 * 96);
+  p.wihT0 = a.take((size_t)512 * 2048); p.wihT1 = a.take((size_t)512 * 2048);
+  p.wpd2 = a.take((size_t)128 * 9 * 64); p.wpd3 = a.take((size_t)256 * 9 * 128); p.wpd4 = a.take((size_t)256 * 9 * 256);
+  p.wpd5 = a.take((size_t)512 * 9 * 256); p.wpd6 = a.take((size_t)512 * 9 * 512); p.wpd7 = a.take((size_t)512 * 4 * 512);
   p.dy1 = a.take(tb * 512); p.dy0 = a.take(tb * 512); p.dx0 = a.take(tb * 512);
   p.d6 = a.take(px2 * 512); p.d6f = a.take(px4 * 512); p.d5 = a.take(px4 * 512);
   p.d4 = a.take(px4 * 256); p.d4f = a.take(px8 * 256); p.d3 = a.take(px8 * 256);
   p.d2 = a.take(px8 * 128); p.d2f = a.take(px16 * 128);
   p.d1 = a.take(px16 * 64); p.d1f = a.take(px32 * 64);
-  p.bnred = reinterpret_cast<double*>(a.take(2 * 512 * 2));
+  p.bnred = reinterpret_cast<double*>(a.take(2 * 2 * 512 * 2));  // 2 layers x (sum g, sum g*xhat) x 512 doubles
   p.bytes = a.off;
   return p;
 }
@@ -87,16 +89,6 @@ CrnnPlan make_plan(int B, int W, int V, void* base) {
     int _rc = (expr);        \
     if (_rc != QEB_OK) return _rc; \
   } while (0)
-
-// torch Conv2d weight (Cout,Cin,kh,kw) -> fprop B operand [Cout][tap][Cin]
-int pack_fprop(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
-  return pack_3d(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin, st);
-}
-// -> dgrad B operand [Cin][flipped tap][Cout]
-int pack_dgrad(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
-  // dst[ci][ft][co] = w[co][ci][taps-1-ft]: walk the source taps backwards with a negative stride
-  return pack_3d(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout, st);
-}
 
 BnParams bn_of(const float* const* params, void* const* buffers, int pw, int pb, int bm) {
   BnParams b;
@@ -136,24 +128,32 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   Img Z5 = img_nhwc(p.z5, B, 4, p.W4, 512), A5 = img_nhwc(p.a5, B, 4, p.W4, 512);
   Img Z6 = img_nhwc(p.z6, B, 4, p.W4, 512), A6f = img_nhwc(p.a6f, B, 4, p.W4, 512), A6 = img_nhwc(p.a6, B, 2, p.W4, 512);
 
+  {  // every weight re-layout of this pass in one launch
+    PackBatch pk;
+    pk.add_fprop(params[P_C2W], p.wp2, 128, 64, 9);
+    pk.add_fprop(params[P_C3W], p.wp3, 256, 128, 9);
+    pk.add_fprop(params[P_C4W], p.wp4, 256, 256, 9);
+    pk.add_fprop(params[P_C5W], p.wp5, 512, 256, 9);
+    pk.add_fprop(params[P_C6W], p.wp6, 512, 512, 9);
+    pk.add_fprop(params[P_C7W], p.wp7, 512, 512, 4);
+    for (int l = 0; l < 2; ++l)
+      for (int d = 0; d < 2; ++d)
+        pk.add_copy(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wih1 : p.wih0) + (size_t)d * 1024 * 512, (long long)1024 * 512);
+    TRY(pack_flush(pk, st));
+  }
   TRY(c1_conv_fwd(X, params[P_C1W], params[P_C1B], 1, A1f, st));
   TRY(maxpool_fwd(A1f, 2, 2, A1, st));
   TcEpilogue ep;
   ep.relu = 1;
-  TRY(pack_fprop(params[P_C2W], p.wp2, 128, 64, 9, st));
   ep.bias = params[P_C2B];
   TRY(tc_conv_fprop(A1, p.wp2, 128, 3, 3, 1, 1, A2f, ep, st));
   TRY(maxpool_fwd(A2f, 2, 2, A2, st));
-  TRY(pack_fprop(params[P_C3W], p.wp3, 256, 128, 9, st));
   ep.bias = params[P_C3B];
   TRY(tc_conv_fprop(A2, p.wp3, 256, 3, 3, 1, 1, A3, ep, st));
-  TRY(pack_fprop(params[P_C4W], p.wp4, 256, 256, 9, st));
   ep.bias = params[P_C4B];
   TRY(tc_conv_fprop(A3, p.wp4, 256, 3, 3, 1, 1, A4f, ep, st));
   TRY(maxpool_fwd(A4f, 2, 1, A4, st));
 
-  TRY(pack_fprop(params[P_C5W], p.wp5, 512, 256, 9, st));
-  TRY(pack_fprop(params[P_C6W], p.wp6, 512, 512, 9, st));
   const BnParams bn1 = bn_of(params, buffers, P_BN1W, P_BN1B, B_BN1_MEAN), bn2 = bn_of(params, buffers, P_BN2W, P_BN2B, B_BN2_MEAN);
   if (bn_train) {
     TRY(fill_zero(p.bnstats, 2 * 2 * 512 * sizeof(double), st));
@@ -182,7 +182,6 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   TRY(maxpool_fwd(A6f, 2, 1, A6, st));
 
   // conv7 writes the sequence-major (T,B,512) tensor directly (map_to_sequence fused)
-  TRY(pack_fprop(params[P_C7W], p.wp7, 512, 512, 4, st));
   Img X0seq;
   X0seq.p = p.x0; X0seq.n = B; X0seq.h = 1; X0seq.w = T; X0seq.c = 512; X0seq.sn = 512; X0seq.sh = 0; X0seq.sw = (long long)B * 512;
   TcEpilogue e7;
@@ -200,8 +199,6 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     float* c = l ? p.c1 : p.c0;
     float* y = l ? p.y1 : p.y0;
     for (int d = 0; d < 2; ++d) {
-      QEB_CUDA(cudaMemcpyAsync(wih + (size_t)d * 1024 * 512, lp[d * 4 + 0], (size_t)1024 * 512 * sizeof(float),
-                               cudaMemcpyDeviceToDevice, st));
       TRY(vec_add(lp[d * 4 + 2], lp[d * 4 + 3], bias + d * 1024, 1024, st));
     }
     TcEpilogue eg;
@@ -242,14 +239,27 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
 
   // ---- Linear
   TRY(fill_zero(p.dlp, (size_t)TB * 96 * sizeof(float), st));
-  TRY(pack_3d(dlogits, p.dlp, 1, TB, V, 0, V, 1, 0, 96, st));
+  TRY(fill_zero(p.wlinT, (size_t)512 * 96 * sizeof(float), st));
+  {  // every re-layout of this pass in one launch
+    PackBatch pk;
+    pk.add(dlogits, p.dlp, 1, TB, V, 0, V, 1, 0, 96);
+    pk.add(params[P_LINW], p.wlinT, 1, 512, V, 0, 1, 512, 0, 96);  // wlinT[c][v] = W[v][c]
+    for (int l = 0; l < 2; ++l)  // d(input) B operand [512][2048]: wihT[c][d*1024 + r] = W_ih_d[r][c]
+      for (int d = 0; d < 2; ++d)
+        pk.add(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wihT1 : p.wihT0) + d * 1024, 1, 512, 1024, 0, 1, 512, 0, 2048);
+    pk.add_dgrad(params[P_C7W], p.wpd7, 512, 512, 4);
+    pk.add_dgrad(params[P_C6W], p.wpd6, 512, 512, 9);
+    pk.add_dgrad(params[P_C5W], p.wpd5, 512, 256, 9);
+    pk.add_dgrad(params[P_C4W], p.wpd4, 256, 256, 9);
+    pk.add_dgrad(params[P_C3W], p.wpd3, 256, 128, 9);
+    pk.add_dgrad(params[P_C2W], p.wpd2, 128, 64, 9);
+    TRY(pack_flush(pk, st));
+  }
   Img DLP = img_nhwc(p.dlp, 1, 1, TB, 96);
   Img DLPv = img_nhwc(p.dlp, 1, 1, TB, V, 96);
   Img Y1 = img_nhwc(p.y1, 1, 1, TB, 512), Y0 = img_nhwc(p.y0, 1, 1, TB, 512), X0 = img_nhwc(p.x0, 1, 1, TB, 512);
   if (grads[P_LINW]) TRY(tc_conv_wgrad(Y1, DLPv, 1, 1, 0, 0, grads[P_LINW], 512, 1, 0, 0, st));
   if (grads[P_LINB]) TRY(colsum_acc(DLPv, grads[P_LINB], st));
-  TRY(fill_zero(p.wlinT, (size_t)512 * 96 * sizeof(float), st));
-  TRY(pack_3d(params[P_LINW], p.wlinT, 1, 512, V, 0, 1, 512, 0, 96, st));  // wlinT[c][v] = W[v][c]
   TRY(tc_conv_fprop(DLP, p.wlinT, 512, 1, 1, 0, 0, img_nhwc(p.dy1, 1, 1, TB, 512), plain, st));
 
   // ---- LSTM layers, top down
@@ -276,9 +286,8 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
       if (lg[d * 4 + 2]) TRY(colsum_acc(DG, lg[d * 4 + 2], st));
       if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], st));
     }
-    // d(input) = dG * [W_ih_fwd ; W_ih_rev]: B operand [512][2048], wihT[c][d*1024 + r] = W_ih_d[r][c]
-    for (int d = 0; d < 2; ++d) TRY(pack_3d(lp[d * 4 + 0], p.wihT + d * 1024, 1, 512, 1024, 0, 1, 512, 0, 2048, st));
-    TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), p.wihT, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512), plain, st));
+    // d(input) = dG * [W_ih_fwd ; W_ih_rev]
+    TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), l ? p.wihT1 : p.wihT0, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512), plain, st));
   }
 
   // ---- conv7 (dz7 = dx0, sequence-major view of a (B,1,T,512) image)
@@ -286,8 +295,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   DZ7.p = p.dx0; DZ7.n = B; DZ7.h = 1; DZ7.w = T; DZ7.c = 512; DZ7.sn = 512; DZ7.sh = 0; DZ7.sw = (long long)B * 512;
   if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, grads[P_C7W], 512 * 4, 4, 2, 1, st));
   if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], st));
-  TRY(pack_dgrad(params[P_C7W], p.wpd, 512, 512, 4, st));
-  TRY(tc_conv_fprop(DZ7, p.wpd, 512, 2, 2, 1, 1, D6, plain, st));
+  TRY(tc_conv_fprop(DZ7, p.wpd7, 512, 2, 2, 1, 1, D6, plain, st));
 
   // ---- conv6 + BN2 + ReLU + pool(2,1), conv5 + BN1 + ReLU
   const bool bn_grads = grads[P_BN1W] || grads[P_BN2W];
@@ -305,39 +313,35 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   }
   if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, grads[P_C6W], 512 * 9, 9, 3, 1, st));
   if (grads[P_C6B]) TRY(colsum_acc(D6f, grads[P_C6B], st));
-  TRY(pack_dgrad(params[P_C6W], p.wpd, 512, 512, 9, st));
   if (bn_train) {
-    TRY(tc_conv_fprop(D6f, p.wpd, 512, 3, 3, 1, 1, D5, plain, st));
+    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, plain, st));
     TRY(bn_bwd_reduce(Z5, D5, p.scsh5, 1, p.bnred + 1024, st));
     TRY(bn_bwd_apply_train(Z5, D5, p.scsh5, 1, p.bnred + 1024, params[P_BN1W], D5, grads[P_BN1W], grads[P_BN1B], st));
   } else if (bn_grads) {
-    TRY(tc_conv_fprop(D6f, p.wpd, 512, 3, 3, 1, 1, D5, plain, st));
+    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, plain, st));
     TRY(bn_bwd_reduce(A5, D5, p.scsh5, 2, p.bnred + 1024, st));
     TRY(bn_bwd_apply_eval(A5, D5, p.scsh5, 2, p.bnred + 1024, D5, grads[P_BN1W], grads[P_BN1B], st));
   } else {
     TcEpilogue e;
     e.scale = p.scsh5; e.mask = &A5;  // dz5 = d(a5) * scale, zero where a5 == 0, fused into the dgrad epilogue
-    TRY(tc_conv_fprop(D6f, p.wpd, 512, 3, 3, 1, 1, D5, e, st));
+    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
   }
   if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, grads[P_C5W], 256 * 9, 9, 3, 1, st));
   if (grads[P_C5B]) TRY(colsum_acc(D5, grads[P_C5B], st));
-  TRY(pack_dgrad(params[P_C5W], p.wpd, 512, 256, 9, st));
-  TRY(tc_conv_fprop(D5, p.wpd, 256, 3, 3, 1, 1, D4, plain, st));
+  TRY(tc_conv_fprop(D5, p.wpd5, 256, 3, 3, 1, 1, D4, plain, st));
 
   // ---- conv4 + ReLU + pool(2,1), conv3 + ReLU
   TRY(maxpool_bwd(A4f, D4, 2, 1, 1, nullptr, nullptr, D4f, st));
   if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, grads[P_C4W], 256 * 9, 9, 3, 1, st));
   if (grads[P_C4B]) TRY(colsum_acc(D4f, grads[P_C4B], st));
-  TRY(pack_dgrad(params[P_C4W], p.wpd, 256, 256, 9, st));
   {
     TcEpilogue e;
     e.mask = &A3;  // ReLU of conv3 fused into the dgrad epilogue
-    TRY(tc_conv_fprop(D4f, p.wpd, 256, 3, 3, 1, 1, D3, e, st));
+    TRY(tc_conv_fprop(D4f, p.wpd4, 256, 3, 3, 1, 1, D3, e, st));
   }
   if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, grads[P_C3W], 128 * 9, 9, 3, 1, st));
   if (grads[P_C3B]) TRY(colsum_acc(D3, grads[P_C3B], st));
-  TRY(pack_dgrad(params[P_C3W], p.wpd, 256, 128, 9, st));
-  TRY(tc_conv_fprop(D3, p.wpd, 128, 3, 3, 1, 1, D2, plain, st));
+  TRY(tc_conv_fprop(D3, p.wpd3, 128, 3, 3, 1, 1, D2, plain, st));
 
   // ---- conv2 + ReLU + pool, conv1 + ReLU + pool
   TRY(maxpool_bwd(A2f, D2, 2, 2, 1, nullptr, nullptr, D2f, st));
@@ -345,8 +349,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   if (grads[P_C2B]) TRY(colsum_acc(D2f, grads[P_C2B], st));
   const bool need_d1 = grads[P_C1W] || grads[P_C1B] || dx;
   if (need_d1) {
-    TRY(pack_dgrad(params[P_C2W], p.wpd, 128, 64, 9, st));
-    TRY(tc_conv_fprop(D2f, p.wpd, 64, 3, 3, 1, 1, D1, plain, st));
+      TRY(tc_conv_fprop(D2f, p.wpd2, 64, 3, 3, 1, 1, D1, plain, st));
     TRY(maxpool_bwd(A1f, D1, 2, 2, 1, nullptr, nullptr, D1f, st));
     if (grads[P_C1W]) TRY(c1_conv_wgrad(X, D1f, grads[P_C1W], grads[P_C1B], st));
     if (dx) TRY(c1_conv_dgrad(D1f, params[P_C1W], img_nhwc(dx, B, 32, W, 1), st));

@@ -41,7 +41,8 @@ struct UnetPlan {
   float *dz1[kLevels - 1], *da1[kLevels - 1], *dz2[kLevels - 1], *dout[kLevels - 1];
   float* scsh;      // kUnits x 4*512
   double* bnstats;  // kUnits x 1024
-  float* wpack;     // one conv's packed weights at a time (largest: 512 x 9 x 512)
+  float *wp[kUnits], *wup[4];    // fprop B operands per conv unit / up-convolution
+  float *wpd[kUnits], *wupd[4];  // dgrad B operands
   float *sA[kLevels], *sB[kLevels], *sC[kLevels];
   double* bnred;    // kUnits x 1024
   size_t bytes;
@@ -67,7 +68,18 @@ UnetPlan make_plan(int B, int H, int W, void* base) {
   }
   p.scsh = a.take((size_t)kUnits * 4 * 512);
   p.bnstats = reinterpret_cast<double*>(a.take((size_t)kUnits * 1024 * 2));
-  p.wpack = a.take((size_t)512 * 9 * 512);
+  for (int blk = 0; blk < 9; ++blk) {
+    // block -> (cin of conv1, cout): encoders 1,32,64,128,256 -> C; decoders (block 5 + j, level 3 - j): 2C -> C
+    const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+    const int cout = p.C[lvl];
+    const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+    p.wp[blk * 2] = a.take((size_t)cout * 9 * cin1); p.wp[blk * 2 + 1] = a.take((size_t)cout * 9 * cout);
+    p.wpd[blk * 2] = a.take((size_t)cout * 9 * cin1); p.wpd[blk * 2 + 1] = a.take((size_t)cout * 9 * cout);
+  }
+  for (int up = 0; up < 4; ++up) {  // up-conv `up` (upconv4..1) maps 2C -> C at level 3 - up
+    const int C = p.C[3 - up];
+    p.wup[up] = a.take((size_t)4 * C * 2 * C); p.wupd[up] = a.take((size_t)4 * C * 2 * C);
+  }
   for (int i = 0; i < kLevels; ++i) {
     p.sA[i] = a.take(p.M[i] * 2 * p.C[i]); p.sB[i] = a.take(p.M[i] * p.C[i]); p.sC[i] = a.take(p.M[i] * p.C[i]);
   }
@@ -81,13 +93,6 @@ UnetPlan make_plan(int B, int H, int W, void* base) {
     int _rc = (expr);        \
     if (_rc != QEB_OK) return _rc; \
   } while (0)
-
-int pack_fprop(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
-  return pack_3d(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin, st);
-}
-int pack_dgrad(const float* w, float* dst, int cout, int cin, int taps, cudaStream_t st) {
-  return pack_3d(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout, st);
-}
 
 struct Ctx {
   const float* const* params;
@@ -126,10 +131,10 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     }
     return bn_apply(z, scsh, 1, out, c.st);
   }
-  TRY(pack_fprop(w, c.p->wpack, cout, in.c, 9, c.st));
+  const float* wp = c.p->wp[unit];
   if (c.bn_train) {
     const TcEpilogue raw;
-    TRY(tc_conv_fprop(in, c.p->wpack, cout, 3, 3, 1, 1, z, raw, c.st));
+    TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
     TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
     TRY(bn_train_finalize(c.p->bnstats + (size_t)unit * 1024, img_pixels(z), cout, bn, scsh, c.st));
     return bn_apply(z, scsh, 1, out, c.st);
@@ -137,7 +142,7 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
   TcEpilogue f;
   f.relu = 1; f.scale = scsh; f.bias = scsh + cout;
-  return tc_conv_fprop(in, c.p->wpack, cout, 3, 3, 1, 1, out, f, c.st);
+  return tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, out, f, c.st);
 }
 
 // backward of one unit. g: gradient at the unit's output (overwritten with the gradient at the conv output);
@@ -163,9 +168,8 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   }
   if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, gr[0], (long long)in.c * 9, 9, 3, 1, c.st));
   if (din) {
-    TRY(pack_dgrad(w, c.p->wpack, g.c, in.c, 9, c.st));
     const TcEpilogue plain;
-    TRY(tc_conv_fprop(g, c.p->wpack, in.c, 3, 3, 1, 1, *din, plain, c.st));
+    TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, plain, c.st));
   }
   return QEB_OK;
 }
@@ -190,6 +194,21 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   Ctx c;
   c.params = params; c.buffers = buffers; c.grads = nullptr; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
+  {  // every weight re-layout of this pass in one launch
+    PackBatch pk;
+    for (int blk = 0; blk < 9; ++blk) {
+      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+      const int cout = p.C[lvl];
+      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      if (cin1 > 1) pk.add_fprop(params[blk * 6], p.wp[blk * 2], cout, cin1, 9);
+      pk.add_fprop(params[blk * 6 + 3], p.wp[blk * 2 + 1], cout, cout, 9);
+    }
+    for (int up = 0; up < 4; ++up) {  // ConvTranspose weight (2C, C, 2, 2) -> B operand [(dh*2+dw)*C + co][2C]
+      const int C = p.C[3 - up];
+      pk.add(params[P_UP + up * 2], p.wup[up], 4, C, 2 * C, 1, 4, (long long)C * 4, (long long)C * 2 * C, 2 * C);
+    }
+    TRY(pack_flush(pk, c.st));
+  }
 
   Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
   for (int i = 0; i < kLevels; ++i) {  // encoder blocks + bottleneck
@@ -208,10 +227,8 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   Img below = img_nhwc(p.bott, B, p.h[4], p.w[4], p.C[4]);
   for (int i = 3; i >= 0; --i) {  // decoder blocks: block index 5 + (3 - i), up-conv index (3 - i)
     const int C = p.C[i], blk = 5 + (3 - i), up = 3 - i;
-    // ConvTranspose weight (2C, C, 2, 2) -> B operand [(dh*2+dw)*C + co][2C]
-    TRY(pack_3d(params[P_UP + up * 2], p.wpack, 4, C, 2 * C, 1, 4, (long long)C * 4, (long long)C * 2 * C, 2 * C, c.st));
     Img upo = img_nhwc(p.cat[i], B, p.h[i], p.w[i], C, 2 * C);
-    TRY(tc_convT_fprop(below, p.wpack, params[P_UP + up * 2 + 1], upo, c.st));
+    TRY(tc_convT_fprop(below, p.wup[up], params[P_UP + up * 2 + 1], upo, c.st));
     Img cat = img_nhwc(p.cat[i], B, p.h[i], p.w[i], 2 * C);
     Img z1 = img_nhwc(p.dz1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.da1[i], B, p.h[i], p.w[i], C);
     Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
@@ -232,6 +249,21 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
   Ctx c;
   c.params = params; c.buffers = nullptr; c.grads = grads; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
+  {
+    PackBatch pk;
+    for (int blk = 0; blk < 9; ++blk) {
+      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+      const int cout = p.C[lvl];
+      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      if (cin1 > 1) pk.add_dgrad(params[blk * 6], p.wpd[blk * 2], cout, cin1, 9);
+      pk.add_dgrad(params[blk * 6 + 3], p.wpd[blk * 2 + 1], cout, cout, 9);
+    }
+    for (int up = 0; up < 4; ++up) {  // dgrad B operand [2C][(dh*2+dw)*C + co] from the torch weight (2C, C, 2, 2)
+      const int C = p.C[3 - up];
+      pk.add(params[P_UP + up * 2], p.wupd[up], 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
+    }
+    TRY(pack_flush(pk, c.st));
+  }
 
   // final 1x1 conv + sigmoid
   Img d0 = img_nhwc(p.dout[0], B, H, W, 32), g0 = img_nhwc(p.sC[0], B, H, W, 32);
@@ -252,11 +284,9 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
     Img below = i < 3 ? img_nhwc(p.dout[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C) : img_nhwc(p.bott, B, p.h[4], p.w[4], 2 * C);
     if (grads[P_UP + up * 2 + 1]) TRY(colsum_acc(dU, grads[P_UP + up * 2 + 1], c.st));
     if (grads[P_UP + up * 2]) TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], c.st));
-    // dgrad B operand [2C][(dh*2+dw)*C + co] from the torch weight (2C, C, 2, 2)
-    TRY(pack_3d(params[P_UP + up * 2], p.wpack, 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C, c.st));
     Img gbelow = img_nhwc(p.sC[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C);
     const TcEpilogue plain;
-    TRY(tc_convT_dgrad(dU, p.wpack, gbelow, plain, c.st));
+    TRY(tc_convT_dgrad(dU, p.wupd[up], gbelow, plain, c.st));
   }
   for (int i = 4; i >= 0; --i) {  // bottleneck, then encoder blocks
     const int C = p.C[i];

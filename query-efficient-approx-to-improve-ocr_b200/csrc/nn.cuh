@@ -53,6 +53,37 @@ int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st);
 // contiguous); entries of a padded destination are expected to be zero-filled by the caller.
 int pack_3d(const float* src, float* dst, int n0, int n1, int n2, long long s0, long long s1, long long s2, long long d0,
             long long d1, cudaStream_t st);
+// the same gather for up to kMax tensors in ONE launch (all weight packs of a network pass)
+struct PackJob {
+  const float* src;
+  float* dst;
+  int n0, n1, n2;
+  long long s0, s1, s2, d0, d1;
+  long long start;  // first element of this job in the batch-wide numbering
+};
+struct PackBatch {
+  enum { kMax = 28 };
+  PackJob jobs[kMax];
+  int n = 0;
+  long long total = 0;
+  void add(const float* src, float* dst, int n0, int n1, int n2, long long s0, long long s1, long long s2, long long d0,
+           long long d1) {
+    PackJob& j = jobs[n++];
+    j.src = src; j.dst = dst; j.n0 = n0; j.n1 = n1; j.n2 = n2; j.s0 = s0; j.s1 = s1; j.s2 = s2; j.d0 = d0; j.d1 = d1;
+    j.start = total;
+    total += (long long)n0 * n1 * n2;
+  }
+  // torch Conv2d weight (Cout,Cin,taps) -> fprop B operand [Cout][tap][Cin]
+  void add_fprop(const float* w, float* dst, int cout, int cin, int taps) {
+    add(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin);
+  }
+  // -> dgrad B operand [Cin][flipped tap][Cout] (source taps walked backwards with a negative stride)
+  void add_dgrad(const float* w, float* dst, int cout, int cin, int taps) {
+    add(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout);
+  }
+  void add_copy(const float* src, float* dst, long long n) { add(src, dst, 1, 1, (int)n, 0, 0, 1, 0, 0); }
+};
+int pack_flush(PackBatch& b, cudaStream_t st);
 
 // ---- direct (SIMT) kernels, nn_ops.cu ---------------------------------------------------------------------------
 // 3x3 pad-1 convolution with ONE input channel: x (n,h,w,1) -> out (n,h,w,cout); w torch layout (cout,1,3,3).

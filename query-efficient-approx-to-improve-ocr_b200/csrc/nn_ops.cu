@@ -325,7 +325,20 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restr
   const int cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
   if (rl < rpb) {
-    for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+    const long long step = (long long)gridDim.x * rpb;
+    long long r = (long long)blockIdx.x * rpb + rl;
+    for (; r + 3 * step < M; r += 4 * step) {  // four independent loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld4(z + (r + u * step) * zs + cq * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w;
+        q[0] = fmaf(v[u].x, v[u].x, q[0]); q[1] = fmaf(v[u].y, v[u].y, q[1]);
+        q[2] = fmaf(v[u].z, v[u].z, q[2]); q[3] = fmaf(v[u].w, v[u].w, q[3]);
+      }
+    }
+    for (; r < M; r += step) {
       const float4 v = ld4(z + r * zs + cq * 4);
       s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
       q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
@@ -418,7 +431,19 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
   if (rl < rpb) {
     const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
     const float4 mu = ld4(scsh + 2 * C + cq * 4), is = ld4(scsh + 3 * C + cq * 4);
-    for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+    const long long step = (long long)gridDim.x * rpb;
+    long long r = (long long)blockIdx.x * rpb + rl;
+    for (; r + step < M; r += 2 * step) {  // two rows (four independent loads) in flight per thread
+      const float4 v0 = ld4(z + r * zs + cq * 4), v1 = ld4(z + (r + step) * zs + cq * 4);
+      const float4 d0 = ld4(dy + r * ds + cq * 4), d1 = ld4(dy + (r + step) * ds + cq * 4);
+      const float4 g0 = bn_masked_grad(v0, d0, sc, sh, relu), g1 = bn_masked_grad(v1, d1, sc, sh, relu);
+      s[0] += g0.x + g1.x; s[1] += g0.y + g1.y; s[2] += g0.z + g1.z; s[3] += g0.w + g1.w;
+      q[0] = fmaf(g0.x, (v0.x - mu.x) * is.x, q[0]); q[1] = fmaf(g0.y, (v0.y - mu.y) * is.y, q[1]);
+      q[2] = fmaf(g0.z, (v0.z - mu.z) * is.z, q[2]); q[3] = fmaf(g0.w, (v0.w - mu.w) * is.w, q[3]);
+      q[0] = fmaf(g1.x, (v1.x - mu.x) * is.x, q[0]); q[1] = fmaf(g1.y, (v1.y - mu.y) * is.y, q[1]);
+      q[2] = fmaf(g1.z, (v1.z - mu.z) * is.z, q[2]); q[3] = fmaf(g1.w, (v1.w - mu.w) * is.w, q[3]);
+    }
+    for (; r < M; r += step) {
       const float4 v = ld4(z + r * zs + cq * 4);
       const float4 g = bn_masked_grad(v, ld4(dy + r * ds + cq * 4), sc, sh, relu);
       s[0] += g.x; s[1] += g.y; s[2] += g.z; s[3] += g.w;
@@ -491,12 +516,23 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
     const int cq = cq0 + threadIdx.x % min(cq_n, kThreads), rl = threadIdx.x / min(cq_n, kThreads);
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     if (rl < rpb && cq < cq_n) {
-      for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
-        const float* p = x + r * xs + cq * 4;
-        if (cq * 4 + 3 < C) {
-          const float4 v = ld4(p);
+      const long long step = (long long)gridDim.x * rpb;
+      long long r = (long long)blockIdx.x * rpb + rl;
+      if (cq * 4 + 3 < C) {
+        for (; r + 3 * step < M; r += 4 * step) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = ld4(x + (r + u * step) * xs + cq * 4);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) { s[0] += v[u].x; s[1] += v[u].y; s[2] += v[u].z; s[3] += v[u].w; }
+        }
+        for (; r < M; r += step) {
+          const float4 v = ld4(x + r * xs + cq * 4);
           s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
-        } else {
+        }
+      } else {
+        for (; r < M; r += step) {
+          const float* p = x + r * xs + cq * 4;
           for (int j = 0; cq * 4 + j < C; ++j) s[j] += p[j];
         }
       }
@@ -535,6 +571,27 @@ __global__ void __launch_bounds__(kThreads) pack3d_kernel(const float* __restric
     const int i1 = (int)(t % n1);
     const long long i0 = t / n1;
     dst[i0 * d0 + i1 * d1 + i2] = src[i0 * s0 + i1 * s1 + (long long)i2 * s2];
+  }
+}
+
+struct PackJobsParam {
+  PackJob j[PackBatch::kMax];
+  int n;
+};
+__global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_constant__ PackJobsParam jobs, long long total) {
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    int lo = 0, hi = jobs.n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs.j[mid].start <= i) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& j = jobs.j[lo];
+    const long long e = i - j.start;
+    const int i2 = (int)(e % j.n2);
+    const long long t = e / j.n2;
+    const int i1 = (int)(t % j.n1);
+    const long long i0 = t / j.n1;
+    j.dst[i0 * j.d0 + i1 * j.d1 + i2] = j.src[i0 * j.s0 + i1 * j.s1 + (long long)i2 * j.s2];
   }
 }
 
@@ -664,7 +721,7 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
 
 static int reduce_grid(long long M, int rpb) {
   long long g = (M + rpb - 1) / rpb;
-  const long long cap = 4 * kNumSMs;
+  const long long cap = 8 * kNumSMs;
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
@@ -780,5 +837,20 @@ int vec_add(const float* a, const float* b, float* out, int n, cudaStream_t st) 
   vec_add_kernel<<<qeb_cdiv(n, 256), 256, 0, st>>>(a, b, out, n);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
+  return QEB_OK;
+}
+
+int pack_flush(PackBatch& b, cudaStream_t st) {
+  if (b.n == 0) return QEB_OK;
+  QEB_REQUIRE(b.n <= PackBatch::kMax, "pack_flush: too many jobs");
+  ProfScope prof("pack", st, 0.0, 8.0 * b.total);
+  PackJobsParam p;
+  for (int i = 0; i < b.n; ++i) p.j[i] = b.jobs[i];
+  p.n = b.n;
+  pack_multi_kernel<<<qeb_grid(b.total, kThreads), kThreads, 0, st>>>(p, b.total);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  b.n = 0;
+  b.total = 0;
   return QEB_OK;
 }

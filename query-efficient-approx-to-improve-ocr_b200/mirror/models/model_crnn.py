@@ -9,11 +9,16 @@ on the reference (models/model_crnn.py:30-32, train_nn_patch.py:94).
 """
 import ctypes
 
+import os
+
 import torch
 import torch.nn as nn
 
 from ... import _lib
 from ..ctc import log_softmax
+
+_POISON = os.environ.get("QEB_POISON_WORKSPACE", "0") == "1"
+
 
 class Convolutional(nn.Module):
     """Parameter container of the conv stack (models/model_crnn.py:34-45)."""
@@ -66,6 +71,8 @@ class _CRNNTrunk(torch.autograd.Function):
         if C != 1 or H != 32 or nbytes == 0:
             raise _lib.QebError(f"qeb CRNN: unsupported input {tuple(x.shape)} (needs (B,1,32,W), W % 4 == 0, vocab <= 96)")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        if _POISON:  # debugging aid: any read of workspace memory the pass did not write shows up as NaN
+            ws.view(torch.float32).fill_(float("nan"))
         T = W // 4 - 1
         logits = torch.empty((T, B, V), dtype=torch.float32, device=x.device)
         _lib.call("qeb_crnn_forward", x.data_ptr(), B, W, V, _ptr_array(params), _ptr_array(buffers), int(bn_train),

@@ -7,11 +7,16 @@ csrc/engine_unet.cu).
 """
 from collections import OrderedDict
 
+import os
+
 import torch
 import torch.nn as nn
 
 from ... import _lib
 from .model_crnn import _alloc_grads, _ptr_array
+
+
+_POISON = os.environ.get("QEB_POISON_WORKSPACE", "0") == "1"
 
 
 class _UNetFn(torch.autograd.Function):
@@ -25,6 +30,8 @@ class _UNetFn(torch.autograd.Function):
         if C != 1 or nbytes == 0:
             raise _lib.QebError(f"qeb UNet: unsupported input {tuple(x.shape)} (needs (B,1,H,W) with H, W multiples of 16)")
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        if _POISON:  # debugging aid: any read of workspace memory the pass did not write shows up as NaN
+            ws.view(torch.float32).fill_(float("nan"))
         y = torch.empty_like(x)
         _lib.call("qeb_unet_forward", x.data_ptr(), B, H, W, _ptr_array(params), _ptr_array(buffers), int(bn_train),
                   ws.data_ptr(), y.data_ptr(), _lib.stream())

@@ -16,6 +16,7 @@ def rel(a, b):
     return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
 def cmp_grads(m, mr, tag, thr=2e-2):
+    if os.environ.get('SYNC'): torch.cuda.synchronize()
     worst = ("", 0.0)
     for (n, p), (_, q) in zip(m.named_parameters(), mr.named_parameters()):
         if q.grad is None:
@@ -23,6 +24,12 @@ def cmp_grads(m, mr, tag, thr=2e-2):
         if p.grad is None:
             print("   MISSING grad", n); continue
         e = rel(p.grad, q.grad)
+        if e > 1e3:
+            big = ((p.grad.abs() > 1e3) | ~torch.isfinite(p.grad)).reshape(-1)
+            idx = big.nonzero().reshape(-1)
+            print("   DEBUG", n, tuple(p.shape), "count", int(big.sum()), "idx", idx[:10].tolist(), idx[-3:].tolist(), "vals",
+                  p.grad.reshape(-1)[idx[:5]].tolist(), "ptr", hex(p.grad.data_ptr()), "base",
+                  None if p.grad._base is None else (hex(p.grad._base.data_ptr()), p.grad._base.numel()))
         if q.grad.norm() < 1e-6:  # analytically-zero gradients (conv bias before train-mode BN)
             e = float((p.grad - q.grad).abs().max())
         if e > worst[1]: worst = (n, e)
