@@ -104,6 +104,85 @@ int qeb_crop_pad_gather(const float* img, int H, int W, const int* boxes, int n,
 int qeb_crop_pad_scatter(const float* gout, int H, int W, const int* boxes, int n, int oh, int ow, float* gimg,
                          void* stream);
 
+/* ==== the two networks (module-level entry points: what nn.Module.forward / autograd backward bind to) ============
+ * All activations are NHWC fp32 inside a caller-owned workspace; the module tensors (B,1,H,W) have one channel and are
+ * therefore passed as they are. params / grads / buffers are arrays of DEVICE pointers living in HOST memory.
+ *
+ * CRNN: models/model_crnn.py:5-56 (Convolutional.forward :47-56, CRNN.forward :16-21 without the log_softmax, which is
+ * qeb_log_softmax_fwd above so that CRNN.backward_hook sees the gradient at the logits, :30-32).
+ * params (36, state_dict order): conv1.w,b .. conv5.w,b, batchnorm1.w,b, conv6.w,b, batchnorm2.w,b, conv7.w,b,
+ *   lstm {weight_ih, weight_hh, bias_ih, bias_hh} for l0, l0_reverse, l1, l1_reverse, linear.w,b.
+ * buffers (6): batchnorm1 {running_mean, running_var, num_batches_tracked(int64)}, batchnorm2 {...}.
+ * x (B,1,32,W), W % 4 == 0; logits (T = W/4 - 1, B, V) dense, V <= 96. bn_train: 1 = batch statistics + running-stat
+ * update (module.train()), 0 = running statistics (set_bn_eval, utils.py:113-115). ws: qeb_crnn_workspace_bytes(),
+ * 256-byte aligned, must stay untouched between forward and backward.
+ * backward: dlogits (T,B,V); grads[i] NULL = skip that gradient, otherwise the gradient is ACCUMULATED into it;
+ * dx (B,1,32,W) or NULL. */
+size_t qeb_crnn_workspace_bytes(int B, int W, int V);
+int qeb_crnn_num_params(void);
+int qeb_crnn_forward(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
+                     void* ws, float* logits, void* stream);
+int qeb_crnn_backward(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
+                      const float* dlogits, float* const* grads, float* dx, void* stream);
+
+/* UNet: models/model_unet.py:7-109 (forward :49-76). params (64): 9 blocks (encoder1..4, bottleneck, decoder4..1) x
+ * {conv1.w, norm1.w, norm1.b, conv2.w, norm2.w, norm2.b}, upconv4..1 {w, b}, conv {w, b}. buffers (54): per block
+ * {norm1.running_mean, running_var, num_batches_tracked, norm2...}. x, y (B,1,H,W), H and W multiples of 16. */
+size_t qeb_unet_workspace_bytes(int B, int H, int W);
+int qeb_unet_num_params(void);
+int qeb_unet_num_buffers(void);
+int qeb_unet_forward(const float* x, int B, int H, int W, const float* const* params, void* const* buffers, int bn_train,
+                     void* ws, float* y, void* stream);
+int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
+                      const float* y, const float* dy, float* const* grads, float* dx, void* stream);
+
+/* ==== building blocks, exported for tests and for callers that compose their own graphs ===========================
+ * Tensor-core contractions (tcgen05 kind::tf32, fp32 accumulate). Activations NHWC with a channel stride (a channel
+ * slice of a wider buffer is passed as base pointer + stride); channel counts on the contracted side are multiples of 32.
+ * conv_fprop: nn.Conv2d stride 1 (models/model_crnn.py:37-45, models/model_unet.py:84-104), nn.Linear and the LSTM input
+ *   projections as 1x1; also every input gradient (flipped, transposed weights). wpacked [n_total][kh*kw*cin] from
+ *   qeb_pack_weight (mode 0 fprop, mode 1 dgrad, mode 2 ConvTranspose fprop). v = acc*scale[c] + bias[c], optional ReLU.
+ * conv_wgrad: dw[co][ci][kh][kw] += ... (torch layout), split-K with fp32 atomics.
+ * convT2x2_*: nn.ConvTranspose2d(k=2, s=2) (models/model_unet.py:25-44) as a per-pixel GEMM + pixel shuffle. */
+int qeb_pack_weight(const float* src, float* dst, int A, int B, int KH, int KW, int mode, void* stream);
+int qeb_nchw_to_nhwc(const float* src, float* dst, int N, int C, int H, int W, int dst_cstride, void* stream);
+int qeb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, int src_cstride, void* stream);
+int qeb_conv_fprop_tc(const float* x, int n_img, int h_in, int w_in, int cin, int x_cstride, const float* wpacked,
+                      int n_total, int kh, int kw, int ph, int pw, const float* bias, const float* scale, int relu,
+                      float* out, int out_cstride, int accumulate, void* stream);
+int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, int w_in, const float* dy, int cout,
+                      int dy_cstride, int n_img, int kh, int kw, int ph, int pw, float* dw, void* stream);
+int qeb_convT2x2_fprop_tc(const float* x, int n_img, int h, int w, int cin, int x_cstride, const float* wpacked,
+                          const float* bias, int cout, float* out, int out_cstride, void* stream);
+int qeb_convT2x2_dgrad_tc(const float* dy, int n_img, int h, int w, int cout, int dy_cstride, const float* wpacked,
+                          int cin, float* dx, int dx_cstride, void* stream);
+int qeb_convT2x2_wgrad_tc(const float* x, int cin, int x_cstride, int h, int w, const float* dy, int cout,
+                          int dy_cstride, int n_img, float* dw, void* stream);
+
+/* One bidirectional LSTM layer, hidden 256 (nn.LSTM(512,256,2,bidirectional=True), models/model_crnn.py:9,19).
+ * gates (T,B,2,1024): x*W_ih^T + b_ih + b_hh on entry (gate order i,f,g,o), overwritten with the activated gates
+ * (forward) and then with the gradients at the pre-activations (backward). cells (T,B,2,256); y, dy (T,B,512). */
+int qeb_lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
+                       void* stream);
+int qeb_lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev,
+                       int T, int B, void* stream);
+
+/* MSELoss()(img, ones) of TrainNNPrep._get_loss (train_nn_patch.py:181-184, train_nn_area.py:177-181). */
+int qeb_mse_ones_fwd(const float* x, long long n, float* loss, void* stream);
+int qeb_mse_ones_bwd(const float* x, long long n, const float* grad_out, float* dx, void* stream);
+
+/* torch.optim.Adam (L2-coupled weight decay; train_nn_patch.py:146-152, train_nn_area.py:149-154) over many tensors in
+ * one launch. table (device): n_tensors entries of qeb_adam_table_entry_bytes() = {float* p, const float* g, float* m,
+ * float* v, int64 n, int64 chunk0}, chunk0 = exclusive prefix sum of ceil(n/1024); step = count after this update. */
+int qeb_adam_table_entry_bytes(void);
+int qeb_adam_multi(const void* table, int n_tensors, long long n_chunks, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, void* stream);
+
+/* Per-launch profiling: CUDA events around every launch of the library on its stream, with the launch site's
+ * algorithmic FLOPs / bytes. report: JSON {"tag": {"launches", "ms", "flops", "bytes"}}, clears the records. */
+void qeb_prof_enable(int on);
+int qeb_prof_report(char* buf, int cap);
+
 #ifdef __cplusplus
 }
 #endif
