@@ -188,6 +188,7 @@ def main():
     import qeb_b200
     from qeb_b200 import _lib
     from qeb_b200.mirror import ctc as qctc
+    from qeb_b200.mirror import dist as qdist
     from qeb_b200.mirror import train_ops
     from qeb_b200.mirror.models.model_crnn import CRNN
     from qeb_b200.mirror.models.model_unet import UNet
@@ -217,17 +218,7 @@ def main():
     unet_params = [p for p in prep.parameters()]
 
     def allreduce_grads():
-        if world == 1:
-            return
-        bases = {id(p.grad._base): p.grad._base for p in unet_params if p.grad is not None and p.grad._base is not None}
-        if len(bases) == 1 and all(p.grad is not None and p.grad._base is not None for p in unet_params):
-            dist.all_reduce(next(iter(bases.values())), op=dist.ReduceOp.AVG)   # one flat 31 MB buffer
-        else:
-            flat = torch.cat([p.grad.reshape(-1) for p in unet_params])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-            off = 0
-            for p in unet_params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p)); off += p.numel()
+        qdist.allreduce_grads(unet_params, average=True)   # one NCCL all-reduce of the flat 31 MB gradient buffer
 
     def step_device():
         prep.train(); crnn.train(); crnn.apply(set_bn_eval)          # train_nn_area.py:277-279

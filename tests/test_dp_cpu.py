@@ -1,0 +1,63 @@
+"""Host-side data-parallel logic on CPU: world_size-2 gloo processes (the N > 1 path of bench.py without GPUs)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT
+
+
+def _worker(rank, world, port, mode, out):
+    sys.path.insert(0, ROOT)
+    import qeb_b200  # noqa: F401
+    from qeb_b200.mirror import dist as qdist
+    from qeb_b200.mirror.models.model_crnn import _alloc_grads
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((4, 3), (7,), (2, 2, 2))]
+    if mode == "flat":      # the layout the qeb backward produces: views of one zero-filled buffer
+        grads = _alloc_grads(params, [True] * len(params))
+        for p, g in zip(params, grads):
+            g.copy_(torch.full_like(p, float(rank + 1)) * p.detach())
+            p.grad = g
+        assert qdist.flat_grad_buffer(params) is not None
+    else:                   # independent gradient tensors (foreign autograd functions)
+        for p in params:
+            p.grad = torch.full_like(p, float(rank + 1)) * p.detach()
+        assert qdist.flat_grad_buffer(params) is None
+    n = qdist.allreduce_grads(params, average=(mode != "sum"))
+    expect = sum(range(1, world + 1)) / (1 if mode == "sum" else world)
+    ok = n == 1 and all(torch.allclose(p.grad, expect * p.detach()) for p in params)
+    lo, hi = qdist.shard_batch(67, rank, world)
+    sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([hi - lo]))
+    ok = ok and sum(int(s) for s in sizes) == 67
+    out[rank] = ok
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["flat", "separate", "sum"])
+def test_allreduce_grads_gloo_world2(mode):
+    world = 2
+    port = 29500 + (os.getpid() + hash(mode)) % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, mode, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))
+
+
+def test_single_process_is_a_noop():
+    sys.path.insert(0, ROOT)
+    import qeb_b200  # noqa: F401
+    from qeb_b200.mirror import dist as qdist
+
+    p = torch.nn.Parameter(torch.ones(3))
+    p.grad = torch.ones(3)
+    assert qdist.allreduce_grads([p]) == 0
+    assert qdist.shard_batch(10, 0, 1) == (0, 10)
