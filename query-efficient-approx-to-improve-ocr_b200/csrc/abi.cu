@@ -44,7 +44,7 @@ QEB_API int qeb_check_device(void) {
 // launching stream, with the launch site's algorithmic FLOPs / bytes. Off by default (two event records per launch).
 namespace {
 struct ProfRec {
-  const char* tag;
+  std::string tag;
   cudaEvent_t e0, e1;
   double flops, bytes;
 };
@@ -58,6 +58,11 @@ int qeb_prof_on() { return g_prof.load(std::memory_order_relaxed); }
 int qeb_prof_begin(const char* tag, cudaStream_t st, double flops, double bytes) {
   ProfRec r;
   r.tag = tag; r.flops = flops; r.bytes = bytes;
+  if (g_prof.load(std::memory_order_relaxed) == 2) {  // detail mode: one bucket per (tag, work size)
+    char suffix[64];
+    snprintf(suffix, sizeof(suffix), "[%.3gGF,%.3gMB]", flops * 1e-9, bytes * 1e-6);
+    r.tag += suffix;
+  }
   if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return -1;
   cudaEventRecord(r.e0, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);

@@ -15,6 +15,7 @@
 // global). Pipelines: smem full/empty mbarriers (kStages deep), one TMEM-full barrier.
 #include "tc_common.cuh"
 #include "nn.cuh"
+#include <stdlib.h>
 
 namespace tc {
 
@@ -316,8 +317,9 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.a_map_per_tap = per_tap;
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
+  static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
   int bn = min(256, max(32, pow2_ceil(n_total)));
-  while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < kNumSMs) bn >>= 1;
+  while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < min_ctas) bn >>= 1;
   if (mode == 1) while (bn > p.up_c) bn >>= 1;
   QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "tc fprop: tile width %d must divide the up-conv channels %d", bn, p.up_c);
   const int n_tiles = qeb_cdiv(n_total, bn);
@@ -589,7 +591,8 @@ int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, in
   int bn = min(256, max(32, pow2_ceil(b_c)));
   const int m_tiles = qeb_cdiv(p.row_blocks, 4), n_tiles = qeb_cdiv(b_c, bn);
   // split-K so that the grid covers the SMs a few times over, at least 8 pixel tiles per CTA
-  int splits = qeb_cdiv(2 * kNumSMs, m_tiles * n_tiles);
+  static const int wg_ctas = getenv("QEB_WG_CTAS") ? atoi(getenv("QEB_WG_CTAS")) : 2 * kNumSMs;
+  int splits = qeb_cdiv(wg_ctas, m_tiles * n_tiles);
   splits = max(1, min(splits, qeb_cdiv(p.tiles_total, 8)));
   p.per_split = qeb_cdiv(p.tiles_total, splits);
   splits = qeb_cdiv(p.tiles_total, p.per_split);

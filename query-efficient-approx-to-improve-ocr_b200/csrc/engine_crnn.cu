@@ -46,6 +46,8 @@ struct CrnnPlan {
   // backward scratch
   float *dlp, *wlinT, *wihT0, *wihT1, *wpd2, *wpd3, *wpd4, *wpd5, *wpd6, *wpd7, *dy1, *dy0, *dx0, *d6, *d6f, *d5, *d4, *d4f, *d3, *d2, *d2f, *d1, *d1f;
   double* bnred;
+  float *dwp2, *dwp3, *dwp4, *dwp5, *dwp6, *dwp7;  // packed [Cout][tap][Cin] weight-gradient accumulators, contiguous
+  size_t dwp_bytes;
   size_t bytes;
 };
 
@@ -80,6 +82,12 @@ CrnnPlan make_plan(int B, int W, int V, void* base) {
   p.d2 = a.take(px8 * 128); p.d2f = a.take(px16 * 128);
   p.d1 = a.take(px16 * 64); p.d1f = a.take(px32 * 64);
   p.bnred = reinterpret_cast<double*>(a.take(2 * 2 * 512 * 2));  // 2 layers x (sum g, sum g*xhat) x 512 doubles
+  {
+    const size_t o0 = a.off;
+    p.dwp2 = a.take((size_t)128 * 9 * 64); p.dwp3 = a.take((size_t)256 * 9 * 128); p.dwp4 = a.take((size_t)256 * 9 * 256);
+    p.dwp5 = a.take((size_t)512 * 9 * 256); p.dwp6 = a.take((size_t)512 * 9 * 512); p.dwp7 = a.take((size_t)512 * 4 * 512);
+    p.dwp_bytes = a.off - o0;
+  }
   p.bytes = a.off;
   return p;
 }
@@ -161,13 +169,11 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     raw.bias = params[P_C5B];
     TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, Z5, raw, st));
     TRY(bn_train_stats(Z5, p.bnstats, st));
-    TRY(bn_train_finalize(p.bnstats, img_pixels(Z5), 512, bn1, p.scsh5, st));
-    TRY(bn_apply(Z5, p.scsh5, 1, A5, st));
+    TRY(bn_train_finalize_apply(Z5, p.bnstats, bn1, p.scsh5, 1, A5, st));
     raw.bias = params[P_C6B];
     TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, Z6, raw, st));
     TRY(bn_train_stats(Z6, p.bnstats + 1024, st));
-    TRY(bn_train_finalize(p.bnstats + 1024, img_pixels(Z6), 512, bn2, p.scsh6, st));
-    TRY(bn_apply(Z6, p.scsh6, 1, A6f, st));
+    TRY(bn_train_finalize_apply(Z6, p.bnstats + 1024, bn2, p.scsh6, 1, A6f, st));
   } else {
     // frozen statistics: y = relu(conv*scale + shift), shift folds the conv bias
     TRY(bn_eval_scsh(512, bn1, params[P_C5B], p.scsh5, st));
@@ -238,6 +244,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   const TcEpilogue plain;
 
   // ---- Linear
+  TRY(fill_zero(p.dwp2, p.dwp_bytes, st));  // packed conv weight-gradient accumulators
   TRY(fill_zero(p.dlp, (size_t)TB * 96 * sizeof(float), st));
   TRY(fill_zero(p.wlinT, (size_t)512 * 96 * sizeof(float), st));
   {  // every re-layout of this pass in one launch
@@ -293,7 +300,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   // ---- conv7 (dz7 = dx0, sequence-major view of a (B,1,T,512) image)
   Img DZ7;
   DZ7.p = p.dx0; DZ7.n = B; DZ7.h = 1; DZ7.w = T; DZ7.c = 512; DZ7.sn = 512; DZ7.sh = 0; DZ7.sw = (long long)B * 512;
-  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, grads[P_C7W], 512 * 4, 4, 2, 1, st));
+  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, p.dwp7, 4 * 512, 1, 2 * 512, 512, st));
   if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], st));
   TRY(tc_conv_fprop(DZ7, p.wpd7, 512, 2, 2, 1, 1, D6, plain, st));
 
@@ -311,7 +318,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   } else {
     TRY(maxpool_bwd(A6f, D6, 2, 1, 1, p.scsh6, nullptr, D6f, st));  // dz6 = routed grad * (a6f > 0) * scale, one pass
   }
-  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, grads[P_C6W], 512 * 9, 9, 3, 1, st));
+  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, p.dwp6, 9 * 512, 1, 3 * 512, 512, st));
   if (grads[P_C6B]) TRY(colsum_acc(D6f, grads[P_C6B], st));
   if (bn_train) {
     TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, plain, st));
@@ -326,26 +333,26 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
     e.scale = p.scsh5; e.mask = &A5;  // dz5 = d(a5) * scale, zero where a5 == 0, fused into the dgrad epilogue
     TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
   }
-  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, grads[P_C5W], 256 * 9, 9, 3, 1, st));
+  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, p.dwp5, 9 * 256, 1, 3 * 256, 256, st));
   if (grads[P_C5B]) TRY(colsum_acc(D5, grads[P_C5B], st));
   TRY(tc_conv_fprop(D5, p.wpd5, 256, 3, 3, 1, 1, D4, plain, st));
 
   // ---- conv4 + ReLU + pool(2,1), conv3 + ReLU
   TRY(maxpool_bwd(A4f, D4, 2, 1, 1, nullptr, nullptr, D4f, st));
-  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, grads[P_C4W], 256 * 9, 9, 3, 1, st));
+  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, p.dwp4, 9 * 256, 1, 3 * 256, 256, st));
   if (grads[P_C4B]) TRY(colsum_acc(D4f, grads[P_C4B], st));
   {
     TcEpilogue e;
     e.mask = &A3;  // ReLU of conv3 fused into the dgrad epilogue
     TRY(tc_conv_fprop(D4f, p.wpd4, 256, 3, 3, 1, 1, D3, e, st));
   }
-  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, grads[P_C3W], 128 * 9, 9, 3, 1, st));
+  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, p.dwp3, 9 * 128, 1, 3 * 128, 128, st));
   if (grads[P_C3B]) TRY(colsum_acc(D3, grads[P_C3B], st));
   TRY(tc_conv_fprop(D3, p.wpd3, 128, 3, 3, 1, 1, D2, plain, st));
 
   // ---- conv2 + ReLU + pool, conv1 + ReLU + pool
   TRY(maxpool_bwd(A2f, D2, 2, 2, 1, nullptr, nullptr, D2f, st));
-  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, grads[P_C2W], 64 * 9, 9, 3, 1, st));
+  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, p.dwp2, 9 * 64, 1, 3 * 64, 64, st));
   if (grads[P_C2B]) TRY(colsum_acc(D2f, grads[P_C2B], st));
   const bool need_d1 = grads[P_C1W] || grads[P_C1B] || dx;
   if (need_d1) {
@@ -353,6 +360,17 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
     TRY(maxpool_bwd(A1f, D1, 2, 2, 1, nullptr, nullptr, D1f, st));
     if (grads[P_C1W]) TRY(c1_conv_wgrad(X, D1f, grads[P_C1W], grads[P_C1B], st));
     if (dx) TRY(c1_conv_dgrad(D1f, params[P_C1W], img_nhwc(dx, B, 32, W, 1), st));
+  }
+  {  // packed conv weight gradients -> torch layout, added into the caller's gradient tensors, one launch
+    PackBatch pk;
+    pk.accumulate = 1;
+    if (grads[P_C2W]) pk.add_unpack_grad(p.dwp2, grads[P_C2W], 128, 64, 9);
+    if (grads[P_C3W]) pk.add_unpack_grad(p.dwp3, grads[P_C3W], 256, 128, 9);
+    if (grads[P_C4W]) pk.add_unpack_grad(p.dwp4, grads[P_C4W], 256, 256, 9);
+    if (grads[P_C5W]) pk.add_unpack_grad(p.dwp5, grads[P_C5W], 512, 256, 9);
+    if (grads[P_C6W]) pk.add_unpack_grad(p.dwp6, grads[P_C6W], 512, 512, 9);
+    if (grads[P_C7W]) pk.add_unpack_grad(p.dwp7, grads[P_C7W], 512, 512, 4);
+    TRY(pack_flush(pk, st));
   }
   return QEB_OK;
 }

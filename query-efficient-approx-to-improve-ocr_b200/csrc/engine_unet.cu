@@ -43,6 +43,8 @@ struct UnetPlan {
   double* bnstats;  // kUnits x 1024
   float *wp[kUnits], *wup[4];    // fprop B operands per conv unit / up-convolution
   float *wpd[kUnits], *wupd[4];  // dgrad B operands
+  float* dwp[kUnits];            // packed [Cout][tap][Cin] weight-gradient accumulators, contiguous
+  size_t dwp_bytes;
   float *sA[kLevels], *sB[kLevels], *sC[kLevels];
   double* bnred;    // kUnits x 1024
   size_t bytes;
@@ -79,6 +81,16 @@ UnetPlan make_plan(int B, int H, int W, void* base) {
   for (int up = 0; up < 4; ++up) {  // up-conv `up` (upconv4..1) maps 2C -> C at level 3 - up
     const int C = p.C[3 - up];
     p.wup[up] = a.take((size_t)4 * C * 2 * C); p.wupd[up] = a.take((size_t)4 * C * 2 * C);
+  }
+  {
+    const size_t o0 = a.off;
+    for (int blk = 0; blk < 9; ++blk) {
+      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+      const int cout = p.C[lvl];
+      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      p.dwp[blk * 2] = a.take((size_t)cout * 9 * cin1); p.dwp[blk * 2 + 1] = a.take((size_t)cout * 9 * cout);
+    }
+    p.dwp_bytes = a.off - o0;
   }
   for (int i = 0; i < kLevels; ++i) {
     p.sA[i] = a.take(p.M[i] * 2 * p.C[i]); p.sB[i] = a.take(p.M[i] * p.C[i]); p.sC[i] = a.take(p.M[i] * p.C[i]);
@@ -125,10 +137,9 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     TRY(c1_conv_fwd(in, w, nullptr, 0, z, c.st));
     if (c.bn_train) {
       TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
-      TRY(bn_train_finalize(c.p->bnstats + (size_t)unit * 1024, img_pixels(z), cout, bn, scsh, c.st));
-    } else {
-      TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
+      return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st);
     }
+    TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
     return bn_apply(z, scsh, 1, out, c.st);
   }
   const float* wp = c.p->wp[unit];
@@ -136,8 +147,7 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     const TcEpilogue raw;
     TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
     TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
-    TRY(bn_train_finalize(c.p->bnstats + (size_t)unit * 1024, img_pixels(z), cout, bn, scsh, c.st));
-    return bn_apply(z, scsh, 1, out, c.st);
+    return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st);
   }
   TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
   TcEpilogue f;
@@ -166,7 +176,7 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     if (din) TRY(c1_conv_dgrad(g, w, *din, c.st));
     return QEB_OK;
   }
-  if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, gr[0], (long long)in.c * 9, 9, 3, 1, c.st));
+  if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.st));
   if (din) {
     const TcEpilogue plain;
     TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, plain, c.st));
@@ -249,6 +259,7 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
   Ctx c;
   c.params = params; c.buffers = nullptr; c.grads = grads; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
+  TRY(fill_zero(p.dwp[0], p.dwp_bytes, c.st));
   {
     PackBatch pk;
     for (int blk = 0; blk < 9; ++blk) {
@@ -314,6 +325,18 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
         TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, nullptr));
       }
     }
+  }
+  {  // packed conv weight gradients -> torch layout, added into the caller's gradient tensors, one launch
+    PackBatch pk;
+    pk.accumulate = 1;
+    for (int blk = 0; blk < 9; ++blk) {
+      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+      const int cout = p.C[lvl];
+      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      if (cin1 > 1 && grads[blk * 6]) pk.add_unpack_grad(p.dwp[blk * 2], grads[blk * 6], cout, cin1, 9);
+      if (grads[blk * 6 + 3]) pk.add_unpack_grad(p.dwp[blk * 2 + 1], grads[blk * 6 + 3], cout, cout, 9);
+    }
+    TRY(pack_flush(pk, c.st));
   }
   return QEB_OK;
 }

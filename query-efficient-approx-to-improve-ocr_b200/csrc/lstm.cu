@@ -50,12 +50,25 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   const int dir = cid & 1, b0 = (cid >> 1) * kBC;
   const int tid = threadIdx.x;
 
-  // W_hh slice, transposed: Wt[k][q*32 + jl] = W_hh[q*256 + 32*rank + jl][k]
+  // W_hh slice, transposed: Wt[k][q*32 + jl] = W_hh[q*256 + 32*rank + jl][k]. Thread = (row, k quad): 16-byte global
+  // loads, eight in flight, conflict-free transposed stores (consecutive threads -> consecutive rows -> banks).
   const float* W = a.w_hh[dir];
-  for (int i = tid; i < kRows * kH; i += kThreads) {
-    const int lr = i / kH, k = i % kH;
+  {
+    const int lr = tid % kRows;
     const int grow = (lr / kUnits) * kH + rank * kUnits + (lr % kUnits);
-    Wt[k * kRows + lr] = __ldg(W + (long long)grow * kH + k);
+    const float4* src = reinterpret_cast<const float4*>(W + (long long)grow * kH);
+#pragma unroll 1
+    for (int kq0 = tid / kRows; kq0 < kH / 4; kq0 += 8 * (kThreads / kRows)) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + kq0 + u * (kThreads / kRows));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = (kq0 + u * (kThreads / kRows)) * 4;
+        Wt[(k + 0) * kRows + lr] = v[u].x; Wt[(k + 1) * kRows + lr] = v[u].y;
+        Wt[(k + 2) * kRows + lr] = v[u].z; Wt[(k + 3) * kRows + lr] = v[u].w;
+      }
+    }
   }
   for (int i = tid; i < 2 * kH * kBC; i += kThreads) hbuf[i] = 0.f;
   cluster.sync();
@@ -82,7 +95,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     float acc[kBC][4];
 #pragma unroll
     for (int i = 0; i < kBC; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int kk = 0; kk < 32; ++kk) {
       const int k = ks * 32 + kk;
       const float4 w4 = *reinterpret_cast<const float4*>(Wt + k * kRows + lq * 4);
@@ -113,11 +126,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     const float ig = sigmoidf_(pre[0]), fg = sigmoidf_(pre[1]), gg = tanhf(pre[2]), og = sigmoidf_(pre[3]);
     c = fg * c + ig * gg;
     const float h = og * tanhf(c);
-    if (live) {
-      grow[0] = ig; grow[kH] = fg; grow[2 * kH] = gg; grow[3 * kH] = og;
-      a.cells[(((long long)t * a.B + b) * 2 + dir) * kH + rank * kUnits + jl] = c;
-      a.y[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + jl] = h;
-    }
     hnext[(rank * kUnits + jl) * kBC + bl] = live ? h : 0.f;
     __syncthreads();
     // broadcast this CTA's 32 x kBC slice (256 contiguous floats) to the other CTAs
@@ -131,7 +139,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
         dst[e] = src[e];
       }
     }
-    cluster.sync();
+    // arrive (release) right after the DSMEM stores; the global stores below are issued after the fence, so the
+    // barrier does not wait for them
+    cluster.barrier_arrive();
+    if (live) {
+      grow[0] = ig; grow[kH] = fg; grow[2 * kH] = gg; grow[3 * kH] = og;
+      a.cells[(((long long)t * a.B + b) * 2 + dir) * kH + rank * kUnits + jl] = c;
+      a.y[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + jl] = h;
+    }
+    cluster.barrier_wait();
   }
 }
 
@@ -153,10 +169,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   const int tid = threadIdx.x;
 
   const float* W = a.w_hh[dir];
-  for (int i = tid; i < kRows * kH; i += kThreads) {
-    const int lr = i / kH, k = i % kH;
+#pragma unroll 4
+  for (int i = tid; i < kRows * kH / 4; i += kThreads) {  // 16-byte copies, rows stay row-major
+    const int lr = i / (kH / 4), kq = i % (kH / 4);
     const int grow = (lr / kUnits) * kH + rank * kUnits + (lr % kUnits);
-    Wr[lr * kH + k] = __ldg(W + (long long)grow * kH + k);
+    reinterpret_cast<float4*>(Wr)[lr * (kH / 4) + kq] = __ldg(reinterpret_cast<const float4*>(W + (long long)grow * kH) + kq);
   }
   for (int i = tid; i < 2 * kCluster * kBC * kUnits; i += kThreads) recv[i] = 0.f;
   cluster.sync();
@@ -198,7 +215,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     float acc[kBC][4];
 #pragma unroll
     for (int i = 0; i < kBC; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-#pragma unroll 4
+#pragma unroll 8
     for (int rr = 0; rr < 32; ++rr) {
       const int lr = rs * 32 + rr;
       const float4 w4 = *reinterpret_cast<const float4*>(Wr + lr * kH + kq * 4);
@@ -227,7 +244,8 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       float* dst = cluster.map_shared_rank(rnext, dst_rank);
       dst[(rank * kBC + bb) * kUnits + (k % kUnits)] = v;
     }
-    cluster.sync();
+    cluster.barrier_arrive();
+    cluster.barrier_wait();
   }
 }
 

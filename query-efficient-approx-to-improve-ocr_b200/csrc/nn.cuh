@@ -66,6 +66,7 @@ struct PackBatch {
   PackJob jobs[kMax];
   int n = 0;
   long long total = 0;
+  int accumulate = 0;  // 1: dst += src for every job of the batch
   void add(const float* src, float* dst, int n0, int n1, int n2, long long s0, long long s1, long long s2, long long d0,
            long long d1) {
     PackJob& j = jobs[n++];
@@ -82,6 +83,11 @@ struct PackBatch {
     add(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout);
   }
   void add_copy(const float* src, float* dst, long long n) { add(src, dst, 1, 1, (int)n, 0, 0, 1, 0, 0); }
+  // packed weight gradient [Cout][tap][Cin] (what the wgrad kernel accumulates into with coalesced atomics) -> torch
+  // layout (Cout,Cin,taps)
+  void add_unpack_grad(const float* packed, float* dw, int cout, int cin, int taps) {
+    add(packed, dw, cout, cin, taps, (long long)taps * cin, 1, cin, (long long)cin * taps, taps);
+  }
 };
 int pack_flush(PackBatch& b, cudaStream_t st);
 
@@ -111,6 +117,9 @@ struct BnParams {
 // [3c,4c) invstd; eval: [2c,3c) beta, [3c,4c) 1/gamma (xhat is recovered from the layer output)
 int bn_train_stats(const Img& z, double* stats, cudaStream_t st);
 int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st);
+// finalize + apply fused (train mode): out = relu?(bn(z)) from the batch sums; writes scsh, updates the running statistics
+int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
+                            cudaStream_t st);
 int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh, cudaStream_t st);
 // out = relu?(z*scale + shift)
 int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st);

@@ -413,6 +413,50 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restr
   }
 }
 
+// train mode, finalize + apply in one launch: every thread derives scale/shift of its four channels from the batch sums
+// (kThreads is a multiple of C/4, so a thread keeps its channel quad over the grid-stride loop); block 0 also stores
+// scale/shift/mean/invstd for the backward and updates the running statistics.
+__global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* __restrict__ z, long long zs, long long M, int C,
+                                                                  const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float* running_mean,
+                                                                  float* running_var, long long* nbt, float eps, float momentum,
+                                                                  float* __restrict__ scsh, int relu, float* __restrict__ out,
+                                                                  long long os) {
+  const int cq_n = C / 4;
+  const int cq = threadIdx.x % cq_n;
+  float sc[4], sh[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = cq * 4 + j;
+    const double mean = stats[c] / (double)M;
+    double var = stats[C + c] / (double)M - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    sc[j] = gamma[c] * invstd;
+    sh[j] = beta[c] - (float)mean * sc[j];
+    if (blockIdx.x == 0 && threadIdx.x < cq_n) {
+      scsh[c] = sc[j];
+      scsh[C + c] = sh[j];
+      scsh[2 * C + c] = (float)mean;
+      scsh[3 * C + c] = invstd;
+      if (running_mean) {
+        const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+  const long long total = M * cq_n;
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
+    const long long r = i / cq_n;
+    const float4 v = ld4(z + r * zs + cq * 4);
+    float4 o = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
+    if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+    st4(out + r * os + cq * 4, o);
+  }
+}
+
 // relu: 0 = none, 1 = mask recomputed from the pre-activation v (z*scale+shift > 0), 2 = v IS the ReLU output (v > 0)
 __device__ __forceinline__ float4 bn_masked_grad(const float4 v, const float4 g, const float4 sc, const float4 sh, int relu) {
   if (!relu) return g;
@@ -578,7 +622,8 @@ struct PackJobsParam {
   PackJob j[PackBatch::kMax];
   int n;
 };
-__global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_constant__ PackJobsParam jobs, long long total) {
+__global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_constant__ PackJobsParam jobs, long long total,
+                                                              int accumulate) {
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     int lo = 0, hi = jobs.n - 1;
     while (lo < hi) {
@@ -591,7 +636,9 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
     const long long t = e / j.n2;
     const int i1 = (int)(t % j.n1);
     const long long i0 = t / j.n1;
-    j.dst[i0 * j.d0 + i1 * j.d1 + i2] = j.src[i0 * j.s0 + i1 * j.s1 + (long long)i2 * j.s2];
+    const float v = j.src[i0 * j.s0 + i1 * j.s1 + (long long)i2 * j.s2];
+    float* d = j.dst + i0 * j.d0 + i1 * j.d1 + i2;
+    *d = accumulate ? *d + v : v;
   }
 }
 
@@ -639,7 +686,7 @@ int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStre
   QEB_REQUIRE(x.c == 1 && (dy.c == 32 || dy.c == 64), "c1_conv_wgrad: 1 -> 32/64 channels only");
   QEB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w && vec4_ok(dy), "c1_conv_wgrad: geometry/alignment");
   const long long n_pix = img_pixels(x);
-  const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 2);
+  const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 4);
   if (dy.c == 32) c1_wgrad_kernel<32><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix);
   else c1_wgrad_kernel<64><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix);
   QEB_LAUNCH_CHECK();
@@ -719,9 +766,15 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   return QEB_OK;
 }
 
-static int reduce_grid(long long M, int rpb) {
-  long long g = (M + rpb - 1) / rpb;
-  const long long cap = 8 * kNumSMs;
+// grid of a column-reduction kernel. Every block ends with one atomic per channel (and statistic), so the block count is
+// what the serialised L2 atomics scale with: give each block at least 64 KB of input (measured: with one block per
+// `rpb` rows the atomics, not the reads, set the run time of the smaller tensors).
+static int reduce_grid(long long M, int rpb, int C) {
+  const long long min_rows = max(1LL, (64LL << 10) / ((long long)C * 4));
+  long long g = (M + min_rows - 1) / min_rows;
+  const long long by_rows = (M + rpb - 1) / rpb;
+  if (g > by_rows) g = by_rows;
+  const long long cap = 4 * kNumSMs;
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
@@ -732,7 +785,7 @@ int bn_train_stats(const Img& z, double* stats, cudaStream_t st) {
   QEB_REQUIRE(z.c <= 1024, "bn_train_stats: at most 1024 channels");
   const long long M = img_pixels(z);
   const int rpb = kThreads / (z.c / 4);
-  bn_stats_kernel<<<reduce_grid(M, rpb), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, M, z.c, stats);
+  bn_stats_kernel<<<reduce_grid(M, rpb, z.c), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, M, z.c, stats);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -751,6 +804,23 @@ int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh,
   ProfScope prof("bn_finalize", st);
   bn_eval_scsh_kernel<<<qeb_cdiv(c, 128), 128, 0, st>>>(c, bn.gamma, bn.beta, bn.running_mean, bn.running_var, bn.eps, conv_bias,
                                                         scsh);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
+                            cudaStream_t st) {
+  ProfScope prof("bn_apply", st, 0.0, 8.0 * z.c * (double)img_pixels(z));
+  REQ_FLAT(z, "bn_train_finalize_apply");
+  REQ_FLAT(out, "bn_train_finalize_apply");
+  QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_train_finalize_apply: shape mismatch");
+  QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_train_finalize_apply: C/4 must divide %d", kThreads);
+  const long long M = img_pixels(z);
+  bn_apply_train_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
+                                                                               bn.running_mean, bn.running_var,
+                                                                               bn.num_batches_tracked, bn.eps, bn.momentum, scsh,
+                                                                               relu, out.p, out.sw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -775,7 +845,7 @@ int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, doub
   QEB_REQUIRE(z.c == dy.c && img_pixels(z) == img_pixels(dy) && z.c <= 1024, "bn_bwd_reduce: shape mismatch");
   const long long M = img_pixels(z);
   const int rpb = kThreads / (z.c / 4);
-  bn_bwd_reduce_kernel<<<reduce_grid(M, rpb), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, dy.p, dy.sw, M, z.c, scsh,
+  bn_bwd_reduce_kernel<<<reduce_grid(M, rpb, 2 * z.c), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, dy.p, dy.sw, M, z.c, scsh,
                                                                                            relu, red);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -815,7 +885,7 @@ int colsum_acc(const Img& x, float* out, cudaStream_t st) {
   const long long M = img_pixels(x);
   const int cq_n = (x.c + 3) / 4;
   const int rpb = max(1, kThreads / cq_n);
-  colsum_kernel<<<reduce_grid(M, rpb), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st>>>(x.p, x.sw, M, x.c, out);
+  colsum_kernel<<<reduce_grid(M, rpb, x.c), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st>>>(x.p, x.sw, M, x.c, out);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -847,10 +917,11 @@ int pack_flush(PackBatch& b, cudaStream_t st) {
   PackJobsParam p;
   for (int i = 0; i < b.n; ++i) p.j[i] = b.jobs[i];
   p.n = b.n;
-  pack_multi_kernel<<<qeb_grid(b.total, kThreads), kThreads, 0, st>>>(p, b.total);
+  pack_multi_kernel<<<qeb_grid(b.total, kThreads), kThreads, 0, st>>>(p, b.total, b.accumulate);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   b.n = 0;
   b.total = 0;
+  b.accumulate = 0;
   return QEB_OK;
 }
