@@ -489,32 +489,49 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
 
   if (t_begin < t_end) {
     if (warp == 0) {
-      if (lane == 0) {
-        int stage = 0;
-        uint32_t phase = 0;
-        const uint32_t bytes = (uint32_t)(n_rb + kBBoxes) * kBoxBytes;
-        for (int t = t_begin; t < t_end; ++t) {
-          const int tw = t % p.tiles_w, th = (t / p.tiles_w) % p.tiles_h, tn = t / (p.tiles_w * p.tiles_h);
-          const int w0 = tw * p.wt, h0 = th * p.ht, n0 = tn * p.nt;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], bytes);
-          for (int i = 0; i < n_rb; ++i) {
-            const int rb = rb0 + i;
-            const int tap = rb / p.a_groups, cg = rb - tap * p.a_groups;
-            if (p.a_map_per_tap) {
-              tma_load_4d(sa + i * kBoxBytes, &tmaps_a.m[tap], &full_bar[stage], cg * 32, w0, h0, n0);
-            } else {
-              const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-              tma_load_4d(sa + i * kBoxBytes, &tmaps_a.m[0], &full_bar[stage], cg * 32, w0 + dx, h0 + dy, n0);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < kBBoxes; ++j)
-            tma_load_4d(sb + j * kBoxBytes, &tmap_b, &full_bar[stage], tile_n * BLOCK_N + j * 32, w0, h0, n0);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      // ===== TMA producer: one lane per box (4 A boxes + BLOCK_N/32 B boxes per stage), issued in parallel; the per-box
+      // constants (tap shift, channel offset, tensor map, smem offset) are computed once, the tile coordinates are
+      // carried as counters so that the steady-state loop has no integer division =====
+      const int nbox = n_rb + kBBoxes;
+      const bool active = lane < nbox;
+      int c0 = 0, sx = 0, sy = 0;
+      uint32_t dst_off = 0;
+      const CUtensorMap* map = &tmap_b;
+      if (lane < n_rb) {
+        const int rb = rb0 + lane;
+        const int tap = rb / p.a_groups, cg = rb - tap * p.a_groups;
+        c0 = cg * 32;
+        dst_off = lane * kBoxBytes;
+        if (p.a_map_per_tap) {
+          map = &tmaps_a.m[tap];
+        } else {
+          map = &tmaps_a.m[0];
+          sy = tap / p.kw - p.ph;
+          sx = tap % p.kw - p.pw;
         }
+      } else if (active) {
+        const int j = lane - n_rb;
+        c0 = tile_n * BLOCK_N + j * 32;
+        dst_off = kABytes + j * kBoxBytes;
+      }
+      int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tn = t_begin / (p.tiles_w * p.tiles_h);
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t bytes = (uint32_t)nbox * kBoxBytes;
+      for (int t = t_begin; t < t_end; ++t) {
+        if (lane == 0) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], bytes);
+        }
+        __syncwarp();
+        if (active)
+          tma_load_4d(smem + stage * Cfg::kStageBytes + dst_off, map, &full_bar[stage], c0, tw * p.wt + sx, th * p.ht + sy,
+                      tn * p.nt);
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) { th = 0; ++tn; }
+        }
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
       if (lane == 0) {
