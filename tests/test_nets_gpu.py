@@ -403,3 +403,63 @@ def test_full_step_trains(q):
     assert losses[-1] < losses[0] and all(np.isfinite(losses))
     assert torch.equal(w0, crnn.linear.weight)
     assert crnn.linear.weight.grad is not None   # the reference also computes (and discards) the surrogate's gradients
+
+
+def test_phase_a_jitter_step_vs_oracle(q):
+    """BASELINE configs[2] shape on one GPU: one inner iteration of the black-box approximation phase
+    (train_nn_area.py:245-275 / train_nn_patch.py:278-309): jitter the preprocessor output, run the surrogate in
+    train mode (batch statistics), CTC against the OCR strings, backward, Adam on the surrogate. The oracle replays the
+    same noise (the kernel returns it) through the reference arithmetic (transform_helper.py:40-41)."""
+    from qeb_b200.mirror import transform_helper as th
+    torch.manual_seed(11)
+    B = 64
+    m = q.CRNN(95, False).to(DEV)
+    m.register_backward_hook(m.backward_hook)
+    mr = copy.deepcopy(m)
+    m.train(); mr.train()
+    opt = q.train_ops.Adam(m.parameters(), lr=1e-4, weight_decay=5e-4)          # train_nn_patch.py:146-148
+    optr = torch.optim.Adam(mr.parameters(), lr=1e-4, weight_decay=5e-4)
+    imgs = torch.rand(B, 1, 32, 128, device=DEV)
+    noiser = th.AddGaussianNoice(std=5, is_stochastic=True, return_noise=True)
+    noisy, noise = th.add_noise(imgs, noiser)
+    assert torch.equal(noisy, torch.clamp(imgs - noise, 0, 1))                    # bit-exact jitter arithmetic
+    sd = noise.view(B, -1).std(dim=1)
+    assert float(sd.max()) < 0.06 and float(noisy.min()) >= 0 and float(noisy.max()) <= 1
+    ylen = torch.randint(1, 12, (B,), dtype=torch.int32)
+    y = torch.randint(1, 95, (int(ylen.sum()),), dtype=torch.int32)
+    il = torch.full((B,), 31, dtype=torch.int32)
+    la = q.ctc.CTCLoss()(m(noisy), y, il, ylen)
+    lb = torch.nn.CTCLoss()(nn_oracle.crnn_forward(mr, noisy), y.to(DEV), il.to(DEV), ylen.to(DEV))
+    assert abs(float(la) - float(lb)) < 1e-3 * abs(float(lb))
+    la.backward(); lb.backward()
+    for (n, p), (_, r) in zip(m.named_parameters(), mr.named_parameters()):
+        if n in ("convo.conv5.bias", "convo.conv6.bias"):
+            continue
+        assert cos(p.grad, r.grad) > 0.99, (n, cos(p.grad, r.grad))
+    opt.step(); optr.step()
+    for (n, p), (_, r) in zip(m.named_parameters(), mr.named_parameters()):
+        # one Adam step moves every weight by ~lr in the direction of sign(grad): compare the updates
+        assert float((p - r).abs().max()) <= 2.1e-4, n
+    assert rel(m.convo.batchnorm1.running_mean, mr.convo.batchnorm1.running_mean) < 1e-3
+
+
+@pytest.mark.parametrize("B,W", [(1, 128), (2, 8), (130, 32)])
+def test_crnn_edge_shapes(q, B, W):
+    """Smallest legal width (W = 8 -> T = 1), a single patch, a batch that is not a multiple of any tile."""
+    torch.manual_seed(B)
+    m = q.CRNN(95, False).to(DEV)
+    mr = copy.deepcopy(m)
+    for mm in (m, mr):               # phase-B mode (cuDNN's RNN backward, which the oracle runs on, needs train())
+        mm.train(); mm.apply(q.utils.set_bn_eval)
+    x = torch.rand(B, 1, 32, W, device=DEV, requires_grad=True)
+    xr = x.detach().clone().requires_grad_(True)
+    lp, lpr = m(x), nn_oracle.crnn_forward(mr, xr)
+    assert lp.shape == lpr.shape == (W // 4 - 1, B, 95)
+    assert float((lp - lpr).abs().max()) < 2e-3
+    g = torch.randn_like(lp)
+    lp.backward(g); lpr.backward(g)
+    assert cos(x.grad, xr.grad) > 0.98
+    with pytest.raises(q.lib.QebError):
+        m(torch.rand(1, 1, 16, 128, device=DEV))     # the reference's map_to_sequence needs H == 32 too
+    with pytest.raises(q.lib.QebError):
+        m(torch.rand(1, 1, 32, 128))                 # CPU tensor: no fallback
