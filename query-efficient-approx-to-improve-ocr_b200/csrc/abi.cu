@@ -1,9 +1,10 @@
 // C-ABI plumbing shared by every entry point: thread-local error string, launch counter, device probe.
-#include "common.cuh"
+#include "nn.cuh"
 #include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -109,5 +110,53 @@ QEB_API int qeb_prof_report(char* buf, int cap) {
     return QEB_ERR_INVALID;
   }
   memcpy(buf, out.c_str(), out.size() + 1);
+  return QEB_OK;
+}
+
+// ---- side stream (nn.cuh)
+namespace {
+struct SideRes {
+  int device = -1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+};
+thread_local SideRes g_side;
+}  // namespace
+
+int SideStream::init(cudaStream_t main_stream) {
+  main = main_stream;
+  static const bool want = !(getenv("QEB_SIDE_STREAM") && atoi(getenv("QEB_SIDE_STREAM")) == 0);
+  enabled = false;
+  if (!want) return QEB_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(main_stream, &cap) != cudaSuccess) { cudaGetLastError(); return QEB_OK; }
+  int dev = 0;
+  QEB_CUDA(cudaGetDevice(&dev));
+  if (g_side.device != dev) {
+    if (g_side.side) { cudaStreamDestroy(g_side.side); cudaEventDestroy(g_side.fork_ev); cudaEventDestroy(g_side.join_ev); }
+    g_side = SideRes();
+    QEB_CUDA(cudaStreamCreateWithFlags(&g_side.side, cudaStreamNonBlocking));
+    QEB_CUDA(cudaEventCreateWithFlags(&g_side.fork_ev, cudaEventDisableTiming));
+    QEB_CUDA(cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming));
+    g_side.device = dev;
+  }
+  side = g_side.side; fork_ev = g_side.fork_ev; join_ev = g_side.join_ev;
+  enabled = true;
+  return QEB_OK;
+}
+
+int SideStream::fork() {
+  if (!enabled) return QEB_OK;
+  QEB_CUDA(cudaEventRecord(fork_ev, main));
+  QEB_CUDA(cudaStreamWaitEvent(side, fork_ev, 0));
+  dirty = true;
+  return QEB_OK;
+}
+
+int SideStream::join() {
+  if (!enabled || !dirty) return QEB_OK;
+  QEB_CUDA(cudaEventRecord(join_ev, side));
+  QEB_CUDA(cudaStreamWaitEvent(main, join_ev, 0));
+  dirty = false;
   return QEB_OK;
 }

@@ -242,6 +242,8 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   Img D4f = img_nhwc(p.d4f, B, 8, p.W4, 256), D4 = img_nhwc(p.d4, B, 4, p.W4, 256);
   Img D5 = img_nhwc(p.d5, B, 4, p.W4, 512), D6f = img_nhwc(p.d6f, B, 4, p.W4, 512), D6 = img_nhwc(p.d6, B, 2, p.W4, 512);
   const TcEpilogue plain;
+  SideStream ss;  // weight / bias gradients run beside the input-gradient chain
+  TRY(ss.init(st));
 
   // ---- Linear
   TRY(fill_zero(p.dwp2, p.dwp_bytes, st));  // packed conv weight-gradient accumulators
@@ -265,8 +267,9 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   Img DLP = img_nhwc(p.dlp, 1, 1, TB, 96);
   Img DLPv = img_nhwc(p.dlp, 1, 1, TB, V, 96);
   Img Y1 = img_nhwc(p.y1, 1, 1, TB, 512), Y0 = img_nhwc(p.y0, 1, 1, TB, 512), X0 = img_nhwc(p.x0, 1, 1, TB, 512);
-  if (grads[P_LINW]) TRY(tc_conv_wgrad(Y1, DLPv, 1, 1, 0, 0, grads[P_LINW], 512, 1, 0, 0, st));
-  if (grads[P_LINB]) TRY(colsum_acc(DLPv, grads[P_LINB], st));
+  TRY(ss.fork());
+  if (grads[P_LINW]) TRY(tc_conv_wgrad(Y1, DLPv, 1, 1, 0, 0, grads[P_LINW], 512, 1, 0, 0, ss.s()));
+  if (grads[P_LINB]) TRY(colsum_acc(DLPv, grads[P_LINB], ss.s()));
   TRY(tc_conv_fprop(DLP, p.wlinT, 512, 1, 1, 0, 0, img_nhwc(p.dy1, 1, 1, TB, 512), plain, st));
 
   // ---- LSTM layers, top down
@@ -279,19 +282,20 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
     const float* dy = l ? p.dy1 : p.dy0;
     const Img Xin = l ? Y0 : X0;
     TRY(lstm_layer_bwd(g, c, dy, lp[1], lp[5], T, B, st));  // g now holds d(pre-activations), (T,B,2,1024)
+    TRY(ss.fork());
     for (int d = 0; d < 2; ++d) {
       Img DG = img_nhwc(g + d * 1024, 1, 1, TB, 1024, 2048);
-      if (lg[d * 4 + 0]) TRY(tc_conv_wgrad(Xin, DG, 1, 1, 0, 0, lg[d * 4 + 0], 512, 1, 0, 0, st));
+      if (lg[d * 4 + 0]) TRY(tc_conv_wgrad(Xin, DG, 1, 1, 0, 0, lg[d * 4 + 0], 512, 1, 0, 0, ss.s()));
       if (lg[d * 4 + 1]) {
         // dW_hh = sum_t dG_t^T h_{t-1} (forward) / h_{t+1} (reverse): the h sequence shifted by one step, zero outside
         Img Hs;
         Hs.p = y + d * kHid; Hs.n = 1; Hs.h = T; Hs.w = B; Hs.c = kHid; Hs.sn = (long long)T * B * 512; Hs.sh = (long long)B * 512; Hs.sw = 512;
         Img DGs;
         DGs.p = g + d * 1024; DGs.n = 1; DGs.h = T; DGs.w = B; DGs.c = 1024; DGs.sn = (long long)T * B * 2048; DGs.sh = (long long)B * 2048; DGs.sw = 2048;
-        TRY(tc_conv_wgrad(Hs, DGs, 1, 1, d ? -1 : 1, 0, lg[d * 4 + 1], kHid, 1, 0, 0, st));
+        TRY(tc_conv_wgrad(Hs, DGs, 1, 1, d ? -1 : 1, 0, lg[d * 4 + 1], kHid, 1, 0, 0, ss.s()));
       }
-      if (lg[d * 4 + 2]) TRY(colsum_acc(DG, lg[d * 4 + 2], st));
-      if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], st));
+      if (lg[d * 4 + 2]) TRY(colsum_acc(DG, lg[d * 4 + 2], ss.s()));
+      if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], ss.s()));
     }
     // d(input) = dG * [W_ih_fwd ; W_ih_rev]
     TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), l ? p.wihT1 : p.wihT0, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512), plain, st));
@@ -300,8 +304,9 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   // ---- conv7 (dz7 = dx0, sequence-major view of a (B,1,T,512) image)
   Img DZ7;
   DZ7.p = p.dx0; DZ7.n = B; DZ7.h = 1; DZ7.w = T; DZ7.c = 512; DZ7.sn = 512; DZ7.sh = 0; DZ7.sw = (long long)B * 512;
-  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, p.dwp7, 4 * 512, 1, 2 * 512, 512, st));
-  if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], st));
+  TRY(ss.fork());
+  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, p.dwp7, 4 * 512, 1, 2 * 512, 512, ss.s()));
+  if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], ss.s()));
   TRY(tc_conv_fprop(DZ7, p.wpd7, 512, 2, 2, 1, 1, D6, plain, st));
 
   // ---- conv6 + BN2 + ReLU + pool(2,1), conv5 + BN1 + ReLU
@@ -318,8 +323,9 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   } else {
     TRY(maxpool_bwd(A6f, D6, 2, 1, 1, p.scsh6, nullptr, D6f, st));  // dz6 = routed grad * (a6f > 0) * scale, one pass
   }
-  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, p.dwp6, 9 * 512, 1, 3 * 512, 512, st));
-  if (grads[P_C6B]) TRY(colsum_acc(D6f, grads[P_C6B], st));
+  TRY(ss.fork());
+  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, p.dwp6, 9 * 512, 1, 3 * 512, 512, ss.s()));
+  if (grads[P_C6B]) TRY(colsum_acc(D6f, grads[P_C6B], ss.s()));
   if (bn_train) {
     TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, plain, st));
     TRY(bn_bwd_reduce(Z5, D5, p.scsh5, 1, p.bnred + 1024, st));
@@ -333,34 +339,40 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
     e.scale = p.scsh5; e.mask = &A5;  // dz5 = d(a5) * scale, zero where a5 == 0, fused into the dgrad epilogue
     TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
   }
-  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, p.dwp5, 9 * 256, 1, 3 * 256, 256, st));
-  if (grads[P_C5B]) TRY(colsum_acc(D5, grads[P_C5B], st));
+  TRY(ss.fork());
+  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, p.dwp5, 9 * 256, 1, 3 * 256, 256, ss.s()));
+  if (grads[P_C5B]) TRY(colsum_acc(D5, grads[P_C5B], ss.s()));
   TRY(tc_conv_fprop(D5, p.wpd5, 256, 3, 3, 1, 1, D4, plain, st));
 
   // ---- conv4 + ReLU + pool(2,1), conv3 + ReLU
   TRY(maxpool_bwd(A4f, D4, 2, 1, 1, nullptr, nullptr, D4f, st));
-  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, p.dwp4, 9 * 256, 1, 3 * 256, 256, st));
-  if (grads[P_C4B]) TRY(colsum_acc(D4f, grads[P_C4B], st));
+  TRY(ss.fork());
+  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, p.dwp4, 9 * 256, 1, 3 * 256, 256, ss.s()));
+  if (grads[P_C4B]) TRY(colsum_acc(D4f, grads[P_C4B], ss.s()));
   {
     TcEpilogue e;
     e.mask = &A3;  // ReLU of conv3 fused into the dgrad epilogue
     TRY(tc_conv_fprop(D4f, p.wpd4, 256, 3, 3, 1, 1, D3, e, st));
   }
-  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, p.dwp3, 9 * 128, 1, 3 * 128, 128, st));
-  if (grads[P_C3B]) TRY(colsum_acc(D3, grads[P_C3B], st));
+  TRY(ss.fork());
+  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, p.dwp3, 9 * 128, 1, 3 * 128, 128, ss.s()));
+  if (grads[P_C3B]) TRY(colsum_acc(D3, grads[P_C3B], ss.s()));
   TRY(tc_conv_fprop(D3, p.wpd3, 128, 3, 3, 1, 1, D2, plain, st));
 
   // ---- conv2 + ReLU + pool, conv1 + ReLU + pool
   TRY(maxpool_bwd(A2f, D2, 2, 2, 1, nullptr, nullptr, D2f, st));
-  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, p.dwp2, 9 * 64, 1, 3 * 64, 64, st));
-  if (grads[P_C2B]) TRY(colsum_acc(D2f, grads[P_C2B], st));
+  TRY(ss.fork());
+  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, p.dwp2, 9 * 64, 1, 3 * 64, 64, ss.s()));
+  if (grads[P_C2B]) TRY(colsum_acc(D2f, grads[P_C2B], ss.s()));
   const bool need_d1 = grads[P_C1W] || grads[P_C1B] || dx;
   if (need_d1) {
       TRY(tc_conv_fprop(D2f, p.wpd2, 64, 3, 3, 1, 1, D1, plain, st));
     TRY(maxpool_bwd(A1f, D1, 2, 2, 1, nullptr, nullptr, D1f, st));
-    if (grads[P_C1W]) TRY(c1_conv_wgrad(X, D1f, grads[P_C1W], grads[P_C1B], st));
+    TRY(ss.fork());
+    if (grads[P_C1W]) TRY(c1_conv_wgrad(X, D1f, grads[P_C1W], grads[P_C1B], ss.s()));
     if (dx) TRY(c1_conv_dgrad(D1f, params[P_C1W], img_nhwc(dx, B, 32, W, 1), st));
   }
+  TRY(ss.join());
   {  // packed conv weight gradients -> torch layout, added into the caller's gradient tensors, one launch
     PackBatch pk;
     pk.accumulate = 1;

@@ -113,6 +113,7 @@ struct Ctx {
   const UnetPlan* p;
   int bn_train;
   cudaStream_t st;
+  SideStream* ss;  // backward only: weight / bias gradients run beside the input-gradient chain
 };
 
 BnParams bn_of(const Ctx& c, int block, int which) {
@@ -171,12 +172,13 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     if (red) TRY(bn_bwd_reduce(out, g, scsh, 2, red, c.st));
     TRY(bn_bwd_apply_eval(out, g, scsh, 2, red, g, gr[1], gr[2], c.st));
   }
+  TRY(c.ss->fork());
   if (in.c == 1) {
-    if (gr[0]) TRY(c1_conv_wgrad(in, g, gr[0], nullptr, c.st));
+    if (gr[0]) TRY(c1_conv_wgrad(in, g, gr[0], nullptr, c.ss->s()));
     if (din) TRY(c1_conv_dgrad(g, w, *din, c.st));
     return QEB_OK;
   }
-  if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.st));
+  if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.ss->s()));
   if (din) {
     const TcEpilogue plain;
     TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, plain, c.st));
@@ -203,6 +205,7 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   const UnetPlan p = make_plan(B, H, W, ws);
   Ctx c;
   c.params = params; c.buffers = buffers; c.grads = nullptr; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
+  c.ss = nullptr;
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
   {  // every weight re-layout of this pass in one launch
     PackBatch pk;
@@ -258,6 +261,9 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
   const UnetPlan p = make_plan(B, H, W, ws);
   Ctx c;
   c.params = params; c.buffers = nullptr; c.grads = grads; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
+  SideStream ss;
+  TRY(ss.init(c.st));
+  c.ss = &ss;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
   TRY(fill_zero(p.dwp[0], p.dwp_bytes, c.st));
   {
@@ -293,12 +299,14 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
     // up-convolution: dU = gcat[:, :C]
     Img dU = img_slice(gcat, 0, C);
     Img below = i < 3 ? img_nhwc(p.dout[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C) : img_nhwc(p.bott, B, p.h[4], p.w[4], 2 * C);
-    if (grads[P_UP + up * 2 + 1]) TRY(colsum_acc(dU, grads[P_UP + up * 2 + 1], c.st));
-    if (grads[P_UP + up * 2]) TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], c.st));
+    TRY(ss.fork());
+    if (grads[P_UP + up * 2 + 1]) TRY(colsum_acc(dU, grads[P_UP + up * 2 + 1], ss.s()));
+    if (grads[P_UP + up * 2]) TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], ss.s()));
     Img gbelow = img_nhwc(p.sC[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C);
     const TcEpilogue plain;
     TRY(tc_convT_dgrad(dU, p.wupd[up], gbelow, plain, c.st));
   }
+  TRY(ss.join());  // the encoder phase re-uses the decoder phase's gradient buffers
   for (int i = 4; i >= 0; --i) {  // bottleneck, then encoder blocks
     const int C = p.C[i];
     Img z1 = img_nhwc(p.ez1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.ea1[i], B, p.h[i], p.w[i], C);
@@ -326,6 +334,7 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
       }
     }
   }
+  TRY(ss.join());
   {  // packed conv weight gradients -> torch layout, added into the caller's gradient tensors, one launch
     PackBatch pk;
     pk.accumulate = 1;

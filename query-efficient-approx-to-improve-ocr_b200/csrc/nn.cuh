@@ -149,3 +149,19 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
 // dy: (T,B,512). gates (activated) are overwritten with the gradients at the pre-activations (T,B,2,1024).
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
                    int B, cudaStream_t st);
+
+// ---- side stream, abi.cu ----------------------------------------------------------------------------------------
+// Weight and bias gradients are off the backward's critical path (only the input gradients feed the next layer), so the
+// engines enqueue them on a second stream and let them fill the tail waves of the dgrad / BatchNorm kernels.
+// fork(): the side stream waits for everything enqueued on the main stream so far; join(): the reverse. The stream and
+// its two events are created lazily per host thread and device and live until the process ends; QEB_SIDE_STREAM=0
+// keeps everything on the caller's stream.
+struct SideStream {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  bool enabled = false, dirty = false;
+  int init(cudaStream_t main_stream);
+  int fork();
+  int join();
+  cudaStream_t s() const { return enabled ? side : main; }
+};
