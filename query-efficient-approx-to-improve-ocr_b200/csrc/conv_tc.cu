@@ -85,6 +85,9 @@ struct FpropParams {
   int mode;                  // 0: plain NHWC store; 1: ConvTranspose 2x2 s2 pixel shuffle (N index = (dh*2+dw)*up_c + co)
   int up_c;
   int accumulate;            // 1: out += result (used when a gradient already holds a partial sum)
+  int stages;                // depth of the shared-memory ring
+  int kb_per_split;          // K blocks (tap x 32-channel slice) per gridDim.z slice; split-K partial sums are combined with
+                             // 16-byte vector reductions into a zero-filled output (plain epilogue only)
   int vec_ok;                // 16-byte aligned rows: float4 stores allowed
   int a_map_per_tap;         // 1: tap selects the A tensor map (ConvTranspose dgrad sub-lattices), no coordinate shift
 };
@@ -100,8 +103,22 @@ struct FpropCfg {
   // several CTAs per SM (3 / 3 / 2 / 1 for BLOCK_N 32 / 64 / 128 / 256) so that one CTA's prologue and epilogue overlap
   // another's main loop; the K loops here are short (9..144 stages), so a deep per-CTA ring buys less than occupancy
   static constexpr int kCtasPerSm = (BLOCK_N >= 256) ? 1 : (BLOCK_N >= 128 ? 2 : 3);
-  static constexpr int kStages = (BLOCK_N >= 256) ? 4 : 3;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kMaxStages = 8;
+  static constexpr int kMaxSmem = 227 * 1024;
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
+  // The ring depth is a launch-time choice: a grid that fills the SMs several times over runs kCtasPerSm CTAs per SM with a
+  // shallow ring each; a grid of about one CTA per SM (deep layers with few pixels) has nothing else on the SM to hide the
+  // TMA round trip, so it gets every byte of shared memory as stages (measured: 3 stages at 1 CTA/SM leave the tensor
+  // pipe ~10 % active with the L2 at ~20 %).
+  static int pick_stages(long long n_ctas) {
+    int resident = (int)((n_ctas + kNumSMs - 1) / kNumSMs);
+    if (resident > kCtasPerSm) resident = kCtasPerSm;
+    if (resident < 1) resident = 1;
+    int stages = (kMaxSmem / resident - 1280) / kStageBytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    return stages;
+  }
 };
 
 template <int BLOCK_N>
@@ -111,9 +128,9 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   using Cfg = FpropCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -121,11 +138,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
   const int w0 = tw * p.wt, h0 = th * p.ht, n0 = tn * p.nt;
   const int num_kb = p.kh * p.kw * p.kchunks;
+  const int kb_begin = blockIdx.z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
+  const bool split = gridDim.z > 1;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < (p.a_map_per_tap ? 4 : 1); ++i) prefetch_tmap(&tmaps_a.m[i]);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -143,17 +162,22 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tap = 0; tap < p.kh * p.kw; ++tap) {
-        const int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
-          else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      int tap = kb_begin / p.kchunks, kc = kb_begin - tap * p.kchunks;
+      int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + kABytes;
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
+        else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
+        tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++tap;
+          dy = tap / p.kw - p.ph;
+          dx = tap % p.kw - p.pw;
         }
       }
     }
@@ -163,7 +187,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -172,10 +196,10 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
 #pragma unroll
         for (int k = 0; k < kBlockK / 8; ++k) {
           // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          mma_tf32_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          mma_tf32_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
         }
         mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       mma_commit(tmem_full_bar);
     }
@@ -231,7 +255,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
             for (int j = 0; j < lim; ++j) v[j] = mk[j] > 0.f ? v[j] : 0.f;
           }
         }
-        if (lim == 32 && p.vec_ok) {
+        if (split) {  // partial sum of this K slice: 16-byte vector reductions (plain epilogue, lim == 32 guaranteed)
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * j), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3])
+                         : "memory");
+        } else if (lim == 32 && p.vec_ok) {
           float4* d4 = reinterpret_cast<float4*>(dst);
           if (p.accumulate) {
 #pragma unroll
@@ -255,18 +285,20 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
 }
 
 template <int BLOCK_N>
-int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p, int m_tiles, int n_tiles,
+int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p_in, int m_tiles, int n_tiles, int splits,
                  cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
+  FpropParams p = p_in;
+  p.stages = Cfg::pick_stages((long long)m_tiles * n_tiles * splits);
   ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  conv_fprop_tc_kernel<BLOCK_N><<<dim3(m_tiles, n_tiles), kThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  conv_fprop_tc_kernel<BLOCK_N><<<dim3(m_tiles, n_tiles, splits), kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -318,8 +350,25 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
   static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
-  int bn = min(256, max(32, pow2_ceil(n_total)));
-  while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < min_ctas) bn >>= 1;
+  static const int allow_split = getenv("QEB_TC_SPLITK") ? atoi(getenv("QEB_TC_SPLITK")) : 1;
+  const int num_kb = kh * kw * (cin / kBlockK);
+  const int bn_max = min(256, max(32, pow2_ceil(n_total)));
+  int bn = bn_max, splits = 1;
+  // Few pixels, long K (the deep UNet levels and their input gradients): narrowing the N tile to fill the SMs makes every
+  // CTA stream the whole A operand for a sliver of MMA work and the per-SM L2 read rate becomes the limit. With a plain
+  // epilogue the K range is split instead and the partial sums are reduced into a zero-filled output.
+  const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && mode == 0 && p.vec_ok && n_total % 32 == 0 &&
+                     out.c == n_total && out.sw == n_total && img_flat(out);
+  if (allow_split && plain && (long long)m_tiles * qeb_cdiv(n_total, bn_max) * 2 <= min_ctas && num_kb >= 16) {
+    splits = min(num_kb / 8, qeb_cdiv(min_ctas, m_tiles * qeb_cdiv(n_total, bn_max)));
+    if (splits < 1) splits = 1;
+  }
+  if (splits == 1) {
+    while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < min_ctas) bn >>= 1;
+  }
+  p.kb_per_split = qeb_cdiv(num_kb, splits);
+  splits = qeb_cdiv(num_kb, p.kb_per_split);
+  if (splits > 1) QEB_CUDA(cudaMemsetAsync(out.p, 0, (size_t)img_pixels(out) * n_total * sizeof(float), st));
   if (mode == 1) while (bn > p.up_c) bn >>= 1;
   QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "tc fprop: tile width %d must divide the up-conv channels %d", bn, p.up_c);
   const int n_tiles = qeb_cdiv(n_total, bn);
@@ -334,10 +383,10 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     if (rc) return rc;
   }
   switch (bn) {
-    case 32: return launch_fprop<32>(ta_in, tb, p, m_tiles, n_tiles, st);
-    case 64: return launch_fprop<64>(ta_in, tb, p, m_tiles, n_tiles, st);
-    case 128: return launch_fprop<128>(ta_in, tb, p, m_tiles, n_tiles, st);
-    default: return launch_fprop<256>(ta_in, tb, p, m_tiles, n_tiles, st);
+    case 32: return launch_fprop<32>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
+    case 64: return launch_fprop<64>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
+    case 128: return launch_fprop<128>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
+    default: return launch_fprop<256>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
   }
 }
 
@@ -446,6 +495,7 @@ struct WgradParams {
   int row_blocks;     // taps * a_groups
   int n_total;        // B-side channels
   int per_split;      // pixel tiles per gridDim.z slice
+  int stages;         // depth of the shared-memory ring
   int a_map_per_tap;  // 1: tap selects the A tensor map (ConvTranspose sub-lattices), no coordinate shift
   float* out;
   long long s_rowc, s_kh, s_kw, s_col;  // element strides of the gradient tensor
@@ -459,9 +509,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   constexpr int kBBoxes = BLOCK_N / 32;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* empty_bar = full_bar + Cfg::kStages;
-  uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -474,7 +524,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < (p.a_map_per_tap ? 4 : 1); ++i) prefetch_tmap(&tmaps_a.m[i]);
     prefetch_tmap(&tmap_b);
-    for (int s = 0; s < Cfg::kStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -531,7 +581,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
           tw = 0;
           if (++th == p.tiles_h) { th = 0; ++tn; }
         }
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
       if (lane == 0) {
@@ -551,7 +601,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
             mma_tf32_ss(tmem_base, adesc, bdesc, idesc, (t > t_begin) || (k != 0));
           }
           mma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         mma_commit(tmem_full_bar);
       }
@@ -585,16 +635,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
 }
 
 template <int BLOCK_N>
-int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams& p, dim3 grid, cudaStream_t st) {
+int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams& p_in, dim3 grid, cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    QEB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
+  WgradParams p = p_in;
+  p.stages = Cfg::pick_stages((long long)grid.x * grid.y * grid.z);
   ProfScope prof("tc_conv_wgrad", st, 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.row_blocks * 32,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.a_groups * 32 + p.n_total) + (double)p.n_total * p.row_blocks * 32));
-  conv_wgrad_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::kSmemBytes, st>>>(ta, tb, p);
+  conv_wgrad_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
