@@ -9,7 +9,9 @@ the UNet. Batch 64 synthetic 32x128 patches per GPU (BASELINE.json configs[1]); 
 For N > 1 launch with torch.distributed.run (one rank per GPU); the batch is sharded 64/GPU (weak scaling) and the
 UNet gradients are all-reduced (AVG) over NCCL once per step.
 
-Prints ONE JSON line on rank 0. `value`: inputs resident in HBM, CUDA-event timing, max over ranks. `e2e`: the same
+Prints ONE JSON line on rank 0. `value`: inputs resident in HBM, CUDA-event timing, max over ranks; forward + losses +
+backward are replayed as one CUDA graph (qeb_b200.graphs.GraphedStep), the all-reduce and Adam follow it; the eagerly
+launched modules are timed too (`variants.eager_modules`). `e2e`: the same
 step through the trainers' calling convention with HOST inputs (pinned image batch -> H2D, label strings encoded on
 the host -> int32 CPU targets -> H2D, loss read back -> D2H) inside the timed region. `roofline`: the kernel family
 with the largest share of the step, measured with CUDA events around every launch of the library in a separate
@@ -67,42 +69,65 @@ def encode(labels, char_to_index):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line). NVML is polled from
+    a thread every 5 ms (nvidia-smi -lms cannot start inside a 0.1-0.5 s region); nvidia-smi is the fallback."""
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.reasons, self.max_mhz, self.power = index, [], set(), None, []
+        self._stop, self._thread, self.source = threading.Event(), None, None
+
+    def _handle(self, nv):
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return nv.nvmlDeviceGetHandleByIndex(self.index)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            h = self._handle(nv)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            masks = [(n, getattr(nv, a)) for n, a in self.REASONS]
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        self.reasons.update(n for n, m in masks if r & m)
+                        self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+                    except Exception:
+                        pass
+                    time.sleep(0.005)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+            self.source = "nvml"
+        except Exception:
+            self.source = None
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join()
+        if not self.sm:  # fallback: one nvidia-smi query right after the timed region
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for nme, v in zip(names, r[4:8]):
-                if v == "Active":
-                    reasons.add(nme)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+                self.sm, self.max_mhz = [float(out[0])], float(out[1])
+                self.reasons = {n for (n, _), v in zip(self.REASONS, out[2:6]) if v.strip() == "Active"}
+                self.source = "nvidia-smi (single sample after the timed region)"
+            except Exception:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock query unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source,
+                "power_w": statistics.median(self.power) if self.power else None}
 
 
 # ------------------------------------------------------------------------------------------------------ reference arm
@@ -164,14 +189,15 @@ def workload_config(n_gpus):
                         "1.0*MSE-to-white + Adam(lr 5e-5) on the UNet; 64 synthetic 32x128 patches per GPU, V=95, T=31",
             "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "patch": [H, W], "parallelism": f"dp{n_gpus}",
             "operand_precision": "tf32 tensor-core operands, fp32 accumulate/activations (reference: fp32)",
-            "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2"}
+            "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2",
+            "launch": "forward+losses+backward replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); all-reduce and Adam outside it"}
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qeb", choices=["qeb", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
@@ -264,18 +290,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms) / steps, out
 
+    # ---- eager arm first (it re-allocates .grad every step; the graph below pins them, so eager runs must precede it)
     for _ in range(args.warmup):
         step_device()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    _lib.reset_launch_count()
-    ms_step, last_loss = timed(step_device, args.steps)
-    launches = _lib.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
+    ms_eager, _ = timed(step_device, args.steps)
     for _ in range(2):
         step_e2e()
-    ms_e2e, _ = timed(step_e2e, args.steps)
+    ms_e2e_eager, _ = timed(step_e2e, args.steps)
     # variant (reported beside the headline, not instead of it): the surrogate's parameter gradients are computed and
     # thrown away by the reference in this phase (train_nn_area.py:280,286 - only optimizer_prep steps); freezing them
     # with requires_grad_(False) is a one-line change on the caller's side that skips those kernels
@@ -329,6 +350,49 @@ def main():
         roofline["launches_per_step"] = v["launches"] / psteps
         roofline["avg_launch_ms"] = v["ms"] / v["launches"]
 
+    # ---- headline arm: the same step captured once as a CUDA graph (qeb_b200.graphs) and replayed; the gradient
+    # all-reduce and the Adam launch stay outside the graph
+    from qeb_b200.graphs import GraphedStep, StaticTargets
+    tg_static = StaticTargets(BATCH, W // 4 - 1, dev).load(y, pred_size, y_size)
+    x_static = x_dev.clone()
+    prep.train(); crnn.train(); crnn.apply(set_bn_eval)
+
+    def fwd_bwd():
+        img = prep(x_static)
+        scores = crnn(img)
+        loss = ctc_loss(scores, tg_static) + SCALAR * train_ops.mse_to_ones(img)
+        loss.backward()
+        return loss
+
+    gstep = GraphedStep(fwd_bwd, modules=[prep, crnn], warmup=3)
+
+    def step_graph():
+        loss = gstep()
+        allreduce_grads()
+        opt.step()
+        return loss
+
+    def step_graph_e2e():
+        x_static.copy_(x_pin, non_blocking=True)                     # host batch -> HBM
+        yy, yy_size = encode(labels, c2i)                             # host-side label encoding, as _call_model
+        tg_static.load(yy, pred_size, yy_size)                        # one pinned staging buffer, one H2D copy
+        loss = gstep()
+        allreduce_grads()
+        opt.step()
+        return loss.item()                                            # D2H read of the step's loss
+
+    for _ in range(args.warmup):
+        step_graph()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, last_loss = timed(step_graph, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = (gstep.launches + 1) * args.steps                      # captured library kernels per replay + Adam
+    for _ in range(2):
+        step_graph_e2e()
+    ms_e2e, _ = timed(step_graph_e2e, args.steps)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -345,15 +409,18 @@ def main():
     if rank == 0:
         value = BATCH * world / (ms_step / 1e3)
         e2e = BATCH * world / (ms_e2e / 1e3)
-        h2d = x_pin.numel() * 4 + (y.numel() + 3 * BATCH) * 4
+        h2d = x_pin.numel() * 4 + tg_static._host.numel() * 4   # image batch + the staged CTC targets / lengths
         line = {"metric": "patches/sec per train step (UNet+CRNN+CTC)", "value": value, "unit": "patches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
                 "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": float(last_loss),
-                "variants": {"surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
-                                                               "note": "skips the CRNN weight gradients the reference computes and discards"}},
+                "variants": {"eager_modules": {"value": BATCH * world / (ms_eager / 1e3), "ms_per_step": ms_eager,
+                                               "e2e_value": BATCH * world / (ms_e2e_eager / 1e3), "e2e_ms_per_step": ms_e2e_eager,
+                                               "note": "the mirror modules called eagerly (no CUDA graph), as an unmodified trainer does"},
+                             "surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
+                                                               "note": "eager; skips the CRNN weight gradients the reference computes and discards"}},
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
         print(json.dumps(line), flush=True)
     if world > 1:

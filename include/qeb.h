@@ -181,6 +181,8 @@ int qeb_adam_multi(const void* table, int n_tensors, long long n_chunks, float l
 /* Per-launch profiling: CUDA events around every launch of the library on its stream, with the launch site's
  * algorithmic FLOPs / bytes. report: JSON {"tag": {"launches", "ms", "flops", "bytes"}}, clears the records. */
 void qeb_prof_enable(int on);
+/* Debugging aid: per-CTA clock64 stamps of the tensor-core fprop kernel (see csrc/conv_tc.cu); NULL = off. */
+void qeb_debug_set_timeline(long long* buf);
 int qeb_prof_report(char* buf, int cap);
 
 #ifdef __cplusplus

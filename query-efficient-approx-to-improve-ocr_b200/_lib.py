@@ -42,6 +42,7 @@ SIGNATURES = {
     "qeb_lstm_layer_fwd": (I, [P, P, P, P, P, I, I, P]),
     "qeb_lstm_layer_bwd": (I, [P, P, P, P, P, I, I, P]),
     "qeb_prof_enable": (None, [I]),
+    "qeb_debug_set_timeline": (None, [P]),
     "qeb_prof_report": (I, [ctypes.c_char_p, I]),
     "qeb_mse_ones_fwd": (I, [P, LL, P, P]),
     "qeb_mse_ones_bwd": (I, [P, LL, P, P, P]),

@@ -1,0 +1,106 @@
+"""Whole-step CUDA graphs for the training step (optional: the eager modules stay the drop-in default).
+
+One phase-B step of the reference (train_nn_area.py:277-287) is ~240 kernel launches of 5-100 us each issued from two C
+calls per network; measured on B200 the host needs 4.5 ms to issue what the GPU executes in 5.4 ms, so any per-step host
+work (label encoding, `loss.item()`) serialises with the GPU. Capturing forward + losses + backward ONCE and replaying
+the graph removes the host from the step: the trainer copies the batch and the encoded labels into static buffers,
+replays, and steps the optimizer.
+
+    tg = StaticTargets(batch=64, max_label_len=31, device=dev)      # static twin of the int32-CPU CTC arguments
+    x = torch.empty(64, 1, 32, 128, device=dev)                      # static input batch
+    def fwd_bwd():
+        img = prep(x); scores = crnn(img)
+        loss = ctc_loss(scores, tg) + scalar * mse_to_ones(img)
+        loss.backward()
+        return loss
+    step = GraphedStep(fwd_bwd, modules=[prep, crnn])                # warm-up + capture
+    for images, labels in loader:
+        x.copy_(images, non_blocking=True); tg.load(y, pred_size, y_size)
+        loss = step()                                                # replay; .grad of every parameter is refreshed
+        optimizer.step()
+
+Everything inside the graph is a kernel of libqeb_sm100.so (plus autograd's small glue kernels); the library's side stream
+for weight gradients forks from and joins the capturing stream, so it is captured as a parallel branch.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .mirror.ctc import PackedTargets
+
+
+class StaticTargets(PackedTargets):
+    """CTC targets / lengths in FIXED device buffers (so a captured graph keeps reading the same addresses).
+
+    `load(targets, input_lengths, target_lengths)` takes the arguments of torch.nn.CTCLoss as the reference builds them
+    (int32 CPU tensors, train_nn_area.py:163-171), stages them in one pinned buffer and issues one H2D copy."""
+
+    def __init__(self, batch, max_label_len, device):
+        device = torch.device(device)
+        self.cap = max(1, batch * max_label_len)
+        self._host = torch.zeros(self.cap + 3 * batch, dtype=torch.int32).pin_memory()
+        self._dev = torch.zeros(self.cap + 3 * batch, dtype=torch.int32, device=device)
+        c, B = self.cap, batch
+        super().__init__(self._dev[:c], self._dev[c:c + B], self._dev[c + B:c + 2 * B], self._dev[c + 2 * B:], max_label_len, B)
+
+    def load(self, targets, input_lengths, target_lengths):
+        B, c = self.B, self.cap
+        tl = torch.as_tensor(target_lengths).to("cpu", torch.int32).reshape(-1)
+        il = torch.as_tensor(input_lengths).to("cpu", torch.int32).reshape(-1)
+        tg = torch.as_tensor(targets).to("cpu", torch.int32)
+        if tl.numel() != B or il.numel() != B:
+            raise RuntimeError(f"StaticTargets: expected {B} input/target lengths, got {il.numel()}/{tl.numel()}")
+        tl_np = tl.numpy()
+        if tg.dim() == 2:
+            tg = torch.cat([tg[b, : tl_np[b]] for b in range(B)])
+        tg = tg.reshape(-1)
+        n_t = int(tl_np.sum())
+        if int(tl_np.max()) > self.max_len or n_t > c:
+            raise _lib.QebError(f"StaticTargets: a label of {int(tl_np.max())} symbols exceeds the captured capacity "
+                                f"{self.max_len} (run this batch through the eager path)")
+        if tg.numel() < n_t:
+            raise RuntimeError("StaticTargets: targets shorter than sum(target_lengths)")
+        h = self._host
+        h[:n_t] = tg[:n_t]
+        offs = np.zeros(B, dtype=np.int32)
+        np.cumsum(tl_np[:-1], out=offs[1:])
+        h[c:c + B] = torch.from_numpy(offs)
+        h[c + B:c + 2 * B] = il
+        h[c + 2 * B:] = tl
+        self._dev.copy_(h, non_blocking=True)
+        return self
+
+
+class GraphedStep:
+    """Capture `fn()` (forward + loss + backward over STATIC tensors) into one CUDA graph and replay it.
+
+    modules: their gradients are set to None before the capture so that backward allocates them from the graph's memory
+    pool; every replay overwrites them in place (no accumulation across replays - call the optimizer after each one).
+    The return value of `fn` (a tensor or a tuple of tensors) is static as well: read it after the replay."""
+
+    def __init__(self, fn, modules=(), warmup=3):
+        if not torch.cuda.is_available():
+            raise _lib.QebError("GraphedStep needs a CUDA device (no CPU fallback)")
+        self.fn, self.modules = fn, list(modules)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):      # warm-up off the default stream, as graph capture requires
+            for _ in range(warmup):
+                self._zero()
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._zero()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+        self.launches = _lib.launch_count() - n0   # kernels of libqeb_sm100.so inside one replay
+
+    def _zero(self):
+        for m in self.modules:
+            m.zero_grad(set_to_none=True)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.out

@@ -68,6 +68,10 @@ def st():
     (1, 1, 1984, 512, 2048, 1, 0, 0),   # LSTM input projection as a GEMM
     (1, 1, 1984, 512, 95, 1, 0, 0),     # Linear: N = 95 (tile overhang, unaligned rows)
     (3, 5, 7, 32, 64, 3, 1, 1),         # ragged: tiles larger than the image
+    (16, 32, 128, 32, 32, 3, 1, 1),     # UNet level 1 at batch 16: window kernel (input tile resident across the 9 taps)
+    (12, 32, 128, 64, 32, 3, 1, 0),     # window kernel, two channel slices
+    (40, 16, 64, 32, 64, 3, 1, 1),      # window kernel, two N tiles, W = 64
+    (70, 10, 40, 64, 64, 3, 1, 0),      # window kernel, odd geometry (last tile of every image is partial)
 ])
 def test_conv_fprop_dgrad_wgrad_tc(q, N, H, W, Cin, Cout, k, p, relu):
     g = torch.Generator(device=DEV).manual_seed(N * 1000 + Cin + Cout)
@@ -463,3 +467,67 @@ def test_crnn_edge_shapes(q, B, W):
         m(torch.rand(1, 1, 16, 128, device=DEV))     # the reference's map_to_sequence needs H == 32 too
     with pytest.raises(q.lib.QebError):
         m(torch.rand(1, 1, 32, 128))                 # CPU tensor: no fallback
+
+
+def test_graphed_step_matches_eager(q):
+    """qeb_b200.graphs: one captured forward+loss+backward replays to the same loss and gradients as the eager modules, and
+    follows new inputs / labels copied into the static buffers."""
+    from qeb_b200.graphs import GraphedStep, StaticTargets
+    from qeb_b200.mirror import ctc as qctc, train_ops
+    from qeb_b200.mirror.models.model_crnn import CRNN
+    from qeb_b200.mirror.models.model_unet import UNet
+    from qeb_b200.mirror.utils import set_bn_eval
+    torch.manual_seed(3)
+    B, V = 16, 95
+    prep, crnn = UNet().to(DEV), CRNN(V, False).to(DEV)
+    crnn.register_backward_hook(crnn.backward_hook)
+    prep.train(); crnn.train(); crnn.apply(set_bn_eval)
+    loss_fn = qctc.CTCLoss()
+    il = torch.full((B,), 31, dtype=torch.int32)
+
+    def batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.rand(B, 1, 32, 128, generator=g)
+        tl = torch.randint(1, 12, (B,), generator=g, dtype=torch.int32)
+        y = torch.randint(1, V, (int(tl.sum()),), generator=g, dtype=torch.int32)
+        return x, y, tl
+
+    def eager(x, y, tl):
+        prep.zero_grad(set_to_none=True); crnn.zero_grad(set_to_none=True)
+        img = prep(x.to(DEV))
+        loss = loss_fn(crnn(img), y, il, tl) + train_ops.mse_to_ones(img)
+        loss.backward()
+        return float(loss), [p.grad.clone() for p in prep.parameters()], [p.grad.clone() for p in crnn.parameters()]
+
+    # BatchNorm running statistics advance at every call: snapshot them so that both arms start from the same state
+    state = {k: v.clone() for k, v in prep.state_dict().items()}
+    ref = [eager(*batch(s)) for s in (11, 12)]
+    prep.load_state_dict(state)
+
+    xs = torch.empty(B, 1, 32, 128, device=DEV)
+    tg = StaticTargets(B, 31, DEV)
+    x0, y0, tl0 = batch(11)
+    xs.copy_(x0); tg.load(y0, il, tl0)
+
+    def fwd_bwd():
+        img = prep(xs)
+        loss = loss_fn(crnn(img), tg) + train_ops.mse_to_ones(img)
+        loss.backward()
+        return loss
+
+    gs = GraphedStep(fwd_bwd, modules=[prep, crnn], warmup=2)
+    assert gs.launches > 100
+    for (x, y, tl), (l_ref, gp_ref, gc_ref) in zip((batch(11), batch(12)), ref):
+        xs.copy_(x); tg.load(y, il, tl)
+        loss = gs()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - l_ref) <= 1e-4 * abs(l_ref)
+        # Gradients are compared at the bar of the other network tests, not bit for bit: split-K partial sums are combined
+        # with fp32 atomics, a last-bit difference that crosses a TF32 truncation boundary in the next layer becomes a
+        # 2^-10 relative jump of that operand, and the backward pass of the random-init networks amplifies it - two EAGER
+        # runs on the same input differ by up to 6 % per parameter tensor (scripts/exp/graph_diff.py, profiles/r1_notes.md).
+        for p_, g_ in zip(list(prep.parameters()) + list(crnn.parameters()), gp_ref + gc_ref):
+            assert cos(p_.grad, g_) > 0.99
+            assert 0.85 < float(p_.grad.norm() / g_.norm().clamp_min(1e-30)) < 1.15
+    with pytest.raises(Exception):
+        tg.load(torch.ones(B * 40, dtype=torch.int32), il, torch.full((B,), 40, dtype=torch.int32))
