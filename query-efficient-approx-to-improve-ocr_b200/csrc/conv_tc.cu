@@ -367,145 +367,6 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
 
-// =================================================================================================================
-// 3x3 pad-1 convolution with the input window kept in shared memory across the nine taps ("window" kernel).
-//
-// conv_fprop_tc_kernel re-loads the shifted 128-pixel tile once per tap, i.e. the L2 -> SM traffic of the A operand is 9x
-// the input; for the 32/64-channel full-resolution UNet layers that traffic (not the tensor pipe, not HBM) is the limit.
-// Here a CTA owns 128 consecutive positions of the zero-PADDED image plane (rows of W+2 positions, linear index
-// L = hp*(W+2) + wp) and loads, per 32-channel slice, ONE TMA box {32 ch, W+2, R rows} that covers positions
-// [L0 - (W+2) - 1, L0 + 127 + (W+2) + 1]; TMA's out-of-bounds zero fill materialises the padding. A tap (dy,dx) is then
-// just the same tile shifted by dy*(W+2)+dx rows of 128 bytes: a K-major SWIZZLE_128B descriptor may start at any
-// 128-byte row because the tensor core applies the swizzle to absolute shared-memory address bits (measured,
-// scripts/exp/base_offset.cu), so the nine taps are nine descriptor offsets into one window. Outputs that fall on
-// padding columns are computed and dropped (2/(W+2) of the MMA work).
-struct WinParams {
-  FpropParams f;       // epilogue configuration, n_img / h_out / w_out / n_total / cin / kchunks
-  int wp;              // W + 2
-  int rows;            // R: padded rows per window box
-  int tiles_per_img;   // ceil(H * wp / 128)
-  int win_bytes;       // R * wp * 128 rounded up to 1024
-  int stage_bytes;     // win_bytes + 9 * BLOCK_N * 128
-};
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, 2)
-conv3x3_win_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const WinParams wp_) {
-  const FpropParams& p = wp_.f;
-  constexpr int kBTile = BLOCK_N * 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * wp_.stage_bytes);
-  uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n = blockIdx.x / wp_.tiles_per_img, t = blockIdx.x - n * wp_.tiles_per_img;
-  const int tile_n = blockIdx.y;
-  const int Wp = wp_.wp;
-  const int L0 = Wp + t * kBlockM;                        // first output position (padded row 1 = image row 0)
-  const int hp_lo = (L0 - Wp - 1 + Wp) / Wp - 1;           // floor((L0 - Wp - 1) / Wp), argument >= -1
-  const int s0 = L0 - hp_lo * Wp;                          // row of position L0 inside the window
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_a);
-    prefetch_tmap(&tmap_b);
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ===== TMA producer: lane 0 loads the window, lanes 1..9 the nine weight tiles of the channel slice =====
-    int stage = 0;
-    uint32_t phase = 0;
-    const uint32_t bytes = (uint32_t)(wp_.rows * Wp * 128 + 9 * kBTile);
-    for (int kc = 0; kc < p.kchunks; ++kc) {
-      if (lane == 0) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], bytes);
-      }
-      __syncwarp();
-      uint8_t* sw = smem + stage * wp_.stage_bytes;
-      if (lane == 0) tma_load_4d(sw, &tmap_a, &full_bar[stage], kc * kBlockK, -1, hp_lo - 1, n);
-      else if (lane < 10)
-        tma_load_2d(sw + wp_.win_bytes + (lane - 1) * kBTile, &tmap_b, &full_bar[stage], (lane - 1) * p.cin + kc * kBlockK,
-                    tile_n * BLOCK_N);
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer: 9 taps x 4 K-steps per channel slice, all from the one resident window =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t sw = smem_u32(smem + stage * wp_.stage_bytes);
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int shift = s0 + (tap / 3 - 1) * Wp + (tap % 3 - 1);   // window row of the tap's first pixel
-          const uint64_t adesc = smem_desc_kmajor_sw128(sw + (uint32_t)shift * 128u);
-          const uint64_t bdesc = smem_desc_kmajor_sw128(sw + wp_.win_bytes + tap * kBTile);
-#pragma unroll
-          for (int k = 0; k < kBlockK / 8; ++k) mma_tf32_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
-        }
-        mma_commit(&empty_bar[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-      mma_commit(tmem_full_bar);
-    }
-  } else {
-    // ===== epilogue: position L0 + r -> (padded row, padded column); padding columns and rows past the image are dropped
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const int L = L0 + r;
-    const int hp = L / Wp, wq = L - hp * Wp;
-    const int h = hp - 1, w = wq - 1;
-    const bool valid = (wq >= 1) && (wq <= p.w_out) && (h < p.h_out);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      const int ncol = tile_n * BLOCK_N + c0;
-      if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, false, reinterpret_cast<float*>(smem) + q * 1024, lane);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
-}
-
-template <int BLOCK_N>
-int launch_win(const CUtensorMap& ta, const CUtensorMap& tb, WinParams& wp, int n_tiles, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv3x3_win_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr = true;
-  }
-  const FpropParams& p = wp.f;
-  const int smem_bytes = p.stages * wp.stage_bytes + 1024 + 256;
-  ProfScope prof("tc_conv_fprop", st, 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * 9 * p.cin,
-                 4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * 9 * p.cin));
-  conv3x3_win_tc_kernel<BLOCK_N><<<dim3(p.n_img * wp.tiles_per_img, n_tiles), kThreads, smem_bytes, st>>>(ta, tb, wp);
-  QEB_LAUNCH_CHECK();
-  qeb_count_launch();
-  return QEB_OK;
-}
-
 template <int BLOCK_N>
 int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p_in, int m_tiles, int n_tiles, int splits,
                  cudaStream_t st) {
@@ -632,53 +493,6 @@ int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int k
               "tc_conv_fprop: output geometry %dx%dx%d does not match input %dx%dx%d k%dx%d p%d,%d", out.n, out.h, out.w, x.n,
               x.h, x.w, kh, kw, ph, pw);
   QEB_REQUIRE(n_total > 0 && n_total <= out.c, "tc_conv_fprop: n_total %d vs out.c %d", n_total, out.c);
-  {  // window kernel: 3x3 pad 1 with few channels on wide images (the L2-traffic-bound layers)
-    static const int allow_win = getenv("QEB_TC_WIN") ? atoi(getenv("QEB_TC_WIN")) : 1;
-    const int Wp = x.w + 2;
-    if (allow_win && kh == 3 && kw == 3 && ph == 1 && pw == 1 && x.c <= 128 && n_total <= 64 && n_total % 32 == 0 && x.w >= 32 &&
-        Wp <= 256 && (long long)x.n * qeb_cdiv((long long)x.h * Wp, kBlockM) >= 2 * kNumSMs) {
-      const int bn = 32;  // N tiles of 32 columns: the window + nine weight tiles then fit twice per SM
-      WinParams wp;
-      FpropParams& p = wp.f;
-      p.n_img = x.n; p.h_out = out.h; p.w_out = out.w;
-      p.wt = p.ht = p.nt = p.tiles_w = p.tiles_h = 0;
-      p.kh = 3; p.kw = 3; p.ph = 1; p.pw = 1;
-      p.cin = x.c; p.kchunks = x.c / kBlockK;
-      p.n_total = n_total;
-      p.bias = ep.bias; p.scale = ep.scale; p.relu = ep.relu;
-      p.out = out.p; p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
-      p.mask = nullptr; p.msn = p.msh = p.msw = 0;
-      bool vec = strides_ok(out);
-      if (ep.mask) {
-        p.mask = ep.mask->p; p.msn = ep.mask->sn; p.msh = ep.mask->sh; p.msw = ep.mask->sw;
-        vec = vec && strides_ok(*ep.mask);
-      }
-      p.vec_ok = vec;
-      p.mode = 0; p.up_c = 1; p.accumulate = ep.accumulate; p.a_map_per_tap = 0; p.kb_per_split = 0; p.timeline = nullptr;
-      wp.wp = Wp;
-      wp.rows = (kBlockM + 2 * Wp + 1) / Wp + 2;
-      wp.tiles_per_img = qeb_cdiv((long long)x.h * Wp, kBlockM);
-      wp.win_bytes = (wp.rows * Wp * 128 + 1023) & ~1023;
-      wp.stage_bytes = wp.win_bytes + 9 * bn * 128;
-      // two CTAs per SM when a single stage fits twice; otherwise as many stages (channel slices in flight) as fit
-      int stages = 1;
-      if (2 * (wp.stage_bytes + 1280) > 227 * 1024) stages = min(p.kchunks, (227 * 1024 - 1280) / wp.stage_bytes);
-      if (stages >= 1 && wp.rows <= 256) {
-        p.stages = stages;
-        CUtensorMap ta1, tb1;
-        const uint32_t abox[4] = {(uint32_t)kBlockK, (uint32_t)Wp, (uint32_t)wp.rows, 1u};
-        int rc = tmap_img(&ta1, x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, abox, 0);
-        if (rc) return rc;
-        const uint64_t ktot = (uint64_t)9 * x.c;
-        const uint64_t dims[2] = {ktot, (uint64_t)n_total};
-        const uint64_t str[1] = {ktot * 4};
-        const uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)bn};
-        rc = make_tmap_f32(&tb1, wpacked, 2, dims, str, bbox);
-        if (rc) return rc;
-        return launch_win<32>(ta1, tb1, wp, n_total / bn, st);
-      }
-    }
-  }
   TmapArray4 ta;
   uint32_t box[4];
   fprop_box(out.h, out.w, box);
@@ -1029,3 +843,4 @@ QEB_API int qeb_convT2x2_wgrad_tc(const float* x, int cin, int x_cstride, int h,
 // Debugging aid: when set, every CTA of conv_fprop_tc_kernel writes 8 int64 {t_entry, t_setup_done, t_first_stage_landed,
 // t_mma_issued, t_accum_ready, t_stores_done, t_exit, smid} (clock64) at buf[8 * linear CTA index]. NULL switches it off.
 QEB_API void qeb_debug_set_timeline(long long* buf) { g_timeline = buf; }
+long long* qeb_debug_timeline() { return g_timeline; }

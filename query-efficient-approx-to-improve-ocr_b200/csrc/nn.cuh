@@ -140,6 +140,8 @@ int fill_zero(void* p, size_t bytes, cudaStream_t st);
 // out = a + b (b may be null)
 int vec_add(const float* a, const float* b, float* out, int n, cudaStream_t st);
 
+long long* qeb_debug_timeline();  // conv_tc.cu: buffer set by qeb_debug_set_timeline, or NULL
+
 // ---- LSTM recurrence, lstm.cu ------------------------------------------------------------------------------------
 // One bidirectional layer, hidden size 256. gates: (T,B,2,4*256) holding x*W_ih^T + b_ih + b_hh on entry (gate order
 // i,f,g,o as torch), overwritten with the ACTIVATED gates; w_hh[dir]: torch layout (1024,256); cells: (T,B,2,256) c_t;

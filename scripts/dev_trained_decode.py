@@ -43,8 +43,11 @@ for it in range(steps):
     m.zero_grad(set_to_none=True)
     loss = loss_fn(m(x.to(dev)), y, il, ylen)
     loss.backward(); opt.step()
+    hist = globals().setdefault("hist", [])
+    hist.append(loss.detach())
     if it % 100 == 0 or it == steps - 1:
-        print(f"step {it} loss {float(loss):.4f} ({time.time()-t0:.1f}s)", flush=True)
+        h = torch.stack(hist[-100:]).float()
+        print(f"step {it} loss {float(loss):.4f} last-100 mean {float(h.mean()):.4f} max {float(h.max()):.4f} ({time.time()-t0:.1f}s)", flush=True)
 m.eval(); mr = copy.deepcopy(m); mr.eval()
 same = correct = total = 0
 with torch.no_grad():

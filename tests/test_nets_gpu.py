@@ -68,10 +68,10 @@ def st():
     (1, 1, 1984, 512, 2048, 1, 0, 0),   # LSTM input projection as a GEMM
     (1, 1, 1984, 512, 95, 1, 0, 0),     # Linear: N = 95 (tile overhang, unaligned rows)
     (3, 5, 7, 32, 64, 3, 1, 1),         # ragged: tiles larger than the image
-    (16, 32, 128, 32, 32, 3, 1, 1),     # UNet level 1 at batch 16: window kernel (input tile resident across the 9 taps)
-    (12, 32, 128, 64, 32, 3, 1, 0),     # window kernel, two channel slices
-    (40, 16, 64, 32, 64, 3, 1, 1),      # window kernel, two N tiles, W = 64
-    (70, 10, 40, 64, 64, 3, 1, 0),      # window kernel, odd geometry (last tile of every image is partial)
+    (16, 32, 128, 32, 32, 3, 1, 1),     # UNet level 1 at batch 16
+    (12, 32, 128, 64, 32, 3, 1, 0),     # two channel slices, 65-wide N overhang none
+    (40, 16, 64, 32, 64, 3, 1, 1),      # two N tiles, W = 64
+    (70, 10, 40, 64, 64, 3, 1, 0),      # odd geometry (last tile of every image is partial)
 ])
 def test_conv_fprop_dgrad_wgrad_tc(q, N, H, W, Cin, Cout, k, p, relu):
     g = torch.Generator(device=DEV).manual_seed(N * 1000 + Cin + Cout)
@@ -173,17 +173,18 @@ def test_lstm_layer_vs_torch(q, T, B):
     y = torch.empty(T, B, 512, device=DEV)
     q.lib.call("qeb_lstm_layer_fwd", gates.data_ptr(), lstm.weight_hh_l0.data_ptr(), lstm.weight_hh_l0_reverse.data_ptr(),
                cells.data_ptr(), y.data_ptr(), T, B, st())
-    assert rel(y, y_ref) < 1e-5
+    # the recurrent operands (W_hh, h, d gates) are rounded to tf32: 2^-12 relative per element
+    assert rel(y, y_ref) < 2e-4
     q.lib.call("qeb_lstm_layer_bwd", gates.data_ptr(), cells.data_ptr(), dy.contiguous().data_ptr(), lstm.weight_hh_l0.data_ptr(),
                lstm.weight_hh_l0_reverse.data_ptr(), T, B, st())
     dg = gates.reshape(T * B, 2, 1024)
     xf = x.reshape(T * B, 512)
-    assert rel(dg[:, 0].T @ xf, lstm.weight_ih_l0.grad) < 1e-4
-    assert rel(dg[:, 1].T @ xf, lstm.weight_ih_l0_reverse.grad) < 1e-4
-    assert rel(dg[:, 1].sum(0), lstm.bias_hh_l0_reverse.grad) < 1e-4
+    assert rel(dg[:, 0].T @ xf, lstm.weight_ih_l0.grad) < 5e-4
+    assert rel(dg[:, 1].T @ xf, lstm.weight_ih_l0_reverse.grad) < 5e-4
+    assert rel(dg[:, 1].sum(0), lstm.bias_hh_l0_reverse.grad) < 5e-4
     hprev = torch.zeros(T, B, 256, device=DEV)
     hprev[1:] = y[:-1, :, :256]
-    assert rel(dg[:, 0].T @ hprev.reshape(T * B, 256), lstm.weight_hh_l0.grad) < 1e-4
+    assert rel(dg[:, 0].T @ hprev.reshape(T * B, 256), lstm.weight_hh_l0.grad) < 5e-4
 
 
 # ------------------------------------------------------------------------------------------------ networks vs golden
