@@ -293,39 +293,42 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int tap = kb_begin / p.kchunks, kc = kb_begin - tap * p.kchunks;
-      int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+    // ===== TMA producer: the whole warp runs the loop (warp-uniform control flow), one elected lane issues. With a
+    // lane-divergent `if (lane == 0)` the compiler cannot keep descriptors and coordinates in uniform registers and wraps
+    // every TMA / MMA instruction in an ELECT + R2UR + BRA.U.ANY lane loop (~60 cycles per instruction) =====
+    int stage = 0;
+    uint32_t phase = 0;
+    int tap = kb_begin / p.kchunks, kc = kb_begin - tap * p.kchunks;
+    int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + kABytes;
         mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
         if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
         else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
         tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++kc == p.kchunks) {
-          kc = 0;
-          ++tap;
-          dy = tap / p.kw - p.ph;
-          dx = tap % p.kw - p.pw;
-        }
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      if (++kc == p.kchunks) {
+        kc = 0;
+        ++tap;
+        dy = tap / p.kw - p.ph;
+        dx = tap % p.kw - p.pw;
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        if (tl && kb == kb_begin) tl[2] = clock64();
-        tc_fence_after();
+    // ===== MMA issuer (warp-uniform loop, elected lane issues - see the producer) =====
+    constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      if (tl && lane == 0 && kb == kb_begin) tl[2] = clock64();
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
         const uint64_t adesc = smem_desc_kmajor_sw128(sa);
         const uint64_t bdesc = smem_desc_kmajor_sw128(sa + kABytes);
@@ -335,11 +338,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
           mma_tf32_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
         }
         mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      mma_commit(tmem_full_bar);
-      if (tl) tl[3] = clock64();
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) mma_commit(tmem_full_bar);
+    __syncwarp();
+    if (tl && lane == 0) tl[3] = clock64();
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
@@ -623,44 +628,40 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
 
   if (t_begin < t_end) {
     if (warp == 0) {
-      // ===== TMA producer: one lane per box (4 A boxes + BLOCK_N/32 B boxes per stage), issued in parallel; the per-box
-      // constants (tap shift, channel offset, tensor map, smem offset) are computed once, the tile coordinates are
-      // carried as counters so that the steady-state loop has no integer division =====
-      const int nbox = n_rb + kBBoxes;
-      const bool active = lane < nbox;
-      int c0 = 0, sx = 0, sy = 0;
-      uint32_t dst_off = 0;
-      const CUtensorMap* map = &tmap_b;
-      if (lane < n_rb) {
-        const int rb = rb0 + lane;
+      // ===== TMA producer: up to 4 A boxes + BLOCK_N/32 B boxes per stage. The per-box constants (tap shift, channel
+      // offset, tensor map) are computed once and the tile coordinates are carried as counters, so the steady-state loop
+      // has no integer division; control flow is warp-uniform and one elected lane issues, which keeps all of it in
+      // uniform registers (see conv_fprop_tc_kernel) =====
+      int ac0[4], asx[4], asy[4], amap[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int rb = rb0 + (j < n_rb ? j : 0);
         const int tap = rb / p.a_groups, cg = rb - tap * p.a_groups;
-        c0 = cg * 32;
-        dst_off = lane * kBoxBytes;
-        if (p.a_map_per_tap) {
-          map = &tmaps_a.m[tap];
-        } else {
-          map = &tmaps_a.m[0];
-          sy = tap / p.kw - p.ph;
-          sx = tap % p.kw - p.pw;
-        }
-      } else if (active) {
-        const int j = lane - n_rb;
-        c0 = tile_n * BLOCK_N + j * 32;
-        dst_off = kABytes + j * kBoxBytes;
+        ac0[j] = cg * 32;
+        amap[j] = p.a_map_per_tap ? tap : 0;
+        asy[j] = p.a_map_per_tap ? 0 : tap / p.kw - p.ph;
+        asx[j] = p.a_map_per_tap ? 0 : tap % p.kw - p.pw;
       }
       int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tn = t_begin / (p.tiles_w * p.tiles_h);
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = (uint32_t)nbox * kBoxBytes;
+      const uint32_t bytes = (uint32_t)(n_rb + kBBoxes) * kBoxBytes;
       for (int t = t_begin; t < t_end; ++t) {
-        if (lane == 0) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sbase = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[stage], bytes);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (j < n_rb)
+              tma_load_4d(sbase + j * kBoxBytes, &tmaps_a.m[amap[j]], &full_bar[stage], ac0[j], tw * p.wt + asx[j], th * p.ht + asy[j],
+                          tn * p.nt);
+#pragma unroll
+          for (int j = 0; j < kBBoxes; ++j)
+            tma_load_4d(sbase + kABytes + j * kBoxBytes, &tmap_b, &full_bar[stage], tile_n * BLOCK_N + j * 32, tw * p.wt, th * p.ht,
+                        tn * p.nt);
         }
         __syncwarp();
-        if (active)
-          tma_load_4d(smem + stage * Cfg::kStageBytes + dst_off, map, &full_bar[stage], c0, tw * p.wt + sx, th * p.ht + sy,
-                      tn * p.nt);
         if (++tw == p.tiles_w) {
           tw = 0;
           if (++th == p.tiles_h) { th = 0; ++tn; }
@@ -668,13 +669,14 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     } else if (warp == 1) {
-      if (lane == 0) {
-        constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 1, 1);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = t_begin; t < t_end; ++t) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+      // MMA issuer: warp-uniform loop, elected lane issues (see conv_fprop_tc_kernel)
+      constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kABytes;
 #pragma unroll
@@ -685,10 +687,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
             mma_tf32_ss(tmem_base, adesc, bdesc, idesc, (t > t_begin) || (k != 0));
           }
           mma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        mma_commit(tmem_full_bar);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) mma_commit(tmem_full_bar);
+      __syncwarp();
     } else {
       const int q = warp & 3;
       const int r = q * 32 + lane;

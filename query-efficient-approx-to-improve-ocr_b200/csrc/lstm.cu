@@ -3,21 +3,26 @@
 //
 // The input projections x*W_ih^T + b_ih + b_hh are tensor-core GEMMs (conv_tc.cu); this file runs the T dependent
 // steps. One cluster of 8 CTAs serves one (direction, chunk of kBC = 16 batch rows); CTA r of the cluster owns hidden
-// units [32r, 32r+32), i.e. 128 of the 1024 gate rows, whose W_hh slice (128 x 256 fp32 = 128 KB) stays in shared memory
-// for the whole sequence as the K-major, 128-byte-swizzled A operand of a tcgen05.mma (kind::tf32, M = 128).
+// units [32r, 32r+32), i.e. 128 of the 1024 gate rows. Its W_hh slice (128 x 256) is loaded ONCE into TENSOR MEMORY
+// (128 lanes x 256 columns, rounded to tf32) and stays there for the whole sequence as the A operand of
+// tcgen05.mma.kind::tf32 (A from TMEM, B from shared memory): with N = 16 an MMA whose A operand comes from shared memory
+// is bound by reading the 4 KB A tile (measured 89 cycles per MMA, 2.9 k cycles per step), from TMEM it is not.
 //
-// Forward step: D[128 gate rows][16 batch] = W_slice (128 x 256) * h_{t-1}^T (256 x 16) is 32 MMAs (K = 8) issued by one
-// thread, accumulator in TMEM. The operand copies of W_hh and h are rounded to tf32 with round-to-nearest (the tensor core
-// itself would truncate); y, c and the saved gate activations stay fp32. Warp q of each half-block reads gate q of its 32
-// units for 8 batch rows from TMEM (tcgen05.ld), adds the x-projection, applies the non-linearity and passes the activated
-// gates through 8 KB of shared memory to the cell threads, which update c and write the 32 new h values per batch row into
-// the B-operand layout; CTA r owns exactly K chunk r of that operand (2 KB) and copies it to the same place in the other 7
-// CTAs of the cluster with 16-byte distributed-shared-memory stores, double-buffered. One cluster barrier per step.
+// Forward step: D[128 gate rows][16 batch] = W_slice * h_{t-1}^T is 32 MMAs (K = 8) issued by one thread. The operand
+// copy of h is rounded to tf32 with round-to-nearest (the tensor core itself would truncate); y, c and the saved gate
+// activations stay fp32. Warp q of each half-block reads gate q of its 32 units for 8 batch rows from TMEM (tcgen05.ld),
+// adds the x-projection, applies the non-linearity and passes the activated gates through 8 KB of shared memory to the
+// cell threads, which update c and write the 32 new h values per batch row into the B-operand layout; CTA r owns exactly
+// K chunk r of that operand (2 KB) and pushes it into the other 7 CTAs with cp.async.bulk (shared::cta ->
+// shared::cluster), which signals the receiver's mbarrier with the byte count. There is no cluster barrier in the loop:
+// the operand is double-buffered and a CTA can only run one step ahead of its slowest peer because it needs that peer's
+// chunk for its next MMA.
 //
 // Backward step: the cell threads form d(gates) for their units and write them as the B operand [16 batch][128 own gate
-// rows]; dh_{t-1}[k][b] partial = W_slice^T (256 x 128) * dgates (128 x 16) is 2 x 16 MMAs (two M = 128 halves of k); the
-// partial sums are read from TMEM and reduce-scattered over DSMEM: CTA dst receives the k range [32 dst, 32 dst + 32) from
-// every CTA and sums the eight contributions when it forms dh in the next step.
+// rows]; dh_{t-1}[k][b] partial = W_slice^T (256 x 128, two M = 128 halves in TMEM) * dgates is 2 x 16 MMAs; warp w reads
+// the k range that belongs to CTA w from TMEM, transposes it through shared memory and pushes the 2 KB block to CTA w with
+// one bulk copy (a reduce-scatter): CTA dst receives its k range from all 8 CTAs and sums the contributions when it forms
+// dh in the next step.
 #include "nn.cuh"
 #include "tc_common.cuh"
 #include <cooperative_groups.h>
@@ -35,15 +40,18 @@ constexpr int kRows = 4 * kUnits;      // 128 gate rows per CTA
 constexpr int kBC = 16;       // batch rows per cluster = MMA N
 constexpr int kThreads = 256;
 
-constexpr int kATile = 128 * 128;        // 16 KB: 128 rows x one 32-element (128-byte) K chunk of an A operand
-constexpr int kBTile = kBC * 128;        // 2 KB: the same K chunk of the B operand
-constexpr size_t kSmemW = 8 * kATile;    // 128 KB
-constexpr int kHBuf = 8 * kBTile;        // 16 KB: one copy of h (hi or lo) for all 256 k
-constexpr size_t kSmemFwd = kSmemW + 2 * kHBuf + 4 * kBC * kUnits * sizeof(float) + 64 + 1024;
-constexpr size_t kSmemBwd = kSmemW + 4 * kBTile + 3 * kCluster * kBC * kUnits * sizeof(float) + 64 + 1024;
-constexpr uint32_t kTmemCols = 32;
+constexpr int kBTile = kBC * 128;        // 2 KB: one 32-element (128-byte) K chunk of a B operand, [16 batch][128 B]
+constexpr int kHBuf = 8 * kBTile;        // 16 KB: h for all 256 k
+constexpr int kBlk = kBC * kUnits;       // floats in one [batch][unit] block (2 KB)
+// TMEM: columns [0,256) hold the A operand, the accumulator follows. 512 columns = the whole tensor memory of the SM; the
+// shared-memory request is padded so that no other CTA can become resident next to a recurrence CTA and wait for TMEM.
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kAccCol = 256;
+constexpr int kChains = 4;   // independent accumulators the K loop of a step is spread over (summed when read)
+constexpr size_t kSmemPad = 200 * 1024;
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return __fdividef(2.f, 1.f + __expf(-2.f * x)) - 1.f; }
 __device__ __forceinline__ float tf32_rn(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -69,7 +77,37 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// this thread's TMEM lane, 16 consecutive columns <- 16 registers
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem], kind::tf32, issued by one thread
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_saddr), "r"(rank));
+  return r;
+}
+// bulk copy own shared memory -> shared memory of a CTA of the cluster; completes `bytes` on the destination's mbarrier
+__device__ __forceinline__ void bulk_copy_to_cluster(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(mbar_cluster)
+               : "memory");
+}
 
 struct LstmArgs {
   float* gates;         // (T,B,2,1024)
@@ -78,49 +116,58 @@ struct LstmArgs {
   float* y;             // (T,B,512)
   const float* dy;      // (T,B,512), backward only
   int T, B;
-  long long* tl;        // debugging aid (qeb_debug_set_timeline): clock64 stamps of cluster 0 / CTA 0, 8 per step
+  long long* tl;        // debugging aid (qeb_debug_set_timeline): clock64 stamps of CTA 0, 8 per step
 };
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) lstm_fwd_kernel(LstmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Ws = smem;                                   // A operand: 8 K chunks x [128 gate rows][128 B]
-  uint8_t* Hs = smem + kSmemW;                          // B operand, double-buffered: [2][8 K chunks][16 batch][128 B]
+  uint8_t* Hs = smem;                                     // B operand, double-buffered: [2][8 K chunks][16 batch][128 B]
   float* act = reinterpret_cast<float*>(Hs + 2 * kHBuf);  // activated gates [q][b][unit]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(act + 4 * kBC * kUnits);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(act + 4 * kBlk);
+  uint64_t* full_bar = mma_bar + 1;                       // [2]: the peers' chunks of h buffer b have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 2);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kCluster;
   const int dir = cid & 1, b0 = (cid >> 1) * kBC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q = warp & 3, bh = warp >> 2;
 
-  // W_hh slice -> swizzled A operand, rounded to tf32. Thread = (row, k quad): a warp reads 512 contiguous bytes of one
-  // row and writes four full 128-byte rows of four K chunks.
-  {
-    const float* W = a.w_hh[dir];
-    for (int i = tid; i < kRows * (kH / 4); i += kThreads) {
-      const int lr = i / (kH / 4), kq = i % (kH / 4);
-      const int grow = (lr / kUnits) * kH + rank * kUnits + (lr % kUnits);
-      float4 v = __ldg(reinterpret_cast<const float4*>(W + (long long)grow * kH) + kq);
-      v.x = tf32_rn(v.x); v.y = tf32_rn(v.y); v.z = tf32_rn(v.z); v.w = tf32_rn(v.w);
-      *reinterpret_cast<float4*>(Ws + sw128_off(lr, kq * 4, kATile)) = v;
-    }
-  }
   for (int i = tid; i < 2 * kHBuf / 16; i += kThreads) reinterpret_cast<float4*>(Hs)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  {
+    // W_hh slice -> TMEM, rounded to tf32: lane = gate row (gate q, unit `lane`), column = k. Warps w and w + 4 share a
+    // lane quarter and take 128 columns each; a thread streams 512 contiguous bytes of its row.
+    const float* W = a.w_hh[dir] + (long long)(q * kH + rank * kUnits + lane) * kH + bh * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(W + c0) + j);
+        v[4 * j] = tf32_rn(w4.x); v[4 * j + 1] = tf32_rn(w4.y); v[4 * j + 2] = tf32_rn(w4.z); v[4 * j + 3] = tf32_rn(w4.w);
+      }
+      tmem_st16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bh * 128 + c0), v);
+    }
+    tmem_st_wait();
+  }
   fence_proxy_async_all();
   tc_fence_before();
   cluster.sync();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   // roles. gate thread: gate q of unit `lane` for batch rows [8 bh, 8 bh + 8); cell thread: unit `lane`, batch rows warp, warp + 8
-  const int q = warp & 3, bh = warp >> 2;
   float c[2] = {0.f, 0.f};
   constexpr uint32_t idesc = instr_desc_tf32(128, kBC, 0, 0);
   const long long gstride = 2 * 4 * kH;  // floats between consecutive batch rows of `gates`
@@ -131,7 +178,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     const int t = dir ? a.T - 1 - s : s;
     const float* g = a.gates + (((long long)t * a.B + b0 + bh * 8) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = (b0 + bh * 8 + j < a.B) ? __ldg(g + j * gstride) : 0.f;
+    for (int j = 0; j < 8; ++j) dst[j] = (b0 + bh * 8 + j < a.B) ? g[j * gstride] : 0.f;
   };
   load_gx(0, gx);
 
@@ -141,38 +188,42 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     uint8_t* hcur = Hs + (s & 1) * kHBuf;
     uint8_t* hnext = Hs + ((s + 1) & 1) * kHBuf;
     if (tl) tl[8 * s + 0] = clock64();
-    if (tid == 0) {
-      fence_proxy_async_all();
+    if (warp == 0) {   // warp-uniform branch + elect.sync: descriptors stay in uniform registers, no per-MMA lane loop
+      if (s > 0) mbar_wait(&full_bar[s & 1], ((s - 1) >> 1) & 1);   // the 7 remote chunks of h_s (own chunk: see below)
+      if (tl) tl[8 * s + 1] = clock64();
       tc_fence_after();
-      const uint32_t wa = smem_u32(Ws), hb = smem_u32(hcur);
+      if (elect_one()) {
+        const uint32_t hb = smem_u32(hcur);
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        const uint64_t adesc = smem_desc_kmajor_sw128(wa + kc * kATile);
-        const uint64_t bdesc = smem_desc_kmajor_sw128(hb + kc * kBTile);
+        for (int kc = 0; kc < 8; ++kc) {
+          const uint64_t bdesc = smem_desc_kmajor_sw128(hb + kc * kBTile);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | k) != 0);
+          for (int k = 0; k < 4; ++k)   // chain k accumulates K steps k, k + 4, ...: kChains independent accumulators
+            mma_tf32_ts(tmem_base + kAccCol + (uint32_t)((k % kChains) * kBC), tmem_base + (uint32_t)(kc * 32 + k * 8), bdesc + 2 * k,
+                        idesc, (kc * 4 + k) >= kChains);
+        }
+        mma_commit(mma_bar);
       }
-      mma_commit(bar);
+      __syncwarp();
     }
-    if (tl) tl[8 * s + 1] = clock64();
     float gx_next[8];
     if (s + 1 < a.T) load_gx(s + 1, gx_next);
-    mbar_wait(bar, s & 1);
+    mbar_wait(mma_bar, s & 1);
     tc_fence_after();
     if (tl) tl[8 * s + 2] = clock64();
-    float pre[8];
-    tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(bh * 8), pre);
+    float pre[kChains][8];
+#pragma unroll
+    for (int ch = 0; ch < kChains; ++ch) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol + (uint32_t)(ch * kBC + bh * 8), pre[ch]);
     tmem_ld_wait();
     tc_fence_before();
-    {
-      float* g = a.gates + (((long long)t * a.B + b0 + bh * 8) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
+    float av[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = pre[j] + gx[j];
-        const float av = q == 2 ? tanhf(v) : sigmoidf_(v);
-        act[(q * kBC + bh * 8 + j) * kUnits + lane] = av;
-        if (b0 + bh * 8 + j < a.B) g[j * gstride] = av;   // saved for the backward pass
-      }
+    for (int j = 0; j < 8; ++j) {
+      float v = gx[j];
+#pragma unroll
+      for (int ch = 0; ch < kChains; ++ch) v += pre[ch][j];
+      av[j] = q == 2 ? fast_tanh(v) : fast_sigmoid(v);
+      act[(q * kBC + bh * 8 + j) * kUnits + lane] = av[j];
     }
     __syncthreads();
     if (tl) tl[8 * s + 3] = clock64();
@@ -184,27 +235,31 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       const float gg = act[(2 * kBC + bl) * kUnits + lane], og = act[(3 * kBC + bl) * kUnits + lane];
       c[p] = fg * c[p] + ig * gg;
       const bool live = b0 + bl < a.B;
-      hv[p] = live ? og * tanhf(c[p]) : 0.f;
+      hv[p] = live ? og * fast_tanh(c[p]) : 0.f;
       // the operand copy of h is rounded to tf32 here (round-to-nearest; the tensor core would truncate)
       *reinterpret_cast<float*>(hnext + sw128_off(bl, rank * kUnits + lane, kBTile)) = tf32_rn(hv[p]);
     }
+    fence_proxy_async_all();   // own chunk: generic-proxy writes -> visible to the bulk copy and to the next step's MMA
     __syncthreads();
     if (tl) tl[8 * s + 4] = clock64();
-    {  // this CTA's K chunk (16 batch rows x 128 B = 2 KB) -> the same place in the 7 peers, 16-byte stores
-      const float4* src = reinterpret_cast<const float4*>(hnext + rank * kBTile);
-      for (int i = tid; i < (kCluster - 1) * (kBTile / 16); i += kThreads) {
-        int dst_rank = i / (kBTile / 16);
-        const int e = i % (kBTile / 16);
-        dst_rank += (dst_rank >= rank);
-        float4* dst = reinterpret_cast<float4*>(cluster.map_shared_rank(hnext + rank * kBTile, dst_rank));
-        dst[e] = src[e];
+    if (tid == 0 && s + 1 < a.T) {
+      // push this CTA's K chunk (16 batch rows x 128 B) into the same place of the 7 peers; arm the own barrier for theirs
+      mbar_expect_tx(&full_bar[(s + 1) & 1], (kCluster - 1) * kBTile);
+      const uint32_t src = smem_u32(hnext + rank * kBTile), bar = smem_u32(&full_bar[(s + 1) & 1]);
+#pragma unroll
+      for (int r = 1; r < kCluster; ++r) {
+        const uint32_t peer = (uint32_t)((rank + r) & (kCluster - 1));
+        bulk_copy_to_cluster(mapa_u32(src, peer), src, kBTile, mapa_u32(bar, peer));
       }
     }
-    fence_proxy_async_all();
     if (tl) tl[8 * s + 5] = clock64();
-    // arrive (release) right after the DSMEM stores; the global stores below are issued after it, so the barrier does
-    // not wait for them
-    cluster.barrier_arrive();
+    // global stores last: a proxy fence waits for the thread's outstanding stores, these drain during the next step
+    {
+      float* g = a.gates + (((long long)t * a.B + b0 + bh * 8) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (b0 + bh * 8 + j < a.B) g[j * gstride] = av[j];   // activated gates, saved for the backward pass
+    }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       const int b = b0 + warp + 8 * p;
@@ -216,55 +271,55 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
 #pragma unroll
     for (int j = 0; j < 8; ++j) gx[j] = gx_next[j];
     if (tl) tl[8 * s + 6] = clock64();
-    cluster.barrier_wait();
-    if (tl) tl[8 * s + 7] = clock64();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster.sync();   // no CTA leaves while a peer may still read the chunk it pushed or write into this CTA
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) lstm_bwd_kernel(LstmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Ws = smem;                    // A operand W_slice^T: [k half 2][gate 4] tiles of [128 k][32 gate rows = 128 B]
-  uint8_t* Dg = smem + kSmemW;           // B operand d(gates): 4 K chunks (one per gate) x [16 batch][128 B]
-  float* recv = reinterpret_cast<float*>(Dg + 4 * kBTile);  // [2][src CTA][batch][unit]
-  float* stage = recv + 2 * kCluster * kBC * kUnits;          // [warp][batch][unit]: transposes the TMEM rows for the scatter
-  uint64_t* bar = reinterpret_cast<uint64_t*>(stage + kCluster * kBC * kUnits);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint8_t* Dg = smem;                                        // B operand d(gates): 4 K chunks (one per gate) x [16 batch][128 B]
+  float* recv = reinterpret_cast<float*>(Dg + 4 * kBTile);   // [2][src CTA][batch][unit]
+  float* stage = recv + 2 * kCluster * kBlk;                 // [2][dst CTA = warp][batch][unit]: sources of the bulk copies
+  uint64_t* mma_bar = reinterpret_cast<uint64_t*>(stage + 2 * kCluster * kBlk);
+  uint64_t* full_bar = mma_bar + 1;                          // [2]: all 8 blocks of recv buffer b have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + 2);
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kCluster;
   const int dir = cid & 1, b0 = (cid >> 1) * kBC;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // W_slice^T -> swizzled A operand (rows = k, K = own gate rows). Lanes = consecutive gate rows of one gate, so the four
-  // scalar stores of a thread's float4 (four consecutive k = four A rows) are bank-conflict free.
-  {
-    const float* W = a.w_hh[dir];
-    for (int i = tid; i < 4 * kUnits * (kH / 4); i += kThreads) {
-      const int jl = i % kUnits, kq = (i / kUnits) % (kH / 4), gq = i / (kUnits * (kH / 4));
-      const int grow = gq * kH + rank * kUnits + jl;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(W + (long long)grow * kH) + kq);
-      const int k = kq * 4;
-      uint8_t* tile = Ws + ((k >> 7) * 4 + gq) * kATile;
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) *reinterpret_cast<float*>(tile + sw128_off((k & 127) + e, jl, 0)) = tf32_rn(vv[e]);
-    }
-  }
-  for (int i = tid; i < 2 * kCluster * kBC * kUnits; i += kThreads) recv[i] = 0.f;
   if (tid == 0) {
-    mbar_init(bar, 1);
+    mbar_init(mma_bar, 1);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, kTmemCols);
-  fence_proxy_async_all();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  {
+    // W_slice^T -> TMEM, rounded to tf32: half mh = warp / 4 of k lives in columns [128 mh, 128 mh + 128); lane = k % 128,
+    // column = own gate row (gate gq, unit jl). For a fixed gate row the 32 lanes of a warp read 32 consecutive k.
+    const int mh = warp >> 2;
+    const float* W = a.w_hh[dir] + (long long)(rank * kUnits) * kH + mh * 128 + (warp & 3) * 32 + lane;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 16) {   // c0 = gq * 32 + jl
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = tf32_rn(__ldg(W + (long long)((c0 >> 5) * kH + (c0 & 31) + j) * kH));
+      tmem_st16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(mh * 128 + c0), v);
+    }
+    tmem_st_wait();
+  }
   tc_fence_before();
   cluster.sync();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   constexpr uint32_t idesc = instr_desc_tf32(128, kBC, 0, 0);
   float dc[2] = {0.f, 0.f};
@@ -289,27 +344,31 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   long long* tl = (a.tl && blockIdx.x == 0 && tid == 0) ? a.tl : nullptr;
   for (int s = 0; s < a.T; ++s) {
     const int t = dir ? s : a.T - 1 - s;
-    const float* rcv = recv + ((s + 1) & 1) * kCluster * kBC * kUnits;  // written during step s-1 (zeros at s = 0)
+    const float* rcv = recv + ((s + 1) & 1) * kCluster * kBlk;  // pushed by the 8 CTAs during step s-1
     if (tl) tl[8 * s + 0] = clock64();
+    if (s > 0) mbar_wait(&full_bar[(s + 1) & 1], ((s - 1) >> 1) & 1);
+    if (tl) tl[8 * s + 1] = clock64();
+    float dgv[2][4];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
       const int bl = warp + 8 * p, b = b0 + bl;
       float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
       if (b < a.B) {
         float dh = sv[p].dy;
+        if (s > 0) {
 #pragma unroll
-        for (int r = 0; r < kCluster; ++r) dh += rcv[(r * kBC + bl) * kUnits + lane];
+          for (int r = 0; r < kCluster; ++r) dh += rcv[(r * kBC + bl) * kUnits + lane];
+        }
         const float ig = sv[p].ig, fg = sv[p].fg, gg = sv[p].gg, og = sv[p].og;
-        const float tcv = tanhf(sv[p].ct);
+        const float tcv = fast_tanh(sv[p].ct);
         d_o = dh * tcv * og * (1.f - og);
         const float dct = dc[p] + dh * og * (1.f - tcv * tcv);
         d_i = dct * gg * ig * (1.f - ig);
         d_g = dct * ig * (1.f - gg * gg);
         d_f = dct * sv[p].cp * fg * (1.f - fg);
         dc[p] = dct * fg;
-        float* g = a.gates + (((long long)t * a.B + b) * 2 + dir) * (4 * kH) + rank * kUnits + lane;
-        g[0] = d_i; g[kH] = d_f; g[2 * kH] = d_g; g[3 * kH] = d_o;   // d(pre-activations) for the weight-gradient GEMMs
       }
+      dgv[p][0] = d_i; dgv[p][1] = d_f; dgv[p][2] = d_g; dgv[p][3] = d_o;
       const uint32_t off = sw128_off(bl, lane, 0);
       // operand copies rounded to tf32 (round-to-nearest; the tensor core would truncate)
       *reinterpret_cast<float*>(Dg + 0 * kBTile + off) = tf32_rn(d_i);
@@ -317,56 +376,83 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       *reinterpret_cast<float*>(Dg + 2 * kBTile + off) = tf32_rn(d_g);
       *reinterpret_cast<float*>(Dg + 3 * kBTile + off) = tf32_rn(d_o);
     }
-    fence_proxy_async_all();
-    __syncthreads();
-    if (tl) tl[8 * s + 1] = clock64();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t wa = smem_u32(Ws), db = smem_u32(Dg);
+    auto store_dgates = [&]() {   // d(pre-activations) for the weight-gradient GEMMs; after the proxy fence (see forward)
 #pragma unroll
-      for (int mh = 0; mh < 2; ++mh) {
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) {
-          const uint64_t adesc = smem_desc_kmajor_sw128(wa + (mh * 4 + gq) * kATile);
-          const uint64_t bdesc = smem_desc_kmajor_sw128(db + gq * kBTile);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) mma_tf32_ss(tmem_base + mh * kBC, adesc + 2 * k, bdesc + 2 * k, idesc, (gq | k) != 0);
+      for (int p = 0; p < 2; ++p) {
+        const int b = b0 + warp + 8 * p;
+        if (b < a.B) {
+          float* g = a.gates + (((long long)t * a.B + b) * 2 + dir) * (4 * kH) + rank * kUnits + lane;
+          g[0] = dgv[p][0]; g[kH] = dgv[p][1]; g[2 * kH] = dgv[p][2]; g[3 * kH] = dgv[p][3];
         }
       }
-      mma_commit(bar);
+    };
+    if (s + 1 == a.T) {   // dh before the first step is not needed
+      store_dgates();
+      break;
     }
-    if (s + 1 < a.T) {
-      sv[0] = load_saved(s + 1, 0);
-      sv[1] = load_saved(s + 1, 1);
-    }
+    fence_proxy_async_all();
+    __syncthreads();
     if (tl) tl[8 * s + 2] = clock64();
-    mbar_wait(bar, s & 1);
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(&full_bar[s & 1], kCluster * kBlk * sizeof(float));   // the 8 blocks the cluster pushes in this step
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t db = smem_u32(Dg);
+#pragma unroll
+        for (int mh = 0; mh < 2; ++mh) {
+#pragma unroll
+          for (int gq = 0; gq < 4; ++gq) {
+            const uint64_t bdesc = smem_desc_kmajor_sw128(db + gq * kBTile);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_tf32_ts(tmem_base + kAccCol + (uint32_t)((mh * kChains + k % kChains) * kBC), tmem_base + (uint32_t)(mh * 128 + gq * 32 + k * 8),
+                          bdesc + 2 * k, idesc, (gq * 4 + k) >= kChains);
+          }
+        }
+        mma_commit(mma_bar);
+      }
+      __syncwarp();
+    }
+    store_dgates();
+    sv[0] = load_saved(s + 1, 0);
+    sv[1] = load_saved(s + 1, 1);
+    mbar_wait(mma_bar, s & 1);
     tc_fence_after();
     if (tl) tl[8 * s + 3] = clock64();
     // warp w reads k = 128 (w / 4) + 32 (w % 4) + lane for the 16 batch rows: exactly the k range of CTA dst = w. A thread
-    // owns one k (one TMEM lane); the block is transposed through shared memory so that the scatter is 16-byte stores of
-    // four consecutive units.
+    // owns one k (one TMEM lane); the block is transposed through shared memory into the receiver's [batch][unit] layout and
+    // pushed with one 2 KB bulk copy. The staging buffer is double-buffered: the copy of step s-2 has been consumed by the
+    // time step s was allowed to start, the one of step s-1 possibly not.
     float v[kBC];
-    tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * kBC), v);
-    tmem_ld_wait();
-    tc_fence_before();
     {
-      float* stg = stage + warp * kBC * kUnits;
+      float vc[kChains][kBC];
+#pragma unroll
+      for (int ch = 0; ch < kChains; ++ch)
+        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCol + (uint32_t)(((warp >> 2) * kChains + ch) * kBC), vc[ch]);
+      tmem_ld_wait();
+      tc_fence_before();
+#pragma unroll
+      for (int j = 0; j < kBC; ++j) {
+        v[j] = vc[0][j];
+#pragma unroll
+        for (int ch = 1; ch < kChains; ++ch) v[j] += vc[ch][j];
+      }
+    }
+    {
+      float* stg = stage + ((s & 1) * kCluster + warp) * kBlk;
 #pragma unroll
       for (int j = 0; j < kBC; ++j) stg[j * kUnits + lane] = v[j];
+      fence_proxy_async_all();
       __syncwarp();
-      float4* rnext = reinterpret_cast<float4*>(cluster.map_shared_rank(recv + (s & 1) * kCluster * kBC * kUnits, warp) + rank * kBC * kUnits);
-#pragma unroll
-      for (int i = 0; i < kBC * kUnits / 4 / 32; ++i) rnext[i * 32 + lane] = reinterpret_cast<const float4*>(stg)[i * 32 + lane];
+      if (lane == 0) {
+        const uint32_t dst = smem_u32(recv + ((s & 1) * kCluster + rank) * kBlk);
+        bulk_copy_to_cluster(mapa_u32(dst, warp), smem_u32(stg), kBlk * sizeof(float), mapa_u32(smem_u32(&full_bar[s & 1]), warp));
+      }
     }
     if (tl) tl[8 * s + 4] = clock64();
-    cluster.barrier_arrive();
-    if (tl) tl[8 * s + 5] = clock64();
-    cluster.barrier_wait();
-    if (tl) tl[8 * s + 6] = clock64();
   }
   tc_fence_before();
-  __syncthreads();
+  cluster.sync();   // no CTA leaves while a peer may still read the block it pushed or write into this CTA
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
@@ -390,13 +476,13 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && y && T > 0 && B > 0, "lstm_layer_fwd: bad arguments");
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemFwd));
+    QEB_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
     attr = true;
   }
   LstmArgs a;
   a.gates = gates; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_rev; a.cells = cells; a.y = y; a.dy = nullptr; a.T = T; a.B = B;
   ProfScope prof("lstm_fwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
-  return launch_cluster((const void*)lstm_fwd_kernel, kSmemFwd, 2 * qeb_cdiv(B, kBC), a, st);
+  return launch_cluster((const void*)lstm_fwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
 
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
@@ -404,14 +490,14 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && dy && T > 0 && B > 0, "lstm_layer_bwd: bad arguments");
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBwd));
+    QEB_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
     attr = true;
   }
   LstmArgs a;
   a.gates = gates; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_rev; a.cells = const_cast<float*>(cells); a.y = nullptr; a.dy = dy;
   a.T = T; a.B = B;
   ProfScope prof("lstm_bwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
-  return launch_cluster((const void*)lstm_bwd_kernel, kSmemBwd, 2 * qeb_cdiv(B, kBC), a, st);
+  return launch_cluster((const void*)lstm_bwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
 
 // C ABI (tests): one bidirectional layer of the recurrence

@@ -13,8 +13,8 @@ cells = torch.empty(T, B, 2, 256, device=DEV); y = torch.empty(T, B, 512, device
 st = torch.cuda.current_stream().cuda_stream
 def fwd(g): _lib.call("qeb_lstm_layer_fwd", g.data_ptr(), w[0].data_ptr(), w[1].data_ptr(), cells.data_ptr(), y.data_ptr(), T, B, st)
 def bwd(g): _lib.call("qeb_lstm_layer_bwd", g.data_ptr(), cells.data_ptr(), dy.data_ptr(), w[0].data_ptr(), w[1].data_ptr(), T, B, st)
-for name, fn, labels in (("fwd", fwd, ["mma issue", "mma wait", "tmem ld + act + sync", "cell + sync", "dsmem copy + fence", "arrive + global stores", "cluster wait"]),
-                         ("bwd", bwd, ["cell + dgates + sync", "mma issue + prefetch", "mma wait", "tmem ld + scatter", "arrive", "cluster wait"])):
+for name, fn, labels in (("fwd", fwd, ["wait peers' h chunks", "mma issue + wait", "tmem ld + act + sync", "cell + fence + sync", "push issue", "global stores"]),
+                         ("bwd", bwd, ["wait peers' dh blocks", "cell + dgates + fence + sync", "mma issue + wait (+ stores, prefetch)", "tmem ld + transpose + push"])):
     g = gates0.clone()
     for _ in range(3): fn(g.clone())
     torch.cuda.synchronize()
@@ -28,7 +28,7 @@ for name, fn, labels in (("fwd", fwd, ["mma issue", "mma wait", "tmem ld + act +
     L.qeb_debug_set_timeline(buf.data_ptr()); fn(g.clone()); torch.cuda.synchronize(); L.qeb_debug_set_timeline(None)
     t = buf.cpu().numpy().reshape(T, 8)
     n = len(labels)
-    d = np.diff(t[:, :n + 1], axis=1)[5:]     # skip the first steps (cold)
+    d = np.diff(t[:, :n + 1], axis=1)[5:T - 1]     # skip the first steps (cold) and the last (no exchange)
     for lab, col in zip(labels, d.T):
         print(f"   {lab:28s} mean {col.mean():8.0f} cyc")
-    print(f"   {'step total':28s} mean {np.diff(t[:, 0])[5:].mean():8.0f} cyc")
+    print(f"   {'step total':28s} mean {np.diff(t[:, 0])[5:T - 1].mean():8.0f} cyc")
