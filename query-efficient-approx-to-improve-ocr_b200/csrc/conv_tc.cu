@@ -88,6 +88,7 @@ struct FpropParams {
   int up_c;
   int accumulate;            // 1: out += result (used when a gradient already holds a partial sum)
   int stages;                // depth of the shared-memory ring
+  int m_tiles, n_tiles, splits;  // tile grid: tile t -> (K slice t / (m*n), N tile (t / m) % n, pixel tile t % m)
   int kb_per_split;          // K blocks (tap x 32-channel slice) per gridDim.z slice; split-K partial sums are combined with
                              // 16-byte vector reductions into a zero-filled output (plain epilogue only)
   int vec_ok;                // 16-byte aligned rows: float4 stores allowed
@@ -103,21 +104,23 @@ template <int BLOCK_N>
 struct FpropCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // several CTAs per SM (3 / 3 / 2 / 1 for BLOCK_N 32 / 64 / 128 / 256) so that one CTA's prologue and epilogue overlap
-  // another's main loop; the K loops here are short (9..144 stages), so a deep per-CTA ring buys less than occupancy
-  static constexpr int kCtasPerSm = (BLOCK_N >= 256) ? 1 : (BLOCK_N >= 128 ? 2 : 3);
+  static constexpr int kEpiBytes = 4 * 4096;   // per epilogue warp: 32 x 32 floats for the store transposition
+  // The kernel is persistent: a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the TMA ring running
+  // across tile boundaries and two TMEM accumulators, so that the epilogue of one tile overlaps the main loop of the
+  // next. Narrow tiles (short main loops, epilogue-heavy) still run two CTAs per SM to double the epilogue warps.
+  static constexpr int kCtasPerSm = (BLOCK_N >= 256) ? 1 : 2;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kMaxStages = 8;
   static constexpr int kMaxSmem = 227 * 1024;
-  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
-  // The ring depth is a launch-time choice: a grid that fills the SMs several times over runs kCtasPerSm CTAs per SM with a
-  // shallow ring each; a grid of about one CTA per SM (deep layers with few pixels) has nothing else on the SM to hide the
-  // TMA round trip, so it gets every byte of shared memory as stages (measured: 3 stages at 1 CTA/SM leave the tensor
-  // pipe ~10 % active with the L2 at ~20 %).
-  static int pick_stages(long long n_ctas) {
-    int resident = (int)((n_ctas + kNumSMs - 1) / kNumSMs);
-    if (resident > kCtasPerSm) resident = kCtasPerSm;
-    if (resident < 1) resident = 1;
-    int stages = (kMaxSmem / resident - 1280) / kStageBytes;
+  static constexpr int kSmBudget = 224 * 1024;   // what resident CTAs share: 228 KB per SM minus 1 KB reserved per CTA and slack
+  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
+  static int resident(long long n_tiles_total) {
+    int r = (int)((n_tiles_total + kNumSMs - 1) / kNumSMs);
+    return r > kCtasPerSm ? kCtasPerSm : (r < 1 ? 1 : r);
+  }
+  // every byte of shared memory the resident CTAs leave goes into ring stages
+  static int pick_stages(long long n_tiles_total) {
+    int stages = (kSmBudget / resident(n_tiles_total) - 1280 - kEpiBytes) / kStageBytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
     return stages;
@@ -192,7 +195,7 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
 // therefore transposed through 4 KB of shared memory (XOR-swizzled 16-byte slots, conflict-free both ways) so that a warp
 // instruction writes 4 complete 128-byte row segments. stg: this warp's staging area (the pipeline ring is idle by then).
 __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float (&v)[32], bool valid, int n, int h, int w,
-                                                    int ncol, bool split, float* stg, int lane) {
+                                                    int ncol, bool split, float* stg, int lane, long long* tle = nullptr) {
   const int lim = min(32, p.n_total - ncol);
   if (lim < 32 || !p.vec_ok) {  // ragged / unaligned rows (warp-uniform): per-thread path
     if (valid) fprop_epilogue_store(p, v, n, h, w, ncol, split);
@@ -226,6 +229,7 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   for (int j = 0; j < 8; ++j)
     *reinterpret_cast<float4*>(stg + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
+  if (tle) tle[9] = clock64();
   const int rsub = lane >> 3, c16 = lane & 7;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -260,19 +264,18 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   using Cfg = FpropCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes);
+  float* epi_stage = reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes + Cfg::kEpiBytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]: accumulator a holds a finished tile
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]: the epilogue has read accumulator a
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, tile_n = blockIdx.y;
-  const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.wt, h0 = th * p.ht, n0 = tn * p.nt;
   const int num_kb = p.kh * p.kw * p.kchunks;
-  const int kb_begin = blockIdx.z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
-  const bool split = gridDim.z > 1;
-  long long* tl = p.timeline ? p.timeline + 8 * (blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) : nullptr;
+  const int mn_tiles = p.m_tiles * p.n_tiles, total_tiles = mn_tiles * p.splits;
+  const bool split = p.splits > 1;
+  long long* tl = p.timeline ? p.timeline + 16 * blockIdx.x : nullptr;
   if (tl && threadIdx.x == 0) { tl[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
 
   if (warp == 0 && lane == 0) {
@@ -282,10 +285,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);   // every epilogue thread arrives
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BLOCK_N);
+  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -298,77 +304,107 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     // every TMA / MMA instruction in an ELECT + R2UR + BRA.U.ANY lane loop (~60 cycles per instruction) =====
     int stage = 0;
     uint32_t phase = 0;
-    int tap = kb_begin / p.kchunks, kc = kb_begin - tap * p.kchunks;
-    int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      if (elect_one()) {
-        uint8_t* sa = smem + stage * Cfg::kStageBytes;
-        uint8_t* sb = sa + kABytes;
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-        if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
-        else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
-        tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
-      }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      if (++kc == p.kchunks) {
-        kc = 0;
-        ++tap;
-        dy = tap / p.kw - p.ph;
-        dx = tap % p.kw - p.pw;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int z = t / mn_tiles, r = t - z * mn_tiles;
+      const int tile_n = r / p.m_tiles, tile_m = r - tile_n * p.m_tiles;
+      const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.wt, h0 = th * p.ht, n0 = tn * p.nt;
+      const int kb_begin = z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
+      int tap = kb_begin / p.kchunks, kc = kb_begin - tap * p.kchunks;
+      int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
+          else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++kc == p.kchunks) {
+          kc = 0;
+          ++tap;
+          dy = tap / p.kw - p.ph;
+          dx = tap % p.kw - p.pw;
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform loop, elected lane issues - see the producer) =====
     constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      if (tl && lane == 0 && kb == kb_begin) tl[2] = clock64();
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int z = t / mn_tiles;
+      const int kb_begin = z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // the epilogue has drained this accumulator (two tiles ago)
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint64_t adesc = smem_desc_kmajor_sw128(sa);
-        const uint64_t bdesc = smem_desc_kmajor_sw128(sa + kABytes);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BLOCK_N);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        if (tl && lane == 0 && t == (int)blockIdx.x && kb == kb_begin) tl[2] = clock64();
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t adesc = smem_desc_kmajor_sw128(sa);
+          const uint64_t bdesc = smem_desc_kmajor_sw128(sa + kABytes);
 #pragma unroll
-        for (int k = 0; k < kBlockK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          mma_tf32_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
+          for (int k = 0; k < kBlockK / 8; ++k) {
+            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            mma_tf32_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
+          }
+          mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         }
-        mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) mma_commit(&tmem_full_bar[acc]);
       __syncwarp();
-      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    if (elect_one()) mma_commit(tmem_full_bar);
-    __syncwarp();
-    if (tl && lane == 0) tl[3] = clock64();
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
     const int r = q * 32 + lane;  // row of the tile = TMEM lane
     const int ww = r % p.wt, hh = (r / p.wt) % p.ht, nn = r / (p.wt * p.ht);
-    const int w = w0 + ww, h = h0 + hh, n = n0 + nn;
-    const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
-    mbar_wait(tmem_full_bar, 0);
-    if (tl && threadIdx.x == 64) tl[4] = clock64();
-    tc_fence_after();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int n_done = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_done) {
+      const int z = t / mn_tiles, rr = t - z * mn_tiles;
+      const int tile_n = rr / p.m_tiles, tile_m = rr - tile_n * p.m_tiles;
+      const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
+      const int w = tw * p.wt + ww, h = th * p.ht + hh, n = tn * p.nt + nn;
+      const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (tl && threadIdx.x == 64 && n_done == 0) tl[4] = clock64();
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (tl && threadIdx.x == 64 && c0 == 0) tl[3] = clock64();  // (debug) overrides the MMA-issued stamp: TMEM read done
-      const int ncol = tile_n * BLOCK_N + c0;  // first GEMM-N column of this chunk
-      if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, reinterpret_cast<float*>(smem) + q * 1024, lane);
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+        tmem_ld_wait();
+        long long* tle = (tl && threadIdx.x == 64 && n_done == 0 && c0 == 0) ? tl : nullptr;
+        if (tle) tle[8] = clock64();
+        const int ncol = tile_n * BLOCK_N + c0;  // first GEMM-N column of this chunk
+        if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle);
+        if (tle) tle[10] = clock64();
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);
+      if (tl && threadIdx.x == 64 && n_done == 0) tl[5] = clock64();
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    if (tl && threadIdx.x == 64) tl[5] = clock64();
+    if (tl && threadIdx.x == 64) tl[3] = n_done;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
 
@@ -382,11 +418,14 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams&
     attr = true;
   }
   FpropParams p = p_in;
-  p.stages = Cfg::pick_stages((long long)m_tiles * n_tiles * splits);
+  const long long total = (long long)m_tiles * n_tiles * splits;
+  p.stages = Cfg::pick_stages(total);
+  p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits;
+  const int grid = (int)(total < (long long)kNumSMs * Cfg::resident(total) ? total : (long long)kNumSMs * Cfg::resident(total));
   ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  conv_fprop_tc_kernel<BLOCK_N><<<dim3(m_tiles, n_tiles, splits), kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
+  conv_fprop_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -449,7 +488,8 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && mode == 0 && p.vec_ok && n_total % 32 == 0 &&
                      out.c == n_total && out.sw == n_total && img_flat(out);
   if (allow_split && plain && (long long)m_tiles * qeb_cdiv(n_total, bn_max) * 2 <= min_ctas && num_kb >= 16) {
-    splits = min(num_kb / 8, qeb_cdiv(min_ctas, m_tiles * qeb_cdiv(n_total, bn_max)));
+    // round DOWN: tiles beyond one per SM would make a few CTAs walk two tiles while the rest idle
+    splits = min(num_kb / 8, min_ctas / (m_tiles * qeb_cdiv(n_total, bn_max)));
     if (splits < 1) splits = 1;
   }
   if (splits == 1) {
@@ -845,6 +885,6 @@ QEB_API int qeb_convT2x2_wgrad_tc(const float* x, int cin, int x_cstride, int h,
 }
 
 // Debugging aid: when set, every CTA of conv_fprop_tc_kernel writes 8 int64 {t_entry, t_setup_done, t_first_stage_landed,
-// t_mma_issued, t_accum_ready, t_stores_done, t_exit, smid} (clock64) at buf[8 * linear CTA index]. NULL switches it off.
+// t_mma_issued, t_accum_ready, t_stores_done, t_exit, smid, ...} (clock64) at buf[16 * CTA index]. NULL switches it off.
 QEB_API void qeb_debug_set_timeline(long long* buf) { g_timeline = buf; }
 long long* qeb_debug_timeline() { return g_timeline; }
