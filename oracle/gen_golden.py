@@ -10,6 +10,9 @@ The fixtures pin the Python-level reference functions on the hot path (the refer
   ctc.npz         torch.nn.CTCLoss CPU, reference call shapes  train_nn_area.py:146-148,174
   crnn.npz        models.model_crnn.CRNN fwd + CTC + bwd       models/model_crnn.py, train_crnn.py:157-162
   unet.npz        models.model_unet.UNet fwd + MSE + bwd       models/model_unet.py, train_nn_area.py:173-182
+  tracking.json / tracking.npz  tracking_utils.generate_ctc_target_batches / weighted_ctc_loss (both weighting modes,
+                  value and gradient at the scores) and LevenshteinWeightGenerator.gen_weights
+                                                               tracking_utils.py:34-75, label_tracking/tracking_methods.py:72-101
 """
 import json
 import os
@@ -312,6 +315,69 @@ def gen_unet(ref):
         json.dump({"param_digest_seed42": digest0, "grad_digest_train": gd}, f)
 
 
+def gen_tracking(ref):
+    """Label-tracking CTC path: a trainer-like object with a label history per image, the reference's target batching,
+    the Levenshtein loss weights and the weighted multi-target CTC loss in both weighting modes."""
+    import importlib
+    import types
+    seed_all(42)
+    tu = ref.tracking_utils
+    tm = importlib.import_module("label_tracking.tracking_methods")
+    char_to_index, _, V = ref.utils.get_char_maps(ref.properties.char_set)
+    names, labels, _ = pos_labels(ref, 24, 5)
+    rng = random.Random(3)
+    alphabet = [c for c in ref.properties.char_set[1:] if c != "`"]
+
+    def corrupt(s):
+        s = list(s)
+        for _ in range(rng.randint(0, 2)):
+            op = rng.choice("sid")
+            pos = rng.randrange(len(s) + 1)
+            if op == "s" and s:
+                s[min(pos, len(s) - 1)] = rng.choice(alphabet)
+            elif op == "i" and len(s) < 14:
+                s.insert(pos, rng.choice(alphabet))
+            elif op == "d" and len(s) > 1:
+                s.pop(min(pos, len(s) - 1))
+        return "".join(s)
+
+    window = 4
+    tracked = {}
+    for n_, l_ in zip(names[:20], labels[:20]):          # 4 images have no history at all
+        tracked[n_] = [corrupt(l_) for _ in range(rng.randint(1, 6))]
+    tracked[names[0]] = ["", corrupt(labels[0]), ""]       # empty OCR labels occur (tess returns '' on blank crops)
+    batch_names = names[:16] + names[20:22]                # 16 with history + 2 without -> gen_weights skips those
+    T, B = 31, 16
+    scores = torch.randn(T, B, V).log_softmax(2).requires_grad_(True)
+    pred_size = torch.tensor([T] * B, dtype=torch.int)
+    out_np, out_js = {"scores": scores.detach().numpy()}, {"tracked": tracked, "names": batch_names, "window": window}
+    for mode in ("levenshtein", "decaying"):
+        obj = types.SimpleNamespace(window_size=window, tracked_labels=tracked, char_to_index=char_to_index, device="cpu",
+                                    weightgen_method=mode, primary_loss_fn=torch.nn.CTCLoss(),
+                                    primary_loss_fn_sample_wise=torch.nn.CTCLoss(reduction="none"))
+        tb = tu.generate_ctc_target_batches(obj, batch_names[:B])
+        args = types.SimpleNamespace(window_size=window, decay_factor=0.7)
+        gen = tm.weightgenerator_factory(mode)(args, "cpu", char_to_index)
+        w = gen.gen_weights(tracked, batch_names) if mode == "levenshtein" else gen.gen_weights(obj, batch_names)
+        if mode == "levenshtein":
+            out_np["lev_weights"] = w.numpy()
+            out_js["target_batches"] = [[t.tolist(), ts.tolist(), idx] for t, ts, idx in tb]
+            # the trainers index the weights of the images in the CTC batch; column 0 belongs to the current label
+            lw = w[:B, 1:]
+        else:
+            out_np["decay_weights"] = w.numpy()
+            lw = w
+        if scores.grad is not None:
+            scores.grad = None
+        loss = tu.weighted_ctc_loss(obj, scores, pred_size, tb, lw)
+        loss.backward()
+        out_np[f"loss_{mode}"] = loss.detach().numpy()
+        out_np[f"grad_{mode}"] = scores.grad.numpy().copy()
+    np.savez_compressed(os.path.join(OUT, "tracking.npz"), **out_np)
+    with open(os.path.join(OUT, "tracking.json"), "w") as f:
+        json.dump(out_js, f)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = refload.load()
@@ -324,6 +390,7 @@ def main():
     gen_ctc(ref)
     gen_crnn(ref)
     gen_unet(ref)
+    gen_tracking(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

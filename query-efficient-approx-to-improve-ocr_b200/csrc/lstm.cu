@@ -47,7 +47,7 @@ constexpr int kBlk = kBC * kUnits;       // floats in one [batch][unit] block (2
 // shared-memory request is padded so that no other CTA can become resident next to a recurrence CTA and wait for TMEM.
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kAccCol = 256;
-constexpr int kChains = 4;   // independent accumulators the K loop of a step is spread over (summed when read)
+constexpr int kChains = 1;   // independent accumulators the K loop of a step can be spread over (measured: no gain, issue-bound before, 20 cycles per MMA now)
 constexpr size_t kSmemPad = 200 * 1024;
 
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
