@@ -162,7 +162,7 @@ def cpu_step_factory(batch, seed=42):
 
 def run_reference(args, rank):
     if rank != 0:
-        return
+        return None
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sample = BATCH if args.steps + args.warmup <= 30 else 16
@@ -181,7 +181,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} steps of {sample} patches, torch {torch.__version__} CPU fp32"},
             "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(n_gpus):
@@ -195,6 +195,21 @@ def workload_config(n_gpus):
 
 # ------------------------------------------------------------------------------------------------------ our arm
 def main():
+    # stdout carries exactly ONE line (the JSON result): everything libraries print while the run is in flight (NCCL's
+    # version banner, warnings) is sent to stderr by pointing fd 1 at fd 2 until the result is ready
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -406,6 +421,7 @@ def main():
         cpu_baseline = {"value": BATCH * n / dt, "unit": "patches/s", "cores": threads, "kind": "port",
                         "sample": f"{n} steps of {BATCH} patches ({dt:.1f} s), oracle/nn_oracle.py on torch {torch.__version__} CPU fp32"}
 
+    line = None
     if rank == 0:
         value = BATCH * world / (ms_step / 1e3)
         e2e = BATCH * world / (ms_e2e / 1e3)
@@ -422,9 +438,9 @@ def main():
                              "surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
                                                                "note": "eager; skips the CRNN weight gradients the reference computes and discards"}},
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
-        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
 if __name__ == "__main__":

@@ -38,6 +38,9 @@ def allreduce_grads(params, average=True, group=None):
     world = dist.get_world_size(group)
     flat = flat_grad_buffer(params)
     if flat is not None:
+        if average and flat.is_cuda and dist.get_backend(group) == "nccl":
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=group)   # the division happens inside the collective
+            return 1
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
         if average:
             flat.div_(world)
