@@ -10,20 +10,23 @@ import torch.distributed as dist
 
 
 def flat_grad_buffer(params):
-    """The single tensor all `.grad`s of `params` are views of, or None if they do not share one base."""
-    base = None
-    for p in params:
-        g = p.grad
-        if g is None:
-            continue
-        b = g._base if g._base is not None else None
-        if b is None:
+    """The single tensor that covers all `.grad`s of `params`, or None if they do not live back to back in one storage.
+    The qeb backward carves the gradients of a network out of one zero-filled buffer (64-float aligned slices);
+    AccumulateGrad adopts them with `.detach()`, which drops the view relation (`._base`), so the test is on the storage:
+    same storage, contiguous tensors, and a covered span no larger than the tensors plus their alignment padding."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return None
+    g0 = grads[0]
+    st = g0.untyped_storage()
+    for g in grads:
+        if g.dtype != g0.dtype or g.device != g0.device or not g.is_contiguous() or g.untyped_storage().data_ptr() != st.data_ptr():
             return None
-        if base is None:
-            base = b
-        elif b.data_ptr() != base.data_ptr() or b.numel() != base.numel():
-            return None
-    return base
+    lo = min(g.storage_offset() for g in grads)
+    hi = max(g.storage_offset() + g.numel() for g in grads)
+    if hi - lo > sum(g.numel() for g in grads) + 64 * len(grads):
+        return None   # a subset with other tensors in between: reducing the span would touch gradients not asked for
+    return torch.empty(0, dtype=g0.dtype, device=g0.device).set_(st, lo, (hi - lo,))
 
 
 def allreduce_grads(params, average=True, group=None):

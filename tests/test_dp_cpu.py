@@ -61,3 +61,36 @@ def test_single_process_is_a_noop():
     p.grad = torch.ones(3)
     assert qdist.allreduce_grads([p]) == 0
     assert qdist.shard_batch(10, 0, 1) == (0, 10)
+
+
+def test_flat_buffer_is_found_behind_autograd():
+    """AccumulateGrad adopts the gradient views with .detach(), which drops `._base`: the flat buffer must still be found
+    (it was not in round 1: every data-parallel step silently took the cat / all-reduce / copy-back path, +0.4 ms)."""
+    sys.path.insert(0, ROOT)
+    import qeb_b200  # noqa: F401
+    from qeb_b200.mirror import dist as qdist
+    from qeb_b200.mirror.models.model_crnn import _alloc_grads
+
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((4, 3), (70,), (2, 2, 2), (5,))]
+
+    class Fn(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, *ps):
+            ctx.ps = ps
+            return sum(p.sum() for p in ps)
+
+        @staticmethod
+        def backward(ctx, g):
+            grads = _alloc_grads(ctx.ps, [True] * len(ctx.ps))
+            for i, gr in enumerate(grads):
+                gr.fill_(float(i + 1))
+            return tuple(grads)
+
+    Fn.apply(*params).backward()
+    assert all(p.grad._base is None for p in params)            # the situation the storage test exists for
+    flat = qdist.flat_grad_buffer(params)
+    assert flat is not None and flat.numel() >= sum(p.numel() for p in params)
+    flat.mul_(2.0)                                               # the all-reduce acts on the gradients themselves
+    assert all(torch.equal(p.grad, torch.full_like(p, 2.0 * (i + 1))) for i, p in enumerate(params))
+    assert qdist.flat_grad_buffer([params[0], params[3]]) is None   # a subset with foreign tensors in between
+    assert qdist.flat_grad_buffer(params[:2]) is not None           # a contiguous prefix is fine
