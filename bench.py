@@ -303,7 +303,10 @@ def run():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms) / steps, out
+        # hand back a number, not the loss tensor: a live loss keeps its autograd graph - and the parameters' AccumulateGrad
+        # nodes, which remember the (legacy default) stream of the eager steps - alive, and a later graph capture fails with
+        # cudaErrorStreamCaptureImplicit when the engine syncs that stream
+        return float(ms) / steps, (float(out.detach()) if torch.is_tensor(out) else out)
 
     # ---- eager arm first (it re-allocates .grad every step; the graph below pins them, so eager runs must precede it)
     for _ in range(args.warmup):
@@ -431,7 +434,7 @@ def run():
                 "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
-                "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": float(last_loss),
+                "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": last_loss,
                 "variants": {"eager_modules": {"value": BATCH * world / (ms_eager / 1e3), "ms_per_step": ms_eager,
                                                "e2e_value": BATCH * world / (ms_e2e_eager / 1e3), "e2e_ms_per_step": ms_e2e_eager,
                                                "note": "the mirror modules called eagerly (no CUDA graph), as an unmodified trainer does"},

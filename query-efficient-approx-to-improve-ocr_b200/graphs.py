@@ -76,7 +76,9 @@ class GraphedStep:
 
     modules: their gradients are set to None before the capture so that backward allocates them from the graph's memory
     pool; every replay overwrites them in place (no accumulation across replays - call the optimizer after each one).
-    The return value of `fn` (a tensor or a tuple of tensors) is static as well: read it after the replay."""
+    The return value of `fn` (a tensor or a tuple of tensors) is static as well: read it after the replay.
+    No autograd graph of an earlier eager step over the same parameters may be alive at capture time (do not keep old loss
+    tensors around): its AccumulateGrad nodes are bound to the default stream, which a capture must not touch."""
 
     def __init__(self, fn, modules=(), warmup=3):
         if not torch.cuda.is_available():
@@ -93,8 +95,16 @@ class GraphedStep:
         self._zero()
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self.out = fn()
+        try:
+            with torch.cuda.graph(self.graph):
+                self.out = fn()
+        except RuntimeError as e:
+            if "legacy stream" in str(e) or "StreamCaptureImplicit" in str(e):
+                raise _lib.QebError(
+                    "GraphedStep: the capture touched the legacy default stream. The usual cause is a loss tensor of an earlier "
+                    "EAGER step that is still referenced: it keeps the parameters' AccumulateGrad nodes (bound to the default "
+                    "stream) alive. Drop such references (keep float(loss), not loss) before capturing.") from e
+            raise
         self.launches = _lib.launch_count() - n0   # kernels of libqeb_sm100.so inside one replay
 
     def _zero(self):
