@@ -61,10 +61,21 @@ struct PackJob {
   long long s0, s1, s2, d0, d1;
   long long start;  // first element of this job in the batch-wide numbering
 };
+// conv weight re-layouts go through a tiled transpose (32 x 32 channels x taps through shared memory, coalesced both ways)
+struct ConvPackJob {
+  const float* src;
+  float* dst;
+  int A, B, taps;   // torch weight (A = Cout, B = Cin, taps); both multiples of 32 for this path
+  int mode;         // 0: dst[a][tap][b] = src[a][b][tap]   fprop B operand
+                    // 1: dst[b][taps-1-tap][a] = src[a][b][tap]   dgrad B operand (flipped taps, channels transposed)
+                    // 2: dst[a][b][tap] (+)= src[a][tap][b]   packed weight gradient -> torch layout
+  int tile_start;   // first 32 x 32 tile of this job in the batch-wide numbering
+};
 struct PackBatch {
   enum { kMax = 28 };
   PackJob jobs[kMax];
-  int n = 0;
+  ConvPackJob cjobs[kMax];
+  int n = 0, nc = 0, ctiles = 0;
   long long total = 0;
   int accumulate = 0;  // 1: dst += src for every job of the batch
   void add(const float* src, float* dst, int n0, int n1, int n2, long long s0, long long s1, long long s2, long long d0,
@@ -74,19 +85,27 @@ struct PackBatch {
     j.start = total;
     total += (long long)n0 * n1 * n2;
   }
+  bool add_conv(const float* src, float* dst, int A, int B, int taps, int mode) {
+    if (A % 32 || B % 32 || taps > 9) return false;
+    ConvPackJob& j = cjobs[nc++];
+    j.src = src; j.dst = dst; j.A = A; j.B = B; j.taps = taps; j.mode = mode; j.tile_start = ctiles;
+    ctiles += (A / 32) * (B / 32);
+    return true;
+  }
   // torch Conv2d weight (Cout,Cin,taps) -> fprop B operand [Cout][tap][Cin]
   void add_fprop(const float* w, float* dst, int cout, int cin, int taps) {
-    add(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin);
+    if (!add_conv(w, dst, cout, cin, taps, 0)) add(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin);
   }
   // -> dgrad B operand [Cin][flipped tap][Cout] (source taps walked backwards with a negative stride)
   void add_dgrad(const float* w, float* dst, int cout, int cin, int taps) {
-    add(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout);
+    if (!add_conv(w, dst, cout, cin, taps, 1))
+      add(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout);
   }
   void add_copy(const float* src, float* dst, long long n) { add(src, dst, 1, 1, (int)n, 0, 0, 1, 0, 0); }
   // packed weight gradient [Cout][tap][Cin] (what the wgrad kernel accumulates into with coalesced atomics) -> torch
   // layout (Cout,Cin,taps)
   void add_unpack_grad(const float* packed, float* dw, int cout, int cin, int taps) {
-    add(packed, dw, cout, cin, taps, (long long)taps * cin, 1, cin, (long long)cin * taps, taps);
+    if (!add_conv(packed, dw, cout, cin, taps, 2)) add(packed, dw, cout, cin, taps, (long long)taps * cin, 1, cin, (long long)cin * taps, taps);
   }
 };
 int pack_flush(PackBatch& b, cudaStream_t st);

@@ -642,6 +642,54 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
   }
 }
 
+struct ConvPackJobsParam {
+  ConvPackJob j[PackBatch::kMax];
+  int n;
+};
+// One block = one tile of 32 output channels (a) x 32 input channels (b) x taps of one job. Phase 1 reads the source
+// in runs of 32 * taps (modes 0, 1) or 32 (mode 2) contiguous floats into smem[a][b * taps + tap] (row pitch 32 * taps + 1);
+// phase 2 writes runs of 32 (modes 0, 1) or 32 * taps (mode 2) contiguous floats. All shared-memory strides (taps, pitch)
+// are odd, so every access is bank-conflict free.
+__global__ void __launch_bounds__(kThreads) conv_pack_kernel(const __grid_constant__ ConvPackJobsParam jobs, int accumulate) {
+  extern __shared__ float tile[];
+  int ji = 0;
+  while (ji + 1 < jobs.n && jobs.j[ji + 1].tile_start <= (int)blockIdx.x) ++ji;
+  const ConvPackJob& j = jobs.j[ji];
+  const int T = j.taps, pitch = 32 * T + 1, run = 32 * T;
+  const int t = blockIdx.x - j.tile_start;
+  const int tb = t % (j.B / 32), ta = t / (j.B / 32);
+  const int a0 = ta * 32, b0 = tb * 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = kThreads / 32;
+  if (j.mode != 2) {
+    for (int a = warp; a < 32; a += nwarp) {
+      const float* s = j.src + ((long long)(a0 + a) * j.B + b0) * T;
+      for (int e = lane; e < run; e += 32) tile[a * pitch + e] = __ldg(s + e);
+    }
+  } else {
+    for (int r = warp; r < 32 * T; r += nwarp) {   // r = a * T + tap
+      const int a = r / T, tap = r - a * T;
+      tile[a * pitch + lane * T + tap] = __ldg(j.src + ((long long)(a0 + a) * T + tap) * j.B + b0 + lane);
+    }
+  }
+  __syncthreads();
+  if (j.mode == 0) {
+    for (int r = warp; r < 32 * T; r += nwarp) {
+      const int a = r / T, tap = r - a * T;
+      j.dst[((long long)(a0 + a) * T + tap) * j.B + b0 + lane] = tile[a * pitch + lane * T + tap];
+    }
+  } else if (j.mode == 1) {
+    for (int r = warp; r < 32 * T; r += nwarp) {
+      const int b = r / T, ft = r - b * T;
+      j.dst[((long long)(b0 + b) * T + ft) * j.A + a0 + lane] = tile[lane * pitch + b * T + (T - 1 - ft)];
+    }
+  } else {
+    for (int a = warp; a < 32; a += nwarp) {
+      float* d = j.dst + ((long long)(a0 + a) * j.B + b0) * T;
+      for (int e = lane; e < run; e += 32) d[e] = accumulate ? d[e] + tile[a * pitch + e] : tile[a * pitch + e];
+    }
+  }
+}
+
 __global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
@@ -911,16 +959,27 @@ int vec_add(const float* a, const float* b, float* out, int n, cudaStream_t st) 
 }
 
 int pack_flush(PackBatch& b, cudaStream_t st) {
-  if (b.n == 0) return QEB_OK;
-  QEB_REQUIRE(b.n <= PackBatch::kMax, "pack_flush: too many jobs");
-  ProfScope prof("pack", st, 0.0, 8.0 * b.total);
-  PackJobsParam p;
-  for (int i = 0; i < b.n; ++i) p.j[i] = b.jobs[i];
-  p.n = b.n;
-  pack_multi_kernel<<<qeb_grid(b.total, kThreads), kThreads, 0, st>>>(p, b.total, b.accumulate);
-  QEB_LAUNCH_CHECK();
-  qeb_count_launch();
-  b.n = 0;
+  QEB_REQUIRE(b.n <= PackBatch::kMax && b.nc <= PackBatch::kMax, "pack_flush: too many jobs");
+  long long conv_elems = 0;
+  for (int i = 0; i < b.nc; ++i) conv_elems += (long long)b.cjobs[i].A * b.cjobs[i].B * b.cjobs[i].taps;
+  ProfScope prof("pack", st, 0.0, 8.0 * (b.total + conv_elems));
+  if (b.n > 0) {
+    PackJobsParam p;
+    for (int i = 0; i < b.n; ++i) p.j[i] = b.jobs[i];
+    p.n = b.n;
+    pack_multi_kernel<<<qeb_grid(b.total, kThreads), kThreads, 0, st>>>(p, b.total, b.accumulate);
+    QEB_LAUNCH_CHECK();
+    qeb_count_launch();
+  }
+  if (b.nc > 0) {
+    ConvPackJobsParam p;
+    for (int i = 0; i < b.nc; ++i) p.j[i] = b.cjobs[i];
+    p.n = b.nc;
+    conv_pack_kernel<<<b.ctiles, kThreads, (32 * (32 * 9 + 1)) * sizeof(float), st>>>(p, b.accumulate);
+    QEB_LAUNCH_CHECK();
+    qeb_count_launch();
+  }
+  b.n = b.nc = b.ctiles = 0;
   b.total = 0;
   b.accumulate = 0;
   return QEB_OK;
