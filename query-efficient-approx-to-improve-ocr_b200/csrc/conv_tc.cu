@@ -94,6 +94,7 @@ struct FpropParams {
   int vec_ok;                // 16-byte aligned rows: float4 stores allowed
   int a_map_per_tap;         // 1: tap selects the A tensor map (ConvTranspose dgrad sub-lattices), no coordinate shift
   long long* timeline;       // debugging aid (qeb_debug_set_timeline): per-CTA clock64 stamps, NULL in production
+  double* stats;             // fused BatchNorm statistics (TcEpilogue::bn_stats), NULL = off; never with split-K
 };
 
 struct TmapArray4 {
@@ -113,14 +114,17 @@ struct FpropCfg {
   static constexpr int kMaxStages = 8;
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kSmBudget = 224 * 1024;   // what resident CTAs share: 228 KB per SM minus 1 KB reserved per CTA and slack
-  static constexpr int smem_bytes(int stages) { return stages * kStageBytes + kEpiBytes + 1024 /*align slack*/ + 256 /*barriers*/; }
+  static constexpr int kStatBytes = 2 * BLOCK_N * 4;   // per-CTA (sum, sum of squares) accumulators of the fused BN statistics
+  static constexpr int smem_bytes(int stages) {
+    return stages * kStageBytes + kEpiBytes + kStatBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  }
   static int resident(long long n_tiles_total) {
     int r = (int)((n_tiles_total + kNumSMs - 1) / kNumSMs);
     return r > kCtasPerSm ? kCtasPerSm : (r < 1 ? 1 : r);
   }
   // every byte of shared memory the resident CTAs leave goes into ring stages
   static int pick_stages(long long n_tiles_total) {
-    int stages = (kSmBudget / resident(n_tiles_total) - 1280 - kEpiBytes) / kStageBytes;
+    int stages = (kSmBudget / resident(n_tiles_total) - 1280 - kEpiBytes - kStatBytes) / kStageBytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
     return stages;
@@ -195,7 +199,8 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
 // therefore transposed through 4 KB of shared memory (XOR-swizzled 16-byte slots, conflict-free both ways) so that a warp
 // instruction writes 4 complete 128-byte row segments. stg: this warp's staging area (the pipeline ring is idle by then).
 __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float (&v)[32], bool valid, int n, int h, int w,
-                                                    int ncol, bool split, float* stg, int lane, long long* tle = nullptr) {
+                                                    int ncol, bool split, float* stg, int lane, long long* tle = nullptr,
+                                                    float* cta_stats = nullptr, int c0_local = 0) {
   const int lim = min(32, p.n_total - ncol);
   if (lim < 32 || !p.vec_ok) {  // ragged / unaligned rows (warp-uniform): per-thread path
     if (valid) fprop_epilogue_store(p, v, n, h, w, ncol, split);
@@ -231,6 +236,7 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   __syncwarp();
   if (tle) tle[9] = clock64();
   const int rsub = lane >> 3, c16 = lane & 7;
+  float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + rsub;
@@ -252,6 +258,24 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
         }
         *reinterpret_cast<float4*>(d) = o;
       }
+      ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+      ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+    }
+  }
+  if (cta_stats) {
+    // fused BatchNorm statistics: this lane holds the sums of channels [4 c16, 4 c16 + 4) over its 8 rows; fold the four
+    // row groups of the warp (lanes c16, c16 + 8, ...) and add into the CTA's shared-memory accumulators
+#pragma unroll
+    for (int off = 8; off <= 16; off <<= 1) {
+      ssum.x += __shfl_xor_sync(FULL_MASK, ssum.x, off); ssum.y += __shfl_xor_sync(FULL_MASK, ssum.y, off);
+      ssum.z += __shfl_xor_sync(FULL_MASK, ssum.z, off); ssum.w += __shfl_xor_sync(FULL_MASK, ssum.w, off);
+      ssq.x += __shfl_xor_sync(FULL_MASK, ssq.x, off); ssq.y += __shfl_xor_sync(FULL_MASK, ssq.y, off);
+      ssq.z += __shfl_xor_sync(FULL_MASK, ssq.z, off); ssq.w += __shfl_xor_sync(FULL_MASK, ssq.w, off);
+    }
+    if (rsub == 0) {
+      float* a = cta_stats + 2 * (c0_local + c16 * 4);
+      atomicAdd(a + 0, ssum.x); atomicAdd(a + 1, ssq.x); atomicAdd(a + 2, ssum.y); atomicAdd(a + 3, ssq.y);
+      atomicAdd(a + 4, ssum.z); atomicAdd(a + 5, ssq.z); atomicAdd(a + 6, ssum.w); atomicAdd(a + 7, ssq.w);
     }
   }
   __syncwarp();
@@ -265,7 +289,8 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes + Cfg::kEpiBytes);
+  float* cta_stats = epi_stage + Cfg::kEpiBytes / 4;   // [BLOCK_N][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kStatBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]: accumulator a holds a finished tile
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]: the epilogue has read accumulator a
@@ -292,6 +317,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kThreads) cta_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -374,9 +400,29 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     int n_done = 0;
+    // fused BatchNorm statistics: the four epilogue warps add into shared-memory accumulators; they are flushed to global
+    // memory (one double atomic per channel and CTA) when the CTA moves to another N tile and at the end
+    int stat_n = -1;
+    auto flush_stats = [&](int tn) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) {
+        const int col = tn * BLOCK_N + c;
+        if (col < p.n_total) {
+          atomicAdd(p.stats + col, (double)cta_stats[2 * c]);
+          atomicAdd(p.stats + p.n_total + col, (double)cta_stats[2 * c + 1]);
+        }
+        cta_stats[2 * c] = 0.f;
+        cta_stats[2 * c + 1] = 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_done) {
       const int z = t / mn_tiles, rr = t - z * mn_tiles;
       const int tile_n = rr / p.m_tiles, tile_m = rr - tile_n * p.m_tiles;
+      if (p.stats && tile_n != stat_n) {
+        if (stat_n >= 0) flush_stats(stat_n);
+        stat_n = tile_n;
+      }
       const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
       const int w = tw * p.wt + ww, h = th * p.ht + hh, n = tn * p.nt + nn;
       const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
@@ -391,7 +437,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         long long* tle = (tl && threadIdx.x == 64 && n_done == 0 && c0 == 0) ? tl : nullptr;
         if (tle) tle[8] = clock64();
         const int ncol = tile_n * BLOCK_N + c0;  // first GEMM-N column of this chunk
-        if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle);
+        if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle, p.stats ? cta_stats : nullptr, c0);
         if (tle) tle[10] = clock64();
       }
       tc_fence_before();
@@ -400,6 +446,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (p.stats && stat_n >= 0) flush_stats(stat_n);
     if (tl && threadIdx.x == 64) tl[3] = n_done;
   }
   tc_fence_before();
@@ -475,6 +522,7 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.mode = mode; p.up_c = up_c > 0 ? up_c : 1; p.accumulate = ep.accumulate;
   p.a_map_per_tap = per_tap;
   p.timeline = g_timeline;
+  p.stats = nullptr;
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
   static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
@@ -498,6 +546,9 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.kb_per_split = qeb_cdiv(num_kb, splits);
   splits = qeb_cdiv(num_kb, p.kb_per_split);
   if (splits > 1) QEB_CUDA(cudaMemsetAsync(out.p, 0, (size_t)img_pixels(out) * n_total * sizeof(float), st));
+  // BatchNorm statistics of the output: fused into the epilogue unless the K range is split (partial sums) or rows are ragged
+  const bool stats_fused = ep.bn_stats && splits == 1 && p.vec_ok && n_total % 32 == 0 && mode == 0;
+  if (stats_fused) p.stats = ep.bn_stats;
   if (mode == 1) while (bn > p.up_c) bn >>= 1;
   QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "tc fprop: tile width %d must divide the up-conv channels %d", bn, p.up_c);
   const int n_tiles = qeb_cdiv(n_total, bn);
@@ -511,12 +562,15 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     int rc = make_tmap_f32(&tb, wpacked, 2, dims, str, box);
     if (rc) return rc;
   }
+  int rc;
   switch (bn) {
-    case 32: return launch_fprop<32>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
-    case 64: return launch_fprop<64>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
-    case 128: return launch_fprop<128>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
-    default: return launch_fprop<256>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
+    case 32: rc = launch_fprop<32>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+    case 64: rc = launch_fprop<64>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+    case 128: rc = launch_fprop<128>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+    default: rc = launch_fprop<256>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
   }
+  if (rc == QEB_OK && ep.bn_stats && !stats_fused) rc = bn_train_stats(out, ep.bn_stats, st);   // separate pass over the output
+  return rc;
 }
 
 void fprop_box(int h_out, int w_out, uint32_t* box) {

@@ -167,12 +167,12 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     TRY(fill_zero(p.bnstats, 2 * 2 * 512 * sizeof(double), st));
     TcEpilogue raw;
     raw.bias = params[P_C5B];
+    raw.bn_stats = p.bnstats;             // BatchNorm statistics out of the conv epilogue
     TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, Z5, raw, st));
-    TRY(bn_train_stats(Z5, p.bnstats, st));
     TRY(bn_train_finalize_apply(Z5, p.bnstats, bn1, p.scsh5, 1, A5, st));
     raw.bias = params[P_C6B];
+    raw.bn_stats = p.bnstats + 1024;
     TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, Z6, raw, st));
-    TRY(bn_train_stats(Z6, p.bnstats + 1024, st));
     TRY(bn_train_finalize_apply(Z6, p.bnstats + 1024, bn2, p.scsh6, 1, A6f, st));
   } else {
     // frozen statistics: y = relu(conv*scale + shift), shift folds the conv bias

@@ -145,9 +145,9 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   }
   const float* wp = c.p->wp[unit];
   if (c.bn_train) {
-    const TcEpilogue raw;
+    TcEpilogue raw;
+    raw.bn_stats = c.p->bnstats + (size_t)unit * 1024;   // per-channel sums come out of the conv epilogue
     TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
-    TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
     return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st);
   }
   TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));

@@ -34,6 +34,9 @@ struct TcEpilogue {
   int relu = 0;
   const Img* mask = nullptr;     // v = (mask(n,h,w,c) > 0) ? v : 0   (ReLU backward of the layer below, fused)
   int accumulate = 0;            // out += v
+  double* bn_stats = nullptr;    // train-mode BatchNorm of the layer above: per-channel sum (first n_total doubles) and sum of
+                                 // squares (next n_total) of the stored values are ADDED to this zero-filled buffer - the
+                                 // separate statistics pass over the conv output disappears
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
