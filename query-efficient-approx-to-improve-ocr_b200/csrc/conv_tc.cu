@@ -94,7 +94,8 @@ struct FpropParams {
   int vec_ok;                // 16-byte aligned rows: float4 stores allowed
   int a_map_per_tap;         // 1: tap selects the A tensor map (ConvTranspose dgrad sub-lattices), no coordinate shift
   long long* timeline;       // debugging aid (qeb_debug_set_timeline): per-CTA clock64 stamps, NULL in production
-  double* stats;             // fused BatchNorm statistics (TcEpilogue::bn_stats), NULL = off; never with split-K
+  double* stats;             // fused BatchNorm statistics (TcEpilogue::bn_stats) or backward reductions (bn_red), NULL = off
+  const float* bn_scsh;      // non-NULL: `mask` holds z of the layer below; mask = z*scale + shift > 0, second sum = g*xhat
 };
 
 struct TmapArray4 {
@@ -237,6 +238,12 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   if (tle) tle[9] = clock64();
   const int rsub = lane >> 3, c16 = lane & 7;
   float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 bsc, bsh, bmu, bis;   // BatchNorm constants of this lane's four channels (fused backward reductions)
+  if (p.bn_scsh) {
+    const float* c4 = p.bn_scsh + ncol + c16 * 4;
+    bsc = __ldg(reinterpret_cast<const float4*>(c4)); bsh = __ldg(reinterpret_cast<const float4*>(c4 + p.n_total));
+    bmu = __ldg(reinterpret_cast<const float4*>(c4 + 2 * p.n_total)); bis = __ldg(reinterpret_cast<const float4*>(c4 + 3 * p.n_total));
+  }
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + rsub;
@@ -245,8 +252,13 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
     const float* m = reinterpret_cast<const float*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(mk), row));
     if (d) {
       d += c16 * 4;
+      float4 xh = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m) {
-        const float4 q4 = __ldg(reinterpret_cast<const float4*>(m) + c16);
+        float4 q4 = __ldg(reinterpret_cast<const float4*>(m) + c16);
+        if (p.bn_scsh) {   // q4 = z of the layer below: xhat for the reduction, relu(bn(z)) > 0 as the mask
+          xh = make_float4((q4.x - bmu.x) * bis.x, (q4.y - bmu.y) * bis.y, (q4.z - bmu.z) * bis.z, (q4.w - bmu.w) * bis.w);
+          q4 = make_float4(fmaf(q4.x, bsc.x, bsh.x), fmaf(q4.y, bsc.y, bsh.y), fmaf(q4.z, bsc.z, bsh.z), fmaf(q4.w, bsc.w, bsh.w));
+        }
         o.x = q4.x > 0.f ? o.x : 0.f; o.y = q4.y > 0.f ? o.y : 0.f; o.z = q4.z > 0.f ? o.z : 0.f; o.w = q4.w > 0.f ? o.w : 0.f;
       }
       if (split) {
@@ -259,7 +271,8 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
         *reinterpret_cast<float4*>(d) = o;
       }
       ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
-      ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y); ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+      if (!p.bn_scsh) xh = o;   // forward statistics: second sum = sum of squares
+      ssq.x = fmaf(o.x, xh.x, ssq.x); ssq.y = fmaf(o.y, xh.y, ssq.y); ssq.z = fmaf(o.z, xh.z, ssq.z); ssq.w = fmaf(o.w, xh.w, ssq.w);
     }
   }
   if (cta_stats) {
@@ -523,6 +536,7 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.a_map_per_tap = per_tap;
   p.timeline = g_timeline;
   p.stats = nullptr;
+  p.bn_scsh = nullptr;
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
   static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
@@ -549,6 +563,15 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   // BatchNorm statistics of the output: fused into the epilogue unless the K range is split (partial sums) or rows are ragged
   const bool stats_fused = ep.bn_stats && splits == 1 && p.vec_ok && n_total % 32 == 0 && mode == 0;
   if (stats_fused) p.stats = ep.bn_stats;
+  // BatchNorm-backward reductions of the layer below: same accumulators, the mask source is that layer's z
+  if (ep.bn_red && ep.bn_z && ep.bn_scsh && !ep.bn_stats && !ep.mask && splits == 1 && p.vec_ok && n_total % 32 == 0 && mode == 0 &&
+      ep.bn_z->c == n_total && ((uintptr_t)ep.bn_z->p & 15) == 0 && ep.bn_z->sn % 4 == 0 && ep.bn_z->sh % 4 == 0 && ep.bn_z->sw % 4 == 0 &&
+      ((uintptr_t)ep.bn_scsh & 15) == 0) {
+    p.mask = ep.bn_z->p; p.msn = ep.bn_z->sn; p.msh = ep.bn_z->sh; p.msw = ep.bn_z->sw;
+    p.bn_scsh = ep.bn_scsh;
+    p.stats = ep.bn_red;
+    if (ep.bn_red_fused) *ep.bn_red_fused = 1;
+  }
   if (mode == 1) while (bn > p.up_c) bn >>= 1;
   QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "tc fprop: tile width %d must divide the up-conv channels %d", bn, p.up_c);
   const int n_tiles = qeb_cdiv(n_total, bn);

@@ -114,7 +114,23 @@ struct Ctx {
   int bn_train;
   cudaStream_t st;
   SideStream* ss;  // backward only: weight / bias gradients run beside the input-gradient chain
+  int* red_done;   // backward only, [kUnits]: 1 = the BatchNorm-backward reductions of that unit were produced by the kernel
+                   // that wrote its output gradient (fused epilogue), the separate reduction pass is skipped
 };
+
+// epilogue of an input-gradient kernel whose output is the gradient at the OUTPUT of conv unit `unit` (train-mode BatchNorm):
+// mask with relu(bn(z)) > 0 and accumulate that unit's BatchNorm-backward reductions
+TcEpilogue grad_into_unit(const Ctx& c, int unit, const Img* z) {
+  TcEpilogue e;
+  static const bool fuse = !(getenv("QEB_BN_RED_FUSE") && atoi(getenv("QEB_BN_RED_FUSE")) == 0);
+  if (fuse && c.bn_train && c.red_done) {
+    e.bn_z = z;
+    e.bn_scsh = c.p->scsh + (size_t)unit * 4 * 512;
+    e.bn_red = c.p->bnred + (size_t)unit * 1024;
+    e.bn_red_fused = &c.red_done[unit];
+  }
+  return e;
+}
 
 BnParams bn_of(const Ctx& c, int block, int which) {
   BnParams b;
@@ -158,14 +174,17 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
 
 // backward of one unit. g: gradient at the unit's output (overwritten with the gradient at the conv output);
 // din: where the gradient at the unit's input goes (nullptr: not needed).
-int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const Img& g, const Img* din) {
+// z_lower: z of the conv unit that produced `in` (NULL: `in` is not the output of a conv unit, e.g. a pooled or concatenated
+// tensor) - its BatchNorm-backward reductions are then fused into this unit's input-gradient kernel.
+int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const Img& g, const Img* din,
+             const Img* z_lower = nullptr) {
   const int unit = block * 2 + which;
   const float* w = c.params[block * 6 + which * 3];
   float* const* gr = c.grads + block * 6 + which * 3;
   const float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
   if (c.bn_train) {
     double* red = c.p->bnred + (size_t)unit * 1024;
-    TRY(bn_bwd_reduce(z, g, scsh, 1, red, c.st));
+    if (!(c.red_done && c.red_done[unit])) TRY(bn_bwd_reduce(z, g, scsh, 1, red, c.st));
     TRY(bn_bwd_apply_train(z, g, scsh, 1, red, nullptr, g, gr[1], gr[2], c.st));
   } else {  // frozen statistics: the mask and xhat come from the layer output
     double* red = gr[1] ? c.p->bnred + (size_t)unit * 1024 : nullptr;
@@ -180,8 +199,8 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   }
   if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.ss->s()));
   if (din) {
-    const TcEpilogue plain;
-    TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, plain, c.st));
+    const TcEpilogue e = (which == 1 && z_lower) ? grad_into_unit(c, unit - 1, z_lower) : TcEpilogue();
+    TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, e, c.st));
   }
   return QEB_OK;
 }
@@ -206,6 +225,7 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   Ctx c;
   c.params = params; c.buffers = buffers; c.grads = nullptr; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
   c.ss = nullptr;
+  c.red_done = nullptr;
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
   {  // every weight re-layout of this pass in one launch
     PackBatch pk;
@@ -264,6 +284,8 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
   SideStream ss;
   TRY(ss.init(c.st));
   c.ss = &ss;
+  int red_done[kUnits] = {0};
+  c.red_done = red_done;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
   TRY(fill_zero(p.dwp[0], p.dwp_bytes, c.st));
   {
@@ -294,7 +316,7 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
     Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
     Img g = img_nhwc(p.sC[i], B, p.h[i], p.w[i], C), ga1 = img_nhwc(p.sB[i], B, p.h[i], p.w[i], C);
     Img gcat = img_nhwc(p.sA[i], B, p.h[i], p.w[i], 2 * C);
-    TRY(unit_bwd(c, blk, 1, a1, z2, out, g, &ga1));
+    TRY(unit_bwd(c, blk, 1, a1, z2, out, g, &ga1, &z1));
     TRY(unit_bwd(c, blk, 0, cat, z1, a1, ga1, &gcat));
     // up-convolution: dU = gcat[:, :C]
     Img dU = img_slice(gcat, 0, C);
@@ -303,8 +325,11 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
     if (grads[P_UP + up * 2 + 1]) TRY(colsum_acc(dU, grads[P_UP + up * 2 + 1], ss.s()));
     if (grads[P_UP + up * 2]) TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], ss.s()));
     Img gbelow = img_nhwc(p.sC[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C);
-    const TcEpilogue plain;
-    TRY(tc_convT_dgrad(dU, p.wupd[up], gbelow, plain, c.st));
+    // `below` is the output of the second conv unit of the block one level down: fuse its BatchNorm-backward reductions
+    const int blk_below = i < 3 ? 5 + (3 - (i + 1)) : 4;
+    const Img z_below = img_nhwc(i < 3 ? p.dz2[i + 1] : p.ez2[4], B, p.h[i + 1], p.w[i + 1], 2 * C);
+    const TcEpilogue e = grad_into_unit(c, blk_below * 2 + 1, &z_below);
+    TRY(tc_convT_dgrad(dU, p.wupd[up], gbelow, e, c.st));
   }
   TRY(ss.join());  // the encoder phase re-uses the decoder phase's gradient buffers
   for (int i = 4; i >= 0; --i) {  // bottleneck, then encoder blocks
@@ -319,7 +344,7 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
       Img skip = img_nhwc(p.sA[i] + C, B, p.h[i], p.w[i], C, 2 * C);
       TRY(maxpool_bwd(out, gpool, 2, 2, 0, nullptr, &skip, g, c.st));
     }
-    TRY(unit_bwd(c, i, 1, a1, z2, out, g, &ga1));
+    TRY(unit_bwd(c, i, 1, a1, z2, out, g, &ga1, &z1));
     if (i > 0) {
       Img in = img_nhwc(p.pool[i - 1], B, p.h[i], p.w[i], p.C[i - 1]);
       Img gin = img_nhwc(p.sA[i], B, p.h[i], p.w[i], p.C[i - 1]);

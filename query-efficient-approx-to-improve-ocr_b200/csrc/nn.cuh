@@ -37,6 +37,14 @@ struct TcEpilogue {
   double* bn_stats = nullptr;    // train-mode BatchNorm of the layer above: per-channel sum (first n_total doubles) and sum of
                                  // squares (next n_total) of the stored values are ADDED to this zero-filled buffer - the
                                  // separate statistics pass over the conv output disappears
+  // Input-gradient kernels whose output is the gradient at relu(bn(z)) of the layer below (train-mode BatchNorm): the ReLU
+  // mask (z*scale + shift > 0) is applied to the stored gradient and the two reductions of the BatchNorm backward
+  // (sum g, sum g*xhat per channel) are ADDED to bn_red - the separate bn_bwd_reduce pass disappears. scsh = [scale | shift |
+  // mean | invstd] (4 x n_total floats). *bn_red_fused is set to 1 when the kernel did it (not with split-K / ragged rows).
+  const Img* bn_z = nullptr;
+  const float* bn_scsh = nullptr;
+  double* bn_red = nullptr;
+  int* bn_red_fused = nullptr;
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
