@@ -217,6 +217,7 @@ def run():
     ap.add_argument("--impl", default="qeb", choices=["qeb", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true", help="profiling runs: only the graph arm (variants are null)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "qeb" else max(args.warmup, 1)
     rank = int(os.environ.get("RANK", "0"))
@@ -309,25 +310,27 @@ def run():
         return float(ms) / steps, (float(out.detach()) if torch.is_tensor(out) else out)
 
     # ---- eager arm first (it re-allocates .grad every step; the graph below pins them, so eager runs must precede it)
-    for _ in range(args.warmup):
-        step_device()
-    ms_eager, _ = timed(step_device, args.steps)
-    for _ in range(2):
-        step_e2e()
-    ms_e2e_eager, _ = timed(step_e2e, args.steps)
-    # variant (reported beside the headline, not instead of it): the surrogate's parameter gradients are computed and
-    # thrown away by the reference in this phase (train_nn_area.py:280,286 - only optimizer_prep steps); freezing them
-    # with requires_grad_(False) is a one-line change on the caller's side that skips those kernels
-    for p_ in crnn.parameters():
-        p_.requires_grad_(False)
-    for _ in range(2):
-        step_device()
-    ms_frozen, _ = timed(step_device, args.steps)
-    for p_ in crnn.parameters():
-        p_.requires_grad_(True)
+    ms_eager = ms_e2e_eager = ms_frozen = None
+    if not args.skip_eager:
+        for _ in range(args.warmup):
+            step_device()
+        ms_eager, _ = timed(step_device, args.steps)
+        for _ in range(2):
+            step_e2e()
+        ms_e2e_eager, _ = timed(step_e2e, args.steps)
+        # variant (reported beside the headline, not instead of it): the surrogate's parameter gradients are computed and
+        # thrown away by the reference in this phase (train_nn_area.py:280,286 - only optimizer_prep steps); freezing them
+        # with requires_grad_(False) is a one-line change on the caller's side that skips those kernels
+        for p_ in crnn.parameters():
+            p_.requires_grad_(False)
+        for _ in range(2):
+            step_device()
+        ms_frozen, _ = timed(step_device, args.steps)
+        for p_ in crnn.parameters():
+            p_.requires_grad_(True)
 
     roofline, kernels = None, None
-    if not args.skip_profile:
+    if not args.skip_profile and not args.skip_eager:
         _lib.prof_enable(True)
         torch.cuda.synchronize()
         _lib.prof_report()  # drop anything recorded so far
@@ -435,11 +438,12 @@ def run():
                 "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
                 "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": last_loss,
-                "variants": {"eager_modules": {"value": BATCH * world / (ms_eager / 1e3), "ms_per_step": ms_eager,
-                                               "e2e_value": BATCH * world / (ms_e2e_eager / 1e3), "e2e_ms_per_step": ms_e2e_eager,
-                                               "note": "the mirror modules called eagerly (no CUDA graph), as an unmodified trainer does"},
-                             "surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
-                                                               "note": "eager; skips the CRNN weight gradients the reference computes and discards"}},
+                "variants": None if args.skip_eager else {
+                    "eager_modules": {"value": BATCH * world / (ms_eager / 1e3), "ms_per_step": ms_eager,
+                                      "e2e_value": BATCH * world / (ms_e2e_eager / 1e3), "e2e_ms_per_step": ms_e2e_eager,
+                                      "note": "the mirror modules called eagerly (no CUDA graph), as an unmodified trainer does"},
+                    "surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
+                                                      "note": "eager; skips the CRNN weight gradients the reference computes and discards"}},
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
     if world > 1:
         dist.destroy_process_group()
