@@ -91,10 +91,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_alpha_kernel(CtcArgs 
     else if (s == 1 && S > 1) al[j] = row[cls[j]];
     if (s < S) la_out[s] = al[j];
   }
+  // The recursion is a chain of T dependent steps of one warp: the row of log-probs of step t + 1 is loaded into registers
+  // while step t is computed, so that the ~1 us global-load latency is off the chain (V <= 128; wider rows load in place).
+  const bool pf = a.V <= 4 * 32;
+  float nxt[4] = {0.f, 0.f, 0.f, 0.f};
+  if (pf && Tb > 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (lane + 32 * k < a.V) nxt[k] = lp[a.st_t + lane + 32 * k];
+  }
   for (int t = 1; t < Tb; ++t) {
     __syncwarp();
     const float* lpt = lp + (long long)t * a.st_t;
-    for (int c = lane; c < a.V; c += 32) row[c] = lpt[c];
+    if (pf) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < a.V) row[lane + 32 * k] = nxt[k];
+      if (t + 1 < Tb) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < a.V) nxt[k] = lpt[a.st_t + lane + 32 * k];
+      }
+    } else {
+      for (int c = lane; c < a.V; c += 32) row[c] = lpt[c];
+    }
     __syncwarp();
     float nw[SPL];
 #pragma unroll
@@ -191,11 +211,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_beta_grad_kernel(CtcB
     be[j] = neg_inf();
   }
 
+  // as in ctc_alpha_kernel: the log-prob row and the alpha values of step t - 1 are loaded while step t is computed
+  const bool pf = a.V <= 4 * 32;
+  float nxt[4] = {0.f, 0.f, 0.f, 0.f}, la_nxt[SPL];
+  {
+    const float* lpt = lp + (long long)(Tb - 1) * a.st_t;
+    if (pf) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < a.V) nxt[k] = lpt[lane + 32 * k];
+    }
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) la_nxt[j] = (j * 32 + lane < S) ? la_in[(long long)(Tb - 1) * a.S + j * 32 + lane] : neg_inf();
+  }
   for (int t = Tb - 1; t >= 0; --t) {
     __syncwarp();
     const float* lpt = lp + (long long)t * a.st_t;
+    float la_cur[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) la_cur[j] = la_nxt[j];
+    if (pf) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < a.V) row[lane + 32 * k] = nxt[k];
+      if (t > 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (lane + 32 * k < a.V) nxt[k] = lpt[lane + 32 * k - a.st_t];
+      }
+    } else {
+      for (int c = lane; c < a.V; c += 32) row[c] = lpt[c];
+    }
+    if (t > 0) {
+#pragma unroll
+      for (int j = 0; j < SPL; ++j)
+        if (j * 32 + lane < S) la_nxt[j] = la_in[(long long)(t - 1) * a.S + j * 32 + lane];
+    }
     for (int c = lane; c < a.V; c += 32) {
-      row[c] = lpt[c];
       accm[c] = neg_inf();
       accs[c] = 0.f;
     }
@@ -234,7 +286,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_beta_grad_kernel(CtcB
       const int s = j * 32 + lane;
       lab[j] = neg_inf();
       if (s < S) {
-        lab[j] = la_in[(long long)t * a.S + s] + be[j];
+        lab[j] = la_cur[j] + be[j];
         if (lab[j] != neg_inf() && lab[j] == lab[j]) atomic_max_float(&accm[cls[j]], lab[j]);
       }
     }
