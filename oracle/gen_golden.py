@@ -13,6 +13,7 @@ The fixtures pin the Python-level reference functions on the hot path (the refer
   tracking.json / tracking.npz  tracking_utils.generate_ctc_target_batches / weighted_ctc_loss (both weighting modes,
                   value and gradient at the scores) and LevenshteinWeightGenerator.gen_weights
                                                                tracking_utils.py:34-75, label_tracking/tracking_methods.py:72-101
+  pruning.json    pruning/methods.topk on the reference's own artifacts (pruning/cer_artifacts/cers_pos*.json)
 """
 import json
 import os
@@ -378,6 +379,28 @@ def gen_tracking(ref):
         json.dump(out_js, f)
 
 
+def gen_pruning(ref):
+    """The reference's own pruning artifacts (pruning/cer_artifacts/*.json, written by pruning/prune_dataset.py with
+    pruning/methods.topk): input name -> mean CER and the kept names, in order, at 10 % and 50 % pruning. These ARE golden
+    vectors held by the reference (data files); the live function is called as well."""
+    import importlib
+    import sys
+    import types
+    art = os.path.join(refload.REFERENCE_ROOT, "pruning", "cer_artifacts")
+    cers = json.load(open(os.path.join(art, "cers_pos.json")))
+    out = {"cers": cers}
+    sys.modules.setdefault("apricot", types.SimpleNamespace(FacilityLocationSelection=None))   # methods.py imports it at the top
+    sys.path.insert(0, os.path.join(refload.REFERENCE_ROOT, "pruning"))
+    methods = importlib.import_module("methods")
+    for pct in (10, 50):
+        kept = json.load(open(os.path.join(art, f"cers_pos_topk_{pct}.json")))
+        live = methods.topk(cers, len(kept))
+        assert list(live.keys()) == list(kept.keys()) and live == kept
+        out[f"topk_{pct}_names"] = list(kept.keys())
+    with open(os.path.join(OUT, "pruning.json"), "w") as f:
+        json.dump(out, f)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = refload.load()
@@ -391,6 +414,7 @@ def main():
     gen_crnn(ref)
     gen_unet(ref)
     gen_tracking(ref)
+    gen_pruning(ref)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

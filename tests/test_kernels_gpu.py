@@ -382,3 +382,19 @@ def test_log_softmax(m):
     yr = torch.log_softmax(xr, 2)
     (yr * w.cpu()).sum().backward()
     assert torch.allclose(y.cpu(), yr, atol=1e-5) and torch.allclose(x.grad.cpu(), xr.grad, atol=1e-4)
+
+
+def test_pruning_topk_matches_reference_artifacts(m):
+    """pruning/methods.topk (8(f).4) on the reference's own artifacts: the kept image names, in order, at 10 % and 50 %
+    pruning of the 3,676-image POS CER table (golden vectors held by the reference, pruning/cer_artifacts/)."""
+    from qeb_b200.mirror.pruning import methods
+    g = json.load(open(os.path.join(GOLDEN, "pruning.json")))
+    for pct in (10, 50):
+        want = g[f"topk_{pct}_names"]
+        got = methods.topk(g["cers"], len(want))
+        assert list(got.keys()) == want
+        assert all(got[n] == g["cers"][n] for n in want)
+    assert methods.topk(g["cers"], 0) == {}
+    assert len(methods.topk(g["cers"], 10 ** 6)) == len(g["cers"])
+    with pytest.raises(Exception):
+        methods.topk({"a": 0.1, "b": 0.1 + 1e-12}, 1)

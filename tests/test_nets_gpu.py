@@ -532,3 +532,39 @@ def test_graphed_step_matches_eager(q):
             assert 0.85 < float(p_.grad.norm() / g_.norm().clamp_min(1e-30)) < 1.15
     with pytest.raises(Exception):
         tg.load(torch.ones(B * 40, dtype=torch.int32), il, torch.full((B,), 40, dtype=torch.int32))
+
+
+def test_validation_batch_matches_reference_loop(q):
+    """mirror/eval_ops.validation_batch (8(f).2) against the statements of the reference's validation loop
+    (train_nn_area.py:327-341) evaluated with the oracle: same strings, same counts, bit-identical CER sums, loss within
+    the CTC tolerance."""
+    from oracle import pyoracle as po
+    from qeb_b200.mirror import eval_ops
+    torch.manual_seed(5)
+    B = 24
+    prep, crnn = q.UNet().to(DEV).eval(), q.CRNN(95, False).to(DEV).eval()
+    c2i = {c: i for i, c in enumerate(CHAR_SET)}
+    i2c = {i: c for i, c in enumerate(CHAR_SET)}
+    x = torch.rand(B, 1, 32, 128, device=DEV)
+    import random
+    rng = random.Random(1)
+    labels = ["".join(rng.choice(CHAR_SET[1:]) for _ in range(rng.randint(1, 9))) for _ in range(B)]
+    fake_ocr = lambda imgs: [l[:-1] + "x" if i % 3 == 0 else l for i, l in enumerate(labels)]   # noqa: E731
+    out = eval_ops.validation_batch(prep, crnn, x, labels, c2i, i2c, ocr=fake_ocr)
+    # the reference's statements on the oracle
+    with torch.no_grad():
+        img_r = nn_oracle.unet_forward(copy.deepcopy(prep).cpu(), x.cpu())
+        sc_r = nn_oracle.crnn_forward(copy.deepcopy(crnn).cpu(), img_r)
+        y, ys = eval_ops.encode_labels(labels, c2i)
+        loss_r = float(torch.nn.CTCLoss()(sc_r, y, torch.full((B,), 31, dtype=torch.int32), ys) +
+                       torch.nn.MSELoss()(img_r, torch.ones_like(img_r)))
+    assert abs(out["loss"] - loss_r) <= 2e-3 * abs(loss_r)
+    # decode + scoring are integer work: judged on the GPU's own scores so that tf32 noise cannot flip an argmax
+    scores = crnn(prep(x))
+    preds_r = po.pred_to_string(scores.detach().cpu().numpy(), i2c)
+    assert out["preds"] == preds_r
+    ocr_labels = fake_ocr(None)
+    assert (out["crt"], out["cer"]) == po.compare_labels(preds_r, labels)
+    assert (out["ocr_crt"], out["ocr_cer"]) == po.compare_labels(ocr_labels, labels)
+    assert (out["matching_crt"], out["matching_cer"]) == po.compare_labels(preds_r, ocr_labels)
+    assert out["ocr_crt"] == B - len(range(0, B, 3))

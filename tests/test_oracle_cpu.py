@@ -201,3 +201,16 @@ def test_nn_oracle_unet_matches_golden():
     m.eval()
     with torch.no_grad():
         np.testing.assert_allclose(nn_oracle.unet_forward(m, x).numpy(), g["y_eval"], atol=2e-6)
+
+
+def test_topk_oracle_against_reference_artifacts():
+    """The one result the reference itself holds for the selection path: pruning/cer_artifacts/
+    cers_pos_topk_*.json = methods.topk = stable descending sort. The oracle's top-k restatement reproduces the kept
+    names in order (fixture copied from the reference's data files by oracle/gen_golden.py gen_pruning)."""
+    g = json.load(open(os.path.join(GOLDEN, "pruning.json")))
+    names = list(g["cers"].keys())
+    v32 = np.array(list(g["cers"].values()), dtype=np.float32)
+    for pct in (10, 50):
+        want = g[f"topk_{pct}_names"]
+        idx = po.topk_query(v32, len(want))
+        assert [names[i] for i in idx] == want
