@@ -96,6 +96,11 @@ int qeb_cer_range_segmented(const float* vals, const int* seg_off, const int* se
 int qeb_gauss_jitter(const float* img, const float* sigma, float mean, float coef, const float* noise_in,
                      unsigned long long seed, long long n_img, int hw, float* out, float* noise_out, void* stream);
 
+/* ---- OCR hand-off: fp32 images in [0,1] -> the uint8 pixels ToPILImage gives the OCR engine for a float tensor
+ * (pic.mul(255).byte(): fp32 multiply, truncation), ocr_helper/tess_helper.py:20-24, eocr_helper.py. x, out: n elements,
+ * 16-byte aligned; the caller copies `out` to pinned host memory with its own asynchronous D2H. */
+int qeb_to_uint8(const float* x, long long n, unsigned char* out, void* stream);
+
 /* ---- crop + centre-pad with 1.0: get_text_stack / padder utils.py:118-141 -------------------------------------
  * img (H,W) fp32; boxes (n,4) int32 x_min,y_min,x_max,y_max; out (n,oh,ow). scatter is the adjoint (atomic adds into
  * a zero-initialised gimg (H,W)). */

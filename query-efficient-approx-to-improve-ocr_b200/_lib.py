@@ -29,6 +29,7 @@ SIGNATURES = {
     "qeb_cer_topk_segmented": (I, [P, P, P, P, I, P, P]),
     "qeb_cer_range_segmented": (I, [P, P, P, P, P, I, P, P, P, P]),
     "qeb_gauss_jitter": (I, [P, P, F, F, P, ULL, LL, I, P, P, P]),
+    "qeb_to_uint8": (I, [P, LL, P, P]),
     "qeb_crop_pad_gather": (I, [P, I, I, P, I, I, I, P, P]),
     "qeb_crop_pad_scatter": (I, [P, I, I, P, I, I, I, P, P]),
     "qeb_pack_weight": (I, [P, P, I, I, I, I, I, P]),

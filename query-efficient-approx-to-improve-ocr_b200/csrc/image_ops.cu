@@ -157,3 +157,38 @@ QEB_API int qeb_crop_pad_scatter(const float* gout, int H, int W, const int* box
   qeb_count_launch();
   return QEB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// OCR hand-off: fp32 images in [0,1] -> the uint8 pixels torchvision's ToPILImage produces for a float tensor
+// (pic.mul(255).byte(): multiply in fp32, truncate), ocr_helper/tess_helper.py:20-24. 16 pixels per thread.
+namespace {
+__global__ void to_uint8_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+  if (i + 16 <= n) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + i) + q);
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      uint32_t pk = 0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk |= (uint32_t)(int)fminf(fmaxf(f[e] * 255.f, 0.f), 255.f) << (8 * e);
+      w[q] = pk;
+    }
+    *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = (uint8_t)(int)fminf(fmaxf(x[j] * 255.f, 0.f), 255.f);
+  }
+}
+}  // namespace
+
+QEB_API int qeb_to_uint8(const float* x, long long n, unsigned char* out, void* stream) {
+  QEB_REQUIRE(x && out && n >= 0, "to_uint8: bad arguments");
+  QEB_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)out & 15) == 0, "to_uint8: 16-byte aligned buffers");
+  if (n == 0) return QEB_OK;
+  ProfScope prof("to_uint8", (cudaStream_t)stream, 0.0, 5.0 * n);
+  to_uint8_kernel<<<qeb_grid(qeb_cdiv(n, 16), 256), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}

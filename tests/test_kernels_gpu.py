@@ -398,3 +398,35 @@ def test_pruning_topk_matches_reference_artifacts(m):
     assert len(methods.topk(g["cers"], 10 ** 6)) == len(g["cers"])
     with pytest.raises(Exception):
         methods.topk({"a": 0.1, "b": 0.1 + 1e-12}, 1)
+
+
+def test_ocr_handoff_uint8_pixels_and_ring(m):
+    """8(f).3: the device conversion gives the pixels ToPILImage(float tensor) gives (pic.mul(255).byte(), tess_helper.py:22),
+    bit for bit, and the pinned ring returns them per ticket."""
+    from qeb_b200.mirror import ocr_handoff as oh
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(37, 1, 32, 128, generator=g)
+    x[0, 0, 0, :8] = torch.tensor([0.0, 1.0, 0.5, 1 / 255, 254.999 / 255, 0.999999, 1e-9, 0.003921569])
+    want = x.mul(255).byte().numpy().reshape(37, 32, 128)
+    xd = x.to(DEV)
+    assert np.array_equal(oh.to_uint8(xd).cpu().numpy().reshape(37, 32, 128), want)
+    odd = torch.rand(3, 1, 5, 7, generator=g)                    # 105 elements: scalar tail path
+    assert np.array_equal(oh.to_uint8(odd.to(DEV)).cpu().numpy(), odd.mul(255).byte().numpy())
+    ring = oh.OcrHandoff(depth=2)
+    t0 = ring.submit(xd)
+    t1 = ring.submit(1.0 - xd)
+    assert np.array_equal(ring.fetch(t0), want)
+    assert np.array_equal(ring.fetch(t1), (1.0 - x).mul(255).byte().numpy().reshape(37, 32, 128))
+    seen = []
+    labels = ring.labels(t1, lambda u8: seen.append(u8.shape) or ["x"] * u8.shape[0])
+    assert labels == ["x"] * 37 and seen == [(37, 32, 128)]
+    ring.submit(xd)
+    with pytest.raises(Exception):
+        ring.fetch(t0)                                           # overwritten: two submits later
+
+    class FakeHelper:                                            # the reference helper's contract: CPU float tensor in
+        def get_labels(self, imgs):
+            self.pixels = imgs.mul(255).byte().numpy()[:, 0]
+            return ["ok"] * imgs.shape[0]
+    h = FakeHelper()
+    assert oh.OcrFromUint8(h)(want) == ["ok"] * 37 and np.array_equal(h.pixels, want)
