@@ -15,12 +15,13 @@
 // global). Pipelines: smem full/empty mbarriers (kStages deep), one TMEM-full barrier.
 #include "tc_common.cuh"
 #include "nn.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace tc {
 
-int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, int swizzle_32b_atom) {
+static int make_tmap_any(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                         const uint32_t* box, CUtensorMapDataType dtype, CUtensorMapSwizzle swz) {
   typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -44,10 +45,8 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     qeb_set_error("tensor map base %p not 16-byte aligned", base);
     return QEB_ERR_INVALID;
   }
-  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, estr,
-                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = encode(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     qeb_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
                   (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0), (unsigned long long)(rank > 2 ? d[2] : 0),
@@ -55,6 +54,18 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
     return QEB_ERR_CUDA;
   }
   return QEB_OK;
+}
+
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, int swizzle_32b_atom) {
+  return make_tmap_any(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
+                       swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+int make_tmap_16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int row_bytes) {
+  return make_tmap_any(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                       row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 }  // namespace tc
@@ -96,15 +107,20 @@ struct FpropParams {
   long long* timeline;       // debugging aid (qeb_debug_set_timeline): per-CTA clock64 stamps, NULL in production
   double* stats;             // fused BatchNorm statistics (TcEpilogue::bn_stats) or backward reductions (bn_red), NULL = off
   const float* bn_scsh;      // non-NULL: `mask` holds z of the layer below; mask = z*scale + shift > 0, second sum = g*xhat
+  int kblk;                  // operand elements per K block: 32 (tf32, or fp16 in 64-byte rows) or 64 (fp16 in 128-byte rows)
+  __half* out16;             // optional fp16 shadow of the output (same element layout as `out`): the next layer's operand
 };
 
 struct TmapArray4 {
   CUtensorMap m[4];
 };
 
-template <int BLOCK_N>
+// ROWB: bytes per operand row in shared memory = one swizzle span: 128 (32 tf32 or 64 fp16) or 64 (32 fp16, layers with
+// 32 input channels)
+template <int BLOCK_N, int ROWB = 128>
 struct FpropCfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 4;
+  static constexpr int kABytes = kBlockM * ROWB;
+  static constexpr int kBBytes = BLOCK_N * ROWB;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBytes = 4 * 4096;   // per epilogue warp: 32 x 32 floats for the store transposition
   // The kernel is persistent: a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the TMA ring running
@@ -269,6 +285,13 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         *reinterpret_cast<float4*>(d) = o;
+        if (p.out16) {   // fp16 shadow, same element offset
+          const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(p.out16 + (d - p.out)) = pk;
+        }
       }
       ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
       if (!p.bn_scsh) xh = o;   // forward statistics: second sum = sum of squares
@@ -294,11 +317,11 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   __syncwarp();
 }
 
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N>::kCtasPerSm)
+template <int BLOCK_N, int ROWB, bool F16>
+__global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
 conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const FpropParams p) {
-  using Cfg = FpropCfg<BLOCK_N>;
+  using Cfg = FpropCfg<BLOCK_N, ROWB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes);
@@ -355,11 +378,11 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
+          uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * kBlockK, w0, h0, n0);
-          else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * kBlockK, w0 + dx, h0 + dy, n0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * kBlockK, tile_n * BLOCK_N);
+          if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * p.kblk, w0, h0, n0);
+          else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * p.kblk, w0 + dx, h0 + dy, n0);
+          tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * p.kblk, tile_n * BLOCK_N);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -373,7 +396,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     }
   } else if (warp == 1) {
     // ===== MMA issuer (warp-uniform loop, elected lane issues - see the producer) =====
-    constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
+    constexpr uint32_t idesc = F16 ? instr_desc_f16(kBlockM, BLOCK_N, 0, 0) : instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -388,12 +411,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint64_t adesc = smem_desc_kmajor_sw128(sa);
-          const uint64_t bdesc = smem_desc_kmajor_sw128(sa + kABytes);
+          const uint64_t adesc = ROWB == 128 ? smem_desc_kmajor_sw128(sa) : smem_desc_kmajor_sw64(sa);
+          const uint64_t bdesc = ROWB == 128 ? smem_desc_kmajor_sw128(sa + Cfg::kABytes) : smem_desc_kmajor_sw64(sa + Cfg::kABytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 8; ++k) {
-            // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            mma_tf32_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
+          for (int k = 0; k < ROWB / 32; ++k) {
+            // one MMA consumes 32 bytes of K (8 tf32 or 16 fp16) of every row: +2 in the (addr >> 4) field per step
+            if (F16) mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
+            else mma_tf32_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
           }
           mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         }
@@ -468,13 +492,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int ROWB, bool F16>
 int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p_in, int m_tiles, int n_tiles, int splits,
                  cudaStream_t st) {
-  using Cfg = FpropCfg<BLOCK_N>;
+  using Cfg = FpropCfg<BLOCK_N, ROWB>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
   FpropParams p = p_in;
@@ -485,7 +509,7 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams&
   ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  conv_fprop_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
+  conv_fprop_tc_kernel<BLOCK_N, ROWB, F16><<<grid, kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -507,11 +531,21 @@ int tmap_img(CUtensorMap* out, const Img& a, const float* base, int c, long long
   const uint64_t str[3] = {(uint64_t)sw * 4, (uint64_t)sh * 4, (uint64_t)sn * 4};
   return make_tmap_f32(out, base, 4, dims, str, box, swz32);
 }
+// the fp16 shadow of an image: same element strides, 2-byte elements; box[0] = elements per K block (64 or 32)
+int tmap_img16(CUtensorMap* out, const Img& a, const void* base16, const uint32_t* box) {
+  const uint64_t dims[4] = {(uint64_t)a.c, (uint64_t)a.w, (uint64_t)a.h, (uint64_t)a.n};
+  const uint64_t str[3] = {(uint64_t)a.sw * 2, (uint64_t)a.sh * 2, (uint64_t)a.sn * 2};
+  return make_tmap_16(out, base16, 4, dims, str, box, (int)box[0] * 2);
+}
+// K-block width of the fp16 path: 64 elements (128-byte rows) when the channel count allows, else 32 (64-byte rows)
+inline int kblk16(int cin) { return cin % 64 == 0 ? 64 : 32; }
+inline bool strides_ok16(const Img& a) { return a.sn % 8 == 0 && a.sh % 8 == 0 && a.sw % 8 == 0; }
 
 // shared driver of the three K-major entry points. a_maps: number of A tensor maps already encoded in ta (1 or 4).
+// f16: the A maps in ta_in describe the fp16 shadow (K block = kblk16(cin) elements) and ep.w16 holds the fp16 weights
 int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const float* wpacked, int n_total, int kh,
                  int kw, int ph, int pw, int cin, const Img& out, int h_out, int w_out, const TcEpilogue& ep, int mode,
-                 int up_c, const float* bias, cudaStream_t st) {
+                 int up_c, const float* bias, cudaStream_t st, bool f16 = false) {
   FpropParams p;
   p.n_img = x_geom.n; p.h_out = h_out; p.w_out = w_out;
   p.wt = min(pow2_ceil(w_out), kBlockM);
@@ -521,7 +555,9 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.tiles_h = qeb_cdiv(h_out, p.ht);
   const int m_tiles = p.tiles_w * p.tiles_h * qeb_cdiv(x_geom.n, p.nt);
   p.kh = kh; p.kw = kw; p.ph = ph; p.pw = pw;
-  p.cin = cin; p.kchunks = cin / kBlockK;
+  const int kblk = f16 ? kblk16(cin) : kBlockK;
+  p.kblk = kblk;
+  p.cin = cin; p.kchunks = cin / kblk;
   p.n_total = n_total;
   p.bias = bias; p.scale = ep.scale; p.relu = ep.relu;
   p.out = out.p; p.osn = out.sn; p.osh = out.sh; p.osw = out.sw;
@@ -537,11 +573,14 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.timeline = g_timeline;
   p.stats = nullptr;
   p.bn_scsh = nullptr;
+  QEB_REQUIRE(!ep.out16 || (p.vec_ok && n_total % 32 == 0 && ((uintptr_t)ep.out16 & 7) == 0),
+              "tc fprop: an fp16 output shadow needs 16-byte aligned output rows and a multiple of 32 channels");
+  p.out16 = static_cast<__half*>(ep.out16);
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
   static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
   static const int allow_split = getenv("QEB_TC_SPLITK") ? atoi(getenv("QEB_TC_SPLITK")) : 1;
-  const int num_kb = kh * kw * (cin / kBlockK);
+  const int num_kb = kh * kw * (cin / kblk);
   const int bn_max = min(256, max(32, pow2_ceil(n_total)));
   int bn = bn_max, splits = 1;
   // Few pixels, long K (the deep UNet levels and their input gradients): narrowing the N tile to fill the SMs makes every
@@ -580,17 +619,33 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   {
     const uint64_t ktot = (uint64_t)kh * kw * cin;
     const uint64_t dims[2] = {ktot, (uint64_t)n_total};
-    const uint64_t str[1] = {ktot * 4};
-    const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)bn};
-    int rc = make_tmap_f32(&tb, wpacked, 2, dims, str, box);
+    const uint64_t str[1] = {ktot * (f16 ? 2 : 4)};
+    const uint32_t box[2] = {(uint32_t)kblk, (uint32_t)bn};
+    int rc = f16 ? make_tmap_16(&tb, ep.w16, 2, dims, str, box, kblk * 2) : make_tmap_f32(&tb, wpacked, 2, dims, str, box);
     if (rc) return rc;
   }
   int rc;
-  switch (bn) {
-    case 32: rc = launch_fprop<32>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-    case 64: rc = launch_fprop<64>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-    case 128: rc = launch_fprop<128>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-    default: rc = launch_fprop<256>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+  if (!f16) {
+    switch (bn) {
+      case 32: rc = launch_fprop<32, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 64: rc = launch_fprop<64, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 128: rc = launch_fprop<128, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      default: rc = launch_fprop<256, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+    }
+  } else if (kblk == 64) {
+    switch (bn) {
+      case 32: rc = launch_fprop<32, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 64: rc = launch_fprop<64, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 128: rc = launch_fprop<128, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      default: rc = launch_fprop<256, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+    }
+  } else {
+    switch (bn) {
+      case 32: rc = launch_fprop<32, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 64: rc = launch_fprop<64, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 128: rc = launch_fprop<128, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      default: rc = launch_fprop<256, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+    }
   }
   if (rc == QEB_OK && ep.bn_stats && !stats_fused) rc = bn_train_stats(out, ep.bn_stats, st);   // separate pass over the output
   return rc;
@@ -618,12 +673,15 @@ int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int k
   TmapArray4 ta;
   uint32_t box[4];
   fprop_box(out.h, out.w, box);
-  int rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
+  const bool f16 = ep.in16 && ep.w16 && strides_ok16(x);
+  if (f16) box[0] = kblk16(x.c);
+  int rc = f16 ? tmap_img16(&ta.m[0], x, ep.in16, box) : tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
   if (rc) return rc;
-  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st);
+  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st, f16);
 }
 
-int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st) {
+int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st,
+                   const TcEpilogue* shadows) {
   QEB_REQUIRE(x.p && wpacked && out.p, "tc_convT_fprop: null pointer");
   QEB_REQUIRE(x.c % 32 == 0 && out.c % 32 == 0, "tc_convT_fprop: channels must be multiples of 32");
   QEB_REQUIRE(strides_ok(x), "tc_convT_fprop: input alignment");
@@ -631,10 +689,13 @@ int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const 
   TmapArray4 ta;
   uint32_t box[4];
   fprop_box(x.h, x.w, box);
-  int rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
-  if (rc) return rc;
   TcEpilogue ep;
-  return fprop_common(ta, false, x, wpacked, 4 * out.c, 1, 1, 0, 0, x.c, out, x.h, x.w, ep, 1, out.c, bias, st);
+  if (shadows) { ep.in16 = shadows->in16; ep.w16 = shadows->w16; ep.out16 = shadows->out16; }
+  const bool f16 = ep.in16 && ep.w16 && strides_ok16(x);
+  if (f16) box[0] = kblk16(x.c);
+  int rc = f16 ? tmap_img16(&ta.m[0], x, ep.in16, box) : tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
+  if (rc) return rc;
+  return fprop_common(ta, false, x, wpacked, 4 * out.c, 1, 1, 0, 0, x.c, out, x.h, x.w, ep, 1, out.c, bias, st, f16);
 }
 
 int tc_convT_dgrad(const Img& dy, const float* wpacked, const Img& dx, const TcEpilogue& ep, cudaStream_t st) {
@@ -947,6 +1008,22 @@ int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
 }
 
 // C ABI: weight gradient of a stride-1 convolution / Linear in torch's layout dw[co][ci][kh][kw], accumulated.
+// the same contraction with fp16 operands (x16: NHWC fp16 image, w16: packed fp16 weights) and an optional fp16 shadow of
+// the fp32 output
+QEB_API int qeb_conv_fprop_tc16(const void* x16, int n_img, int h_in, int w_in, int cin, int x_cstride, const void* w16,
+                                int n_total, int kh, int kw, int ph, int pw, const float* bias, const float* scale, int relu,
+                                float* out, int out_cstride, void* out16, void* stream) {
+  QEB_REQUIRE(x16 && w16, "conv_fprop_tc16: null operand");
+  QEB_REQUIRE(h_in + 2 * ph - kh + 1 > 0 && w_in + 2 * pw - kw + 1 > 0, "conv_fprop_tc16: empty output");
+  QEB_REQUIRE(x_cstride % 8 == 0, "conv_fprop_tc16: the channel stride must be a multiple of 8 (16-byte rows)");
+  Img xi = img_nhwc(reinterpret_cast<float*>(const_cast<void*>(x16)), n_img, h_in, w_in, cin, x_cstride);   // geometry only
+  Img oi = img_nhwc(out, n_img, h_in + 2 * ph - kh + 1, w_in + 2 * pw - kw + 1, n_total, out_cstride);
+  TcEpilogue ep;
+  ep.bias = bias; ep.scale = scale; ep.relu = relu;
+  ep.in16 = x16; ep.w16 = w16; ep.out16 = out16;
+  return tc_conv_fprop(xi, reinterpret_cast<const float*>(w16), n_total, kh, kw, ph, pw, oi, ep, (cudaStream_t)stream);
+}
+
 QEB_API int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, int w_in, const float* dy, int cout,
                               int dy_cstride, int n_img, int kh, int kw, int ph, int pw, float* dw, void* stream) {
   Img xi = img_nhwc(const_cast<float*>(x), n_img, h_in, w_in, cin, x_cstride);

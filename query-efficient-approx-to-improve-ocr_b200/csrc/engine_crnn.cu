@@ -12,6 +12,8 @@
 // update (phase A, train_nn_patch.py:226) or frozen running statistics folded into the conv epilogue (phase B after
 // set_bn_eval, utils.py:113-115).
 #include "nn.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -46,6 +48,10 @@ struct CrnnPlan {
   // backward scratch
   float *dlp, *wlinT, *wihT0, *wihT1, *wpd2, *wpd3, *wpd4, *wpd5, *wpd6, *wpd7, *dy1, *dy0, *dx0, *d6, *d6f, *d5, *d4, *d4f, *d3, *d2, *d2f, *d1, *d1f;
   double* bnred;
+  // fp16 operand shadows of the forward pass (kind::f16 tensor-core path): activations that feed a contraction, and the
+  // forward B operands. Typed void*: only the kernels look inside.
+  void *a1h, *a2h, *a3h, *a4h, *a5h, *a6h, *x0h, *y0h, *y1h;
+  void *wp2h, *wp3h, *wp4h, *wp5h, *wp6h, *wp7h, *wih0h, *wih1h, *wlinh;
   float *dwp2, *dwp3, *dwp4, *dwp5, *dwp6, *dwp7;  // packed [Cout][tap][Cin] weight-gradient accumulators, contiguous
   size_t dwp_bytes;
   size_t bytes;
@@ -88,8 +94,22 @@ CrnnPlan make_plan(int B, int W, int V, void* base) {
     p.dwp5 = a.take((size_t)512 * 9 * 256); p.dwp6 = a.take((size_t)512 * 9 * 512); p.dwp7 = a.take((size_t)512 * 4 * 512);
     p.dwp_bytes = a.off - o0;
   }
+  {
+    auto half = [&](size_t n) { return static_cast<void*>(a.take((n + 1) / 2)); };
+    p.a1h = half(px16 * 64); p.a2h = half(px8 * 128); p.a3h = half(px8 * 256); p.a4h = half(px4 * 256);
+    p.a5h = half(px4 * 512); p.a6h = half(px2 * 512); p.x0h = half(tb * 512); p.y0h = half(tb * 512); p.y1h = half(tb * 512);
+    p.wp2h = half((size_t)128 * 9 * 64); p.wp3h = half((size_t)256 * 9 * 128); p.wp4h = half((size_t)256 * 9 * 256);
+    p.wp5h = half((size_t)512 * 9 * 256); p.wp6h = half((size_t)512 * 9 * 512); p.wp7h = half((size_t)512 * 4 * 512);
+    p.wih0h = half((size_t)2048 * 512); p.wih1h = half((size_t)2048 * 512); p.wlinh = half((size_t)96 * 512);
+  }
   p.bytes = a.off;
   return p;
+}
+
+// forward contractions with fp16 operands (default) or tf32 operands read from the fp32 tensors (QEB_FP16_FWD=0)
+bool fp16_fwd() {
+  static const bool on = !(getenv("QEB_FP16_FWD") && atoi(getenv("QEB_FP16_FWD")) == 0);
+  return on;
 }
 
 #define TRY(expr)            \
@@ -136,31 +156,56 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   Img Z5 = img_nhwc(p.z5, B, 4, p.W4, 512), A5 = img_nhwc(p.a5, B, 4, p.W4, 512);
   Img Z6 = img_nhwc(p.z6, B, 4, p.W4, 512), A6f = img_nhwc(p.a6f, B, 4, p.W4, 512), A6 = img_nhwc(p.a6, B, 2, p.W4, 512);
 
+  const bool h = fp16_fwd();
   {  // every weight re-layout of this pass in one launch
     PackBatch pk;
-    pk.add_fprop(params[P_C2W], p.wp2, 128, 64, 9);
-    pk.add_fprop(params[P_C3W], p.wp3, 256, 128, 9);
-    pk.add_fprop(params[P_C4W], p.wp4, 256, 256, 9);
-    pk.add_fprop(params[P_C5W], p.wp5, 512, 256, 9);
-    pk.add_fprop(params[P_C6W], p.wp6, 512, 512, 9);
-    pk.add_fprop(params[P_C7W], p.wp7, 512, 512, 4);
-    for (int l = 0; l < 2; ++l)
-      for (int d = 0; d < 2; ++d)
-        pk.add_copy(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wih1 : p.wih0) + (size_t)d * 1024 * 512, (long long)1024 * 512);
+    if (h) {   // fp16 B operands; the fp32 packs are not needed by the forward pass then
+      pk.add_fprop16(params[P_C2W], p.wp2h, 128, 64, 9);
+      pk.add_fprop16(params[P_C3W], p.wp3h, 256, 128, 9);
+      pk.add_fprop16(params[P_C4W], p.wp4h, 256, 256, 9);
+      pk.add_fprop16(params[P_C5W], p.wp5h, 512, 256, 9);
+      pk.add_fprop16(params[P_C6W], p.wp6h, 512, 512, 9);
+      pk.add_fprop16(params[P_C7W], p.wp7h, 512, 512, 4);
+      for (int l = 0; l < 2; ++l)
+        for (int d = 0; d < 2; ++d) {
+          __half* dst = static_cast<__half*>(l ? p.wih1h : p.wih0h) + (size_t)d * 1024 * 512;
+          pk.add_copy(params[P_LSTM0 + l * 8 + d * 4], reinterpret_cast<float*>(dst), (long long)1024 * 512);
+          pk.last_to_half();
+        }
+      pk.add_copy(params[P_LINW], static_cast<float*>(p.wlinh), (long long)V * 512);
+      pk.last_to_half();
+    } else {
+      pk.add_fprop(params[P_C2W], p.wp2, 128, 64, 9);
+      pk.add_fprop(params[P_C3W], p.wp3, 256, 128, 9);
+      pk.add_fprop(params[P_C4W], p.wp4, 256, 256, 9);
+      pk.add_fprop(params[P_C5W], p.wp5, 512, 256, 9);
+      pk.add_fprop(params[P_C6W], p.wp6, 512, 512, 9);
+      pk.add_fprop(params[P_C7W], p.wp7, 512, 512, 4);
+      for (int l = 0; l < 2; ++l)
+        for (int d = 0; d < 2; ++d)
+          pk.add_copy(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wih1 : p.wih0) + (size_t)d * 1024 * 512, (long long)1024 * 512);
+    }
     TRY(pack_flush(pk, st));
   }
+  // shadows(in, w, out): the fp16 copies a contraction reads / writes in fp16 mode (nulls otherwise: tf32 path)
+  auto shadows = [&](TcEpilogue& e, const void* in16, const void* w16, void* out16) {
+    e.in16 = h ? in16 : nullptr; e.w16 = h ? w16 : nullptr; e.out16 = h ? out16 : nullptr;
+  };
   TRY(c1_conv_fwd(X, params[P_C1W], params[P_C1B], 1, A1f, st));
-  TRY(maxpool_fwd(A1f, 2, 2, A1, st));
+  TRY(maxpool_fwd(A1f, 2, 2, A1, st, h ? p.a1h : nullptr));
   TcEpilogue ep;
   ep.relu = 1;
   ep.bias = params[P_C2B];
+  shadows(ep, p.a1h, p.wp2h, nullptr);
   TRY(tc_conv_fprop(A1, p.wp2, 128, 3, 3, 1, 1, A2f, ep, st));
-  TRY(maxpool_fwd(A2f, 2, 2, A2, st));
+  TRY(maxpool_fwd(A2f, 2, 2, A2, st, h ? p.a2h : nullptr));
   ep.bias = params[P_C3B];
+  shadows(ep, p.a2h, p.wp3h, p.a3h);
   TRY(tc_conv_fprop(A2, p.wp3, 256, 3, 3, 1, 1, A3, ep, st));
   ep.bias = params[P_C4B];
+  shadows(ep, p.a3h, p.wp4h, nullptr);
   TRY(tc_conv_fprop(A3, p.wp4, 256, 3, 3, 1, 1, A4f, ep, st));
-  TRY(maxpool_fwd(A4f, 2, 1, A4, st));
+  TRY(maxpool_fwd(A4f, 2, 1, A4, st, h ? p.a4h : nullptr));
 
   const BnParams bn1 = bn_of(params, buffers, P_BN1W, P_BN1B, B_BN1_MEAN), bn2 = bn_of(params, buffers, P_BN2W, P_BN2B, B_BN2_MEAN);
   if (bn_train) {
@@ -168,10 +213,12 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     TcEpilogue raw;
     raw.bias = params[P_C5B];
     raw.bn_stats = p.bnstats;             // BatchNorm statistics out of the conv epilogue
+    shadows(raw, p.a4h, p.wp5h, nullptr);
     TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, Z5, raw, st));
-    TRY(bn_train_finalize_apply(Z5, p.bnstats, bn1, p.scsh5, 1, A5, st));
+    TRY(bn_train_finalize_apply(Z5, p.bnstats, bn1, p.scsh5, 1, A5, st, h ? p.a5h : nullptr));
     raw.bias = params[P_C6B];
     raw.bn_stats = p.bnstats + 1024;
+    shadows(raw, p.a5h, p.wp6h, nullptr);
     TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, Z6, raw, st));
     TRY(bn_train_finalize_apply(Z6, p.bnstats + 1024, bn2, p.scsh6, 1, A6f, st));
   } else {
@@ -181,22 +228,26 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     TcEpilogue f;
     f.relu = 1;
     f.scale = p.scsh5; f.bias = p.scsh5 + 512;
+    shadows(f, p.a4h, p.wp5h, p.a5h);
     TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, A5, f, st));
     f.scale = p.scsh6; f.bias = p.scsh6 + 512;
+    shadows(f, p.a5h, p.wp6h, nullptr);
     TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, A6f, f, st));
   }
-  TRY(maxpool_fwd(A6f, 2, 1, A6, st));
+  TRY(maxpool_fwd(A6f, 2, 1, A6, st, h ? p.a6h : nullptr));
 
   // conv7 writes the sequence-major (T,B,512) tensor directly (map_to_sequence fused)
   Img X0seq;
   X0seq.p = p.x0; X0seq.n = B; X0seq.h = 1; X0seq.w = T; X0seq.c = 512; X0seq.sn = 512; X0seq.sh = 0; X0seq.sw = (long long)B * 512;
   TcEpilogue e7;
   e7.bias = params[P_C7B];
+  shadows(e7, p.a6h, p.wp7h, p.x0h);
   TRY(tc_conv_fprop(A6, p.wp7, 512, 2, 2, 0, 0, X0seq, e7, st));
 
   // two bidirectional LSTM layers: input projection GEMM (both directions at once, N = 2048) + recurrence
   const int TB = T * B;
   float* xin = p.x0;
+  const void* xin16 = p.x0h;
   for (int l = 0; l < 2; ++l) {
     const float* const* lp = params + P_LSTM0 + l * 8;
     float* wih = l ? p.wih1 : p.wih0;
@@ -204,17 +255,21 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     float* g = l ? p.g1 : p.g0;
     float* c = l ? p.c1 : p.c0;
     float* y = l ? p.y1 : p.y0;
+    void* y16 = l ? p.y1h : p.y0h;
     for (int d = 0; d < 2; ++d) {
       TRY(vec_add(lp[d * 4 + 2], lp[d * 4 + 3], bias + d * 1024, 1024, st));
     }
     TcEpilogue eg;
     eg.bias = bias;
+    shadows(eg, xin16, l ? p.wih1h : p.wih0h, nullptr);
     TRY(tc_conv_fprop(img_nhwc(xin, 1, 1, TB, 512), wih, 2048, 1, 1, 0, 0, img_nhwc(g, 1, 1, TB, 2048), eg, st));
-    TRY(lstm_layer_fwd(g, lp[1], lp[5], c, y, T, B, st));
+    TRY(lstm_layer_fwd(g, lp[1], lp[5], c, y, T, B, st, h ? y16 : nullptr));
     xin = y;
+    xin16 = y16;
   }
   TcEpilogue el;
   el.bias = params[P_LINB];
+  shadows(el, p.y1h, p.wlinh, nullptr);
   TRY(tc_conv_fprop(img_nhwc(p.y1, 1, 1, TB, 512), params[P_LINW], V, 1, 1, 0, 0, img_nhwc(logits, 1, 1, TB, V), el, st));
   return QEB_OK;
 }

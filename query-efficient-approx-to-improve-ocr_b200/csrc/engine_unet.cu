@@ -9,6 +9,8 @@
 // sums by a reduction kernel, normalise+ReLU by an elementwise kernel) and is folded into the conv epilogue in
 // eval mode.
 #include "nn.cuh"
+#include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -47,6 +49,10 @@ struct UnetPlan {
   size_t dwp_bytes;
   float *sA[kLevels], *sB[kLevels], *sC[kLevels];
   double* bnred;    // kUnits x 1024
+  // fp16 operand shadows of the forward pass (kind::f16 tensor-core path), same element layouts as their fp32 twins
+  __half *ea1h[kLevels], *pool_h[kLevels - 1], *cat_h[kLevels - 1], *bott_h;
+  __half *da1h[kLevels - 1], *dout_h[kLevels - 1];
+  __half *wph[kUnits], *wuph[4];
   size_t bytes;
 };
 
@@ -96,8 +102,32 @@ UnetPlan make_plan(int B, int H, int W, void* base) {
     p.sA[i] = a.take(p.M[i] * 2 * p.C[i]); p.sB[i] = a.take(p.M[i] * p.C[i]); p.sC[i] = a.take(p.M[i] * p.C[i]);
   }
   p.bnred = reinterpret_cast<double*>(a.take((size_t)kUnits * 1024 * 2));
+  {
+    auto half = [&](size_t n) { return reinterpret_cast<__half*>(a.take((n + 1) / 2)); };
+    for (int i = 0; i < kLevels; ++i) p.ea1h[i] = half(p.M[i] * p.C[i]);
+    p.bott_h = half(p.M[4] * p.C[4]);
+    for (int i = 0; i < kLevels - 1; ++i) {
+      p.pool_h[i] = half(p.M[i + 1] * p.C[i]);
+      p.cat_h[i] = half(p.M[i] * 2 * p.C[i]);
+      p.da1h[i] = half(p.M[i] * p.C[i]);
+      p.dout_h[i] = half(p.M[i] * p.C[i]);
+    }
+    for (int blk = 0; blk < 9; ++blk) {
+      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+      const int cout = p.C[lvl];
+      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      p.wph[blk * 2] = half((size_t)cout * 9 * cin1); p.wph[blk * 2 + 1] = half((size_t)cout * 9 * cout);
+    }
+    for (int up = 0; up < 4; ++up) p.wuph[up] = half((size_t)4 * p.C[3 - up] * 2 * p.C[3 - up]);
+  }
   p.bytes = a.off;
   return p;
+}
+
+// forward contractions with fp16 operands (default) or tf32 operands read from the fp32 tensors (QEB_FP16_FWD=0)
+bool fp16_fwd() {
+  static const bool on = !(getenv("QEB_FP16_FWD") && atoi(getenv("QEB_FP16_FWD")) == 0);
+  return on;
 }
 
 #define TRY(expr)            \
@@ -143,8 +173,10 @@ BnParams bn_of(const Ctx& c, int block, int which) {
   return b;
 }
 
-// one conv3x3 (no bias) + BN + ReLU unit. z: raw conv output (train mode only), out: activation.
-int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out) {
+// one conv3x3 (no bias) + BN + ReLU unit. z: raw conv output (train mode only), out: activation. in16 / out16: fp16 shadows
+// of `in` / `out` (NULL: tf32 operands from the fp32 tensors / no shadow wanted).
+int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const __half* in16 = nullptr,
+             __half* out16 = nullptr) {
   const int unit = block * 2 + which;
   const float* w = c.params[block * 6 + which * 3];
   float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
@@ -154,21 +186,24 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     TRY(c1_conv_fwd(in, w, nullptr, 0, z, c.st));
     if (c.bn_train) {
       TRY(bn_train_stats(z, c.p->bnstats + (size_t)unit * 1024, c.st));
-      return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st);
+      return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st, out16);
     }
     TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
-    return bn_apply(z, scsh, 1, out, c.st);
+    return bn_apply(z, scsh, 1, out, c.st, out16);
   }
   const float* wp = c.p->wp[unit];
   if (c.bn_train) {
     TcEpilogue raw;
     raw.bn_stats = c.p->bnstats + (size_t)unit * 1024;   // per-channel sums come out of the conv epilogue
+    if (in16) { raw.in16 = in16; raw.w16 = c.p->wph[unit]; }
     TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
-    return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st);
+    return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st, out16);
   }
   TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
   TcEpilogue f;
   f.relu = 1; f.scale = scsh; f.bias = scsh + cout;
+  if (in16) { f.in16 = in16; f.w16 = c.p->wph[unit]; }
+  f.out16 = out16;
   return tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, out, f, c.st);
 }
 
@@ -227,47 +262,62 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   c.ss = nullptr;
   c.red_done = nullptr;
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
+  const bool h16 = fp16_fwd();
   {  // every weight re-layout of this pass in one launch
     PackBatch pk;
     for (int blk = 0; blk < 9; ++blk) {
       const int lvl = blk < 5 ? blk : 3 - (blk - 5);
       const int cout = p.C[lvl];
       const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
-      if (cin1 > 1) pk.add_fprop(params[blk * 6], p.wp[blk * 2], cout, cin1, 9);
-      pk.add_fprop(params[blk * 6 + 3], p.wp[blk * 2 + 1], cout, cout, 9);
+      if (h16) {   // fp16 B operands; the fp32 packs are not needed by the forward pass then
+        if (cin1 > 1) pk.add_fprop16(params[blk * 6], p.wph[blk * 2], cout, cin1, 9);
+        pk.add_fprop16(params[blk * 6 + 3], p.wph[blk * 2 + 1], cout, cout, 9);
+      } else {
+        if (cin1 > 1) pk.add_fprop(params[blk * 6], p.wp[blk * 2], cout, cin1, 9);
+        pk.add_fprop(params[blk * 6 + 3], p.wp[blk * 2 + 1], cout, cout, 9);
+      }
     }
     for (int up = 0; up < 4; ++up) {  // ConvTranspose weight (2C, C, 2, 2) -> B operand [(dh*2+dw)*C + co][2C]
       const int C = p.C[3 - up];
-      pk.add(params[P_UP + up * 2], p.wup[up], 4, C, 2 * C, 1, 4, (long long)C * 4, (long long)C * 2 * C, 2 * C);
+      pk.add(params[P_UP + up * 2], h16 ? reinterpret_cast<float*>(p.wuph[up]) : p.wup[up], 4, C, 2 * C, 1, 4, (long long)C * 4,
+             (long long)C * 2 * C, 2 * C);
+      if (h16) pk.last_to_half();
     }
     TRY(pack_flush(pk, c.st));
   }
 
   Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
+  const __half* in16 = nullptr;   // fp16 shadow of `in` (none for the one-channel network input)
   for (int i = 0; i < kLevels; ++i) {  // encoder blocks + bottleneck
     const int C = p.C[i];
     Img z1 = img_nhwc(p.ez1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.ea1[i], B, p.h[i], p.w[i], C);
     Img z2 = img_nhwc(p.ez2[i], B, p.h[i], p.w[i], C);
     Img out = i < 4 ? img_nhwc(p.cat[i] + C, B, p.h[i], p.w[i], C, 2 * C) : img_nhwc(p.bott, B, p.h[i], p.w[i], C);
-    TRY(unit_fwd(c, i, 0, in, z1, a1));
-    TRY(unit_fwd(c, i, 1, a1, z2, out));
+    __half* out16 = h16 ? (i < 4 ? p.cat_h[i] + C : p.bott_h) : nullptr;   // same channel slice of the fp16 concat buffer
+    TRY(unit_fwd(c, i, 0, in, z1, a1, in16, h16 ? p.ea1h[i] : nullptr));
+    TRY(unit_fwd(c, i, 1, a1, z2, out, h16 ? p.ea1h[i] : nullptr, out16));
     if (i < 4) {
       Img pl = img_nhwc(p.pool[i], B, p.h[i + 1], p.w[i + 1], C);
-      TRY(maxpool_fwd(out, 2, 2, pl, c.st));
+      TRY(maxpool_fwd(out, 2, 2, pl, c.st, h16 ? p.pool_h[i] : nullptr));
       in = pl;
+      in16 = h16 ? p.pool_h[i] : nullptr;
     }
   }
   Img below = img_nhwc(p.bott, B, p.h[4], p.w[4], p.C[4]);
+  const __half* below16 = h16 ? p.bott_h : nullptr;
   for (int i = 3; i >= 0; --i) {  // decoder blocks: block index 5 + (3 - i), up-conv index (3 - i)
     const int C = p.C[i], blk = 5 + (3 - i), up = 3 - i;
     Img upo = img_nhwc(p.cat[i], B, p.h[i], p.w[i], C, 2 * C);
-    TRY(tc_convT_fprop(below, p.wup[up], params[P_UP + up * 2 + 1], upo, c.st));
+    TcEpilogue sh;
+    if (h16) { sh.in16 = below16; sh.w16 = p.wuph[up]; sh.out16 = p.cat_h[i]; }
+    TRY(tc_convT_fprop(below, p.wup[up], params[P_UP + up * 2 + 1], upo, c.st, &sh));
     Img cat = img_nhwc(p.cat[i], B, p.h[i], p.w[i], 2 * C);
     Img z1 = img_nhwc(p.dz1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.da1[i], B, p.h[i], p.w[i], C);
     Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
-    TRY(unit_fwd(c, blk, 0, cat, z1, a1));
-    TRY(unit_fwd(c, blk, 1, a1, z2, out));
+    TRY(unit_fwd(c, blk, 0, cat, z1, a1, h16 ? p.cat_h[i] : nullptr, h16 ? p.da1h[i] : nullptr));
+    TRY(unit_fwd(c, blk, 1, a1, z2, out, h16 ? p.da1h[i] : nullptr, (h16 && i > 0) ? p.dout_h[i] : nullptr));
     below = out;
+    below16 = h16 ? p.dout_h[i] : nullptr;
   }
   return o1_conv_sigmoid_fwd(below, params[P_CONVW], params[P_CONVB], y, c.st);
 }

@@ -25,6 +25,7 @@
 // dh in the next step.
 #include "nn.cuh"
 #include "tc_common.cuh"
+#include <cuda_fp16.h>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -114,6 +115,7 @@ struct LstmArgs {
   const float* w_hh[2]; // (1024,256) per direction
   float* cells;         // (T,B,2,256)
   float* y;             // (T,B,512)
+  __half* y16;          // optional fp16 shadow of y (operand of the next projection GEMM), forward only
   const float* dy;      // (T,B,512), backward only
   int T, B;
   long long* tl;        // debugging aid (qeb_debug_set_timeline): clock64 stamps of CTA 0, 8 per step
@@ -266,6 +268,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       if (b < a.B) {
         a.cells[(((long long)t * a.B + b) * 2 + dir) * kH + rank * kUnits + lane] = c[p];
         a.y[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + lane] = hv[p];
+        if (a.y16) a.y16[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + lane] = __float2half_rn(hv[p]);
       }
     }
 #pragma unroll
@@ -472,7 +475,7 @@ int launch_cluster(const void* fn, size_t smem, int n_clusters, LstmArgs& args, 
 }  // namespace
 
 int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
-                   cudaStream_t st) {
+                   cudaStream_t st, void* y16) {
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && y && T > 0 && B > 0, "lstm_layer_fwd: bad arguments");
   static bool attr = false;
   if (!attr) {
@@ -481,6 +484,7 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
   }
   LstmArgs a;
   a.gates = gates; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_rev; a.cells = cells; a.y = y; a.dy = nullptr; a.T = T; a.B = B;
+  a.y16 = static_cast<__half*>(y16);
   ProfScope prof("lstm_fwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
   return launch_cluster((const void*)lstm_fwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
@@ -495,6 +499,7 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
   }
   LstmArgs a;
   a.gates = gates; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_rev; a.cells = const_cast<float*>(cells); a.y = nullptr; a.dy = dy;
+  a.y16 = nullptr;
   a.T = T; a.B = B;
   ProfScope prof("lstm_bwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
   return launch_cluster((const void*)lstm_bwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
@@ -503,7 +508,7 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
 // C ABI (tests): one bidirectional layer of the recurrence
 QEB_API int qeb_lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
                                void* stream) {
-  return lstm_layer_fwd(gates, w_hh_fwd, w_hh_rev, cells, y, T, B, (cudaStream_t)stream);
+  return lstm_layer_fwd(gates, w_hh_fwd, w_hh_rev, cells, y, T, B, (cudaStream_t)stream, nullptr);
 }
 QEB_API int qeb_lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev,
                                int T, int B, void* stream) {

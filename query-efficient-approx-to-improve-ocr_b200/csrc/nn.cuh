@@ -45,12 +45,20 @@ struct TcEpilogue {
   const float* bn_scsh = nullptr;
   double* bn_red = nullptr;
   int* bn_red_fused = nullptr;
+  // fp16 operand shadows (forward pass): when BOTH in16 (the input tensor as fp16, same element layout / strides as the
+  // fp32 Img) and w16 (the packed weights as fp16, same layout as wpacked) are given, the contraction runs with
+  // kind::f16 operands - same 11-bit significand as tf32, round-to-nearest instead of truncation, half the operand bytes.
+  // out16: optional fp16 shadow of the output (same element layout as `out`), written by the epilogue for the next layer.
+  const void* in16 = nullptr;
+  const void* w16 = nullptr;
+  void* out16 = nullptr;
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
                   const TcEpilogue& ep, cudaStream_t st);
 // ConvTranspose2d 2x2 stride 2: x (n,h,w,cin) -> out (n,2h,2w,cout). wpacked: [(dh*2+dw)*cout + co][cin]; bias (cout).
-int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st);
+int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st,
+                   const TcEpilogue* shadows = nullptr);   // shadows: only in16 / w16 / out16 are read
 // its input gradient: dy (n,2h,2w,cout) -> dx (n,h,w,cin). wpacked: [cin][(dh*2+dw)*cout + co].
 int tc_convT_dgrad(const Img& dy, const float* wpacked, const Img& dx, const TcEpilogue& ep, cudaStream_t st);
 // weight gradient, accumulated with atomics: dw[co*s_co + ci*s_ci + ky*s_kh + kx*s_kw] += sum_pix x(pix+tap, ci) dy(pix, co)
@@ -71,6 +79,7 @@ struct PackJob {
   int n0, n1, n2;
   long long s0, s1, s2, d0, d1;
   long long start;  // first element of this job in the batch-wide numbering
+  int half_out;     // 1: dst is an fp16 buffer (forward operand copies of weights)
 };
 // conv weight re-layouts go through a tiled transpose (32 x 32 channels x taps through shared memory, coalesced both ways)
 struct ConvPackJob {
@@ -81,6 +90,7 @@ struct ConvPackJob {
                     // 1: dst[b][taps-1-tap][a] = src[a][b][tap]   dgrad B operand (flipped taps, channels transposed)
                     // 2: dst[a][b][tap] (+)= src[a][tap][b]   packed weight gradient -> torch layout
   int tile_start;   // first 32 x 32 tile of this job in the batch-wide numbering
+  int half_out;     // mode 0 only: dst is an fp16 buffer
 };
 struct PackBatch {
   enum { kMax = 28 };
@@ -94,18 +104,26 @@ struct PackBatch {
     PackJob& j = jobs[n++];
     j.src = src; j.dst = dst; j.n0 = n0; j.n1 = n1; j.n2 = n2; j.s0 = s0; j.s1 = s1; j.s2 = s2; j.d0 = d0; j.d1 = d1;
     j.start = total;
+    j.half_out = 0;
     total += (long long)n0 * n1 * n2;
   }
+  void last_to_half() { if (n > 0) jobs[n - 1].half_out = 1; }   // the job just added writes fp16 (dst cast from a half buffer)
   bool add_conv(const float* src, float* dst, int A, int B, int taps, int mode) {
     if (A % 32 || B % 32 || taps > 9) return false;
     ConvPackJob& j = cjobs[nc++];
-    j.src = src; j.dst = dst; j.A = A; j.B = B; j.taps = taps; j.mode = mode; j.tile_start = ctiles;
+    j.src = src; j.dst = dst; j.A = A; j.B = B; j.taps = taps; j.mode = mode; j.tile_start = ctiles; j.half_out = 0;
     ctiles += (A / 32) * (B / 32);
     return true;
   }
   // torch Conv2d weight (Cout,Cin,taps) -> fprop B operand [Cout][tap][Cin]
   void add_fprop(const float* w, float* dst, int cout, int cin, int taps) {
     if (!add_conv(w, dst, cout, cin, taps, 0)) add(w, dst, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin);
+  }
+  // the same B operand as fp16 (dst16: a buffer of cout*taps*cin halves)
+  void add_fprop16(const float* w, void* dst16, int cout, int cin, int taps) {
+    float* d = static_cast<float*>(dst16);
+    if (add_conv(w, d, cout, cin, taps, 0)) cjobs[nc - 1].half_out = 1;
+    else { add(w, d, cout, taps, cin, (long long)cin * taps, 1, taps, (long long)taps * cin, cin); last_to_half(); }
   }
   // -> dgrad B operand [Cin][flipped tap][Cout] (source taps walked backwards with a negative stride)
   void add_dgrad(const float* w, float* dst, int cout, int cin, int taps) {
@@ -132,7 +150,7 @@ int o1_conv_sigmoid_fwd(const Img& x, const float* w, const float* b, float* y, 
 int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const float* dy, const Img& dx, float* dw, float* db,
                         cudaStream_t st);
 // max pooling (ph x pw window = stride), NHWC
-int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st);
+int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, void* out16 = nullptr);  // out16: fp16 shadow
 // dx = routed dy (first maximal element wins) * chan_scale[c] (if given), zeroed where x <= 0 when relu_mask, plus `add`
 // (same shape as x) if given
 int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
@@ -149,10 +167,10 @@ int bn_train_stats(const Img& z, double* stats, cudaStream_t st);
 int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st);
 // finalize + apply fused (train mode): out = relu?(bn(z)) from the batch sums; writes scsh, updates the running statistics
 int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
-                            cudaStream_t st);
+                            cudaStream_t st, void* out16 = nullptr);   // out16: fp16 shadow of out (same element layout)
 int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh, cudaStream_t st);
 // out = relu?(z*scale + shift)
-int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st);
+int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st, void* out16 = nullptr);
 // backward through relu(bn(z)): red: [0,c) sum g, [c,2c) sum g*xhat (double), g = dy * (z*scale+shift > 0 if relu)
 int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, double* red, cudaStream_t st);
 // train: dz = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M); dgamma += sum_gx, dbeta += sum_g (when given)
@@ -177,7 +195,7 @@ long long* qeb_debug_timeline();  // conv_tc.cu: buffer set by qeb_debug_set_tim
 // i,f,g,o as torch), overwritten with the ACTIVATED gates; w_hh[dir]: torch layout (1024,256); cells: (T,B,2,256) c_t;
 // y: (T,B,512) [forward | reverse].
 int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
-                   cudaStream_t st);
+                   cudaStream_t st, void* y16 = nullptr);
 // dy: (T,B,512). gates (activated) are overwritten with the gradients at the pre-activations (T,B,2,1024).
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
                    int B, cudaStream_t st);

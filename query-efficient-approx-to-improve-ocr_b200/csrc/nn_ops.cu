@@ -9,6 +9,7 @@
 //   - bias gradients (column sums), ReLU backward.
 // Layout: NHWC fp32 (nn.cuh Img). All kernels are grid-stride with float4 accesses along the channel dimension.
 #include "nn.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -26,6 +27,15 @@ __host__ __device__ inline Geo geo(const Img& a) {
   g.h = a.h; g.w = a.w; g.sn = a.sn; g.sh = a.sh; g.sw = a.sw;
   return g;
 }
+// fp16 shadow of four consecutive channels (the tensor-core operand copy of an activation): 8-byte store
+__device__ __forceinline__ void st4h(__half* p, const float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<const uint32_t*>(&a);
+  pk.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = pk;
+}
+
 __device__ __forceinline__ long long pix_off(const Geo& g, long long pix) {
   const int w = (int)(pix % g.w);
   const long long t = pix / g.w;
@@ -236,7 +246,7 @@ __global__ void __launch_bounds__(kThreads) o1_bwd_kernel(const float* __restric
 // ------------------------------------------------------------------------------------------------ max pooling
 template <int PH, int PW>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, Geo gx, float* __restrict__ out,
-                                                               Geo go, int cq_n, long long total) {
+                                                               Geo go, int cq_n, long long total, __half* __restrict__ out16) {
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int cq = (int)(i % cq_n);
     const long long pix = i / cq_n;
@@ -259,6 +269,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
         m.w = (v.w > m.w || v.w != v.w) ? v.w : m.w;
       }
     st4(out + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, m);
+    if (out16) st4h(out16 + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, m);
   }
 }
 
@@ -399,7 +410,7 @@ __global__ void bn_eval_scsh_kernel(int C, const float* __restrict__ gamma, cons
 
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restrict__ z, long long zs, long long M, int C,
                                                             const float* __restrict__ scsh, int relu, float* __restrict__ out,
-                                                            long long os) {
+                                                            long long os, __half* __restrict__ out16) {
   const int cq_n = C / 4;
   const long long total = M * cq_n;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -410,6 +421,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restr
     float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     st4(out + r * os + cq * 4, o);
+    if (out16) st4h(out16 + r * os + cq * 4, o);
   }
 }
 
@@ -421,7 +433,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
                                                                   const float* __restrict__ beta, float* running_mean,
                                                                   float* running_var, long long* nbt, float eps, float momentum,
                                                                   float* __restrict__ scsh, int relu, float* __restrict__ out,
-                                                                  long long os) {
+                                                                  long long os, __half* __restrict__ out16) {
   const int cq_n = C / 4;
   const int cq = threadIdx.x % cq_n;
   float sc[4], sh[4];
@@ -454,6 +466,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
     float4 o = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     st4(out + r * os + cq * 4, o);
+    if (out16) st4h(out16 + r * os + cq * 4, o);
   }
 }
 
@@ -637,6 +650,10 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
     const int i1 = (int)(t % j.n1);
     const long long i0 = t / j.n1;
     const float v = j.src[i0 * j.s0 + i1 * j.s1 + (long long)i2 * j.s2];
+    if (j.half_out) {   // fp16 operand copy (forward weights)
+      reinterpret_cast<__half*>(j.dst)[i0 * j.d0 + i1 * j.d1 + i2] = __float2half_rn(v);
+      continue;
+    }
     float* d = j.dst + i0 * j.d0 + i1 * j.d1 + i2;
     *d = accumulate ? *d + v : v;
   }
@@ -675,7 +692,9 @@ __global__ void __launch_bounds__(kThreads) conv_pack_kernel(const __grid_consta
   if (j.mode == 0) {
     for (int r = warp; r < 32 * T; r += nwarp) {
       const int a = r / T, tap = r - a * T;
-      j.dst[((long long)(a0 + a) * T + tap) * j.B + b0 + lane] = tile[a * pitch + lane * T + tap];
+      const long long o = ((long long)(a0 + a) * T + tap) * j.B + b0 + lane;
+      if (j.half_out) reinterpret_cast<__half*>(j.dst)[o] = __float2half_rn(tile[a * pitch + lane * T + tap]);
+      else j.dst[o] = tile[a * pitch + lane * T + tap];
     }
   } else if (j.mode == 1) {
     for (int r = warp; r < 32 * T; r += nwarp) {
@@ -776,15 +795,16 @@ int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const floa
   return QEB_OK;
 }
 
-int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st) {
+int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, void* out16) {
   ProfScope prof("maxpool_fwd", st, 0.0, 4.0 * x.c * ((double)img_pixels(x) + (double)img_pixels(out)));
   QEB_REQUIRE(vec4_ok(x) && vec4_ok(out) && x.c == out.c, "maxpool_fwd: channel count / alignment");
   QEB_REQUIRE(x.h == out.h * ph && x.w == out.w * pw && x.n == out.n, "maxpool_fwd: input must be a multiple of the window");
   const int cq_n = x.c / 4;
   const long long total = img_pixels(out) * cq_n;
   const int g = qeb_grid(total, kThreads);
-  if (ph == 2 && pw == 2) maxpool_fwd_kernel<2, 2><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total);
-  else if (ph == 2 && pw == 1) maxpool_fwd_kernel<2, 1><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total);
+  __half* o16 = static_cast<__half*>(out16);
+  if (ph == 2 && pw == 2) maxpool_fwd_kernel<2, 2><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total, o16);
+  else if (ph == 2 && pw == 1) maxpool_fwd_kernel<2, 1><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total, o16);
   else QEB_REQUIRE(false, "maxpool_fwd: window %dx%d not supported", ph, pw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -858,7 +878,7 @@ int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh,
 }
 
 int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
-                            cudaStream_t st) {
+                            cudaStream_t st, void* out16) {
   ProfScope prof("bn_apply", st, 0.0, 8.0 * z.c * (double)img_pixels(z));
   REQ_FLAT(z, "bn_train_finalize_apply");
   REQ_FLAT(out, "bn_train_finalize_apply");
@@ -868,19 +888,20 @@ int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& b
   bn_apply_train_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
                                                                                bn.running_mean, bn.running_var,
                                                                                bn.num_batches_tracked, bn.eps, bn.momentum, scsh,
-                                                                               relu, out.p, out.sw);
+                                                                               relu, out.p, out.sw, static_cast<__half*>(out16));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
 }
 
-int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st) {
+int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st, void* out16) {
   ProfScope prof("bn_apply", st, 0.0, 8.0 * z.c * (double)img_pixels(z));
   REQ_FLAT(z, "bn_apply");
   REQ_FLAT(out, "bn_apply");
   QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_apply: shape mismatch");
   const long long M = img_pixels(z);
-  bn_apply_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw);
+  bn_apply_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw,
+                                                                          static_cast<__half*>(out16));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;

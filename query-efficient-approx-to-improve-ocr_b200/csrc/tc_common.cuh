@@ -112,6 +112,10 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint64_t smem_desc_kmajor_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// K-major operand tile with rows of 64 B (32 fp16), 64-byte swizzle: 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t smem_desc_kmajor_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 // MN-major tf32 operand tile. 32-bit MN-major operands only exist in the SWIZZLE_128B_BASE32B layout (32-byte chunks
 // XOR-swizzled inside 128-byte rows, pattern period 4 rows; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of
 // 4 K-rows x 128 B (32 tf32 along M/N). lbo = byte stride between 32-wide M/N groups, sbo = between 4-row K groups.
@@ -124,6 +128,18 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, int a_mn, i
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// kind::f16 (fp16 or bf16 operands, chosen per operand), fp32 accumulate, K-major operands
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N, int a_bf16, int b_bf16) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (K = 16 per instruction), issued by one thread
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 #endif  // __CUDACC__
 
 // ------------------------------------------------------------------------------------------ host side
@@ -133,5 +149,8 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, int a_mn, i
 // swizzle_32b_atom: 0 = SWIZZLE_128B (K-major operands), 1 = SWIZZLE_128B_ATOM_32B (MN-major tf32 operands).
 int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, int swizzle_32b_atom = 0);
+// the same for 2-byte elements (fp16 / bf16 share the encoding): row_bytes = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
+int make_tmap_16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, int row_bytes);
 
 }  // namespace tc

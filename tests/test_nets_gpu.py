@@ -568,3 +568,36 @@ def test_validation_batch_matches_reference_loop(q):
     assert (out["ocr_crt"], out["ocr_cer"]) == po.compare_labels(ocr_labels, labels)
     assert (out["matching_crt"], out["matching_cer"]) == po.compare_labels(preds_r, ocr_labels)
     assert out["ocr_crt"] == B - len(range(0, B, 3))
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,p,relu", [
+    (8, 32, 128, 32, 32, 3, 1, 0),      # 32 input channels: 64-byte operand rows (SWIZZLE_64B)
+    (8, 16, 64, 64, 64, 3, 1, 1),       # 64-element K blocks
+    (4, 8, 32, 128, 256, 3, 1, 0),
+    (64, 2, 8, 512, 512, 3, 1, 0),      # split-K with fp16 operands
+    (2, 2, 31, 512, 512, 2, 0, 0),      # conv7 geometry (2x2, no padding)
+    (1, 1, 1984, 512, 2048, 1, 0, 0),   # LSTM input projection
+    (3, 5, 7, 96, 64, 3, 1, 1),         # 96 channels: not a multiple of 64 -> 32-element K blocks; ragged tiles
+])
+def test_conv_fprop_fp16_operands(q, N, H, W, Cin, Cout, k, p, relu):
+    """kind::f16 operand path of the fprop kernel (forward pass): exact on fp16-representable inputs up to fp32 accumulation
+    order, and within fp16 rounding (2^-11 relative per operand) of the fp32 convolution; fp16 output shadow = RN(output)."""
+    g = torch.Generator(device=DEV).manual_seed(N * 1000 + Cin + Cout)
+    x = torch.randn(N, H, W, Cin, device=DEV, generator=g)
+    w = torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5
+    bias = torch.randn(Cout, device=DEV, generator=g)
+    x16 = x.half()
+    wp16 = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous().half()
+    Ho, Wo = H + 2 * p - k + 1, W + 2 * p - k + 1
+    out = torch.zeros(N, Ho, Wo, Cout, device=DEV)
+    out16 = torch.zeros(N, Ho, Wo, Cout, device=DEV, dtype=torch.float16)
+    q.lib.call("qeb_conv_fprop_tc16", x16.data_ptr(), N, H, W, Cin, Cin, wp16.data_ptr(), Cout, k, k, p, p, bias.data_ptr(), None, relu,
+               out.data_ptr(), Cout, out16.data_ptr(), st())
+    ref16 = F.conv2d(x16.double().permute(0, 3, 1, 2), w.half().double(), bias.double(), padding=p)
+    ref32 = F.conv2d(x.double().permute(0, 3, 1, 2), w.double(), bias.double(), padding=p)
+    if relu:
+        ref16, ref32 = ref16.relu(), ref32.relu()
+    ref16, ref32 = ref16.permute(0, 2, 3, 1), ref32.permute(0, 2, 3, 1)
+    assert rel(out, ref16) < 5e-6          # the products of fp16 operands are exact in fp32; only the summation order differs
+    assert rel(out, ref32) < 1e-3          # operand rounding: 2^-11 relative each
+    assert torch.equal(out16, out.half())
