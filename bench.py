@@ -188,7 +188,7 @@ def workload_config(n_gpus):
     return {"workload": "configs[1]: train_nn_area phase B step - UNet(train BN) + CRNN surrogate (BN frozen) fwd/bwd + CTC(mean) + "
                         "1.0*MSE-to-white + Adam(lr 5e-5) on the UNet; 64 synthetic 32x128 patches per GPU, V=95, T=31",
             "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "patch": [H, W], "parallelism": f"dp{n_gpus}",
-            "operand_precision": "tf32 tensor-core operands, fp32 accumulate/activations (reference: fp32)",
+            "operand_precision": "tensor-core operands with an 11-bit significand (fp16 copies in the forward pass, tf32 reads of fp32 in the backward pass), fp32 accumulation / activations / gradients / parameters (reference: fp32)",
             "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2",
             "launch": "forward+losses+backward replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); all-reduce and Adam outside it"}
 
@@ -360,8 +360,9 @@ def run():
             peak = peaks.get("bf16_tflops", 1590.0)
             ach = v["flops"] / v["ms"] / 1e9
             roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                        "traffic": traffic, "peak_source": ("measured bf16 dense burst (MEASURED_PEAKS.json); the kernel is kind::tf32, "
-                                                            "nominally half the bf16 rate" if peaks else "fallback 1590 bf16")}
+                        "traffic": traffic, "peak_source": ("measured bf16 dense burst (MEASURED_PEAKS.json); the family is kind::f16 in the forward "
+                                                            "pass and kind::tf32 (nominally half the rate) in the backward pass"
+                                                            if peaks else "fallback 1590 bf16")}
         else:
             peak = peaks.get("hbm_gbs", 6650.0)
             ach = v["bytes"] / v["ms"] / 1e6
@@ -434,7 +435,7 @@ def run():
         h2d = x_pin.numel() * 4 + tg_static._host.numel() * 4   # image batch + the staged CTC targets / lengths
         line = {"metric": "patches/sec per train step (UNet+CRNN+CTC)", "value": value, "unit": "patches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(world),
+                "vs_baseline": None, "dtype": "fp16/tf32", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
                 "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": last_loss,
