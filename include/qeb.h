@@ -141,13 +141,6 @@ int qeb_unet_forward(const float* x, int B, int H, int W, const float* const* pa
 int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
                       const float* y, const float* dy, float* const* grads, float* dx, void* stream);
 
-/* fp16-operand variant of qeb_conv_fprop_tc (forward pass): x16 = the input as NHWC fp16 (channel stride a multiple of
- * 8), w16 = the packed weights [n_total][kh*kw*cin] as fp16; fp32 accumulation and fp32 output as above, out16 (nullable) =
- * fp16 shadow of the output for the next layer. Same 11-bit significand as tf32, rounded to nearest. */
-int qeb_conv_fprop_tc16(const void* x16, int n_img, int h_in, int w_in, int cin, int x_cstride, const void* w16,
-                        int n_total, int kh, int kw, int ph, int pw, const float* bias, const float* scale, int relu,
-                        float* out, int out_cstride, void* out16, void* stream);
-
 /* ==== building blocks, exported for tests and for callers that compose their own graphs ===========================
  * Tensor-core contractions (tcgen05 kind::tf32, fp32 accumulate). Activations NHWC with a channel stride (a channel
  * slice of a wider buffer is passed as base pointer + stride); channel counts on the contracted side are multiples of 32.
@@ -162,6 +155,13 @@ int qeb_nhwc_to_nchw(const float* src, float* dst, int N, int C, int H, int W, i
 int qeb_conv_fprop_tc(const float* x, int n_img, int h_in, int w_in, int cin, int x_cstride, const float* wpacked,
                       int n_total, int kh, int kw, int ph, int pw, const float* bias, const float* scale, int relu,
                       float* out, int out_cstride, int accumulate, void* stream);
+
+/* fp16-operand variant of qeb_conv_fprop_tc (forward pass): x16 = the input as NHWC fp16 (channel stride a multiple of
+ * 8), w16 = the packed weights [n_total][kh*kw*cin] as fp16; fp32 accumulation and fp32 output as above, out16 (nullable) =
+ * fp16 shadow of the output for the next layer. Same 11-bit significand as tf32, rounded to nearest. */
+int qeb_conv_fprop_tc16(const void* x16, int n_img, int h_in, int w_in, int cin, int x_cstride, const void* w16,
+                        int n_total, int kh, int kw, int ph, int pw, const float* bias, const float* scale, int relu,
+                        float* out, int out_cstride, void* out16, void* stream);
 int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, int w_in, const float* dy, int cout,
                       int dy_cstride, int n_img, int kh, int kw, int ph, int pw, float* dw, void* stream);
 int qeb_convT2x2_fprop_tc(const float* x, int n_img, int h, int w, int cin, int x_cstride, const float* wpacked,

@@ -1,4 +1,4 @@
-// Implicit-GEMM convolution / GEMM on tcgen05 (kind::tf32, fp32 accumulate in TMEM), operands staged by TMA.
+// Implicit-GEMM convolution / GEMM on tcgen05 (fp32 accumulate in TMEM), operands staged by TMA.
 //
 // One kernel family serves every dense contraction of the hot path whose operands are K-major:
 //   conv fprop    models/model_crnn.py:47-56 (conv2..conv7), models/model_unet.py:_block (all but the 1-channel conv)
@@ -6,13 +6,17 @@
 //   GEMM          LSTM input projections (nn.LSTM, models/model_crnn.py:9,19), Linear (models/model_crnn.py:10,20),
 //                 ConvTranspose2d 2x2 s2 (models/model_unet.py:25-44) as a per-pixel GEMM with a pixel-shuffle store
 //
-// Data layout: activations NHWC fp32 in HBM (channels contiguous, arbitrary channel stride so that concat buffers
-// are read/written in place); weights packed [Cout][tap][Cin] (K-major). A CTA computes a 128-pixel x BLOCK_N
-// output tile: for every filter tap and 32-channel slice one 4-D TMA box {32 ch, Wt, Ht, Nt} (Wt*Ht*Nt = 128
-// output pixels, shifted by the tap, out-of-bounds = zero padding) lands in shared memory as the K-major
-// 128B-swizzled A tile, one 2-D box {32, BLOCK_N} as the B tile; four tcgen05.mma (K=8 each) consume the stage.
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (tcgen05.ld -> bias/ReLU ->
-// global). Pipelines: smem full/empty mbarriers (kStages deep), one TMEM-full barrier.
+// Data layout: activations NHWC fp32 in HBM (channels contiguous, arbitrary channel stride so that concat buffers are
+// read/written in place), optionally shadowed by fp16 copies with the same element layout; weights packed
+// [Cout][tap][Cin] (K-major). The kernel is persistent: a CTA walks 128-pixel x BLOCK_N output tiles; for every filter tap
+// and K block (32 tf32 channels, or 64 / 32 fp16 channels = one 128- / 64-byte swizzled row) one 4-D TMA box
+// {channels, Wt, Ht, Nt} (Wt*Ht*Nt = 128 output pixels, shifted by the tap, out-of-bounds = zero padding) lands in shared
+// memory as the K-major A tile, one 2-D box {channels, BLOCK_N} as the B tile; tcgen05.mma (kind::tf32 K = 8 or kind::f16
+// K = 16 per instruction) consume the stage into one of two TMEM accumulators.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue (tcgen05.ld -> scale / bias / ReLU /
+// mask / BatchNorm sums -> transposed through shared memory -> global, fp32 and optional fp16 shadow). Pipelines: smem
+// full/empty mbarriers (2-8 stages, running across tiles), TMEM full/empty barriers per accumulator.
+// The weight-gradient kernel (conv_wgrad_tc_kernel, below) reads both operands MN-major straight from the activations.
 #include "tc_common.cuh"
 #include "nn.cuh"
 #include <cuda_fp16.h>
@@ -1007,7 +1011,6 @@ int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
   return wgrad_common(ta, tb, p, dy.c, x.c, st);
 }
 
-// C ABI: weight gradient of a stride-1 convolution / Linear in torch's layout dw[co][ci][kh][kw], accumulated.
 // the same contraction with fp16 operands (x16: NHWC fp16 image, w16: packed fp16 weights) and an optional fp16 shadow of
 // the fp32 output
 QEB_API int qeb_conv_fprop_tc16(const void* x16, int n_img, int h_in, int w_in, int cin, int x_cstride, const void* w16,
@@ -1024,6 +1027,7 @@ QEB_API int qeb_conv_fprop_tc16(const void* x16, int n_img, int h_in, int w_in, 
   return tc_conv_fprop(xi, reinterpret_cast<const float*>(w16), n_total, kh, kw, ph, pw, oi, ep, (cudaStream_t)stream);
 }
 
+// C ABI: weight gradient of a stride-1 convolution / Linear in torch's layout dw[co][ci][kh][kw], accumulated.
 QEB_API int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, int w_in, const float* dy, int cout,
                               int dy_cstride, int n_img, int kh, int kw, int ph, int pw, float* dw, void* stream) {
   Img xi = img_nhwc(const_cast<float*>(x), n_img, h_in, w_in, cin, x_cstride);
