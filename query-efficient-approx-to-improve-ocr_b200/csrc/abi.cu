@@ -160,3 +160,8 @@ int SideStream::join() {
   dirty = false;
   return QEB_OK;
 }
+
+bool qeb_pdl_enabled() {
+  static const bool on = !(getenv("QEB_PDL") && atoi(getenv("QEB_PDL")) == 0);
+  return on;
+}

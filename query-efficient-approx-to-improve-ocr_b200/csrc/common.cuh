@@ -64,6 +64,31 @@ struct ProfScope {
   }
 };
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------------
+// A training step is ~230 short kernels in a row; with plain stream order every kernel pays launch latency + the ramp of
+// its first wave after the previous grid has drained. Kernels of the step are launched with the programmatic-stream-
+// serialization attribute (also captured into CUDA graphs as programmatic edges): the next grid may be scheduled while the
+// previous one is still running, and blocks in qeb_pdl_sync() - the FIRST statement of every kernel launched this way -
+// until the previous grid has completed and its memory is visible. QEB_PDL=0 launches everything with full serialization.
+bool qeb_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void qeb_pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t qeb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = qeb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 #ifdef __CUDACC__
 constexpr unsigned FULL_MASK = 0xffffffffu;
 

@@ -362,6 +362,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  qeb_pdl_sync();   // everything above (tensor-map prefetch, barrier init, TMEM allocation) overlaps the previous grid's tail
   if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (warp == 0) {
@@ -513,8 +514,7 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams&
   ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  conv_fprop_tc_kernel<BLOCK_N, ROWB, F16><<<grid, kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
-  QEB_LAUNCH_CHECK();
+  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16>, grid, kThreads, Cfg::smem_bytes(p.stages), st, ta, tb, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -807,6 +807,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  qeb_pdl_sync();
 
   if (t_begin < t_end) {
     if (warp == 0) {
@@ -916,8 +917,7 @@ int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams&
   p.stages = Cfg::pick_stages((long long)grid.x * grid.y * grid.z);
   ProfScope prof("tc_conv_wgrad", st, 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.row_blocks * 32,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.a_groups * 32 + p.n_total) + (double)p.n_total * p.row_blocks * 32));
-  conv_wgrad_tc_kernel<BLOCK_N><<<grid, kThreads, Cfg::smem_bytes(p.stages), st>>>(ta, tb, p);
-  QEB_LAUNCH_CHECK();
+  QEB_CUDA(qeb_launch(conv_wgrad_tc_kernel<BLOCK_N>, grid, kThreads, Cfg::smem_bytes(p.stages), st, ta, tb, p));
   qeb_count_launch();
   return QEB_OK;
 }

@@ -50,6 +50,7 @@ struct CtcArgs {
 
 template <int SPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_alpha_kernel(CtcArgs a) {
+  qeb_pdl_sync();
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * kWarpsPerBlock + warp;
@@ -167,6 +168,7 @@ struct CtcBwdArgs {
 
 template <int SPL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_beta_grad_kernel(CtcBwdArgs g) {
+  qeb_pdl_sync();
   const CtcArgs& a = g.f;
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -310,6 +312,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_beta_grad_kernel(CtcB
 // loss reduction: out[0] = mean_b(nll_b / max(1, L_b)) (mean) or sum_b nll_b (sum); single warp, fixed order.
 __global__ void ctc_reduce_kernel(const float* nll, const int* target_lengths, int B, int reduction, int zero_infinity,
                                   float* out) {
+  qeb_pdl_sync();
   float acc = 0.f;
   for (int b = threadIdx.x; b < B; b += 32) {
     float v = nll[b];
@@ -325,6 +328,7 @@ __global__ void ctc_reduce_kernel(const float* nll, const int* target_lengths, i
 }
 
 __global__ void ctc_zero_inf_kernel(float* nll, int B) {
+  qeb_pdl_sync();
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B && nll[b] == INFINITY) nll[b] = 0.f;
 }
@@ -332,6 +336,7 @@ __global__ void ctc_zero_inf_kernel(float* nll, int B) {
 // ---------------------------------------------------------------------------------------------
 // log-softmax over the last (class) dimension, one warp per row
 __global__ void log_softmax_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int V) {
+  qeb_pdl_sync();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -349,6 +354,7 @@ __global__ void log_softmax_fwd_kernel(const float* __restrict__ x, float* __res
 // dx = dy - exp(y) * sum(dy)
 __global__ void log_softmax_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy,
                                        float* __restrict__ dx, long long rows, int V) {
+  qeb_pdl_sync();
   const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -389,14 +395,14 @@ QEB_API int qeb_ctc_fwd(const float* log_probs, long long st_t, long long st_b, 
   const size_t smem = (size_t)kWarpsPerBlock * V * sizeof(float);
   QEB_REQUIRE(smem <= 48 * 1024, "ctc_fwd: V=%d too large", V);
   int rc = dispatch_spl(a.S, [&](auto spl) {
-    ctc_alpha_kernel<decltype(spl)::value><<<grid, kWarpsPerBlock * 32, smem, st>>>(a);
+    QEB_CUDA(qeb_launch(ctc_alpha_kernel<decltype(spl)::value>, grid, kWarpsPerBlock * 32, smem, st, a));
     return 0;
   });
   (void)rc;
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   if (loss_out && reduction != 0) {
-    ctc_reduce_kernel<<<1, 32, 0, st>>>(nll, target_lengths, B, reduction, zero_infinity, loss_out);
+    QEB_CUDA(qeb_launch(ctc_reduce_kernel, 1, 32, 0, st, nll, target_lengths, B, reduction, zero_infinity, loss_out));
     QEB_LAUNCH_CHECK();
     qeb_count_launch();
   }
@@ -429,7 +435,7 @@ QEB_API int qeb_ctc_bwd(const float* log_probs, long long st_t, long long st_b, 
   const size_t smem = (size_t)kWarpsPerBlock * 3 * V * sizeof(float);
   QEB_REQUIRE(smem <= 48 * 1024, "ctc_bwd: V=%d too large", V);
   dispatch_spl(g.f.S, [&](auto spl) {
-    ctc_beta_grad_kernel<decltype(spl)::value><<<grid, kWarpsPerBlock * 32, smem, st>>>(g);
+    QEB_CUDA(qeb_launch(ctc_beta_grad_kernel<decltype(spl)::value>, grid, kWarpsPerBlock * 32, smem, st, g));
     return 0;
   });
   QEB_LAUNCH_CHECK();
@@ -440,7 +446,7 @@ QEB_API int qeb_ctc_bwd(const float* log_probs, long long st_t, long long st_b, 
 QEB_API int qeb_log_softmax_fwd(const float* x, float* y, long long rows, int V, void* stream) {
   QEB_REQUIRE(x && y && rows > 0 && V > 0, "log_softmax_fwd: bad args");
   ProfScope prof("log_softmax", (cudaStream_t)stream, 0.0, 8.0 * rows * V);
-  log_softmax_fwd_kernel<<<qeb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, y, rows, V);
+  QEB_CUDA(qeb_launch(log_softmax_fwd_kernel, qeb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream, x, y, rows, V));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -449,7 +455,7 @@ QEB_API int qeb_log_softmax_fwd(const float* x, float* y, long long rows, int V,
 QEB_API int qeb_log_softmax_bwd(const float* y, const float* dy, float* dx, long long rows, int V, void* stream) {
   QEB_REQUIRE(y && dy && dx && rows > 0 && V > 0, "log_softmax_bwd: bad args");
   ProfScope prof("log_softmax", (cudaStream_t)stream, 0.0, 12.0 * rows * V);
-  log_softmax_bwd_kernel<<<qeb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(y, dy, dx, rows, V);
+  QEB_CUDA(qeb_launch(log_softmax_bwd_kernel, qeb_cdiv(rows, 8), 256, 0, (cudaStream_t)stream, y, dy, dx, rows, V));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;

@@ -148,6 +148,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  qeb_pdl_sync();
   {
     // W_hh slice -> TMEM, rounded to tf32: lane = gate row (gate q, unit `lane`), column = k. Warps w and w + 4 share a
     // lane quarter and take 128 columns each; a thread streams 512 contiguous bytes of its row.
@@ -306,6 +307,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  qeb_pdl_sync();
   {
     // W_slice^T -> TMEM, rounded to tf32: half mh = warp / 4 of k lives in columns [128 mh, 128 mh + 128); lane = k % 128,
     // column = own gate row (gate gq, unit jl). For a fixed gate row the 32 lanes of a warp read 32 consecutive k.
@@ -466,6 +468,11 @@ int launch_cluster(const void* fn, size_t smem, int n_clusters, LstmArgs& args, 
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = qeb_pdl_enabled() ? 1 : 0;
   void* kargs[] = {&args};
   QEB_CUDA(cudaLaunchKernelExC(&cfg, fn, kargs));
   qeb_count_launch();

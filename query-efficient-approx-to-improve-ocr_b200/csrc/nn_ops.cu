@@ -52,6 +52,7 @@ template <int COUT>
 __global__ void __launch_bounds__(kThreads) c1_fwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int relu, float* __restrict__ out,
                                                           Geo go, long long n_pix) {
+  qeb_pdl_sync();
   constexpr int CQ = COUT / 4;
   const int cq = threadIdx.x % CQ;
   float wr[4][9], br[4];
@@ -93,6 +94,7 @@ template <int COUT>
 __global__ void __launch_bounds__(kThreads) c1_wgrad_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
                                                             Geo gd, float* __restrict__ dw, float* __restrict__ dbias,
                                                             long long n_pix) {
+  qeb_pdl_sync();
   constexpr int CQ = COUT / 4;
   constexpr int PPB = kThreads / CQ;  // pixels per block iteration
   const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) c1_wgrad_kernel(const float* __restr
 template <int COUT>
 __global__ void __launch_bounds__(kThreads) c1_dgrad_kernel(const float* __restrict__ dy, Geo gd, const float* __restrict__ w,
                                                             float* __restrict__ dx, Geo gx, long long n_pix) {
+  qeb_pdl_sync();
   constexpr int CQ = COUT / 4;
   const int cq = threadIdx.x % CQ;
   float wr[4][9];
@@ -187,6 +190,7 @@ __global__ void __launch_bounds__(kThreads) c1_dgrad_kernel(const float* __restr
 template <int CIN>
 __global__ void __launch_bounds__(kThreads) o1_fwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ w,
                                                           const float* __restrict__ b, float* __restrict__ y, long long n_pix) {
+  qeb_pdl_sync();
   constexpr int CQ = CIN / 4;
   const int cq = threadIdx.x % CQ;
   const float4 wv = ld4(w + cq * 4);
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(kThreads) o1_bwd_kernel(const float* __restric
                                                           const float* __restrict__ y, const float* __restrict__ dy,
                                                           float* __restrict__ dx, Geo gdx, float* __restrict__ dw,
                                                           float* __restrict__ db, long long n_pix) {
+  qeb_pdl_sync();
   constexpr int CQ = CIN / 4;
   constexpr int PPB = kThreads / CQ;
   const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
@@ -247,6 +252,7 @@ __global__ void __launch_bounds__(kThreads) o1_bwd_kernel(const float* __restric
 template <int PH, int PW>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, Geo gx, float* __restrict__ out,
                                                                Geo go, int cq_n, long long total, __half* __restrict__ out16) {
+  qeb_pdl_sync();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int cq = (int)(i % cq_n);
     const long long pix = i / cq_n;
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
                                                                Geo gd, int relu_mask, const float* __restrict__ chan_scale,
                                                                const float* __restrict__ add, Geo ga, float* __restrict__ dx,
                                                                Geo gdx, int cq_n, long long total) {
+  qeb_pdl_sync();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int cq = (int)(i % cq_n);
     const long long pix = i / cq_n;
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
 // z: [M][C] rows `zs` floats apart. thread = (row lane, channel quad).
 __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restrict__ z, long long zs, long long M, int C,
                                                             double* __restrict__ stats) {
+  qeb_pdl_sync();
   const int cq_n = C / 4, rpb = kThreads / cq_n;
   const int cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -374,6 +382,7 @@ __global__ void __launch_bounds__(kThreads) bn_stats_kernel(const float* __restr
 __global__ void bn_finalize_kernel(const double* __restrict__ stats, long long count, int C, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* running_mean, float* running_var,
                                    long long* nbt, float eps, float momentum, float* __restrict__ scsh) {
+  qeb_pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
@@ -396,6 +405,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, long long c
 __global__ void bn_eval_scsh_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                     const float* __restrict__ conv_bias, float* __restrict__ scsh) {
+  qeb_pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = 1.f / sqrtf(rv[c] + eps);
@@ -411,6 +421,7 @@ __global__ void bn_eval_scsh_kernel(int C, const float* __restrict__ gamma, cons
 __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restrict__ z, long long zs, long long M, int C,
                                                             const float* __restrict__ scsh, int relu, float* __restrict__ out,
                                                             long long os, __half* __restrict__ out16) {
+  qeb_pdl_sync();
   const int cq_n = C / 4;
   const long long total = M * cq_n;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
@@ -434,6 +445,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
                                                                   float* running_var, long long* nbt, float eps, float momentum,
                                                                   float* __restrict__ scsh, int relu, float* __restrict__ out,
                                                                   long long os, __half* __restrict__ out16) {
+  qeb_pdl_sync();
   const int cq_n = C / 4;
   const int cq = threadIdx.x % cq_n;
   float sc[4], sh[4];
@@ -482,6 +494,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __
                                                                  const float* __restrict__ dy, long long ds, long long M, int C,
                                                                  const float* __restrict__ scsh, int relu,
                                                                  double* __restrict__ red) {
+  qeb_pdl_sync();
   const int cq_n = C / 4, rpb = kThreads / cq_n;
   const int cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -531,6 +544,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
                                                                 const double* __restrict__ red, int mode,
                                                                 float* __restrict__ dz, long long dzs, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta) {
+  qeb_pdl_sync();
   const int cq_n = C / 4;
   const long long total = M * cq_n;
   if (blockIdx.x == 0 && dgamma) {
@@ -566,6 +580,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
 
 __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x, long long xs, long long M, int C,
                                                           float* __restrict__ out) {
+  qeb_pdl_sync();
   const int cq_n = (C + 3) / 4, rpb = max(1, kThreads / cq_n);
   extern __shared__ float sm[];  // [rpb][cq_n*4]
   const int Cp = cq_n * 4;
@@ -608,6 +623,7 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
 
 __global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const float* __restrict__ a, Geo ga, const float* __restrict__ dy,
                                                             Geo gd, float* __restrict__ dx, Geo gx, int cq_n, long long total) {
+  qeb_pdl_sync();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int cq = (int)(i % cq_n);
     const long long pix = i / cq_n;
@@ -621,6 +637,7 @@ __global__ void __launch_bounds__(kThreads) relu_bwd_kernel(const float* __restr
 __global__ void __launch_bounds__(kThreads) pack3d_kernel(const float* __restrict__ src, float* __restrict__ dst, int n0, int n1,
                                                           int n2, long long s0, long long s1, long long s2, long long d0,
                                                           long long d1) {
+  qeb_pdl_sync();
   const long long total = (long long)n0 * n1 * n2;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     const int i2 = (int)(i % n2);
@@ -637,6 +654,7 @@ struct PackJobsParam {
 };
 __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_constant__ PackJobsParam jobs, long long total,
                                                               int accumulate) {
+  qeb_pdl_sync();
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
     int lo = 0, hi = jobs.n - 1;
     while (lo < hi) {
@@ -668,6 +686,7 @@ struct ConvPackJobsParam {
 // phase 2 writes runs of 32 (modes 0, 1) or 32 * taps (mode 2) contiguous floats. All shared-memory strides (taps, pitch)
 // are odd, so every access is bank-conflict free.
 __global__ void __launch_bounds__(kThreads) conv_pack_kernel(const __grid_constant__ ConvPackJobsParam jobs, int accumulate) {
+  qeb_pdl_sync();
   extern __shared__ float tile[];
   int ji = 0;
   while (ji + 1 < jobs.n && jobs.j[ji + 1].tile_start <= (int)blockIdx.x) ++ji;
@@ -710,6 +729,7 @@ __global__ void __launch_bounds__(kThreads) conv_pack_kernel(const __grid_consta
 }
 
 __global__ void vec_add_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n) {
+  qeb_pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
 }
@@ -729,7 +749,7 @@ int pack_3d(const float* src, float* dst, int n0, int n1, int n2, long long s0, 
   ProfScope prof("pack", st, 0.0, 8.0 * n0 * n1 * n2);
   const long long total = (long long)n0 * n1 * n2;
   if (total == 0) return QEB_OK;
-  pack3d_kernel<<<qeb_grid(total, kThreads), kThreads, 0, st>>>(src, dst, n0, n1, n2, s0, s1, s2, d0, d1);
+  QEB_CUDA(qeb_launch(pack3d_kernel, qeb_grid(total, kThreads), kThreads, 0, st, src, dst, n0, n1, n2, s0, s1, s2, d0, d1));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -741,8 +761,8 @@ int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const
   QEB_REQUIRE(x.n == out.n && x.h == out.h && x.w == out.w && vec4_ok(out), "c1_conv_fwd: geometry/alignment");
   const long long n_pix = img_pixels(x);
   const int g = qeb_grid(n_pix * (out.c / 4), kThreads, 4);
-  if (out.c == 32) c1_fwd_kernel<32><<<g, kThreads, 0, st>>>(x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix);
-  else c1_fwd_kernel<64><<<g, kThreads, 0, st>>>(x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix);
+  if (out.c == 32) QEB_CUDA(qeb_launch(c1_fwd_kernel<32>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix));
+  else QEB_CUDA(qeb_launch(c1_fwd_kernel<64>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -754,8 +774,8 @@ int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStre
   QEB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w && vec4_ok(dy), "c1_conv_wgrad: geometry/alignment");
   const long long n_pix = img_pixels(x);
   const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 4);
-  if (dy.c == 32) c1_wgrad_kernel<32><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix);
-  else c1_wgrad_kernel<64><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix);
+  if (dy.c == 32) QEB_CUDA(qeb_launch(c1_wgrad_kernel<32>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix));
+  else QEB_CUDA(qeb_launch(c1_wgrad_kernel<64>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -767,8 +787,8 @@ int c1_conv_dgrad(const Img& dy, const float* w, const Img& dx, cudaStream_t st)
   QEB_REQUIRE(dx.n == dy.n && dx.h == dy.h && dx.w == dy.w && vec4_ok(dy), "c1_conv_dgrad: geometry/alignment");
   const long long n_pix = img_pixels(dx);
   const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 8);
-  if (dy.c == 32) c1_dgrad_kernel<32><<<g, kThreads, 0, st>>>(dy.p, geo(dy), w, dx.p, geo(dx), n_pix);
-  else c1_dgrad_kernel<64><<<g, kThreads, 0, st>>>(dy.p, geo(dy), w, dx.p, geo(dx), n_pix);
+  if (dy.c == 32) QEB_CUDA(qeb_launch(c1_dgrad_kernel<32>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_pix));
+  else QEB_CUDA(qeb_launch(c1_dgrad_kernel<64>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -778,7 +798,7 @@ int o1_conv_sigmoid_fwd(const Img& x, const float* w, const float* b, float* y, 
   ProfScope prof("o1_conv_sigmoid_fwd", st, 2.0 * (double)img_pixels(x) * x.c, 4.0 * (double)img_pixels(x) * (1 + x.c));
   QEB_REQUIRE(x.c == 32 && vec4_ok(x), "o1_conv_sigmoid_fwd: 32 input channels, aligned");
   const long long n_pix = img_pixels(x);
-  o1_fwd_kernel<32><<<qeb_grid(n_pix * 8, kThreads, 8), kThreads, 0, st>>>(x.p, geo(x), w, b, y, n_pix);
+  QEB_CUDA(qeb_launch(o1_fwd_kernel<32>, qeb_grid(n_pix * 8, kThreads, 8), kThreads, 0, st, x.p, geo(x), w, b, y, n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -789,7 +809,7 @@ int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const floa
   ProfScope prof("o1_conv_sigmoid_bwd", st, 4.0 * (double)img_pixels(x) * x.c, 4.0 * (double)img_pixels(x) * (2 + 2 * x.c));
   QEB_REQUIRE(x.c == 32 && dx.c == 32 && vec4_ok(x) && vec4_ok(dx), "o1_conv_sigmoid_bwd: 32 channels, aligned");
   const long long n_pix = img_pixels(x);
-  o1_bwd_kernel<32><<<qeb_grid(n_pix * 8, kThreads, 2), kThreads, 0, st>>>(x.p, geo(x), w, y, dy, dx.p, geo(dx), dw, db, n_pix);
+  QEB_CUDA(qeb_launch(o1_bwd_kernel<32>, qeb_grid(n_pix * 8, kThreads, 2), kThreads, 0, st, x.p, geo(x), w, y, dy, dx.p, geo(dx), dw, db, n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -803,8 +823,8 @@ int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, v
   const long long total = img_pixels(out) * cq_n;
   const int g = qeb_grid(total, kThreads);
   __half* o16 = static_cast<__half*>(out16);
-  if (ph == 2 && pw == 2) maxpool_fwd_kernel<2, 2><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total, o16);
-  else if (ph == 2 && pw == 1) maxpool_fwd_kernel<2, 1><<<g, kThreads, 0, st>>>(x.p, geo(x), out.p, geo(out), cq_n, total, o16);
+  if (ph == 2 && pw == 2) QEB_CUDA(qeb_launch(maxpool_fwd_kernel<2, 2>, g, kThreads, 0, st, x.p, geo(x), out.p, geo(out), cq_n, total, o16));
+  else if (ph == 2 && pw == 1) QEB_CUDA(qeb_launch(maxpool_fwd_kernel<2, 1>, g, kThreads, 0, st, x.p, geo(x), out.p, geo(out), cq_n, total, o16));
   else QEB_REQUIRE(false, "maxpool_fwd: window %dx%d not supported", ph, pw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -823,11 +843,11 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   Geo ga = add ? geo(*add) : geo(x);
   const float* ap = add ? add->p : nullptr;
   if (ph == 2 && pw == 2)
-    maxpool_bwd_kernel<2, 2><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
-                                                     total);
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
+                                                     total));
   else if (ph == 2 && pw == 1)
-    maxpool_bwd_kernel<2, 1><<<g, kThreads, 0, st>>>(x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
-                                                     total);
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 1>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
+                                                     total));
   else QEB_REQUIRE(false, "maxpool_bwd: window %dx%d not supported", ph, pw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -853,7 +873,7 @@ int bn_train_stats(const Img& z, double* stats, cudaStream_t st) {
   QEB_REQUIRE(z.c <= 1024, "bn_train_stats: at most 1024 channels");
   const long long M = img_pixels(z);
   const int rpb = kThreads / (z.c / 4);
-  bn_stats_kernel<<<reduce_grid(M, rpb, z.c), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, M, z.c, stats);
+  QEB_CUDA(qeb_launch(bn_stats_kernel, reduce_grid(M, rpb, z.c), kThreads, 2 * rpb * z.c * sizeof(float), st, z.p, z.sw, M, z.c, stats));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -861,8 +881,8 @@ int bn_train_stats(const Img& z, double* stats, cudaStream_t st) {
 
 int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st) {
   ProfScope prof("bn_finalize", st);
-  bn_finalize_kernel<<<qeb_cdiv(c, 128), 128, 0, st>>>(stats, count, c, bn.gamma, bn.beta, bn.running_mean, bn.running_var,
-                                                       bn.num_batches_tracked, bn.eps, bn.momentum, scsh);
+  QEB_CUDA(qeb_launch(bn_finalize_kernel, qeb_cdiv(c, 128), 128, 0, st, stats, count, c, bn.gamma, bn.beta, bn.running_mean, bn.running_var,
+                                                       bn.num_batches_tracked, bn.eps, bn.momentum, scsh));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -870,8 +890,8 @@ int bn_train_finalize(const double* stats, long long count, int c, const BnParam
 
 int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh, cudaStream_t st) {
   ProfScope prof("bn_finalize", st);
-  bn_eval_scsh_kernel<<<qeb_cdiv(c, 128), 128, 0, st>>>(c, bn.gamma, bn.beta, bn.running_mean, bn.running_var, bn.eps, conv_bias,
-                                                        scsh);
+  QEB_CUDA(qeb_launch(bn_eval_scsh_kernel, qeb_cdiv(c, 128), 128, 0, st, c, bn.gamma, bn.beta, bn.running_mean, bn.running_var, bn.eps, conv_bias,
+                                                        scsh));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -885,10 +905,10 @@ int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& b
   QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_train_finalize_apply: shape mismatch");
   QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_train_finalize_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
-  bn_apply_train_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
+  QEB_CUDA(qeb_launch(bn_apply_train_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
                                                                                bn.running_mean, bn.running_var,
                                                                                bn.num_batches_tracked, bn.eps, bn.momentum, scsh,
-                                                                               relu, out.p, out.sw, static_cast<__half*>(out16));
+                                                                               relu, out.p, out.sw, static_cast<__half*>(out16)));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -900,8 +920,8 @@ int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStre
   REQ_FLAT(out, "bn_apply");
   QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_apply: shape mismatch");
   const long long M = img_pixels(z);
-  bn_apply_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw,
-                                                                          static_cast<__half*>(out16));
+  QEB_CUDA(qeb_launch(bn_apply_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw,
+                                                                          static_cast<__half*>(out16)));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -914,8 +934,8 @@ int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, doub
   QEB_REQUIRE(z.c == dy.c && img_pixels(z) == img_pixels(dy) && z.c <= 1024, "bn_bwd_reduce: shape mismatch");
   const long long M = img_pixels(z);
   const int rpb = kThreads / (z.c / 4);
-  bn_bwd_reduce_kernel<<<reduce_grid(M, rpb, 2 * z.c), kThreads, 2 * rpb * z.c * sizeof(float), st>>>(z.p, z.sw, dy.p, dy.sw, M, z.c, scsh,
-                                                                                           relu, red);
+  QEB_CUDA(qeb_launch(bn_bwd_reduce_kernel, reduce_grid(M, rpb, 2 * z.c), kThreads, 2 * rpb * z.c * sizeof(float), st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh,
+                                                                                           relu, red));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -930,8 +950,8 @@ static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu
   QEB_REQUIRE(z.c == dy.c && z.c == dz.c && img_pixels(z) == img_pixels(dy) && img_pixels(z) == img_pixels(dz),
               "bn_bwd_apply: shape mismatch");
   const long long M = img_pixels(z);
-  bn_bwd_apply_kernel<<<qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st>>>(z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
-                                                                             dz.p, dz.sw, dgamma, dbeta);
+  QEB_CUDA(qeb_launch(bn_bwd_apply_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
+                                                                             dz.p, dz.sw, dgamma, dbeta));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -954,7 +974,7 @@ int colsum_acc(const Img& x, float* out, cudaStream_t st) {
   const long long M = img_pixels(x);
   const int cq_n = (x.c + 3) / 4;
   const int rpb = max(1, kThreads / cq_n);
-  colsum_kernel<<<reduce_grid(M, rpb, x.c), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st>>>(x.p, x.sw, M, x.c, out);
+  QEB_CUDA(qeb_launch(colsum_kernel, reduce_grid(M, rpb, x.c), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st, x.p, x.sw, M, x.c, out));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -965,7 +985,7 @@ int relu_bwd(const Img& a, const Img& dy, const Img& dx, cudaStream_t st) {
   QEB_REQUIRE(vec4_ok(a) && vec4_ok(dy) && vec4_ok(dx) && a.c == dy.c && a.c == dx.c, "relu_bwd: channel count / alignment");
   const int cq_n = a.c / 4;
   const long long total = img_pixels(a) * cq_n;
-  relu_bwd_kernel<<<qeb_grid(total, kThreads), kThreads, 0, st>>>(a.p, geo(a), dy.p, geo(dy), dx.p, geo(dx), cq_n, total);
+  QEB_CUDA(qeb_launch(relu_bwd_kernel, qeb_grid(total, kThreads), kThreads, 0, st, a.p, geo(a), dy.p, geo(dy), dx.p, geo(dx), cq_n, total));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -973,7 +993,7 @@ int relu_bwd(const Img& a, const Img& dy, const Img& dx, cudaStream_t st) {
 
 int vec_add(const float* a, const float* b, float* out, int n, cudaStream_t st) {
   ProfScope prof("vec_add", st, 0.0, 12.0 * n);
-  vec_add_kernel<<<qeb_cdiv(n, 256), 256, 0, st>>>(a, b, out, n);
+  QEB_CUDA(qeb_launch(vec_add_kernel, qeb_cdiv(n, 256), 256, 0, st, a, b, out, n));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -988,7 +1008,7 @@ int pack_flush(PackBatch& b, cudaStream_t st) {
     PackJobsParam p;
     for (int i = 0; i < b.n; ++i) p.j[i] = b.jobs[i];
     p.n = b.n;
-    pack_multi_kernel<<<qeb_grid(b.total, kThreads), kThreads, 0, st>>>(p, b.total, b.accumulate);
+    QEB_CUDA(qeb_launch(pack_multi_kernel, qeb_grid(b.total, kThreads), kThreads, 0, st, p, b.total, b.accumulate));
     QEB_LAUNCH_CHECK();
     qeb_count_launch();
   }
@@ -996,7 +1016,7 @@ int pack_flush(PackBatch& b, cudaStream_t st) {
     ConvPackJobsParam p;
     for (int i = 0; i < b.nc; ++i) p.j[i] = b.cjobs[i];
     p.n = b.nc;
-    conv_pack_kernel<<<b.ctiles, kThreads, (32 * (32 * 9 + 1)) * sizeof(float), st>>>(p, b.accumulate);
+    QEB_CUDA(qeb_launch(conv_pack_kernel, b.ctiles, kThreads, (32 * (32 * 9 + 1)) * sizeof(float), st, p, b.accumulate));
     QEB_LAUNCH_CHECK();
     qeb_count_launch();
   }

@@ -11,6 +11,7 @@ constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) mse_ones_fwd_kernel(const float* __restrict__ x, long long n, float inv_n,
                                                                 float* __restrict__ loss) {
+  qeb_pdl_sync();
   float s = 0.f;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
     const float d = x[i] - 1.f;
@@ -29,6 +30,7 @@ __global__ void __launch_bounds__(kThreads) mse_ones_fwd_kernel(const float* __r
 
 __global__ void __launch_bounds__(kThreads) mse_ones_bwd_kernel(const float* __restrict__ x, long long n, float two_inv_n,
                                                                 const float* __restrict__ gout, float* __restrict__ dx) {
+  qeb_pdl_sync();
   const float g = __ldg(gout) * two_inv_n;
   for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads)
     dx[i] = (x[i] - 1.f) * g;
@@ -46,6 +48,7 @@ struct AdamTensor {
 __global__ void __launch_bounds__(kThreads) adam_multi_kernel(const AdamTensor* __restrict__ tab, int n_tensors,
                                                               long long n_chunks, float lr, float beta1, float beta2, float eps,
                                                               float weight_decay, float bc1, float bc2_sqrt) {
+  qeb_pdl_sync();
   for (long long c = blockIdx.x; c < n_chunks; c += gridDim.x) {
     int lo = 0, hi = n_tensors - 1;  // last tensor whose chunk0 <= c
     while (lo < hi) {
@@ -79,7 +82,7 @@ QEB_API int qeb_mse_ones_fwd(const float* x, long long n, float* loss, void* str
   cudaStream_t st = (cudaStream_t)stream;
   ProfScope prof("mse", st, 0.0, 4.0 * n);
   QEB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
-  mse_ones_fwd_kernel<<<qeb_grid(n, kThreads, 4), kThreads, 0, st>>>(x, n, 1.f / (float)n, loss);
+  QEB_CUDA(qeb_launch(mse_ones_fwd_kernel, qeb_grid(n, kThreads, 4), kThreads, 0, st, x, n, 1.f / (float)n, loss));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -89,7 +92,7 @@ QEB_API int qeb_mse_ones_fwd(const float* x, long long n, float* loss, void* str
 QEB_API int qeb_mse_ones_bwd(const float* x, long long n, const float* grad_out, float* dx, void* stream) {
   QEB_REQUIRE(x && grad_out && dx && n > 0, "mse_ones_bwd: bad arguments");
   ProfScope prof("mse", (cudaStream_t)stream, 0.0, 8.0 * n);
-  mse_ones_bwd_kernel<<<qeb_grid(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(x, n, 2.f / (float)n, grad_out, dx);
+  QEB_CUDA(qeb_launch(mse_ones_bwd_kernel, qeb_grid(n, kThreads), kThreads, 0, (cudaStream_t)stream, x, n, 2.f / (float)n, grad_out, dx));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -106,8 +109,8 @@ QEB_API int qeb_adam_multi(const void* table, int n_tensors, long long n_chunks,
   long long g = n_chunks;
   if (g > 16LL * kNumSMs) g = 16LL * kNumSMs;
   ProfScope prof("adam", (cudaStream_t)stream, 0.0, 28.0 * 1024 * n_chunks);
-  adam_multi_kernel<<<(int)g, kThreads, 0, (cudaStream_t)stream>>>(static_cast<const AdamTensor*>(table), n_tensors, n_chunks, lr,
-                                                                   beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2));
+  QEB_CUDA(qeb_launch(adam_multi_kernel, (int)g, kThreads, 0, (cudaStream_t)stream, static_cast<const AdamTensor*>(table), n_tensors, n_chunks, lr,
+                                                                   beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2)));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
