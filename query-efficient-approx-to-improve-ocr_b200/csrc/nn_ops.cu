@@ -47,11 +47,38 @@ __device__ __forceinline__ long long pix_off(const Geo& g, long long pix) {
 bool vec4_ok(const Img& a) { return ((uintptr_t)a.p & 15) == 0 && a.sn % 4 == 0 && a.sh % 4 == 0 && a.sw % 4 == 0 && a.c % 4 == 0; }
 
 // ------------------------------------------------------------------------------------------------ conv, Cin = 1
-// thread = (pixel, 4 output channels); weights of the 4 channels live in registers
+// thread = (4 consecutive pixels of a row, 4 output channels). The 3 x 6 input window of the pixel quad is loaded once
+// (18 scalar loads for 4 pixels instead of 36), index arithmetic is 32-bit and amortised over the quad. w % 4 == 0.
+// A quad index q = ((n * h + hv) * (w / 4) + wq) decomposes the image; CQ = COUT / 4 threads share a quad.
+struct QuadPos {
+  int n, hv, w0;
+};
+__device__ __forceinline__ QuadPos quad_pos(int q, int h, int wq_n) {
+  QuadPos p;
+  const int row = q / wq_n;
+  p.w0 = (q - row * wq_n) * 4;
+  p.n = row / h;
+  p.hv = row - p.n * h;
+  return p;
+}
+// xv[r][c] = x(hv - 1 + r, w0 - 1 + c), zero outside the image
+__device__ __forceinline__ void load_window(const float* __restrict__ xb, const Geo& gx, int hv, int w0, float (&xv)[3][6]) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int hh = hv + r - 1;
+    const bool rok = hh >= 0 && hh < gx.h;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const int ww = w0 + c - 1;
+      xv[r][c] = (rok && ww >= 0 && ww < gx.w) ? __ldg(xb + (long long)hh * gx.sh + (long long)ww * gx.sw) : 0.f;
+    }
+  }
+}
+
 template <int COUT>
 __global__ void __launch_bounds__(kThreads) c1_fwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ w,
                                                           const float* __restrict__ bias, int relu, float* __restrict__ out,
-                                                          Geo go, long long n_pix) {
+                                                          Geo go, int n_quads) {
   qeb_pdl_sync();
   constexpr int CQ = COUT / 4;
   const int cq = threadIdx.x % CQ;
@@ -62,30 +89,27 @@ __global__ void __launch_bounds__(kThreads) c1_fwd_kernel(const float* __restric
     for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cq * 4 + j) * 9 + t);
     br[j] = bias ? __ldg(bias + cq * 4 + j) : 0.f;
   }
-  const long long stride = (long long)gridDim.x * (kThreads / CQ);
-  for (long long pix = (long long)blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ; pix < n_pix; pix += stride) {
-    const int wv = (int)(pix % gx.w);
-    const long long t = pix / gx.w;
-    const int hv = (int)(t % gx.h);
-    const long long n = t / gx.h;
-    const float* xb = x + n * gx.sn;
-    float xv[9];
+  const int wq_n = gx.w / 4;
+  const int stride = gridDim.x * (kThreads / CQ);
+  for (int q = blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ; q < n_quads; q += stride) {
+    const QuadPos qp = quad_pos(q, gx.h, wq_n);
+    float xv[3][6];
+    load_window(x + (long long)qp.n * gx.sn, gx, qp.hv, qp.w0, xv);
+    float* ob = out + (long long)qp.n * go.sn + (long long)qp.hv * go.sh + (long long)qp.w0 * go.sw + cq * 4;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int px = 0; px < 4; ++px) {
+      float acc[4];
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int hh = hv + ky - 1, ww = wv + kx - 1;
-        xv[ky * 3 + kx] = (hh >= 0 && hh < gx.h && ww >= 0 && ww < gx.w) ? __ldg(xb + hh * gx.sh + ww * gx.sw) : 0.f;
+      for (int j = 0; j < 4; ++j) {
+        float a = br[j];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a = fmaf(xv[ky][px + kx], wr[j][ky * 3 + kx], a);
+        acc[j] = relu ? fmaxf(a, 0.f) : a;
       }
-    float acc[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = br[j];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(xv[k], wr[j][k], a);
-      acc[j] = relu ? fmaxf(a, 0.f) : a;
+      st4(ob + (long long)px * go.sw, make_float4(acc[0], acc[1], acc[2], acc[3]));
     }
-    st4(out + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
   }
 }
 
@@ -93,38 +117,42 @@ __global__ void __launch_bounds__(kThreads) c1_fwd_kernel(const float* __restric
 template <int COUT>
 __global__ void __launch_bounds__(kThreads) c1_wgrad_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
                                                             Geo gd, float* __restrict__ dw, float* __restrict__ dbias,
-                                                            long long n_pix) {
+                                                            int n_quads) {
   qeb_pdl_sync();
   constexpr int CQ = COUT / 4;
-  constexpr int PPB = kThreads / CQ;  // pixels per block iteration
+  constexpr int PPB = kThreads / CQ;  // pixel quads per block iteration
   const int cq = threadIdx.x % CQ, pl = threadIdx.x / CQ;
   float acc[4][10];
 #pragma unroll
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int t = 0; t < 10; ++t) acc[j][t] = 0.f;
-  const long long stride = (long long)gridDim.x * PPB;
-  for (long long pix = (long long)blockIdx.x * PPB + pl; pix < n_pix; pix += stride) {
-    const int wv = (int)(pix % gx.w);
-    const long long t = pix / gx.w;
-    const int hv = (int)(t % gx.h);
-    const long long n = t / gx.h;
-    const float* xb = x + n * gx.sn;
-    const float4 g = ld4(dy + n * gd.sn + hv * gd.sh + wv * gd.sw + cq * 4);
-    const float gv[4] = {g.x, g.y, g.z, g.w};
+  const int wq_n = gx.w / 4;
+  const int stride = gridDim.x * PPB;
+  for (int q = blockIdx.x * PPB + pl; q < n_quads; q += stride) {
+    const QuadPos qp = quad_pos(q, gx.h, wq_n);
+    float xv[3][6];
+    load_window(x + (long long)qp.n * gx.sn, gx, qp.hv, qp.w0, xv);
+    const float* db = dy + (long long)qp.n * gd.sn + (long long)qp.hv * gd.sh + (long long)qp.w0 * gd.sw + cq * 4;
+    float4 g4[4];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
+    for (int px = 0; px < 4; ++px) g4[px] = ld4(db + (long long)px * gd.sw);
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int hh = hv + ky - 1, ww = wv + kx - 1;
-        const float xv = (hh >= 0 && hh < gx.h && ww >= 0 && ww < gx.w) ? __ldg(xb + hh * gx.sh + ww * gx.sw) : 0.f;
+    for (int px = 0; px < 4; ++px) {
+      const float gv[4] = {g4[px].x, g4[px].y, g4[px].z, g4[px].w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[j][ky * 3 + kx] = fmaf(gv[j], xv, acc[j][ky * 3 + kx]);
-      }
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j][9] += gv[j];
+        for (int kx = 0; kx < 3; ++kx) {
+          const float xe = xv[ky][px + kx];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j][ky * 3 + kx] = fmaf(gv[j], xe, acc[j][ky * 3 + kx]);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j][9] += gv[j];
+    }
   }
-  // reduce over the PPB pixel lanes of the block through shared memory, then one atomic per (channel, tap)
+  // reduce over the PPB quad lanes of the block through shared memory, then one atomic per (channel, tap)
   __shared__ float red[PPB][CQ * 4 + 1];
   for (int t = 0; t < 10; ++t) {
     __syncthreads();
@@ -140,10 +168,11 @@ __global__ void __launch_bounds__(kThreads) c1_wgrad_kernel(const float* __restr
   }
 }
 
-// dx[h][w] = sum_{ky,kx,co} dy[h-ky+1][w-kx+1][co] * w[co][ky][kx];  CQ lanes per pixel, shuffle-reduced
+// dx[h][w] = sum_{ky,kx,co} dy[h-ky+1][w-kx+1][co] * w[co][ky][kx]; CQ lanes per pixel quad (4 channels each), the
+// 3 x 6 window of dy vectors is loaded once for the four pixels, partial sums are shuffle-reduced over the CQ lanes
 template <int COUT>
 __global__ void __launch_bounds__(kThreads) c1_dgrad_kernel(const float* __restrict__ dy, Geo gd, const float* __restrict__ w,
-                                                            float* __restrict__ dx, Geo gx, long long n_pix) {
+                                                            float* __restrict__ dx, Geo gx, int n_quads) {
   qeb_pdl_sync();
   constexpr int CQ = COUT / 4;
   const int cq = threadIdx.x % CQ;
@@ -152,37 +181,49 @@ __global__ void __launch_bounds__(kThreads) c1_dgrad_kernel(const float* __restr
   for (int j = 0; j < 4; ++j)
 #pragma unroll
     for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(w + (cq * 4 + j) * 9 + t);
-  const long long stride = (long long)gridDim.x * (kThreads / CQ);
-  const long long n_iter = (n_pix + stride - 1) / stride;
-  long long pix = (long long)blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ;
-  for (long long it = 0; it < n_iter; ++it, pix += stride) {  // uniform trip count: shuffles below need full warps
-    float a = 0.f;
-    int wv = 0, hv = 0;
-    long long n = 0;
-    const bool live = pix < n_pix;
+  const int wq_n = gx.w / 4;
+  const int stride = gridDim.x * (kThreads / CQ);
+  const int n_iter = (n_quads + stride - 1) / stride;
+  int q = blockIdx.x * (kThreads / CQ) + threadIdx.x / CQ;
+  for (int it = 0; it < n_iter; ++it, q += stride) {  // uniform trip count: shuffles below need full warps
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool live = q < n_quads;
+    QuadPos qp = {0, 0, 0};
     if (live) {
-      wv = (int)(pix % gx.w);
-      const long long t = pix / gx.w;
-      hv = (int)(t % gx.h);
-      n = t / gx.h;
-      const float* db = dy + n * gd.sn + cq * 4;
+      qp = quad_pos(q, gx.h, wq_n);
+      const float* db = dy + (long long)qp.n * gd.sn + cq * 4;
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+      for (int r = 0; r < 3; ++r) {   // dy row hv - 1 + r contributes with ky = 2 - r
+        const int hh = qp.hv + r - 1;
+        if (hh < 0 || hh >= gd.h) continue;
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const int hh = hv - ky + 1, ww = wv - kx + 1;
-          if (hh >= 0 && hh < gd.h && ww >= 0 && ww < gd.w) {
-            const float4 g = ld4(db + hh * gd.sh + ww * gd.sw);
-            a = fmaf(g.x, wr[0][ky * 3 + kx], a);
-            a = fmaf(g.y, wr[1][ky * 3 + kx], a);
-            a = fmaf(g.z, wr[2][ky * 3 + kx], a);
-            a = fmaf(g.w, wr[3][ky * 3 + kx], a);
+        for (int c = 0; c < 6; ++c) {   // dy column w0 - 1 + c contributes to pixel px with kx = px + 1 - (c - 1) ... kx = px - c + 2
+          const int ww = qp.w0 + c - 1;
+          if (ww < 0 || ww >= gd.w) continue;
+          const float4 g = ld4(db + (long long)hh * gd.sh + (long long)ww * gd.sw);
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const int kx = px - c + 2;
+            if (kx >= 0 && kx < 3) {
+              const int tap = (2 - r) * 3 + kx;
+              a[px] = fmaf(g.x, wr[0][tap], a[px]);
+              a[px] = fmaf(g.y, wr[1][tap], a[px]);
+              a[px] = fmaf(g.z, wr[2][tap], a[px]);
+              a[px] = fmaf(g.w, wr[3][tap], a[px]);
+            }
           }
         }
+      }
     }
 #pragma unroll
-    for (int o = CQ / 2; o > 0; o >>= 1) a += __shfl_xor_sync(FULL_MASK, a, o);
-    if (live && cq == 0) dx[n * gx.sn + hv * gx.sh + wv * gx.sw] = a;
+    for (int o = CQ / 2; o > 0; o >>= 1) {
+#pragma unroll
+      for (int px = 0; px < 4; ++px) a[px] += __shfl_xor_sync(FULL_MASK, a[px], o);
+    }
+    if (live && cq < 4) {   // lane cq writes pixel cq of the quad
+      const float v = cq == 0 ? a[0] : (cq == 1 ? a[1] : (cq == 2 ? a[2] : a[3]));
+      dx[(long long)qp.n * gx.sn + (long long)qp.hv * gx.sh + (long long)(qp.w0 + cq) * gx.sw] = v;
+    }
   }
 }
 
@@ -759,10 +800,11 @@ int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const
   ProfScope prof("c1_conv_fwd", st, 18.0 * (double)img_pixels(x) * out.c, 4.0 * (double)img_pixels(x) * (1 + out.c));
   QEB_REQUIRE(x.c == 1 && (out.c == 32 || out.c == 64), "c1_conv_fwd: 1 -> 32/64 channels only (got %d -> %d)", x.c, out.c);
   QEB_REQUIRE(x.n == out.n && x.h == out.h && x.w == out.w && vec4_ok(out), "c1_conv_fwd: geometry/alignment");
-  const long long n_pix = img_pixels(x);
-  const int g = qeb_grid(n_pix * (out.c / 4), kThreads, 4);
-  if (out.c == 32) QEB_CUDA(qeb_launch(c1_fwd_kernel<32>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix));
-  else QEB_CUDA(qeb_launch(c1_fwd_kernel<64>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_pix));
+  QEB_REQUIRE(x.w % 4 == 0 && img_pixels(x) / 4 < (1ll << 30), "c1_conv_fwd: the width must be a multiple of 4");
+  const int n_quads = (int)(img_pixels(x) / 4);
+  const int g = qeb_grid((long long)n_quads * (out.c / 4), kThreads, 4);
+  if (out.c == 32) QEB_CUDA(qeb_launch(c1_fwd_kernel<32>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_quads));
+  else QEB_CUDA(qeb_launch(c1_fwd_kernel<64>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_quads));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -772,10 +814,11 @@ int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStre
   ProfScope prof("c1_conv_wgrad", st, 18.0 * (double)img_pixels(x) * dy.c, 4.0 * (double)img_pixels(x) * (1 + dy.c));
   QEB_REQUIRE(x.c == 1 && (dy.c == 32 || dy.c == 64), "c1_conv_wgrad: 1 -> 32/64 channels only");
   QEB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w && vec4_ok(dy), "c1_conv_wgrad: geometry/alignment");
-  const long long n_pix = img_pixels(x);
-  const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 4);
-  if (dy.c == 32) QEB_CUDA(qeb_launch(c1_wgrad_kernel<32>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix));
-  else QEB_CUDA(qeb_launch(c1_wgrad_kernel<64>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_pix));
+  QEB_REQUIRE(x.w % 4 == 0 && img_pixels(x) / 4 < (1ll << 30), "c1_conv_wgrad: the width must be a multiple of 4");
+  const int n_quads = (int)(img_pixels(x) / 4);
+  const int g = qeb_grid((long long)n_quads * (dy.c / 4), kThreads, 4);
+  if (dy.c == 32) QEB_CUDA(qeb_launch(c1_wgrad_kernel<32>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_quads));
+  else QEB_CUDA(qeb_launch(c1_wgrad_kernel<64>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_quads));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -785,10 +828,11 @@ int c1_conv_dgrad(const Img& dy, const float* w, const Img& dx, cudaStream_t st)
   ProfScope prof("c1_conv_dgrad", st, 18.0 * (double)img_pixels(dx) * dy.c, 4.0 * (double)img_pixels(dx) * (1 + dy.c));
   QEB_REQUIRE(dx.c == 1 && (dy.c == 32 || dy.c == 64), "c1_conv_dgrad: 1 <- 32/64 channels only");
   QEB_REQUIRE(dx.n == dy.n && dx.h == dy.h && dx.w == dy.w && vec4_ok(dy), "c1_conv_dgrad: geometry/alignment");
-  const long long n_pix = img_pixels(dx);
-  const int g = qeb_grid(n_pix * (dy.c / 4), kThreads, 8);
-  if (dy.c == 32) QEB_CUDA(qeb_launch(c1_dgrad_kernel<32>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_pix));
-  else QEB_CUDA(qeb_launch(c1_dgrad_kernel<64>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_pix));
+  QEB_REQUIRE(dx.w % 4 == 0 && img_pixels(dx) / 4 < (1ll << 30), "c1_conv_dgrad: the width must be a multiple of 4");
+  const int n_quads = (int)(img_pixels(dx) / 4);
+  const int g = qeb_grid((long long)n_quads * (dy.c / 4), kThreads, 8);
+  if (dy.c == 32) QEB_CUDA(qeb_launch(c1_dgrad_kernel<32>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_quads));
+  else QEB_CUDA(qeb_launch(c1_dgrad_kernel<64>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_quads));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
