@@ -290,7 +290,9 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
         }
         *reinterpret_cast<float4*>(d) = o;
         if (p.out16) {   // fp16 shadow, same element offset
-          const __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+          // (saturating: a value beyond fp16's range becomes +-65504, not inf; the fp32 output keeps the exact value)
+          const __half2 h0 = __floats2half2_rn(fminf(fmaxf(o.x, -65504.f), 65504.f), fminf(fmaxf(o.y, -65504.f), 65504.f));
+          const __half2 h1 = __floats2half2_rn(fminf(fmaxf(o.z, -65504.f), 65504.f), fminf(fmaxf(o.w, -65504.f), 65504.f));
           uint2 pk;
           pk.x = *reinterpret_cast<const uint32_t*>(&h0);
           pk.y = *reinterpret_cast<const uint32_t*>(&h1);

@@ -245,15 +245,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     fence_proxy_async_all();   // own chunk: generic-proxy writes -> visible to the bulk copy and to the next step's MMA
     __syncthreads();
     if (tl) tl[8 * s + 4] = clock64();
-    if (tid == 0 && s + 1 < a.T) {
-      // push this CTA's K chunk (16 batch rows x 128 B) into the same place of the 7 peers; arm the own barrier for theirs
-      mbar_expect_tx(&full_bar[(s + 1) & 1], (kCluster - 1) * kBTile);
-      const uint32_t src = smem_u32(hnext + rank * kBTile), bar = smem_u32(&full_bar[(s + 1) & 1]);
+    if (warp == 0 && s + 1 < a.T) {   // warp-uniform branch + elected lane: the copy instructions take uniform operands
+      if (elect_one()) {
+        // push this CTA's K chunk (16 batch rows x 128 B) into the same place of the 7 peers; arm the own barrier for theirs
+        mbar_expect_tx(&full_bar[(s + 1) & 1], (kCluster - 1) * kBTile);
+        const uint32_t src = smem_u32(hnext + rank * kBTile), bar = smem_u32(&full_bar[(s + 1) & 1]);
 #pragma unroll
-      for (int r = 1; r < kCluster; ++r) {
-        const uint32_t peer = (uint32_t)((rank + r) & (kCluster - 1));
-        bulk_copy_to_cluster(mapa_u32(src, peer), src, kBTile, mapa_u32(bar, peer));
+        for (int r = 1; r < kCluster; ++r) {
+          const uint32_t peer = (uint32_t)((rank + r) & (kCluster - 1));
+          bulk_copy_to_cluster(mapa_u32(src, peer), src, kBTile, mapa_u32(bar, peer));
+        }
       }
+      __syncwarp();
     }
     if (tl) tl[8 * s + 5] = clock64();
     // global stores last: a proxy fence waits for the thread's outstanding stores, these drain during the next step
@@ -449,7 +452,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       for (int j = 0; j < kBC; ++j) stg[j * kUnits + lane] = v[j];
       fence_proxy_async_all();
       __syncwarp();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t dst = smem_u32(recv + ((s & 1) * kCluster + rank) * kBlk);
         bulk_copy_to_cluster(mapa_u32(dst, warp), smem_u32(stg), kBlk * sizeof(float), mapa_u32(smem_u32(&full_bar[s & 1]), warp));
       }

@@ -28,8 +28,10 @@ __host__ __device__ inline Geo geo(const Img& a) {
   return g;
 }
 // fp16 shadow of four consecutive channels (the tensor-core operand copy of an activation): 8-byte store
+// (values beyond fp16's range saturate at +-65504 instead of becoming inf: the fp32 tensor keeps the exact value)
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
 __device__ __forceinline__ void st4h(__half* p, const float4 v) {
-  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  const __half2 a = __floats2half2_rn(sat16(v.x), sat16(v.y)), b = __floats2half2_rn(sat16(v.z), sat16(v.w));
   uint2 pk;
   pk.x = *reinterpret_cast<const uint32_t*>(&a);
   pk.y = *reinterpret_cast<const uint32_t*>(&b);

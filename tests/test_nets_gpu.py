@@ -601,3 +601,16 @@ def test_conv_fprop_fp16_operands(q, N, H, W, Cin, Cout, k, p, relu):
     assert rel(out, ref16) < 5e-6          # the products of fp16 operands are exact in fp32; only the summation order differs
     assert rel(out, ref32) < 1e-3          # operand rounding: 2^-11 relative each
     assert torch.equal(out16, out.half())
+
+
+def test_fp16_shadow_saturates(q):
+    """An activation beyond fp16's range must not turn into inf in the operand copy (the fp32 tensor keeps the value)."""
+    N, H, W, C = 1, 4, 32, 32
+    x16 = torch.full((N, H, W, C), 60000.0, device=DEV).half()
+    wp16 = torch.ones(C, C, device=DEV).half()          # 1x1 conv: every output = 32 * 60000 = 1.92e6
+    out = torch.zeros(N, H, W, C, device=DEV)
+    out16 = torch.zeros(N, H, W, C, device=DEV, dtype=torch.float16)
+    q.lib.call("qeb_conv_fprop_tc16", x16.data_ptr(), N, H, W, C, C, wp16.data_ptr(), C, 1, 1, 0, 0, None, None, 0,
+               out.data_ptr(), C, out16.data_ptr(), st())
+    assert torch.allclose(out, torch.full_like(out, 1.92e6))
+    assert torch.isfinite(out16).all() and float(out16.max()) == 65504.0
