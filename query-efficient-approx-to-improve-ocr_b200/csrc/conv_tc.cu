@@ -189,7 +189,9 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
         v[4 * j + 3] = q4.w > 0.f ? v[4 * j + 3] : 0.f;
       }
     } else {
-      for (int j = 0; j < lim; ++j) v[j] = mk[j] > 0.f ? v[j] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)   // static indices + predicate: a run-time trip count would put v[] into local memory
+        if (j < lim) v[j] = mk[j] > 0.f ? v[j] : 0.f;
     }
   }
   if (split) {  // partial sum of this K slice: 16-byte vector reductions (plain epilogue, lim == 32 guaranteed)
@@ -211,7 +213,9 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
       for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
   } else {
-    for (int j = 0; j < lim; ++j) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < lim) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
   }
 }
 

@@ -152,7 +152,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   {
     // W_hh slice -> TMEM, rounded to tf32: lane = gate row (gate q, unit `lane`), column = k. Warps w and w + 4 share a
     // lane quarter and take 128 columns each; a thread streams 512 contiguous bytes of its row.
-    const float* W = a.w_hh[dir] + (long long)(q * kH + rank * kUnits + lane) * kH + bh * 128;
+    const float* W = (dir ? a.w_hh[1] : a.w_hh[0]) + (long long)(q * kH + rank * kUnits + lane) * kH + bh * 128;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 16) {
       float v[16];
@@ -177,7 +177,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
 
   // x-projections of this thread's gate row for its 8 batch rows, loaded one step ahead
   float gx[8];
-  auto load_gx = [&](int s, float* dst) {
+  auto load_gx = [&](int s, float (&dst)[8]) {   // array by reference: a pointer parameter would force gx into local memory
     const int t = dir ? a.T - 1 - s : s;
     const float* g = a.gates + (((long long)t * a.B + b0 + bh * 8) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
 #pragma unroll
@@ -315,7 +315,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     // W_slice^T -> TMEM, rounded to tf32: half mh = warp / 4 of k lives in columns [128 mh, 128 mh + 128); lane = k % 128,
     // column = own gate row (gate gq, unit jl). For a fixed gate row the 32 lanes of a warp read 32 consecutive k.
     const int mh = warp >> 2;
-    const float* W = a.w_hh[dir] + (long long)(rank * kUnits) * kH + mh * 128 + (warp & 3) * 32 + lane;
+    const float* W = (dir ? a.w_hh[1] : a.w_hh[0]) + (long long)(rank * kUnits) * kH + mh * 128 + (warp & 3) * 32 + lane;
 #pragma unroll 1
     for (int c0 = 0; c0 < 128; c0 += 16) {   // c0 = gq * 32 + jl
       float v[16];
