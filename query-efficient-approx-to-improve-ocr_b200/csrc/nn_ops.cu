@@ -322,6 +322,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
   }
 }
 
+__device__ __forceinline__ float comp4(float4 q, int j) { return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w)); }
+
 template <int PH, int PW>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
                                                                Geo gd, int relu_mask, const float* __restrict__ chan_scale,
@@ -336,29 +338,29 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
     const int hv = (int)(t % gd.h);
     const long long n = t / gd.h;
     const float* xb = x + n * gx.sn + (long long)(hv * PH) * gx.sh + (long long)(wv * PW) * gx.sw + cq * 4;
-    float v[PH * PW][4];
+    float4 v[PH * PW];   // accessed through comp4() with compile-time indices only: stays in registers
 #pragma unroll
     for (int a = 0; a < PH; ++a)
 #pragma unroll
-      for (int b = 0; b < PW; ++b) {
-        const float4 q = ld4(xb + a * gx.sh + b * gx.sw);
-        v[a * PW + b][0] = q.x; v[a * PW + b][1] = q.y; v[a * PW + b][2] = q.z; v[a * PW + b][3] = q.w;
-      }
+      for (int b = 0; b < PW; ++b) v[a * PW + b] = ld4(xb + a * gx.sh + b * gx.sw);
     float4 g4 = ld4(dy + n * gd.sn + hv * gd.sh + wv * gd.sw + cq * 4);
     if (chan_scale) {
       const float4 s4 = ld4(chan_scale + cq * 4);
       g4.x *= s4.x; g4.y *= s4.y; g4.z *= s4.z; g4.w *= s4.w;
     }
-    const float g[4] = {g4.x, g4.y, g4.z, g4.w};
     int arg[4];
+    bool pass[4];   // ReLU mask of the winning element, decided here so that the scatter loop below never indexes v[] by arg[]
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int best = 0;
-      float m = v[0][j];
+      float m = comp4(v[0], j);
 #pragma unroll
-      for (int k = 1; k < PH * PW; ++k)
-        if (v[k][j] > m || v[k][j] != v[k][j]) { m = v[k][j]; best = k; }
+      for (int k = 1; k < PH * PW; ++k) {
+        const float c = comp4(v[k], j);
+        if (c > m || c != c) { m = c; best = k; }
+      }
       arg[j] = best;
+      pass[j] = !relu_mask || m > 0.f;
     }
 #pragma unroll
     for (int a = 0; a < PH; ++a)
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
         const int k = a * PW + b;
         float o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) o[j] = (arg[j] == k && (!relu_mask || v[k][j] > 0.f)) ? g[j] : 0.f;
+        for (int j = 0; j < 4; ++j) o[j] = (arg[j] == k && pass[j]) ? comp4(g4, j) : 0.f;
         const long long off = n * gdx.sn + (long long)(hv * PH + a) * gdx.sh + (long long)(wv * PW + b) * gdx.sw + cq * 4;
         if (add) {
           const float4 q = ld4(add + n * ga.sn + (long long)(hv * PH + a) * ga.sh + (long long)(wv * PW + b) * ga.sw + cq * 4);
