@@ -296,12 +296,12 @@ template <int PH, int PW>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, Geo gx, float* __restrict__ out,
                                                                Geo go, int cq_n, long long total, __half* __restrict__ out16) {
   qeb_pdl_sync();
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const int cq = (int)(i % cq_n);
-    const long long pix = i / cq_n;
-    const int wv = (int)(pix % go.w);
-    const long long t = pix / go.w;
-    const int hv = (int)(t % go.h);
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < (int)total; i += gridDim.x * kThreads) {   // 32-bit index math (host check)
+    const int cq = i % cq_n;
+    const int pix = i / cq_n;
+    const int wv = pix % go.w;
+    const int t = pix / go.w;
+    const int hv = t % go.h;
     const long long n = t / go.h;
     const float* xb = x + n * gx.sn + (long long)(hv * PH) * gx.sh + (long long)(wv * PW) * gx.sw + cq * 4;
     float4 m = ld4(xb);
@@ -330,12 +330,12 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
                                                                const float* __restrict__ add, Geo ga, float* __restrict__ dx,
                                                                Geo gdx, int cq_n, long long total) {
   qeb_pdl_sync();
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const int cq = (int)(i % cq_n);
-    const long long pix = i / cq_n;
-    const int wv = (int)(pix % gd.w);
-    const long long t = pix / gd.w;
-    const int hv = (int)(t % gd.h);
+  for (int i = blockIdx.x * kThreads + threadIdx.x; i < (int)total; i += gridDim.x * kThreads) {   // 32-bit index math (host check)
+    const int cq = i % cq_n;
+    const int pix = i / cq_n;
+    const int wv = pix % gd.w;
+    const int t = pix / gd.w;
+    const int hv = t % gd.h;
     const long long n = t / gd.h;
     const float* xb = x + n * gx.sn + (long long)(hv * PH) * gx.sh + (long long)(wv * PW) * gx.sw + cq * 4;
     float4 v[PH * PW];   // accessed through comp4() with compile-time indices only: stays in registers
@@ -468,12 +468,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restr
                                                             long long os, __half* __restrict__ out16) {
   qeb_pdl_sync();
   const int cq_n = C / 4;
-  const long long total = M * cq_n;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const int cq = (int)(i % cq_n);
-    const long long r = i / cq_n;
+  const int cq = threadIdx.x % cq_n;   // kThreads is a multiple of C/4 (host check): constant channel quad, no division in the loop
+  const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
+  const long long rstep = (long long)gridDim.x * (kThreads / cq_n);
+  for (long long r = (long long)blockIdx.x * (kThreads / cq_n) + threadIdx.x / cq_n; r < M; r += rstep) {
     const float4 v = ld4(z + r * zs + cq * 4);
-    const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
     float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
     st4(out + r * os + cq * 4, o);
@@ -516,9 +515,8 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
-  const long long total = M * cq_n;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const long long r = i / cq_n;
+  const long long rstep = (long long)gridDim.x * (kThreads / cq_n);
+  for (long long r = (long long)blockIdx.x * (kThreads / cq_n) + threadIdx.x / cq_n; r < M; r += rstep) {
     const float4 v = ld4(z + r * zs + cq * 4);
     float4 o = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
@@ -591,33 +589,37 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
                                                                 float* __restrict__ dbeta) {
   qeb_pdl_sync();
   const int cq_n = C / 4;
-  const long long total = M * cq_n;
   if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += kThreads) {
       dgamma[c] += (float)red[C + c];
       dbeta[c] += (float)red[c];
     }
   }
+  // kThreads is a multiple of C/4 (checked on the host): a thread keeps its channel quad over the grid-stride loop, so the
+  // per-channel constants - including the fp64 -> fp32 conversions of the batch reductions - are formed once per thread and
+  // the row index advances without a division
   const float invM = 1.f / (float)M;
-  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < total; i += (long long)gridDim.x * kThreads) {
-    const int cq = (int)(i % cq_n);
-    const long long r = i / cq_n;
-    const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
+  const int cq = threadIdx.x % cq_n;
+  const float4 sc = ld4(scsh + cq * 4), sh = ld4(scsh + C + cq * 4);
+  float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = mu, mg = mu, mx = mu;
+  if (mode != 1) {
+    mu = ld4(scsh + 2 * C + cq * 4); is = ld4(scsh + 3 * C + cq * 4);
+    mg = make_float4((float)red[cq * 4] * invM, (float)red[cq * 4 + 1] * invM, (float)red[cq * 4 + 2] * invM, (float)red[cq * 4 + 3] * invM);
+    mx = make_float4((float)red[C + cq * 4] * invM, (float)red[C + cq * 4 + 1] * invM, (float)red[C + cq * 4 + 2] * invM,
+                     (float)red[C + cq * 4 + 3] * invM);
+  }
+  const long long rstep = (long long)gridDim.x * (kThreads / cq_n);
+  for (long long r = (long long)blockIdx.x * (kThreads / cq_n) + threadIdx.x / cq_n; r < M; r += rstep) {
     const float4 v = ld4(z + r * zs + cq * 4);
     const float4 g = bn_masked_grad(v, ld4(dy + r * ds + cq * 4), sc, sh, relu);
     float4 o;
     if (mode == 1) {
       o = make_float4(g.x * sc.x, g.y * sc.y, g.z * sc.z, g.w * sc.w);
     } else {
-      const float4 mu = ld4(scsh + 2 * C + cq * 4), is = ld4(scsh + 3 * C + cq * 4);
-      const float mg[4] = {(float)red[cq * 4] * invM, (float)red[cq * 4 + 1] * invM, (float)red[cq * 4 + 2] * invM,
-                           (float)red[cq * 4 + 3] * invM};
-      const float mx[4] = {(float)red[C + cq * 4] * invM, (float)red[C + cq * 4 + 1] * invM, (float)red[C + cq * 4 + 2] * invM,
-                           (float)red[C + cq * 4 + 3] * invM};
-      o.x = sc.x * (g.x - mg[0] - (v.x - mu.x) * is.x * mx[0]);
-      o.y = sc.y * (g.y - mg[1] - (v.y - mu.y) * is.y * mx[1]);
-      o.z = sc.z * (g.z - mg[2] - (v.z - mu.z) * is.z * mx[2]);
-      o.w = sc.w * (g.w - mg[3] - (v.w - mu.w) * is.w * mx[3]);
+      o.x = sc.x * (g.x - mg.x - (v.x - mu.x) * is.x * mx.x);
+      o.y = sc.y * (g.y - mg.y - (v.y - mu.y) * is.y * mx.y);
+      o.z = sc.z * (g.z - mg.z - (v.z - mu.z) * is.z * mx.z);
+      o.w = sc.w * (g.w - mg.w - (v.w - mu.w) * is.w * mx.w);
     }
     st4(dz + r * dzs + cq * 4, o);
   }
@@ -869,6 +871,7 @@ int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, v
   QEB_REQUIRE(x.h == out.h * ph && x.w == out.w * pw && x.n == out.n, "maxpool_fwd: input must be a multiple of the window");
   const int cq_n = x.c / 4;
   const long long total = img_pixels(out) * cq_n;
+  QEB_REQUIRE(total < (1ll << 31), "maxpool_fwd: tensor too large for 32-bit indexing");
   const int g = qeb_grid(total, kThreads);
   __half* o16 = static_cast<__half*>(out16);
   if (ph == 2 && pw == 2) QEB_CUDA(qeb_launch(maxpool_fwd_kernel<2, 2>, g, kThreads, 0, st, x.p, geo(x), out.p, geo(out), cq_n, total, o16));
@@ -887,6 +890,7 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   QEB_REQUIRE(!add || (vec4_ok(*add) && add->c == x.c), "maxpool_bwd: add tensor");
   const int cq_n = x.c / 4;
   const long long total = img_pixels(dy) * cq_n;
+  QEB_REQUIRE(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
   const int g = qeb_grid(total, kThreads);
   Geo ga = add ? geo(*add) : geo(x);
   const float* ap = add ? add->p : nullptr;
@@ -967,6 +971,7 @@ int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStre
   REQ_FLAT(z, "bn_apply");
   REQ_FLAT(out, "bn_apply");
   QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_apply: shape mismatch");
+  QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
   QEB_CUDA(qeb_launch(bn_apply_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw,
                                                                           static_cast<__half*>(out16)));
@@ -997,6 +1002,7 @@ static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu
   REQ_FLAT(dz, "bn_bwd_apply");
   QEB_REQUIRE(z.c == dy.c && z.c == dz.c && img_pixels(z) == img_pixels(dy) && img_pixels(z) == img_pixels(dz),
               "bn_bwd_apply: shape mismatch");
+  QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_bwd_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
   QEB_CUDA(qeb_launch(bn_bwd_apply_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
                                                                              dz.p, dz.sw, dgamma, dbeta));
