@@ -364,6 +364,279 @@ __global__ void log_softmax_bwd_kernel(const float* __restrict__ y, const float*
   for (int c = lane; c < V; c += 32) dx[r * V + c] = dy[r * V + c] - expf(y[r * V + c]) * s;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Block-per-sequence variants (the default whenever the panels fit in shared memory). The recursions above are chains of
+// T dependent steps of ONE warp, and at B = 64 the whole loss is 64 such chains: what matters is the length of one step.
+// Here a block of four warps first stages the sequence's whole (T, V) log-prob panel (and, in the backward kernel, its
+// (T, S) log-alpha panel) with 4-byte cp.async copies - one global round trip instead of one per step - then warp 0 runs
+// the chain out of shared memory. In the backward kernel the chain only stores log(alpha * beta); the per-class
+// log-sum-exp and the gradient rows (the expensive part: shared-memory atomics, V exp/log per frame) are computed
+// afterwards by all four warps, one frame per warp at a time, off the chain.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kSeqThreads = 128;
+constexpr size_t kSeqSmemMax = 160 * 1024;
+
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+  return v;
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(kSeqThreads) ctc_alpha_seq_kernel(CtcArgs a) {
+  qeb_pdl_sync();
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int L = a.target_lengths[b];
+  const int Tb = min(a.input_lengths[b], a.T);
+  const int off = a.tgt_offsets[b];
+  const int S = 2 * L + 1;
+  const int col = a.batch_index ? a.batch_index[b] : b;
+  const float* lp = a.lp + (long long)col * a.st_b;
+  float* la_out = a.log_alpha + (long long)b * a.T * a.S;
+  if (Tb <= 0) {  // as in ctc_alpha_kernel
+    if (threadIdx.x == 0) a.nll[b] = (L == 0) ? 0.f : INFINITY;
+    return;
+  }
+  float* panel = smem;  // [Tb][V]
+  for (int t = warp; t < Tb; t += kSeqThreads / 32)
+    for (int c = lane; c < a.V; c += 32) cp_async4(panel + t * a.V + c, lp + (long long)t * a.st_t + c);
+  int cls[SPL];
+  bool skip[SPL];
+  float al[SPL];
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int s = j * 32 + lane;
+    cls[j] = a.blank;
+    skip[j] = false;
+    if (s < S && (s & 1)) {
+      cls[j] = a.targets[off + (s >> 1)];
+      if (s >= 3) skip[j] = (a.targets[off + (s >> 1) - 1] != cls[j]);
+    }
+    al[j] = neg_inf();
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if (warp != 0) return;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int s = j * 32 + lane;
+    if (s == 0) al[j] = panel[a.blank];
+    else if (s == 1 && S > 1) al[j] = panel[cls[j]];
+    if (s < S) la_out[s] = al[j];
+  }
+  for (int t = 1; t < Tb; ++t) {
+    const float* row = panel + t * a.V;
+    float nw[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const int s = j * 32 + lane;
+      const float emit = row[cls[j]];
+      const float up1 = __shfl_up_sync(FULL_MASK, al[j], 1);
+      const float up2 = __shfl_up_sync(FULL_MASK, al[j], 2);
+      float p31 = neg_inf(), p30 = neg_inf();
+      if (j > 0) {
+        p31 = __shfl_sync(FULL_MASK, al[j - 1], 31);
+        p30 = __shfl_sync(FULL_MASK, al[j - 1], 30);
+      }
+      const float la1 = al[j];
+      const float la2 = (lane == 0) ? p31 : up1;
+      float la3 = (lane == 0) ? p30 : (lane == 1 ? p31 : up2);
+      if (!skip[j]) la3 = neg_inf();
+      nw[j] = (s < S) ? lse3(la1, la2, la3) + emit : neg_inf();
+    }
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      al[j] = nw[j];
+      const int s = j * 32 + lane;
+      if (s < S) la_out[(long long)t * a.S + s] = al[j];
+    }
+  }
+  // -log(alpha_T(2L) + alpha_T(2L - 1)) from the registers that hold the last frame
+  float l1 = neg_inf(), l2 = neg_inf();
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const float v1 = __shfl_sync(FULL_MASK, al[j], (2 * L) & 31);
+    const float v2 = __shfl_sync(FULL_MASK, al[j], (2 * L - 1) & 31);
+    if (j == ((2 * L) >> 5)) l1 = v1;
+    if (L > 0 && j == ((2 * L - 1) >> 5)) l2 = v2;
+  }
+  if (lane == 0) {
+    float r;
+    if (L == 0) {
+      r = -l1;
+    } else {
+      float m = fmaxf(l1, l2);
+      if (m == neg_inf()) m = 0.f;
+      r = -(logf(expf(l1 - m) + expf(l2 - m)) + m);
+    }
+    a.nll[b] = r;
+  }
+}
+
+template <int SPL>
+__global__ void __launch_bounds__(kSeqThreads) ctc_beta_grad_seq_kernel(CtcBwdArgs g) {
+  qeb_pdl_sync();
+  const CtcArgs& a = g.f;
+  extern __shared__ float smem[];
+  constexpr int kWarps = kSeqThreads / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int L = a.target_lengths[b];
+  const int Tb = max(0, min(a.input_lengths[b], a.T));
+  const int off = a.tgt_offsets[b];
+  const int S = 2 * L + 1;
+  const int col = a.batch_index ? a.batch_index[b] : b;
+  const float* lp = a.lp + (long long)col * a.st_b;
+  const float* la_in = a.log_alpha + (long long)b * a.T * a.S;
+  float* gr = g.grad + (long long)col * g.gst_b;
+  const float nll = a.nll[b];
+  float go;
+  if (g.reduction == 0) go = g.grad_out[b];
+  else if (g.reduction == 1) go = g.grad_out[0] / (float)(L > 1 ? L : 1) / (float)a.B;
+  else go = g.grad_out[0];
+  const bool zero_all = g.zero_infinity && (nll == INFINITY);
+
+  float* panel = smem;                    // [T][V]   log-probs
+  float* ab = panel + a.T * a.V;          // [T][a.S] log alpha, then log(alpha * beta)
+  float* accm = ab + a.T * a.S + warp * 2 * a.V;   // per warp: running max / sum per class
+  float* accs = accm + a.V;
+
+  for (int t = Tb + warp; t < a.T; t += kWarps)   // frames past the input length carry zero gradient
+    for (int c = lane; c < a.V; c += 32) gr[(long long)t * g.gst_t + c] = 0.f;
+  if (Tb == 0) return;
+  for (int t = warp; t < Tb; t += kWarps) {
+    for (int c = lane; c < a.V; c += 32) cp_async4(panel + t * a.V + c, lp + (long long)t * a.st_t + c);
+    for (int s = lane; s < S; s += 32) cp_async4(ab + t * a.S + s, la_in + (long long)t * a.S + s);
+  }
+  int cls[SPL];
+  bool skip[SPL];  // transition to s+2 allowed
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    const int s = j * 32 + lane;
+    cls[j] = a.blank;
+    skip[j] = false;
+    if (s < S && (s & 1)) {
+      cls[j] = a.targets[off + (s >> 1)];
+      if (s + 2 < S) skip[j] = (a.targets[off + (s >> 1) + 1] != cls[j]);
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  if (warp == 0) {   // the chain: beta_t from beta_{t+1}, all operands in shared memory
+    float be[SPL];
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) be[j] = neg_inf();
+    for (int t = Tb - 1; t >= 0; --t) {
+      const float* row = panel + t * a.V;
+      float nw[SPL];
+      if (t == Tb - 1) {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          const int s = j * 32 + lane;
+          nw[j] = neg_inf();
+          if (s == 2 * L) nw[j] = row[a.blank];
+          else if (L > 0 && s == 2 * L - 1) nw[j] = row[cls[j]];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          const int s = j * 32 + lane;
+          const float emit = row[cls[j]];
+          const float dn1 = __shfl_down_sync(FULL_MASK, be[j], 1);
+          const float dn2 = __shfl_down_sync(FULL_MASK, be[j], 2);
+          float n0 = neg_inf(), n1 = neg_inf();
+          if (j + 1 < SPL) {
+            n0 = __shfl_sync(FULL_MASK, be[j + 1], 0);
+            n1 = __shfl_sync(FULL_MASK, be[j + 1], 1);
+          }
+          const float lb1 = be[j];
+          const float lb2 = (lane == 31) ? n0 : dn1;
+          float lb3 = (lane == 31) ? n1 : (lane == 30 ? n0 : dn2);
+          if (!skip[j]) lb3 = neg_inf();
+          nw[j] = (s < S) ? lse3(lb1, lb2, lb3) + emit : neg_inf();
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < SPL; ++j) {
+        be[j] = nw[j];
+        const int s = j * 32 + lane;
+        if (s < S) ab[t * a.S + s] += be[j];
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int t = warp; t < Tb; t += kWarps) {   // gradient rows, one frame per warp at a time
+    const float* row = panel + t * a.V;
+    for (int c = lane; c < a.V; c += 32) {
+      accm[c] = neg_inf();
+      accs[c] = 0.f;
+    }
+    float lab[SPL];
+    bool ok[SPL];
+    float bm = neg_inf();
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const int s = j * 32 + lane;
+      lab[j] = (s < S) ? ab[t * a.S + s] : neg_inf();
+      ok[j] = s < S && lab[j] != neg_inf() && lab[j] == lab[j];
+      if (ok[j] && cls[j] == a.blank) bm = fmaxf(bm, lab[j]);
+    }
+    __syncwarp();
+    // the blank class collects every other state: warp reduction instead of 32 atomics on one address
+    bm = warp_max_f(bm);
+    float bs = 0.f;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      if (ok[j] && cls[j] == a.blank) bs += expf(lab[j] - bm);
+      else if (ok[j]) atomic_max_float(&accm[cls[j]], lab[j]);
+    }
+    bs = warp_sum_f(bs);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < SPL; ++j)
+      if (ok[j] && cls[j] != a.blank) atomicAdd(&accs[cls[j]], expf(lab[j] - accm[cls[j]]));
+    if (lane == 0 && bm != neg_inf()) {
+      accm[a.blank] = bm;
+      accs[a.blank] = bs;
+    }
+    __syncwarp();
+    for (int c = lane; c < a.V; c += 32) {
+      const float res = (accm[c] == neg_inf()) ? neg_inf() : logf(accs[c]) + accm[c];
+      const float l = row[c];
+      float v = (expf(l) - expf(res + nll - l)) * go;
+      if (zero_all) v = 0.f;
+      gr[(long long)t * g.gst_t + c] = v;
+    }
+    __syncwarp();
+  }
+}
+
+inline bool ctc_seq_enabled() {
+  static const bool on = !(getenv("QEB_CTC_SEQ") && atoi(getenv("QEB_CTC_SEQ")) == 0);
+  return on;
+}
+template <typename K>
+int ctc_seq_smem_attr(K kernel) {
+  QEB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSeqSmemMax));
+  return QEB_OK;
+}
+
 template <typename F>
 int dispatch_spl(int S, F&& f) {
   if (S <= 64) return f(std::integral_constant<int, 2>());
@@ -394,11 +667,19 @@ QEB_API int qeb_ctc_fwd(const float* log_probs, long long st_t, long long st_b, 
   const int grid = qeb_cdiv(B, kWarpsPerBlock);
   const size_t smem = (size_t)kWarpsPerBlock * V * sizeof(float);
   QEB_REQUIRE(smem <= 48 * 1024, "ctc_fwd: V=%d too large", V);
+  const size_t seq_smem = (size_t)T * V * sizeof(float);
   int rc = dispatch_spl(a.S, [&](auto spl) {
-    QEB_CUDA(qeb_launch(ctc_alpha_kernel<decltype(spl)::value>, grid, kWarpsPerBlock * 32, smem, st, a));
+    constexpr int kSpl = decltype(spl)::value;
+    if (ctc_seq_enabled() && seq_smem <= kSeqSmemMax) {   // block per sequence, panels in shared memory
+      static const int attr = ctc_seq_smem_attr(ctc_alpha_seq_kernel<kSpl>);
+      if (attr) return attr;
+      QEB_CUDA(qeb_launch(ctc_alpha_seq_kernel<kSpl>, B, kSeqThreads, seq_smem, st, a));
+      return 0;
+    }
+    QEB_CUDA(qeb_launch(ctc_alpha_kernel<kSpl>, grid, kWarpsPerBlock * 32, smem, st, a));
     return 0;
   });
-  (void)rc;
+  if (rc) return rc;
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   if (loss_out && reduction != 0) {
@@ -434,10 +715,19 @@ QEB_API int qeb_ctc_bwd(const float* log_probs, long long st_t, long long st_b, 
   const int grid = qeb_cdiv(B, kWarpsPerBlock);
   const size_t smem = (size_t)kWarpsPerBlock * 3 * V * sizeof(float);
   QEB_REQUIRE(smem <= 48 * 1024, "ctc_bwd: V=%d too large", V);
-  dispatch_spl(g.f.S, [&](auto spl) {
-    QEB_CUDA(qeb_launch(ctc_beta_grad_kernel<decltype(spl)::value>, grid, kWarpsPerBlock * 32, smem, st, g));
+  const size_t seq_smem = ((size_t)T * (V + g.f.S) + (size_t)(kSeqThreads / 32) * 2 * V) * sizeof(float);
+  int rc = dispatch_spl(g.f.S, [&](auto spl) {
+    constexpr int kSpl = decltype(spl)::value;
+    if (ctc_seq_enabled() && seq_smem <= kSeqSmemMax) {
+      static const int attr = ctc_seq_smem_attr(ctc_beta_grad_seq_kernel<kSpl>);
+      if (attr) return attr;
+      QEB_CUDA(qeb_launch(ctc_beta_grad_seq_kernel<kSpl>, B, kSeqThreads, seq_smem, st, g));
+      return 0;
+    }
+    QEB_CUDA(qeb_launch(ctc_beta_grad_kernel<kSpl>, grid, kWarpsPerBlock * 32, smem, st, g));
     return 0;
   });
+  if (rc) return rc;
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;

@@ -336,7 +336,7 @@ def test_ctc_golden(m):
         assert rel_err(lp.grad.cpu().numpy(), g["subset_grad"]) < 1e-4
 
 
-@pytest.mark.parametrize("T,B,V", [(31, 64, 95), (31, 512, 95), (63, 96, 95), (200, 5, 30)])
+@pytest.mark.parametrize("T,B,V", [(31, 64, 95), (31, 512, 95), (63, 96, 95), (200, 5, 30), (600, 3, 95)])  # the last two: panels too large for shared memory (warp-per-sequence kernels)
 def test_ctc_vs_torch_cpu(m, T, B, V):
     g = torch.Generator().manual_seed(T + B)
     logits = torch.randn(T, B, V, generator=g) * 3
