@@ -349,8 +349,9 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
         DGs.p = g + d * 1024; DGs.n = 1; DGs.h = T; DGs.w = B; DGs.c = 1024; DGs.sn = (long long)T * B * 2048; DGs.sh = (long long)B * 2048; DGs.sw = 2048;
         TRY(tc_conv_wgrad(Hs, DGs, 1, 1, d ? -1 : 1, 0, lg[d * 4 + 1], kHid, 1, 0, 0, ss.s()));
       }
-      if (lg[d * 4 + 2]) TRY(colsum_acc(DG, lg[d * 4 + 2], ss.s()));
-      if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], ss.s()));
+      // b_ih and b_hh receive the same gradient: one pass over dG
+      if (lg[d * 4 + 2]) TRY(colsum_acc(DG, lg[d * 4 + 2], ss.s(), lg[d * 4 + 3]));
+      else if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], ss.s()));
     }
     // d(input) = dG * [W_ih_fwd ; W_ih_rev]
     TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), l ? p.wihT1 : p.wihT0, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512), plain, st));

@@ -181,7 +181,7 @@ int bn_bwd_apply_train(const Img& z, const Img& dy, const float* scsh, int relu,
 int bn_bwd_apply_eval(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const Img& dz,
                       float* dgamma, float* dbeta, cudaStream_t st);
 // out[c] += sum over pixels of x(pix, c)   (bias gradients)
-int colsum_acc(const Img& x, float* out, cudaStream_t st);
+int colsum_acc(const Img& x, float* out, cudaStream_t st, float* out2 = nullptr);   // out2: a second accumulator receiving the same sums
 // dx = dy * (a > 0)
 int relu_bwd(const Img& a, const Img& dy, const Img& dx, cudaStream_t st);
 int fill_zero(void* p, size_t bytes, cudaStream_t st);

@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
 }
 
 __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x, long long xs, long long M, int C,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, float* __restrict__ out2) {
   qeb_pdl_sync();
   const int cq_n = (C + 3) / 4, rpb = max(1, kThreads / cq_n);
   extern __shared__ float sm[];  // [rpb][cq_n*4]
@@ -663,6 +663,7 @@ __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restric
       float a = 0.f;
       for (int i = 0; i < rpb; ++i) a += sm[i * Cp + c];
       atomicAdd(out + c, a);
+      if (out2) atomicAdd(out2 + c, a);
     }
     __syncthreads();
   }
@@ -1022,13 +1023,13 @@ int bn_bwd_apply_eval(const Img& z, const Img& dy, const float* scsh, int relu, 
   return bn_bwd_apply(z, dy, scsh, relu, red, 1, dz, red ? dgamma : nullptr, red ? dbeta : nullptr, st);
 }
 
-int colsum_acc(const Img& x, float* out, cudaStream_t st) {
+int colsum_acc(const Img& x, float* out, cudaStream_t st, float* out2) {
   ProfScope prof("colsum", st, 0.0, 4.0 * x.c * (double)img_pixels(x));
   QEB_REQUIRE(img_flat(x) && ((uintptr_t)x.p & 15) == 0 && x.sw % 4 == 0, "colsum_acc: packed, 16-byte aligned rows");
   const long long M = img_pixels(x);
   const int cq_n = (x.c + 3) / 4;
   const int rpb = max(1, kThreads / cq_n);
-  QEB_CUDA(qeb_launch(colsum_kernel, reduce_grid(M, rpb, x.c), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st, x.p, x.sw, M, x.c, out));
+  QEB_CUDA(qeb_launch(colsum_kernel, reduce_grid(M, rpb, x.c), kThreads, (size_t)rpb * cq_n * 4 * sizeof(float), st, x.p, x.sw, M, x.c, out, out2));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
