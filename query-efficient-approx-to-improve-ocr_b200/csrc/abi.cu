@@ -127,7 +127,9 @@ int SideStream::init(cudaStream_t main_stream) {
   main = main_stream;
   static const bool want = !(getenv("QEB_SIDE_STREAM") && atoi(getenv("QEB_SIDE_STREAM")) == 0);
   enabled = false;
-  if (!want) return QEB_OK;
+  // per-kernel profiling (qeb_prof_enable) times every launch with events on its own stream: keep the launches serialised
+  // then, like ncu does, so that a kernel's duration is its own and not its share of an SM it had to split
+  if (!want || qeb_prof_on()) return QEB_OK;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(main_stream, &cap) != cudaSuccess) { cudaGetLastError(); return QEB_OK; }
   int dev = 0;
