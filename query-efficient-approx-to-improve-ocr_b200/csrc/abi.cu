@@ -118,7 +118,7 @@ namespace {
 struct SideRes {
   int device = -1;
   cudaStream_t side = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, mark_ev = nullptr;
 };
 thread_local SideRes g_side;
 }  // namespace
@@ -135,14 +135,17 @@ int SideStream::init(cudaStream_t main_stream) {
   int dev = 0;
   QEB_CUDA(cudaGetDevice(&dev));
   if (g_side.device != dev) {
-    if (g_side.side) { cudaStreamDestroy(g_side.side); cudaEventDestroy(g_side.fork_ev); cudaEventDestroy(g_side.join_ev); }
+    if (g_side.side) {
+      cudaStreamDestroy(g_side.side); cudaEventDestroy(g_side.fork_ev); cudaEventDestroy(g_side.join_ev); cudaEventDestroy(g_side.mark_ev);
+    }
     g_side = SideRes();
     QEB_CUDA(cudaStreamCreateWithFlags(&g_side.side, cudaStreamNonBlocking));
     QEB_CUDA(cudaEventCreateWithFlags(&g_side.fork_ev, cudaEventDisableTiming));
     QEB_CUDA(cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming));
+    QEB_CUDA(cudaEventCreateWithFlags(&g_side.mark_ev, cudaEventDisableTiming));
     g_side.device = dev;
   }
-  side = g_side.side; fork_ev = g_side.fork_ev; join_ev = g_side.join_ev;
+  side = g_side.side; fork_ev = g_side.fork_ev; join_ev = g_side.join_ev; mark_ev = g_side.mark_ev;
   enabled = true;
   return QEB_OK;
 }
@@ -160,6 +163,20 @@ int SideStream::join() {
   QEB_CUDA(cudaEventRecord(join_ev, side));
   QEB_CUDA(cudaStreamWaitEvent(main, join_ev, 0));
   dirty = false;
+  return QEB_OK;
+}
+
+int SideStream::mark() {
+  if (!enabled) return QEB_OK;
+  QEB_CUDA(cudaEventRecord(mark_ev, side));
+  marked = true;
+  return QEB_OK;
+}
+
+int SideStream::wait_mark() {
+  if (!enabled || !marked) return QEB_OK;
+  QEB_CUDA(cudaStreamWaitEvent(main, mark_ev, 0));
+  marked = false;
   return QEB_OK;
 }
 

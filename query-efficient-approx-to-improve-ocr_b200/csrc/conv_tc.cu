@@ -776,6 +776,7 @@ struct WgradParams {
   int a_map_per_tap;  // 1: tap selects the A tensor map (ConvTranspose sub-lattices), no coordinate shift
   float* out;
   long long s_rowc, s_kh, s_kw, s_col;  // element strides of the gradient tensor
+  long long* timeline;  // debugging aid (qeb_debug_set_timeline), NULL in production
 };
 
 template <int BLOCK_N>
@@ -797,6 +798,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   const int t_end = min(t_begin + p.per_split, p.tiles_total);
   const int rb0 = tile_m * 4;
   const int n_rb = min(4, p.row_blocks - rb0);
+  long long* tl = p.timeline ? p.timeline + 16 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
+  if (tl && threadIdx.x == 0) { tl[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < (p.a_map_per_tap ? 4 : 1); ++i) prefetch_tmap(&tmaps_a.m[i]);
@@ -814,6 +817,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   qeb_pdl_sync();
+  if (tl && threadIdx.x == 0) tl[1] = clock64();
 
   if (t_begin < t_end) {
     if (warp == 0) {
@@ -865,6 +869,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (tl && lane == 0 && t == t_begin) tl[2] = clock64();
         if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + kABytes;
@@ -892,6 +897,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
                        (long long)(tap % p.kw) * p.s_kw;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
+      if (tl && threadIdx.x == 64) tl[4] = clock64();
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         float v[32];
@@ -904,11 +910,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
             if (ncol + j < p.n_total) atomicAdd(row_out + (long long)(ncol + j) * p.s_col, v[j]);
         }
       }
+      if (tl && threadIdx.x == 64) tl[5] = clock64();
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (tl && threadIdx.x == 32) { tl[6] = clock64(); tl[3] = t_end - t_begin; }
 }
 
 template <int BLOCK_N>
@@ -970,6 +978,7 @@ int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, f
   QEB_REQUIRE(strides_ok(x) && strides_ok(dy), "tc_conv_wgrad: operands must be 16-byte aligned, strides multiples of 4");
   QEB_REQUIRE(x.n == dy.n, "tc_conv_wgrad: batch mismatch");
   WgradParams p;
+  p.timeline = g_timeline;
   uint32_t box[4];
   wgrad_geometry(p, dy.n, dy.h, dy.w, box);
   p.kh = kh; p.kw = kw; p.ph = ph; p.pw = pw;
@@ -996,6 +1005,7 @@ int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
   QEB_REQUIRE(x.n == dy.n && dy.h == 2 * x.h && dy.w == 2 * x.w, "tc_convT_wgrad: dy must be 2x x");
   // M side: (tap, co) from the four sub-lattices of dy; N side: ci. dw[ci][co][dh][dw].
   WgradParams p;
+  p.timeline = g_timeline;
   uint32_t box[4];
   wgrad_geometry(p, x.n, x.h, x.w, box);
   p.kh = 2; p.kw = 2; p.ph = 0; p.pw = 0;

@@ -157,6 +157,8 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   Img Z6 = img_nhwc(p.z6, B, 4, p.W4, 512), A6f = img_nhwc(p.a6f, B, 4, p.W4, 512), A6 = img_nhwc(p.a6, B, 2, p.W4, 512);
 
   const bool h = fp16_fwd();
+  SideStream ss;
+  TRY(ss.init(st));
   {  // every weight re-layout of this pass in one launch
     PackBatch pk;
     if (h) {   // fp16 B operands; the fp32 packs are not needed by the forward pass then
@@ -185,7 +187,9 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
         for (int d = 0; d < 2; ++d)
           pk.add_copy(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wih1 : p.wih0) + (size_t)d * 1024 * 512, (long long)1024 * 512);
     }
-    TRY(pack_flush(pk, st));
+    TRY(ss.fork());   // beside conv1 (direct kernel, no packed weights) and its pooling
+    TRY(pack_flush(pk, ss.s()));
+    TRY(ss.mark());
   }
   // shadows(in, w, out): the fp16 copies a contraction reads / writes in fp16 mode (nulls otherwise: tf32 path)
   auto shadows = [&](TcEpilogue& e, const void* in16, const void* w16, void* out16) {
@@ -193,6 +197,7 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   };
   TRY(c1_conv_fwd(X, params[P_C1W], params[P_C1B], 1, A1f, st));
   TRY(maxpool_fwd(A1f, 2, 2, A1, st, h ? p.a1h : nullptr));
+  TRY(ss.wait_mark());
   TcEpilogue ep;
   ep.relu = 1;
   ep.bias = params[P_C2B];
@@ -301,7 +306,6 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   TRY(ss.init(st));
 
   // ---- Linear
-  TRY(fill_zero(p.dwp2, p.dwp_bytes, st));  // packed conv weight-gradient accumulators
   TRY(fill_zero(p.dlp, (size_t)TB * 96 * sizeof(float), st));
   TRY(fill_zero(p.wlinT, (size_t)512 * 96 * sizeof(float), st));
   {  // every re-layout of this pass in one launch
@@ -311,13 +315,20 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
     for (int l = 0; l < 2; ++l)  // d(input) B operand [512][2048]: wihT[c][d*1024 + r] = W_ih_d[r][c]
       for (int d = 0; d < 2; ++d)
         pk.add(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wihT1 : p.wihT0) + d * 1024, 1, 512, 1024, 0, 1, 512, 0, 2048);
+    TRY(pack_flush(pk, st));
+  }
+  {  // the conv stack's input-gradient operands are not needed before the LSTM layers are done: side stream
+    PackBatch pk;
     pk.add_dgrad(params[P_C7W], p.wpd7, 512, 512, 4);
     pk.add_dgrad(params[P_C6W], p.wpd6, 512, 512, 9);
     pk.add_dgrad(params[P_C5W], p.wpd5, 512, 256, 9);
     pk.add_dgrad(params[P_C4W], p.wpd4, 256, 256, 9);
     pk.add_dgrad(params[P_C3W], p.wpd3, 256, 128, 9);
     pk.add_dgrad(params[P_C2W], p.wpd2, 128, 64, 9);
-    TRY(pack_flush(pk, st));
+    TRY(ss.fork());
+    TRY(fill_zero(p.dwp2, p.dwp_bytes, ss.s()));  // packed conv weight-gradient accumulators: only side-stream kernels add into them
+    TRY(pack_flush(pk, ss.s()));
+    TRY(ss.mark());
   }
   Img DLP = img_nhwc(p.dlp, 1, 1, TB, 96);
   Img DLPv = img_nhwc(p.dlp, 1, 1, TB, V, 96);
@@ -363,6 +374,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   TRY(ss.fork());
   if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, p.dwp7, 4 * 512, 1, 2 * 512, 512, ss.s()));
   if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], ss.s()));
+  TRY(ss.wait_mark());
   TRY(tc_conv_fprop(DZ7, p.wpd7, 512, 2, 2, 1, 1, D6, plain, st));
 
   // ---- conv6 + BN2 + ReLU + pool(2,1), conv5 + BN1 + ReLU

@@ -261,6 +261,8 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   c.params = params; c.buffers = buffers; c.grads = nullptr; c.p = &p; c.bn_train = bn_train; c.st = (cudaStream_t)stream;
   c.ss = nullptr;
   c.red_done = nullptr;
+  SideStream ss;
+  TRY(ss.init(c.st));
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
   const bool h16 = fp16_fwd();
   {  // every weight re-layout of this pass in one launch
@@ -283,7 +285,10 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
              (long long)C * 2 * C, 2 * C);
       if (h16) pk.last_to_half();
     }
-    TRY(pack_flush(pk, c.st));
+    // beside the first (one-channel, direct) convolution unit, which reads no packed weights
+    TRY(ss.fork());
+    TRY(pack_flush(pk, ss.s()));
+    TRY(ss.mark());
   }
 
   Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
@@ -295,6 +300,7 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
     Img out = i < 4 ? img_nhwc(p.cat[i] + C, B, p.h[i], p.w[i], C, 2 * C) : img_nhwc(p.bott, B, p.h[i], p.w[i], C);
     __half* out16 = h16 ? (i < 4 ? p.cat_h[i] + C : p.bott_h) : nullptr;   // same channel slice of the fp16 concat buffer
     TRY(unit_fwd(c, i, 0, in, z1, a1, in16, h16 ? p.ea1h[i] : nullptr));
+    TRY(ss.wait_mark());   // the packed weights (first pass of the loop only)
     TRY(unit_fwd(c, i, 1, a1, z2, out, h16 ? p.ea1h[i] : nullptr, out16));
     if (i < 4) {
       Img pl = img_nhwc(p.pool[i], B, p.h[i + 1], p.w[i + 1], C);
@@ -337,7 +343,6 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
   int red_done[kUnits] = {0};
   c.red_done = red_done;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
-  TRY(fill_zero(p.dwp[0], p.dwp_bytes, c.st));
   {
     PackBatch pk;
     for (int blk = 0; blk < 9; ++blk) {
@@ -351,13 +356,17 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
       const int C = p.C[3 - up];
       pk.add(params[P_UP + up * 2], p.wupd[up], 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
     }
-    TRY(pack_flush(pk, c.st));
+    TRY(ss.fork());   // beside the final 1x1 conv's backward kernel
+    TRY(fill_zero(p.dwp[0], p.dwp_bytes, ss.s()));   // packed weight-gradient accumulators: only side-stream kernels add into them
+    TRY(pack_flush(pk, ss.s()));
+    TRY(ss.mark());
   }
 
   // final 1x1 conv + sigmoid
   Img d0 = img_nhwc(p.dout[0], B, H, W, 32), g0 = img_nhwc(p.sC[0], B, H, W, 32);
   QEB_REQUIRE(grads[P_CONVW] && grads[P_CONVB], "unet_backward: the final conv's gradients are required");
   TRY(o1_conv_sigmoid_bwd(d0, params[P_CONVW], y, dy, g0, grads[P_CONVW], grads[P_CONVB], c.st));
+  TRY(ss.wait_mark());
 
   for (int i = 0; i <= 3; ++i) {  // decoder blocks, top (full resolution) first
     const int C = p.C[i], blk = 5 + (3 - i), up = 3 - i;

@@ -208,10 +208,14 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
 // keeps everything on the caller's stream.
 struct SideStream {
   cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
-  bool enabled = false, dirty = false;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, mark_ev = nullptr;
+  bool enabled = false, dirty = false, marked = false;
   int init(cudaStream_t main_stream);
   int fork();
   int join();
+  // mark(): remember the side stream's current position; wait_mark(): the main stream waits for that position only (not
+  // for side work queued after it). Used for the weight re-layouts, which run beside the first kernels of a pass.
+  int mark();
+  int wait_mark();
   cudaStream_t s() const { return enabled ? side : main; }
 };
