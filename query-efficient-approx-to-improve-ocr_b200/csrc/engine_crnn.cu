@@ -189,8 +189,17 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     }
     TRY(ss.fork());   // beside conv1 (direct kernel, no packed weights) and its pooling
     TRY(pack_flush(pk, ss.s()));
-    TRY(ss.mark());
   }
+  // the other parameter-only preparations ride along: summed LSTM biases, folded frozen-BatchNorm scale / shift
+  const BnParams bn1 = bn_of(params, buffers, P_BN1W, P_BN1B, B_BN1_MEAN), bn2 = bn_of(params, buffers, P_BN2W, P_BN2B, B_BN2_MEAN);
+  for (int l = 0; l < 2; ++l)
+    for (int d = 0; d < 2; ++d)
+      TRY(vec_add(params[P_LSTM0 + l * 8 + d * 4 + 2], params[P_LSTM0 + l * 8 + d * 4 + 3], (l ? p.bias1 : p.bias0) + d * 1024, 1024, ss.s()));
+  if (!bn_train) {
+    TRY(bn_eval_scsh(512, bn1, params[P_C5B], p.scsh5, ss.s()));
+    TRY(bn_eval_scsh(512, bn2, params[P_C6B], p.scsh6, ss.s()));
+  }
+  TRY(ss.mark());
   // shadows(in, w, out): the fp16 copies a contraction reads / writes in fp16 mode (nulls otherwise: tf32 path)
   auto shadows = [&](TcEpilogue& e, const void* in16, const void* w16, void* out16) {
     e.in16 = h ? in16 : nullptr; e.w16 = h ? w16 : nullptr; e.out16 = h ? out16 : nullptr;
@@ -212,7 +221,6 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   TRY(tc_conv_fprop(A3, p.wp4, 256, 3, 3, 1, 1, A4f, ep, st));
   TRY(maxpool_fwd(A4f, 2, 1, A4, st, h ? p.a4h : nullptr));
 
-  const BnParams bn1 = bn_of(params, buffers, P_BN1W, P_BN1B, B_BN1_MEAN), bn2 = bn_of(params, buffers, P_BN2W, P_BN2B, B_BN2_MEAN);
   if (bn_train) {
     TRY(fill_zero(p.bnstats, 2 * 2 * 512 * sizeof(double), st));
     TcEpilogue raw;
@@ -227,9 +235,7 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, Z6, raw, st));
     TRY(bn_train_finalize_apply(Z6, p.bnstats + 1024, bn2, p.scsh6, 1, A6f, st));
   } else {
-    // frozen statistics: y = relu(conv*scale + shift), shift folds the conv bias
-    TRY(bn_eval_scsh(512, bn1, params[P_C5B], p.scsh5, st));
-    TRY(bn_eval_scsh(512, bn2, params[P_C6B], p.scsh6, st));
+    // frozen statistics: y = relu(conv*scale + shift), shift folds the conv bias (scsh5 / scsh6 prepared above)
     TcEpilogue f;
     f.relu = 1;
     f.scale = p.scsh5; f.bias = p.scsh5 + 512;
@@ -261,9 +267,6 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     float* c = l ? p.c1 : p.c0;
     float* y = l ? p.y1 : p.y0;
     void* y16 = l ? p.y1h : p.y0h;
-    for (int d = 0; d < 2; ++d) {
-      TRY(vec_add(lp[d * 4 + 2], lp[d * 4 + 3], bias + d * 1024, 1024, st));
-    }
     TcEpilogue eg;
     eg.bias = bias;
     shadows(eg, xin16, l ? p.wih1h : p.wih0h, nullptr);

@@ -146,6 +146,7 @@ struct Ctx {
   SideStream* ss;  // backward only: weight / bias gradients run beside the input-gradient chain
   int* red_done;   // backward only, [kUnits]: 1 = the BatchNorm-backward reductions of that unit were produced by the kernel
                    // that wrote its output gradient (fused epilogue), the separate reduction pass is skipped
+  bool scsh_ready = false;   // eval-mode forward: scale / shift of units 1.. were folded on the side stream beforehand
 };
 
 // epilogue of an input-gradient kernel whose output is the gradient at the OUTPUT of conv unit `unit` (train-mode BatchNorm):
@@ -199,7 +200,7 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
     return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st, out16);
   }
-  TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
+  if (!c.scsh_ready) TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
   TcEpilogue f;
   f.relu = 1; f.scale = scsh; f.bias = scsh + cout;
   if (in16) { f.in16 = in16; f.w16 = c.p->wph[unit]; }
@@ -288,6 +289,13 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
     // beside the first (one-channel, direct) convolution unit, which reads no packed weights
     TRY(ss.fork());
     TRY(pack_flush(pk, ss.s()));
+    if (!bn_train && ss.enabled) {   // frozen statistics: fold every unit's scale / shift here too (unit 0 is needed at once: main)
+      for (int unit = 1; unit < kUnits; ++unit) {
+        const int blk = unit / 2, lvl = blk < 5 ? blk : 3 - (blk - 5);
+        TRY(bn_eval_scsh(p.C[lvl], bn_of(c, blk, unit & 1), nullptr, p.scsh + (size_t)unit * 4 * 512, ss.s()));
+      }
+      c.scsh_ready = true;
+    }
     TRY(ss.mark());
   }
 
