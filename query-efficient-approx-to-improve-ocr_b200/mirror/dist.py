@@ -5,6 +5,7 @@ train_nn_patch.py:278-303) across ranks is new functionality defined by north_st
 sample-local, so the only exchange is the sum / mean of the parameter gradients. The qeb backward hands autograd views
 of ONE flat gradient buffer per network, so the exchange is a single NCCL call on 31 MB (UNet) or 35 MB (CRNN).
 """
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -64,3 +65,53 @@ def shard_batch(n, rank, world):
     base, rem = divmod(n, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def global_topk(local_cers, k, group=None, local_topk=None):
+    """Stable global top-k over the ranks' CER shards: the indices `argsort(all, descending, stable)[:k]`
+    of the concatenation of the shards in rank order - what `TopKCERSampler.query` (selection_utils.py:144-151) and
+    `pruning/methods.topk` (:5-8) compute on one process - returned on every rank as an int64 tensor of GLOBAL indices.
+
+    Each rank reduces its shard to its own stable top-k on the device (`qeb_cer_topk_segmented`), the ranks all-gather the
+    k (value, index) candidates (12 bytes each) and merge them by (value descending, global index ascending); any element of
+    the global top-k is in its shard's top-k, and ties keep the lower global index exactly as the stable sort does.
+    local_topk(values_f32_numpy, k) -> int64 indices: the shard reduction; defaults to the device kernel (tests on CPU
+    processes pass the oracle here - the host-side merge is what they cover)."""
+    vals = torch.as_tensor(local_cers, dtype=torch.float32).cpu().numpy().reshape(-1)
+    if local_topk is None:
+        from . import selection_utils
+        local_topk = selection_utils.topk_cer_indices
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world = dist.get_world_size(group) if multi else 1
+    rank = dist.get_rank(group) if multi else 0
+    k = int(k)
+    if k <= 0:
+        return torch.zeros(0, dtype=torch.long)
+    kl = min(k, len(vals))
+    idx = np.asarray(local_topk(vals, kl), dtype=np.int64).reshape(-1) if kl > 0 else np.zeros(0, dtype=np.int64)
+    if not multi:
+        return torch.from_numpy(idx)
+    # shard sizes -> global offsets; candidates padded to k entries (count travels with them)
+    sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(vals)], dtype=torch.long), group=group)
+    offs = np.concatenate([[0], np.cumsum([int(s) for s in sizes])])
+    cand_v = torch.full((k,), float("-inf"), dtype=torch.float32)
+    cand_i = torch.full((k + 1,), -1, dtype=torch.long)
+    cand_v[:kl] = torch.from_numpy(vals[idx])
+    cand_i[:kl] = torch.from_numpy(idx + offs[rank])
+    cand_i[k] = kl
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    all_v = [torch.empty(k, dtype=torch.float32, device=dev) for _ in range(world)]
+    all_i = [torch.empty(k + 1, dtype=torch.long, device=dev) for _ in range(world)]
+    dist.all_gather(all_v, cand_v.to(dev), group=group)
+    dist.all_gather(all_i, cand_i.to(dev), group=group)
+    vs, gs = [], []
+    for v, i in zip(all_v, all_i):
+        i = i.cpu().numpy()
+        n = int(i[k])
+        vs.append(v.cpu().numpy()[:n])
+        gs.append(i[:n])
+    v, g = np.concatenate(vs), np.concatenate(gs)
+    order = np.lexsort((g, -v.astype(np.float64)))   # primary: value descending; ties: global index ascending
+    return torch.from_numpy(g[order[:k]].astype(np.int64))

@@ -94,3 +94,38 @@ def test_flat_buffer_is_found_behind_autograd():
     assert all(torch.equal(p.grad, torch.full_like(p, 2.0 * (i + 1))) for i, p in enumerate(params))
     assert qdist.flat_grad_buffer([params[0], params[3]]) is None   # a subset with foreign tensors in between
     assert qdist.flat_grad_buffer(params[:2]) is not None           # a contiguous prefix is fine
+
+
+def _topk_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import qeb_b200  # noqa: F401
+    from qeb_b200.mirror import dist as qdist
+    from oracle import pyoracle as po
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.RandomState(7)
+    # tie-heavy values (CERs are small rationals), ragged shards, one shard shorter than k
+    allv = (rng.randint(0, 12, size=1000) / 4.0).astype(np.float32)
+    cuts = [0, 5, 1000]
+    shard = allv[cuts[rank]:cuts[rank + 1]]
+    ok = True
+    for k in (1, 7, 64, 1000, 1500):
+        got = qdist.global_topk(shard, k, local_topk=lambda v, kk: po.topk_query(v, kk)).numpy()
+        want = np.argsort(-allv.astype(np.float64), kind="stable")[:k]
+        ok = ok and np.array_equal(got, want)
+    ok = ok and len(qdist.global_topk(shard, 0, local_topk=lambda v, kk: po.topk_query(v, kk))) == 0
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_global_topk_gloo_world2():
+    """8(e): global top-k = per-rank stable top-k + all-gather of the candidates + merge; equals the one-process stable sort."""
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_topk_worker, args=(world, port, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world))

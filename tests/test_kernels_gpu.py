@@ -430,3 +430,13 @@ def test_ocr_handoff_uint8_pixels_and_ring(m):
             return ["ok"] * imgs.shape[0]
     h = FakeHelper()
     assert oh.OcrFromUint8(h)(want) == ["ok"] * 37 and np.array_equal(h.pixels, want)
+
+
+def test_global_topk_single_process_uses_device_kernel(m):
+    """mirror/dist.global_topk without a process group: the shard reduction alone (qeb_cer_topk_segmented)."""
+    from qeb_b200.mirror import dist as qdist
+    rng = np.random.RandomState(3)
+    v = (rng.randint(0, 40, size=5000) / 8.0).astype(np.float32)
+    for k in (1, 33, 5000, 6000):
+        got = qdist.global_topk(v, k).numpy()
+        assert np.array_equal(got, np.argsort(-v.astype(np.float64), kind="stable")[:k])
