@@ -151,10 +151,19 @@ struct Ctx {
 
 // epilogue of an input-gradient kernel whose output is the gradient at the OUTPUT of conv unit `unit` (train-mode BatchNorm):
 // mask with relu(bn(z)) > 0 and accumulate that unit's BatchNorm-backward reductions
+bool pool_fuse() {
+  static const bool fuse = !(getenv("QEB_BN_POOL_FUSE") && atoi(getenv("QEB_BN_POOL_FUSE")) == 0);
+  return fuse;
+}
+
+bool red_fuse() {
+  static const bool fuse = !(getenv("QEB_BN_RED_FUSE") && atoi(getenv("QEB_BN_RED_FUSE")) == 0);
+  return fuse;
+}
+
 TcEpilogue grad_into_unit(const Ctx& c, int unit, const Img* z) {
   TcEpilogue e;
-  static const bool fuse = !(getenv("QEB_BN_RED_FUSE") && atoi(getenv("QEB_BN_RED_FUSE")) == 0);
-  if (fuse && c.bn_train && c.red_done) {
+  if (red_fuse() && c.bn_train && c.red_done) {
     e.bn_z = z;
     e.bn_scsh = c.p->scsh + (size_t)unit * 4 * 512;
     e.bn_red = c.p->bnred + (size_t)unit * 1024;
@@ -177,7 +186,7 @@ BnParams bn_of(const Ctx& c, int block, int which) {
 // one conv3x3 (no bias) + BN + ReLU unit. z: raw conv output (train mode only), out: activation. in16 / out16: fp16 shadows
 // of `in` / `out` (NULL: tf32 operands from the fp32 tensors / no shadow wanted).
 int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const __half* in16 = nullptr,
-             __half* out16 = nullptr) {
+             __half* out16 = nullptr, const Img* pool = nullptr, __half* pool16 = nullptr) {
   const int unit = block * 2 + which;
   const float* w = c.params[block * 6 + which * 3];
   float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
@@ -198,6 +207,7 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     raw.bn_stats = c.p->bnstats + (size_t)unit * 1024;   // per-channel sums come out of the conv epilogue
     if (in16) { raw.in16 = in16; raw.w16 = c.p->wph[unit]; }
     TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
+    if (pool) return bn_train_finalize_apply_pool(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, out, out16, *pool, pool16, c.st);
     return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st, out16);
   }
   if (!c.scsh_ready) TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
@@ -309,10 +319,13 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
     __half* out16 = h16 ? (i < 4 ? p.cat_h[i] + C : p.bott_h) : nullptr;   // same channel slice of the fp16 concat buffer
     TRY(unit_fwd(c, i, 0, in, z1, a1, in16, h16 ? p.ea1h[i] : nullptr));
     TRY(ss.wait_mark());   // the packed weights (first pass of the loop only)
-    TRY(unit_fwd(c, i, 1, a1, z2, out, h16 ? p.ea1h[i] : nullptr, out16));
+    const bool pool_fused = i < 4 && bn_train && pool_fuse();   // train mode: BatchNorm + ReLU + 2x2 pooling in one pass over z2
+    Img pl_f = img_nhwc(p.pool[i < 4 ? i : 0], B, p.h[i < 4 ? i + 1 : 1], p.w[i < 4 ? i + 1 : 1], C);
+    TRY(unit_fwd(c, i, 1, a1, z2, out, h16 ? p.ea1h[i] : nullptr, out16, pool_fused ? &pl_f : nullptr,
+                 pool_fused && h16 ? p.pool_h[i] : nullptr));
     if (i < 4) {
       Img pl = img_nhwc(p.pool[i], B, p.h[i + 1], p.w[i + 1], C);
-      TRY(maxpool_fwd(out, 2, 2, pl, c.st, h16 ? p.pool_h[i] : nullptr));
+      if (!pool_fused) TRY(maxpool_fwd(out, 2, 2, pl, c.st, h16 ? p.pool_h[i] : nullptr));
       in = pl;
       in16 = h16 ? p.pool_h[i] : nullptr;
     }
@@ -409,7 +422,14 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
       // gradient at the encoder output = skip-connection part of the concat gradient + routed pooling gradient
       Img gpool = img_nhwc(p.sA[i + 1], B, p.h[i + 1], p.w[i + 1], C);
       Img skip = img_nhwc(p.sA[i] + C, B, p.h[i], p.w[i], C, 2 * C);
-      TRY(maxpool_bwd(out, gpool, 2, 2, 0, nullptr, &skip, g, c.st));
+      static const bool pool_red = !(getenv("QEB_BN_RED_FUSE_POOL") && atoi(getenv("QEB_BN_RED_FUSE_POOL")) == 0);
+      if (bn_train && pool_red) {   // + the BatchNorm-backward reductions of this block's second unit (its output is `out`)
+        const int unit = i * 2 + 1;
+        TRY(maxpool_bwd(out, gpool, 2, 2, 0, nullptr, &skip, g, c.st, &z2, p.scsh + (size_t)unit * 4 * 512, p.bnred + (size_t)unit * 1024));
+        red_done[unit] = 1;
+      } else {
+        TRY(maxpool_bwd(out, gpool, 2, 2, 0, nullptr, &skip, g, c.st));
+      }
     }
     TRY(unit_bwd(c, i, 1, a1, z2, out, g, &ga1, &z1));
     if (i > 0) {

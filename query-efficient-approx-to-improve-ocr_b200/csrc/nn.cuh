@@ -153,8 +153,10 @@ int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const floa
 int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, void* out16 = nullptr);  // out16: fp16 shadow
 // dx = routed dy (first maximal element wins) * chan_scale[c] (if given), zeroed where x <= 0 when relu_mask, plus `add`
 // (same shape as x) if given
+// bn_z / bn_scsh / bn_red (all or none): dx is the gradient at the output of a train-mode conv + BN + ReLU unit with
+// pre-activation bn_z; that unit's BatchNorm-backward reductions are accumulated into bn_red[2C] in the same pass
 int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
-                const Img& dx, cudaStream_t st);
+                const Img& dx, cudaStream_t st, const Img* bn_z = nullptr, const float* bn_scsh = nullptr, double* bn_red = nullptr);
 // batch norm over all pixels of z (train: batch statistics; eval: running statistics)
 struct BnParams {
   const float* gamma; const float* beta;
@@ -167,7 +169,10 @@ int bn_train_stats(const Img& z, double* stats, cudaStream_t st);
 int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st);
 // finalize + apply fused (train mode): out = relu?(bn(z)) from the batch sums; writes scsh, updates the running statistics
 int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
-                            cudaStream_t st, void* out16 = nullptr);   // out16: fp16 shadow of out (same element layout)
+                            cudaStream_t st, void* out16 = nullptr);
+// the same (ReLU on) fused with the 2 x 2 max pooling of the unit's output: writes out (+ out16) and pool (+ pool16)
+int bn_train_finalize_apply_pool(const Img& z, const double* stats, const BnParams& bn, float* scsh, const Img& out, void* out16,
+                                 const Img& pool, void* pool16, cudaStream_t st);   // out16: fp16 shadow of out (same element layout)
 int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh, cudaStream_t st);
 // out = relu?(z*scale + shift)
 int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStream_t st, void* out16 = nullptr);

@@ -291,6 +291,14 @@ __global__ void __launch_bounds__(kThreads) o1_bwd_kernel(const float* __restric
   }
 }
 
+// relu: 0 = none, 1 = mask recomputed from the pre-activation v (z*scale+shift > 0), 2 = v IS the ReLU output (v > 0)
+__device__ __forceinline__ float4 bn_masked_grad(const float4 v, const float4 g, const float4 sc, const float4 sh, int relu) {
+  if (!relu) return g;
+  if (relu == 2) return make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f);
+  return make_float4(fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f,
+                     fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f);
+}
+
 // ------------------------------------------------------------------------------------------------ max pooling
 template <int PH, int PW>
 __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __restrict__ x, Geo gx, float* __restrict__ out,
@@ -328,8 +336,18 @@ template <int PH, int PW>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
                                                                Geo gd, int relu_mask, const float* __restrict__ chan_scale,
                                                                const float* __restrict__ add, Geo ga, float* __restrict__ dx,
-                                                               Geo gdx, int cq_n, long long total) {
+                                                               Geo gdx, int cq_n, long long total, const float* __restrict__ bn_z,
+                                                               Geo gz, const float* __restrict__ bn_scsh, double* __restrict__ bn_red) {
   qeb_pdl_sync();
+  // bn_red != NULL: dx is the gradient at the output of a train-mode conv + BN + ReLU unit whose pre-activation is bn_z; its
+  // BatchNorm-backward reductions (sum of masked g, sum of masked g * xhat) are accumulated here instead of in a separate
+  // pass over (z, dx). kThreads is a multiple of cq_n (host check): a thread keeps its channel quad.
+  float rs[4] = {0.f, 0.f, 0.f, 0.f}, rq[4] = {0.f, 0.f, 0.f, 0.f};
+  float4 bsc, bsh, bmu, bis;
+  if (bn_red) {
+    const int C = cq_n * 4, cq = threadIdx.x % cq_n;
+    bsc = ld4(bn_scsh + cq * 4); bsh = ld4(bn_scsh + C + cq * 4); bmu = ld4(bn_scsh + 2 * C + cq * 4); bis = ld4(bn_scsh + 3 * C + cq * 4);
+  }
   for (int i = blockIdx.x * kThreads + threadIdx.x; i < (int)total; i += gridDim.x * kThreads) {   // 32-bit index math (host check)
     const int cq = i % cq_n;
     const int pix = i / cq_n;
@@ -376,7 +394,29 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
           o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w;
         }
         st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
+        if (bn_red) {
+          const float4 zv = ld4(bn_z + n * gz.sn + (long long)(hv * PH + a) * gz.sh + (long long)(wv * PW + b) * gz.sw + cq * 4);
+          const float4 gm = bn_masked_grad(zv, make_float4(o[0], o[1], o[2], o[3]), bsc, bsh, 1);
+          rs[0] += gm.x; rs[1] += gm.y; rs[2] += gm.z; rs[3] += gm.w;
+          rq[0] = fmaf(gm.x, (zv.x - bmu.x) * bis.x, rq[0]); rq[1] = fmaf(gm.y, (zv.y - bmu.y) * bis.y, rq[1]);
+          rq[2] = fmaf(gm.z, (zv.z - bmu.z) * bis.z, rq[2]); rq[3] = fmaf(gm.w, (zv.w - bmu.w) * bis.w, rq[3]);
+        }
       }
+  }
+  if (bn_red) {   // block reduction over the row lanes of each channel, then one double atomic per channel and block
+    extern __shared__ float sm[];
+    const int C = cq_n * 4, rpb = kThreads / cq_n, cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
+    float* ss = sm;
+    float* sq = sm + rpb * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { ss[rl * C + cq * 4 + j] = rs[j]; sq[rl * C + cq * 4 + j] = rq[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kThreads) {
+      double a = 0.0, b = 0.0;
+      for (int r = 0; r < rpb; ++r) { a += ss[r * C + c]; b += sq[r * C + c]; }
+      atomicAdd(bn_red + c, a);
+      atomicAdd(bn_red + C + c, b);
+    }
   }
 }
 
@@ -483,16 +523,11 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restr
 // train mode, finalize + apply in one launch: every thread derives scale/shift of its four channels from the batch sums
 // (kThreads is a multiple of C/4, so a thread keeps its channel quad over the grid-stride loop); block 0 also stores
 // scale/shift/mean/invstd for the backward and updates the running statistics.
-__global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* __restrict__ z, long long zs, long long M, int C,
-                                                                  const double* __restrict__ stats, const float* __restrict__ gamma,
-                                                                  const float* __restrict__ beta, float* running_mean,
-                                                                  float* running_var, long long* nbt, float eps, float momentum,
-                                                                  float* __restrict__ scsh, int relu, float* __restrict__ out,
-                                                                  long long os, __half* __restrict__ out16) {
-  qeb_pdl_sync();
+__device__ __forceinline__ void bn_train_scale_shift(long long M, int C, int cq, const double* __restrict__ stats,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     float* running_mean, float* running_var, long long* nbt, float eps,
+                                                     float momentum, float* __restrict__ scsh, float (&sc)[4], float (&sh)[4]) {
   const int cq_n = C / 4;
-  const int cq = threadIdx.x % cq_n;
-  float sc[4], sh[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c = cq * 4 + j;
@@ -515,6 +550,19 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0 && nbt) *nbt += 1;
+}
+
+__global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* __restrict__ z, long long zs, long long M, int C,
+                                                                  const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, float* running_mean,
+                                                                  float* running_var, long long* nbt, float eps, float momentum,
+                                                                  float* __restrict__ scsh, int relu, float* __restrict__ out,
+                                                                  long long os, __half* __restrict__ out16) {
+  qeb_pdl_sync();
+  const int cq_n = C / 4;
+  const int cq = threadIdx.x % cq_n;
+  float sc[4], sh[4];
+  bn_train_scale_shift(M, C, cq, stats, gamma, beta, running_mean, running_var, nbt, eps, momentum, scsh, sc, sh);
   const long long rstep = (long long)gridDim.x * (kThreads / cq_n);
   for (long long r = (long long)blockIdx.x * (kThreads / cq_n) + threadIdx.x / cq_n; r < M; r += rstep) {
     const float4 v = ld4(z + r * zs + cq * 4);
@@ -525,12 +573,48 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
   }
 }
 
-// relu: 0 = none, 1 = mask recomputed from the pre-activation v (z*scale+shift > 0), 2 = v IS the ReLU output (v > 0)
-__device__ __forceinline__ float4 bn_masked_grad(const float4 v, const float4 g, const float4 sc, const float4 sh, int relu) {
-  if (!relu) return g;
-  if (relu == 2) return make_float4(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f, v.z > 0.f ? g.z : 0.f, v.w > 0.f ? g.w : 0.f);
-  return make_float4(fmaf(v.x, sc.x, sh.x) > 0.f ? g.x : 0.f, fmaf(v.y, sc.y, sh.y) > 0.f ? g.y : 0.f,
-                     fmaf(v.z, sc.z, sh.z) > 0.f ? g.z : 0.f, fmaf(v.w, sc.w, sh.w) > 0.f ? g.w : 0.f);
+// the same (with ReLU) fused with the 2 x 2 max pooling that follows the unit in the UNet encoder blocks: one pass over z
+// writes the activation (+ fp16 shadow) and the pooled activation (+ shadow). thread = (pooled pixel, channel quad)
+__global__ void __launch_bounds__(kThreads) bn_apply_train_pool_kernel(const float* __restrict__ z, Geo gz, long long M, int C,
+                                                                       const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                                       const float* __restrict__ beta, float* running_mean,
+                                                                       float* running_var, long long* nbt, float eps, float momentum,
+                                                                       float* __restrict__ scsh, float* __restrict__ out, Geo go,
+                                                                       __half* __restrict__ out16, float* __restrict__ pool, Geo gp,
+                                                                       __half* __restrict__ pool16, int n_pooled) {
+  qeb_pdl_sync();
+  const int cq_n = C / 4;
+  const int cq = threadIdx.x % cq_n;
+  float sc[4], sh[4];
+  bn_train_scale_shift(M, C, cq, stats, gamma, beta, running_mean, running_var, nbt, eps, momentum, scsh, sc, sh);
+  const int rstep = gridDim.x * (kThreads / cq_n);
+  for (int r = blockIdx.x * (kThreads / cq_n) + threadIdx.x / cq_n; r < n_pooled; r += rstep) {
+    const int wv = r % gp.w, t = r / gp.w, hv = t % gp.h;
+    const long long n = t / gp.h;
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float4 v = ld4(z + n * gz.sn + (long long)(2 * hv + a) * gz.sh + (long long)(2 * wv + b) * gz.sw + cq * 4);
+        const float4 o = make_float4(fmaxf(fmaf(v.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(v.y, sc[1], sh[1]), 0.f),
+                                     fmaxf(fmaf(v.z, sc[2], sh[2]), 0.f), fmaxf(fmaf(v.w, sc[3], sh[3]), 0.f));
+        const long long oo = n * go.sn + (long long)(2 * hv + a) * go.sh + (long long)(2 * wv + b) * go.sw + cq * 4;
+        st4(out + oo, o);
+        if (out16) st4h(out16 + oo, o);
+        if (a == 0 && b == 0) {
+          m = o;
+        } else {   // NaN-propagating max, the first maximum wins (as maxpool_fwd_kernel)
+          m.x = (o.x > m.x || o.x != o.x) ? o.x : m.x;
+          m.y = (o.y > m.y || o.y != o.y) ? o.y : m.y;
+          m.z = (o.z > m.z || o.z != o.z) ? o.z : m.z;
+          m.w = (o.w > m.w || o.w != o.w) ? o.w : m.w;
+        }
+      }
+    const long long po = n * gp.sn + (long long)hv * gp.sh + (long long)wv * gp.sw + cq * 4;
+    st4(pool + po, m);
+    if (pool16) st4h(pool16 + po, m);
+  }
 }
 
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const float* __restrict__ z, long long zs,
@@ -884,7 +968,7 @@ int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, v
 }
 
 int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
-                const Img& dx, cudaStream_t st) {
+                const Img& dx, cudaStream_t st, const Img* bn_z, const float* bn_scsh, double* bn_red) {
   ProfScope prof("maxpool_bwd", st, 0.0, 4.0 * x.c * (2 * (double)img_pixels(x) + (double)img_pixels(dy) + (add ? (double)img_pixels(x) : 0.0)));
   QEB_REQUIRE(vec4_ok(x) && vec4_ok(dy) && vec4_ok(dx) && x.c == dy.c && x.c == dx.c, "maxpool_bwd: channel count / alignment");
   QEB_REQUIRE(x.h == dy.h * ph && x.w == dy.w * pw && x.n == dy.n, "maxpool_bwd: input must be a multiple of the window");
@@ -892,15 +976,25 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   const int cq_n = x.c / 4;
   const long long total = img_pixels(dy) * cq_n;
   QEB_REQUIRE(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
-  const int g = qeb_grid(total, kThreads);
+  int g = qeb_grid(total, kThreads);
   Geo ga = add ? geo(*add) : geo(x);
   const float* ap = add ? add->p : nullptr;
+  const bool red = bn_z && bn_scsh && bn_red;
+  size_t smem = 0;
+  if (red) {
+    QEB_REQUIRE(vec4_ok(*bn_z) && bn_z->c == x.c && bn_z->n == x.n && bn_z->h == x.h && bn_z->w == x.w && kThreads % cq_n == 0,
+                "maxpool_bwd: fused BatchNorm reductions need z of the pooled tensor's shape and C/4 dividing %d", kThreads);
+    smem = (size_t)2 * (kThreads / cq_n) * x.c * sizeof(float);
+    g = min(g, 4 * kNumSMs);   // every block ends with 2C double atomics: a few blocks per SM, grid-stride over the rest
+  }
+  const Geo gz = red ? geo(*bn_z) : geo(x);
+  const float* zp = red ? bn_z->p : nullptr;
   if (ph == 2 && pw == 2)
-    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
-                                                     total));
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
+                                                     total, zp, gz, bn_scsh, red ? bn_red : nullptr));
   else if (ph == 2 && pw == 1)
-    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 1>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
-                                                     total));
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 1>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
+                                                     total, zp, gz, bn_scsh, red ? bn_red : nullptr));
   else QEB_REQUIRE(false, "maxpool_bwd: window %dx%d not supported", ph, pw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -962,6 +1056,23 @@ int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& b
                                                                                bn.running_mean, bn.running_var,
                                                                                bn.num_batches_tracked, bn.eps, bn.momentum, scsh,
                                                                                relu, out.p, out.sw, static_cast<__half*>(out16)));
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int bn_train_finalize_apply_pool(const Img& z, const double* stats, const BnParams& bn, float* scsh, const Img& out, void* out16,
+                                 const Img& pool, void* pool16, cudaStream_t st) {
+  ProfScope prof("bn_apply", st, 0.0, (8.0 * z.c + 1.0 * z.c) * (double)img_pixels(z));
+  QEB_REQUIRE(vec4_ok(z) && vec4_ok(out) && vec4_ok(pool) && z.c == out.c && z.c == pool.c, "bn_train_finalize_apply_pool: channels / alignment");
+  QEB_REQUIRE(z.n == out.n && z.h == out.h && z.w == out.w && pool.n == z.n && z.h == 2 * pool.h && z.w == 2 * pool.w,
+              "bn_train_finalize_apply_pool: shapes (the pooled tensor is half the unit's height and width)");
+  QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_train_finalize_apply_pool: C/4 must divide %d", kThreads);
+  const long long M = img_pixels(z), np = img_pixels(pool);
+  QEB_REQUIRE(np * (z.c / 4) < (1ll << 31), "bn_train_finalize_apply_pool: tensor too large for 32-bit indexing");
+  QEB_CUDA(qeb_launch(bn_apply_train_pool_kernel, qeb_grid(np * (z.c / 4), kThreads), kThreads, 0, st, z.p, geo(z), M, z.c, stats, bn.gamma,
+                      bn.beta, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.eps, bn.momentum, scsh, out.p, geo(out),
+                      static_cast<__half*>(out16), pool.p, geo(pool), static_cast<__half*>(pool16), (int)np));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
