@@ -943,8 +943,10 @@ namespace {
 int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, int a_c, int b_c, cudaStream_t st) {
   int bn = min(256, max(32, pow2_ceil(b_c)));
   const int m_tiles = qeb_cdiv(p.row_blocks, 4), n_tiles = qeb_cdiv(b_c, bn);
-  // split-K so that the grid covers the SMs a few times over, at least 8 pixel tiles per CTA
-  static const int wg_ctas = getenv("QEB_WG_CTAS") ? atoi(getenv("QEB_WG_CTAS")) : 2 * kNumSMs;
+  // split-K so that the grid is about ONE CTA per SM, at least 8 pixel tiles per CTA: every CTA ends with a red.global.add
+  // epilogue that retires at ~13 B per clock and SM (10 k cycles for a 128 x 256 tile, scripts/exp/wgrad_timeline.py), so a
+  // second wave of CTAs pays setup + epilogue twice (same-box A/B: 296 CTAs 3.68 ms per step, 148 CTAs 3.65 ms)
+  static const int wg_ctas = getenv("QEB_WG_CTAS") ? atoi(getenv("QEB_WG_CTAS")) : kNumSMs;
   int splits = qeb_cdiv(wg_ctas, m_tiles * n_tiles);
   splits = max(1, min(splits, qeb_cdiv(p.tiles_total, 8)));
   p.per_split = qeb_cdiv(p.tiles_total, splits);

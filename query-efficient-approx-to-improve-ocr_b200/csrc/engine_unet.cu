@@ -163,7 +163,11 @@ bool red_fuse() {
 
 TcEpilogue grad_into_unit(const Ctx& c, int unit, const Img* z) {
   TcEpilogue e;
-  if (red_fuse() && c.bn_train && c.red_done) {
+  // fused only from `min_c` channels up: on the 32 / 64-channel layers the epilogue is the kernel's bottleneck already and the
+  // separate reduction pass (3-4 TB/s) is cheaper than the longer epilogue (same-box A/B: 3.71 ms fused everywhere, 3.68 ms
+  // from 128 channels or not at all)
+  static const int min_c = getenv("QEB_BN_RED_FUSE_MINC") ? atoi(getenv("QEB_BN_RED_FUSE_MINC")) : 128;
+  if (red_fuse() && c.bn_train && c.red_done && z && z->c >= min_c) {
     e.bn_z = z;
     e.bn_scsh = c.p->scsh + (size_t)unit * 4 * 512;
     e.bn_red = c.p->bnred + (size_t)unit * 1024;
