@@ -8,6 +8,8 @@
 //     and backward (models/model_crnn.py:42-44,52-53; models/model_unet.py:93-106)
 //   - bias gradients (column sums), ReLU backward.
 // Layout: NHWC fp32 (nn.cuh Img). All kernels are grid-stride with float4 accesses along the channel dimension.
+#include <mutex>
+#include <unordered_map>
 #include "nn.cuh"
 #include <cuda_fp16.h>
 
@@ -866,6 +868,30 @@ __global__ void vec_add_kernel(const float* __restrict__ a, const float* __restr
   if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
 }
 
+// Grid of a grid-stride kernel = enough blocks for `total` threads, at most ONE resident wave (occupancy API, cached per
+// kernel): with a fixed "8 blocks per SM" cap a kernel that fits 3 blocks per SM ran 2.7 waves, the last one at a third of
+// the occupancy (ncu: c1_* kernels at 22-32 % active warps).
+int resident_grid(const void* kernel, long long total, int threads, size_t smem = 0) {
+  static std::mutex mu;
+  static std::unordered_map<const void*, int> cache;
+  int bps = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(kernel);
+    if (it != cache.end()) bps = it->second;
+  }
+  if (!bps) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, threads, smem) != cudaSuccess || bps < 1) { cudaGetLastError(); bps = 4; }
+    std::lock_guard<std::mutex> lk(mu);
+    cache[kernel] = bps;
+  }
+  long long g = (total + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * bps;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+#define RGRID(kernel, total) resident_grid(reinterpret_cast<const void*>(kernel), (total), kThreads)
+
 #define REQ_FLAT(img, what) QEB_REQUIRE(img_flat(img) && vec4_ok(img), what ": tensor must be a packed NHWC view with 16-byte aligned rows")
 
 }  // namespace
@@ -893,7 +919,8 @@ int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const
   QEB_REQUIRE(x.n == out.n && x.h == out.h && x.w == out.w && vec4_ok(out), "c1_conv_fwd: geometry/alignment");
   QEB_REQUIRE(x.w % 4 == 0 && img_pixels(x) / 4 < (1ll << 30), "c1_conv_fwd: the width must be a multiple of 4");
   const int n_quads = (int)(img_pixels(x) / 4);
-  const int g = qeb_grid((long long)n_quads * (out.c / 4), kThreads, 4);
+  const long long nthr = (long long)n_quads * (out.c / 4);
+  const int g = out.c == 32 ? RGRID(c1_fwd_kernel<32>, nthr) : RGRID(c1_fwd_kernel<64>, nthr);
   if (out.c == 32) QEB_CUDA(qeb_launch(c1_fwd_kernel<32>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_quads));
   else QEB_CUDA(qeb_launch(c1_fwd_kernel<64>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_quads));
   QEB_LAUNCH_CHECK();
@@ -907,7 +934,8 @@ int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStre
   QEB_REQUIRE(x.n == dy.n && x.h == dy.h && x.w == dy.w && vec4_ok(dy), "c1_conv_wgrad: geometry/alignment");
   QEB_REQUIRE(x.w % 4 == 0 && img_pixels(x) / 4 < (1ll << 30), "c1_conv_wgrad: the width must be a multiple of 4");
   const int n_quads = (int)(img_pixels(x) / 4);
-  const int g = qeb_grid((long long)n_quads * (dy.c / 4), kThreads, 4);
+  const long long nthr = (long long)n_quads * (dy.c / 4);
+  const int g = dy.c == 32 ? RGRID(c1_wgrad_kernel<32>, nthr) : RGRID(c1_wgrad_kernel<64>, nthr);
   if (dy.c == 32) QEB_CUDA(qeb_launch(c1_wgrad_kernel<32>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_quads));
   else QEB_CUDA(qeb_launch(c1_wgrad_kernel<64>, g, kThreads, 0, st, x.p, geo(x), dy.p, geo(dy), dw, dbias, n_quads));
   QEB_LAUNCH_CHECK();
@@ -921,7 +949,8 @@ int c1_conv_dgrad(const Img& dy, const float* w, const Img& dx, cudaStream_t st)
   QEB_REQUIRE(dx.n == dy.n && dx.h == dy.h && dx.w == dy.w && vec4_ok(dy), "c1_conv_dgrad: geometry/alignment");
   QEB_REQUIRE(dx.w % 4 == 0 && img_pixels(dx) / 4 < (1ll << 30), "c1_conv_dgrad: the width must be a multiple of 4");
   const int n_quads = (int)(img_pixels(dx) / 4);
-  const int g = qeb_grid((long long)n_quads * (dy.c / 4), kThreads, 8);
+  const long long nthr = (long long)n_quads * (dy.c / 4);
+  const int g = dy.c == 32 ? RGRID(c1_dgrad_kernel<32>, nthr) : RGRID(c1_dgrad_kernel<64>, nthr);
   if (dy.c == 32) QEB_CUDA(qeb_launch(c1_dgrad_kernel<32>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_quads));
   else QEB_CUDA(qeb_launch(c1_dgrad_kernel<64>, g, kThreads, 0, st, dy.p, geo(dy), w, dx.p, geo(dx), n_quads));
   QEB_LAUNCH_CHECK();
