@@ -1005,7 +1005,7 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   const int cq_n = x.c / 4;
   const long long total = img_pixels(dy) * cq_n;
   QEB_REQUIRE(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
-  int g = qeb_grid(total, kThreads);
+  int g = (ph == 2 && pw == 2) ? RGRID((maxpool_bwd_kernel<2, 2>), total) : RGRID((maxpool_bwd_kernel<2, 1>), total);
   Geo ga = add ? geo(*add) : geo(x);
   const float* ap = add ? add->p : nullptr;
   const bool red = bn_z && bn_scsh && bn_red;
@@ -1081,7 +1081,7 @@ int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& b
   QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_train_finalize_apply: shape mismatch");
   QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_train_finalize_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
-  QEB_CUDA(qeb_launch(bn_apply_train_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
+  QEB_CUDA(qeb_launch(bn_apply_train_kernel, RGRID(bn_apply_train_kernel, M * (z.c / 4)), kThreads, 0, st, z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
                                                                                bn.running_mean, bn.running_var,
                                                                                bn.num_batches_tracked, bn.eps, bn.momentum, scsh,
                                                                                relu, out.p, out.sw, static_cast<__half*>(out16)));
@@ -1099,7 +1099,7 @@ int bn_train_finalize_apply_pool(const Img& z, const double* stats, const BnPara
   QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_train_finalize_apply_pool: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z), np = img_pixels(pool);
   QEB_REQUIRE(np * (z.c / 4) < (1ll << 31), "bn_train_finalize_apply_pool: tensor too large for 32-bit indexing");
-  QEB_CUDA(qeb_launch(bn_apply_train_pool_kernel, qeb_grid(np * (z.c / 4), kThreads), kThreads, 0, st, z.p, geo(z), M, z.c, stats, bn.gamma,
+  QEB_CUDA(qeb_launch(bn_apply_train_pool_kernel, RGRID(bn_apply_train_pool_kernel, np * (z.c / 4)), kThreads, 0, st, z.p, geo(z), M, z.c, stats, bn.gamma,
                       bn.beta, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.eps, bn.momentum, scsh, out.p, geo(out),
                       static_cast<__half*>(out16), pool.p, geo(pool), static_cast<__half*>(pool16), (int)np));
   QEB_LAUNCH_CHECK();
@@ -1114,7 +1114,7 @@ int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStre
   QEB_REQUIRE(z.c == out.c && img_pixels(z) == img_pixels(out), "bn_apply: shape mismatch");
   QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
-  QEB_CUDA(qeb_launch(bn_apply_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw,
+  QEB_CUDA(qeb_launch(bn_apply_kernel, RGRID(bn_apply_kernel, M * (z.c / 4)), kThreads, 0, st, z.p, z.sw, M, z.c, scsh, relu, out.p, out.sw,
                                                                           static_cast<__half*>(out16)));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -1145,7 +1145,7 @@ static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu
               "bn_bwd_apply: shape mismatch");
   QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_bwd_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
-  QEB_CUDA(qeb_launch(bn_bwd_apply_kernel, qeb_grid(M * (z.c / 4), kThreads), kThreads, 0, st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
+  QEB_CUDA(qeb_launch(bn_bwd_apply_kernel, RGRID(bn_bwd_apply_kernel, M * (z.c / 4)), kThreads, 0, st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
                                                                              dz.p, dz.sw, dgamma, dbeta));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
