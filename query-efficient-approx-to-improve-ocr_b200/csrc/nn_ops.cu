@@ -962,7 +962,7 @@ int o1_conv_sigmoid_fwd(const Img& x, const float* w, const float* b, float* y, 
   ProfScope prof("o1_conv_sigmoid_fwd", st, 2.0 * (double)img_pixels(x) * x.c, 4.0 * (double)img_pixels(x) * (1 + x.c));
   QEB_REQUIRE(x.c == 32 && vec4_ok(x), "o1_conv_sigmoid_fwd: 32 input channels, aligned");
   const long long n_pix = img_pixels(x);
-  QEB_CUDA(qeb_launch(o1_fwd_kernel<32>, qeb_grid(n_pix * 8, kThreads, 8), kThreads, 0, st, x.p, geo(x), w, b, y, n_pix));
+  QEB_CUDA(qeb_launch(o1_fwd_kernel<32>, RGRID(o1_fwd_kernel<32>, n_pix * 8), kThreads, 0, st, x.p, geo(x), w, b, y, n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
@@ -973,7 +973,7 @@ int o1_conv_sigmoid_bwd(const Img& x, const float* w, const float* y, const floa
   ProfScope prof("o1_conv_sigmoid_bwd", st, 4.0 * (double)img_pixels(x) * x.c, 4.0 * (double)img_pixels(x) * (2 + 2 * x.c));
   QEB_REQUIRE(x.c == 32 && dx.c == 32 && vec4_ok(x) && vec4_ok(dx), "o1_conv_sigmoid_bwd: 32 channels, aligned");
   const long long n_pix = img_pixels(x);
-  QEB_CUDA(qeb_launch(o1_bwd_kernel<32>, qeb_grid(n_pix * 8, kThreads, 2), kThreads, 0, st, x.p, geo(x), w, y, dy, dx.p, geo(dx), dw, db, n_pix));
+  QEB_CUDA(qeb_launch(o1_bwd_kernel<32>, RGRID(o1_bwd_kernel<32>, n_pix * 8), kThreads, 0, st, x.p, geo(x), w, y, dy, dx.p, geo(dx), dw, db, n_pix));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
