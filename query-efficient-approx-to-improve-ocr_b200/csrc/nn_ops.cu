@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
 
 __device__ __forceinline__ float comp4(float4 q, int j) { return j == 0 ? q.x : (j == 1 ? q.y : (j == 2 ? q.z : q.w)); }
 
-template <int PH, int PW>
+template <int PH, int PW, bool RED>
 __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __restrict__ x, Geo gx, const float* __restrict__ dy,
                                                                Geo gd, int relu_mask, const float* __restrict__ chan_scale,
                                                                const float* __restrict__ add, Geo ga, float* __restrict__ dx,
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
   // pass over (z, dx). kThreads is a multiple of cq_n (host check): a thread keeps its channel quad.
   float rs[4] = {0.f, 0.f, 0.f, 0.f}, rq[4] = {0.f, 0.f, 0.f, 0.f};
   float4 bsc, bsh, bmu, bis;
-  if (bn_red) {
+  if constexpr (RED) {
     const int C = cq_n * 4, cq = threadIdx.x % cq_n;
     bsc = ld4(bn_scsh + cq * 4); bsh = ld4(bn_scsh + C + cq * 4); bmu = ld4(bn_scsh + 2 * C + cq * 4); bis = ld4(bn_scsh + 3 * C + cq * 4);
   }
@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
           o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w;
         }
         st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
-        if (bn_red) {
+        if constexpr (RED) {
           const float4 zv = ld4(bn_z + n * gz.sn + (long long)(hv * PH + a) * gz.sh + (long long)(wv * PW + b) * gz.sw + cq * 4);
           const float4 gm = bn_masked_grad(zv, make_float4(o[0], o[1], o[2], o[3]), bsc, bsh, 1);
           rs[0] += gm.x; rs[1] += gm.y; rs[2] += gm.z; rs[3] += gm.w;
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
         }
       }
   }
-  if (bn_red) {   // block reduction over the row lanes of each channel, then one double atomic per channel and block
+  if constexpr (RED) {   // block reduction over the row lanes of each channel, then one double atomic per channel and block
     extern __shared__ float sm[];
     const int C = cq_n * 4, rpb = kThreads / cq_n, cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
     float* ss = sm;
@@ -1005,10 +1005,12 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   const int cq_n = x.c / 4;
   const long long total = img_pixels(dy) * cq_n;
   QEB_REQUIRE(total < (1ll << 31), "maxpool_bwd: tensor too large for 32-bit indexing");
-  int g = (ph == 2 && pw == 2) ? RGRID((maxpool_bwd_kernel<2, 2>), total) : RGRID((maxpool_bwd_kernel<2, 1>), total);
+  const bool red = bn_z && bn_scsh && bn_red;
+  if (!red) bn_red = nullptr;
+  int g = (ph == 2 && pw == 2) ? (red ? RGRID((maxpool_bwd_kernel<2, 2, true>), total) : RGRID((maxpool_bwd_kernel<2, 2, false>), total))
+                               : RGRID((maxpool_bwd_kernel<2, 1, false>), total);
   Geo ga = add ? geo(*add) : geo(x);
   const float* ap = add ? add->p : nullptr;
-  const bool red = bn_z && bn_scsh && bn_red;
   size_t smem = 0;
   if (red) {
     QEB_REQUIRE(vec4_ok(*bn_z) && bn_z->c == x.c && bn_z->n == x.n && bn_z->h == x.h && bn_z->w == x.w && kThreads % cq_n == 0,
@@ -1018,12 +1020,16 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   }
   const Geo gz = red ? geo(*bn_z) : geo(x);
   const float* zp = red ? bn_z->p : nullptr;
-  if (ph == 2 && pw == 2)
-    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
-                                                     total, zp, gz, bn_scsh, red ? bn_red : nullptr));
+  QEB_REQUIRE(!red || (ph == 2 && pw == 2), "maxpool_bwd: fused BatchNorm reductions exist for the 2x2 window only");
+  if (ph == 2 && pw == 2 && red)
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2, true>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx),
+                        cq_n, total, zp, gz, bn_scsh, bn_red));
+  else if (ph == 2 && pw == 2)
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2, false>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx),
+                        cq_n, total, zp, gz, bn_scsh, (double*)nullptr));
   else if (ph == 2 && pw == 1)
-    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 1>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx), cq_n,
-                                                     total, zp, gz, bn_scsh, red ? bn_red : nullptr));
+    QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 1, false>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx),
+                        cq_n, total, zp, gz, bn_scsh, (double*)nullptr));
   else QEB_REQUIRE(false, "maxpool_bwd: window %dx%d not supported", ph, pw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
