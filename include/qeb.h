@@ -191,9 +191,12 @@ int qeb_adam_multi(const void* table, int n_tensors, long long n_chunks, float l
                    float weight_decay, int step, void* stream);
 
 /* Per-launch profiling: CUDA events around every launch of the library on its stream, with the launch site's
- * algorithmic FLOPs / bytes. report: JSON {"tag": {"launches", "ms", "flops", "bytes"}}, clears the records. */
+ * algorithmic FLOPs / bytes. report: JSON {"tag": {"launches", "ms", "flops", "bytes"}}, clears the records. While it is
+ * on, the module calls keep everything on the caller's stream (no side stream), so a launch's duration is its own.
+ * on = 2: one record per (tag, work size). */
 void qeb_prof_enable(int on);
-/* Debugging aid: per-CTA clock64 stamps of the tensor-core fprop kernel (see csrc/conv_tc.cu); NULL = off. */
+/* Debugging aid: per-CTA clock64 stamps (16 int64 per CTA) of the tensor-core fprop / dgrad and weight-gradient kernels
+ * (see csrc/conv_tc.cu, scripts/dev_timeline.py, scripts/exp/wgrad_timeline.py); NULL = off. */
 void qeb_debug_set_timeline(long long* buf);
 int qeb_prof_report(char* buf, int cap);
 
