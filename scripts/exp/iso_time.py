@@ -1,4 +1,6 @@
-"""Isolated (no side-stream contention) timings of the up-convolution input gradient and the weight-gradient kernel at the step's shapes."""
+"""Isolated (no side-stream contention, L2 flushed) timings of the up-convolution input gradient and the weight-gradient kernel
+at the step's shapes. The weight-gradient call goes through the C ABI, i.e. into torch's (Cout, Cin, kh, kw) layout, whose
+reduction epilogue is 3.4x slower than the packed layout the engines use (profiles/r1_notes.md 18)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
@@ -30,7 +32,7 @@ for (h, w, C) in [(16, 64, 32), (8, 32, 64), (4, 16, 128), (2, 8, 256)]:   # dx 
     t = timeit(f)
     gf = 2.0 * B * h * w * 2 * C * 4 * C / 1e9
     mb = 4.0 * (B * 4 * h * w * C + B * h * w * 2 * C) / 1e6
-    print(f"  dx {h}x{w}x{2*C}: {t:7.1f} us  {gf/t*1e3:7.1f} TF/s  {mb/t:7.0f} GB/s")
+    print(f"  dx {h}x{w}x{2*C}: {t:7.1f} us  {gf/t*1e3:7.1f} TF/s  {mb/t*1e3:7.0f} GB/s")
 print("conv wgrad 3x3")
 for (h, w, ci, co) in [(32, 128, 32, 32), (32, 128, 64, 32), (16, 64, 32, 64), (16, 64, 64, 64), (16, 64, 128, 64), (8, 32, 64, 128), (8, 32, 128, 128),
                        (8, 32, 256, 128), (4, 16, 256, 256), (2, 8, 512, 512), (16, 64, 64, 128), (8, 32, 128, 256), (8, 32, 256, 256), (4, 32, 256, 512), (4, 32, 512, 512)]:
@@ -41,4 +43,4 @@ for (h, w, ci, co) in [(32, 128, 32, 32), (32, 128, 64, 32), (16, 64, 32, 64), (
     t = timeit(f)
     gf = 2.0 * B * h * w * ci * co * 9 / 1e9
     mb = 4.0 * B * h * w * (ci + co) / 1e6
-    print(f"  {h}x{w} {ci}->{co}: {t:7.1f} us  {gf/t*1e3:7.1f} TF/s  {mb/t:7.0f} GB/s (operands once)")
+    print(f"  {h}x{w} {ci}->{co}: {t:7.1f} us  {gf/t*1e3:7.1f} TF/s  {mb/t*1e3:7.0f} GB/s (operands once)")
