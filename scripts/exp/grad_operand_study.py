@@ -111,6 +111,8 @@ def main():
 
         report(f"UNet conv weights (phase-B step, B = {B})", step, [p for n, p in unet.named_parameters() if "conv" in n and p.dim() == 4 and "upconv" not in n])
         report(f"CRNN conv weights (same step)", step, [p for n, p in crnn.named_parameters() if "conv" in n and p.dim() == 4])
+        x.requires_grad_(True)   # the end of the input-gradient chain: every dgrad of both networks in sequence
+        report("gradient at the UNet input (all input-gradient contractions chained)", step, [x])
     finally:
         torch.nn.Conv2d.forward = orig
 
