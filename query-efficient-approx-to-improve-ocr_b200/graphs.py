@@ -1,7 +1,7 @@
 """Whole-step CUDA graphs for the training step (optional: the eager modules stay the drop-in default).
 
 One phase-B step of the reference (train_nn_area.py:277-287) is ~240 kernel launches of 5-100 us each issued from two C
-calls per network; measured on B200 the host needs 4.5 ms to issue what the GPU executes in 5.4 ms, so any per-step host
+calls per network; measured on B200 the host needs about as long to issue them as the GPU to execute them (3.8 ms), so any per-step host
 work (label encoding, `loss.item()`) serialises with the GPU. Capturing forward + losses + backward ONCE and replaying
 the graph removes the host from the step: the trainer copies the batch and the encoded labels into static buffers,
 replays, and steps the optimizer.
