@@ -86,6 +86,12 @@ int qeb_greedy_decode(const float* scores, long long st_t, long long st_b, int T
  * made on the host, concatenated like out_idx. work: scratch, same size as vals. points_out: optional. */
 int qeb_cer_topk_segmented(const float* vals, const int* seg_off, const int* seg_k, const int* out_off, int n_seg,
                            long long* out_idx, void* stream);
+/* One segment of ANY size (dataset-wide top-k: pruning/methods.py:5-8; the per-rank shard reduction of a sharded top-k):
+ * the same order as above - out_idx[r] = index of the r-th largest value, equal values lowest index first - through a
+ * 64-bit-key sort instead of the per-warp ranking, which is quadratic in the segment size. k is clamped to n.
+ * work: qeb_cer_topk_global_workspace_bytes(n) bytes, 8-byte aligned. */
+size_t qeb_cer_topk_global_workspace_bytes(long long n);
+int qeb_cer_topk_global(const float* vals, long long n, long long k, void* work, long long* out_idx, void* stream);
 int qeb_cer_range_segmented(const float* vals, const int* seg_off, const int* seg_k, const int* out_off,
                             const float* rands, int n_seg, float* work, long long* out_idx, float* points_out,
                             void* stream);
@@ -95,6 +101,12 @@ int qeb_cer_range_segmented(const float* vals, const int* seg_off, const int* se
  * mean + sigma[image] * N(0,1) from Philox4x32-10(seed). img/out/noise: (n_img, hw) fp32, hw % 4 == 0, 16B aligned. */
 int qeb_gauss_jitter(const float* img, const float* sigma, float mean, float coef, const float* noise_in,
                      unsigned long long seed, long long n_img, int hw, float* out, float* noise_out, void* stream);
+/* The same with the Philox key read from DEVICE memory (key = *seed_dev + seed_offset) at execution time: inside a captured
+ * CUDA graph a by-value seed would be frozen and every replay would repeat the noise of the inner-loop copies
+ * (train_nn_patch.py:278-296). */
+int qeb_gauss_jitter_devseed(const float* img, const float* sigma, float mean, float coef,
+                             const unsigned long long* seed_dev, unsigned long long seed_offset, long long n_img, int hw,
+                             float* out, float* noise_out, void* stream);
 
 /* ---- OCR hand-off: fp32 images in [0,1] -> the uint8 pixels ToPILImage gives the OCR engine for a float tensor
  * (pic.mul(255).byte(): fp32 multiply, truncation), ocr_helper/tess_helper.py:20-24, eocr_helper.py. x, out: n elements,

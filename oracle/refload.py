@@ -13,11 +13,37 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("QEB_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIPPED_ROOT = os.path.join(_REPO, "baseline", "_ref")   # git-ignored copy made by install() - it travels to the GPU box
+
+
+def _pick_root():
+    for cand in (os.environ.get("QEB_REFERENCE_ROOT"), "/root/reference", SHIPPED_ROOT):
+        if cand and os.path.isdir(os.path.join(cand, "models")):
+            return cand
+    return os.environ.get("QEB_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "models"))
+
+
+def install(src="/root/reference", dst=SHIPPED_ROOT):
+    """Copy the UNMODIFIED reference tree (python sources + its small JSON artifacts; 7 MB) to baseline/_ref so that the
+    drop-in trainer tests and the reference arm of bench.py can run it on the GPU box, where /root/reference does not exist.
+    The reference has no setup.py / pyproject.toml, so `pip install --target baseline/_ref /root/reference` has nothing to
+    build: a byte-for-byte copy is the install. baseline/_ref is git-ignored (never committed), not gpurun-ignored."""
+    import shutil
+
+    if not os.path.isdir(os.path.join(src, "models")):
+        return None
+    if os.path.isdir(dst):
+        shutil.rmtree(dst)
+    shutil.copytree(src, dst, ignore=shutil.ignore_patterns(".git", "__pycache__", "*.pyc"))
+    return dst
 
 
 def _stub(name, **attrs):

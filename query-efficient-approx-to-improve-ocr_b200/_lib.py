@@ -27,8 +27,11 @@ SIGNATURES = {
     "qeb_levenshtein_batch": (I, [P, P, P, P, P, P, I, I, I, P, P, P, P]),
     "qeb_greedy_decode": (I, [P, LL, LL, I, I, I, I, P, P, P, P]),
     "qeb_cer_topk_segmented": (I, [P, P, P, P, I, P, P]),
+    "qeb_cer_topk_global_workspace_bytes": (SZ, [LL]),
+    "qeb_cer_topk_global": (I, [P, LL, LL, P, P, P]),
     "qeb_cer_range_segmented": (I, [P, P, P, P, P, I, P, P, P, P]),
     "qeb_gauss_jitter": (I, [P, P, F, F, P, ULL, LL, I, P, P, P]),
+    "qeb_gauss_jitter_devseed": (I, [P, P, F, F, P, ULL, LL, I, P, P, P]),
     "qeb_to_uint8": (I, [P, LL, P, P]),
     "qeb_crop_pad_gather": (I, [P, I, I, P, I, I, I, P, P]),
     "qeb_crop_pad_scatter": (I, [P, I, I, P, I, I, I, P, P]),

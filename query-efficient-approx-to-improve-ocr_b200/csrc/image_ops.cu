@@ -46,8 +46,10 @@ __device__ __forceinline__ float jitter1(float img, float noise, float coef) {
 
 // hw4 = pixels per image / 4
 __global__ void jitter_kernel(const float4* __restrict__ img, const float* __restrict__ sigma, float mean, float coef,
-                              const float4* __restrict__ noise_in, unsigned long long seed, long long n_img, int hw4,
+                              const float4* __restrict__ noise_in, unsigned long long seed,
+                              const unsigned long long* __restrict__ seed_dev, long long n_img, int hw4,
                               float4* __restrict__ out, float4* __restrict__ noise_out) {
+  if (seed_dev) seed += *seed_dev;   // seed kept in device memory: a captured CUDA graph draws fresh noise on every replay
   const long long total = n_img * hw4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long im = i / hw4;
@@ -115,9 +117,9 @@ __global__ void crop_pad_scatter_kernel(const float* __restrict__ gout, int H, i
 }  // namespace
 
 // img/out/noise: (n_img, hw) fp32 contiguous, hw % 4 == 0, 16-byte aligned. noise_in NULL => Philox noise from seed.
-QEB_API int qeb_gauss_jitter(const float* img, const float* sigma, float mean, float coef, const float* noise_in,
-                             unsigned long long seed, long long n_img, int hw, float* out, float* noise_out,
-                             void* stream) {
+static int gauss_jitter_impl(const float* img, const float* sigma, float mean, float coef, const float* noise_in,
+                             unsigned long long seed, const unsigned long long* seed_dev, long long n_img, int hw, float* out,
+                             float* noise_out, void* stream) {
   if (n_img == 0) return QEB_OK;
   QEB_REQUIRE(img && out && n_img > 0 && hw > 0, "gauss_jitter: bad args");
   QEB_REQUIRE(noise_in || sigma, "gauss_jitter: need sigma when noise is generated");
@@ -126,11 +128,27 @@ QEB_API int qeb_gauss_jitter(const float* img, const float* sigma, float mean, f
               "gauss_jitter: buffers must be 16-byte aligned");
   const long long total = n_img * (hw / 4);
   const int grid = qeb_grid(total, 256);
+  ProfScope prof("jitter", (cudaStream_t)stream, 0.0, 8.0 * n_img * hw);
   jitter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)img, sigma, mean, coef, (const float4*)noise_in,
-                                                        seed, n_img, hw / 4, (float4*)out, (float4*)noise_out);
+                                                        seed, seed_dev, n_img, hw / 4, (float4*)out, (float4*)noise_out);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
+}
+
+QEB_API int qeb_gauss_jitter(const float* img, const float* sigma, float mean, float coef, const float* noise_in,
+                             unsigned long long seed, long long n_img, int hw, float* out, float* noise_out,
+                             void* stream) {
+  return gauss_jitter_impl(img, sigma, mean, coef, noise_in, seed, nullptr, n_img, hw, out, noise_out, stream);
+}
+
+// the same with the Philox key taken from DEVICE memory (key = seed + *seed_dev): the form a captured CUDA graph needs,
+// where a by-value seed would be frozen into the graph and every replay would repeat the noise
+QEB_API int qeb_gauss_jitter_devseed(const float* img, const float* sigma, float mean, float coef,
+                                     const unsigned long long* seed_dev, unsigned long long seed_offset, long long n_img,
+                                     int hw, float* out, float* noise_out, void* stream) {
+  QEB_REQUIRE(seed_dev, "gauss_jitter_devseed: null seed pointer");
+  return gauss_jitter_impl(img, sigma, mean, coef, nullptr, seed_offset, seed_dev, n_img, hw, out, noise_out, stream);
 }
 
 QEB_API int qeb_crop_pad_gather(const float* img, int H, int W, const int* boxes, int n, int oh, int ow, float* out,
@@ -163,21 +181,25 @@ QEB_API int qeb_crop_pad_scatter(const float* gout, int H, int W, const int* box
 // (pic.mul(255).byte(): multiply in fp32, truncate), ocr_helper/tess_helper.py:20-24. 16 pixels per thread.
 namespace {
 __global__ void to_uint8_kernel(const float* __restrict__ x, long long n, uint8_t* __restrict__ out) {
-  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 16;
-  if (i + 16 <= n) {
-    uint32_t w[4];
+  // grid-stride over groups of 16 pixels: the grid is capped at a few waves of the SMs, the loop covers any n
+  const long long groups = (n + 15) / 16;
+  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
+    const long long i = g * 16;
+    if (i + 16 <= n) {
+      uint32_t w[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + i) + q);
-      const float f[4] = {v.x, v.y, v.z, v.w};
-      uint32_t pk = 0;
+      for (int q = 0; q < 4; ++q) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + i) + q);
+        const float f[4] = {v.x, v.y, v.z, v.w};
+        uint32_t pk = 0;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) pk |= (uint32_t)(int)fminf(fmaxf(f[e] * 255.f, 0.f), 255.f) << (8 * e);
-      w[q] = pk;
+        for (int e = 0; e < 4; ++e) pk |= (uint32_t)(int)fminf(fmaxf(f[e] * 255.f, 0.f), 255.f) << (8 * e);
+        w[q] = pk;
+      }
+      *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (long long j = i; j < n; ++j) out[j] = (uint8_t)(int)fminf(fmaxf(x[j] * 255.f, 0.f), 255.f);
     }
-    *reinterpret_cast<uint4*>(out + i) = make_uint4(w[0], w[1], w[2], w[3]);
-  } else {
-    for (long long j = i; j < n; ++j) out[j] = (uint8_t)(int)fminf(fmaxf(x[j] * 255.f, 0.f), 255.f);
   }
 }
 }  // namespace

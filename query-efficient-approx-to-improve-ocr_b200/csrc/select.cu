@@ -105,7 +105,101 @@ __global__ void range_segmented_kernel(const float* __restrict__ vals, const int
   }
 }
 
+// ---- one LARGE segment (dataset-wide top-k: pruning/methods.py:5-8, the per-rank shard reduction of dist.global_topk) --------
+// The warp kernel above ranks a segment with n^2 comparisons - right for minibatch-sized segments (n <= 1024), hopeless for
+// 10^5..10^7 CERs. Here every element becomes ONE 64-bit key (~desc_key(value) << 32 | index): ascending key order is
+// "value descending, index ascending", keys are distinct, so any comparison sort gives exactly the stable order. The keys
+// are sorted with a bitonic network: chunks of 2048 keys in shared memory (all sub-stages with stride < 2048), strides
+// >= 2048 as global compare-exchange passes. O(n log^2 n) compare-exchanges, 8 MB per pass at n = 1 M: HBM-bound passes.
+constexpr int kSortChunk = 2048;   // keys per block in the shared-memory kernels (512 threads x 4)
+
+__global__ void topk_keys_kernel(const float* __restrict__ vals, long long n, long long n_pad, unsigned long long* __restrict__ keys) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += (long long)gridDim.x * blockDim.x)
+    keys[i] = i < n ? ((unsigned long long)(~desc_key(vals[i])) << 32) | (unsigned long long)i : ~0ull;
+}
+
+__device__ __forceinline__ void cmp_swap(unsigned long long& a, unsigned long long& b, bool up) {
+  if ((a > b) == up) { const unsigned long long t = a; a = b; b = t; }
+}
+
+// sub-stages j = j_hi, j_hi/2, ..., 1 of stage k on one 2048-key chunk held in shared memory; full_sort: all stages
+// k = 2 .. 2048 (the initial chunk sort)
+__global__ void __launch_bounds__(512) bitonic_shared_kernel(unsigned long long* __restrict__ keys, long long k, int full_sort) {
+  __shared__ unsigned long long s[kSortChunk];
+  const long long base = (long long)blockIdx.x * kSortChunk;
+  for (int i = threadIdx.x; i < kSortChunk; i += 512) s[i] = keys[base + i];
+  __syncthreads();
+  for (long long kk = full_sort ? 2 : k; kk <= k; kk <<= 1) {
+    for (int j = (int)(kk < kSortChunk ? kk >> 1 : kSortChunk >> 1); j > 0; j >>= 1) {
+      for (int t = threadIdx.x; t < kSortChunk / 2; t += 512) {
+        const int lo = 2 * t - (t & (j - 1));        // index with bit j clear
+        const bool up = ((base + lo) & kk) == 0;
+        cmp_swap(s[lo], s[lo + j], up);
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < kSortChunk; i += 512) keys[base + i] = s[i];
+}
+
+// one global compare-exchange pass: stage k, stride j (>= kSortChunk)
+__global__ void bitonic_global_kernel(unsigned long long* __restrict__ keys, long long n_pad, long long k, long long j) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_pad / 2; t += (long long)gridDim.x * blockDim.x) {
+    const long long lo = 2 * t - (t & (j - 1));
+    unsigned long long a = keys[lo], b = keys[lo + j];
+    const bool up = (lo & k) == 0;
+    if ((a > b) == up) { keys[lo] = b; keys[lo + j] = a; }
+  }
+}
+
+__global__ void topk_emit_kernel(const unsigned long long* __restrict__ keys, long long k, long long* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (long long)(keys[i] & 0xffffffffull);
+}
+
+long long sort_pad(long long n) {
+  long long p = kSortChunk;
+  while (p < n) p <<= 1;
+  return p;
+}
+
 }  // namespace
+
+// Stable top-k of ONE segment of any size: out_idx[r] = index of the r-th largest value, equal values lowest index first
+// (= argsort(descending, stable)[:k]); k is clamped to n. work: qeb_cer_topk_global_workspace_bytes(n) bytes.
+QEB_API size_t qeb_cer_topk_global_workspace_bytes(long long n) { return n > 0 ? (size_t)sort_pad(n) * 8 : 0; }
+
+QEB_API int qeb_cer_topk_global(const float* vals, long long n, long long k, void* work, long long* out_idx, void* stream) {
+  if (n <= 0 || k <= 0) return QEB_OK;
+  QEB_REQUIRE(vals && work && out_idx, "cer_topk_global: null pointer");
+  QEB_REQUIRE(n < (1ll << 32), "cer_topk_global: n=%lld does not fit the 32-bit index field", n);
+  QEB_REQUIRE(((uintptr_t)work & 7) == 0, "cer_topk_global: workspace must be 8-byte aligned");
+  if (k > n) k = n;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long* keys = static_cast<unsigned long long*>(work);
+  const long long n_pad = sort_pad(n);
+  ProfScope prof("topk_global", st, 0.0, 4.0 * n + 8.0 * k);
+  topk_keys_kernel<<<qeb_grid(n_pad, 256), 256, 0, st>>>(vals, n, n_pad, keys);
+  QEB_LAUNCH_CHECK();
+  const int chunks = (int)(n_pad / kSortChunk);
+  bitonic_shared_kernel<<<chunks, 512, 0, st>>>(keys, kSortChunk, 1);
+  QEB_LAUNCH_CHECK();
+  int launches = 2;
+  for (long long kk = 2 * kSortChunk; kk <= n_pad; kk <<= 1) {
+    for (long long j = kk >> 1; j >= kSortChunk; j >>= 1) {
+      bitonic_global_kernel<<<qeb_grid(n_pad / 2, 256), 256, 0, st>>>(keys, n_pad, kk, j);
+      QEB_LAUNCH_CHECK();
+      ++launches;
+    }
+    bitonic_shared_kernel<<<chunks, 512, 0, st>>>(keys, kk, 0);
+    QEB_LAUNCH_CHECK();
+    ++launches;
+  }
+  topk_emit_kernel<<<qeb_grid(k, 256), 256, 0, st>>>(keys, k, out_idx);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch(launches + 1);
+  return QEB_OK;
+}
 
 // vals: concatenated fp32 CERs of all segments; seg_off (n_seg+1); seg_k (n_seg) requested picks per segment;
 // out_off (n_seg) exclusive prefix sum of min(k, n); out_idx: int64 indices local to the segment.

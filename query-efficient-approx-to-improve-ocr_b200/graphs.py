@@ -38,7 +38,12 @@ class StaticTargets(PackedTargets):
     def __init__(self, batch, max_label_len, device):
         device = torch.device(device)
         self.cap = max(1, batch * max_label_len)
-        self._host = torch.zeros(self.cap + 3 * batch, dtype=torch.int32).pin_memory()
+        # two pinned staging buffers, each with the event of the H2D copy last issued from it: load() never rewrites host
+        # memory that a queued copy (behind a graph replay, with no per-step sync in the caller's loop) still has to read
+        self._hosts = [torch.zeros(self.cap + 3 * batch, dtype=torch.int32).pin_memory() for _ in range(2)]
+        self._events = [None, None]
+        self._slot = 0
+        self._host = self._hosts[0]
         self._dev = torch.zeros(self.cap + 3 * batch, dtype=torch.int32, device=device)
         c, B = self.cap, batch
         super().__init__(self._dev[:c], self._dev[c:c + B], self._dev[c + B:c + 2 * B], self._dev[c + 2 * B:], max_label_len, B)
@@ -60,7 +65,10 @@ class StaticTargets(PackedTargets):
                                 f"{self.max_len} (run this batch through the eager path)")
         if tg.numel() < n_t:
             raise RuntimeError("StaticTargets: targets shorter than sum(target_lengths)")
-        h = self._host
+        self._slot ^= 1
+        h = self._host = self._hosts[self._slot]
+        if self._events[self._slot] is not None:
+            self._events[self._slot].synchronize()   # the copy issued from this buffer two loads ago has finished
         h[:n_t] = tg[:n_t]
         offs = np.zeros(B, dtype=np.int32)
         np.cumsum(tl_np[:-1], out=offs[1:])
@@ -68,6 +76,10 @@ class StaticTargets(PackedTargets):
         h[c + B:c + 2 * B] = il
         h[c + 2 * B:] = tl
         self._dev.copy_(h, non_blocking=True)
+        if self._dev.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._events[self._slot] = ev
         return self
 
 

@@ -25,9 +25,36 @@ def _device_of(images):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+_WARP_SEGMENT_MAX = 1024   # the per-warp ranking kernel is quadratic in the segment size: larger segments are sorted
+
+
+def topk_global_device(vals_dev, k):
+    """Stable top-k of ONE device-resident fp32 vector of any size (qeb_cer_topk_global): int64 device indices."""
+    n = vals_dev.numel()
+    k = min(int(k), n)
+    out = torch.empty(max(k, 0), dtype=torch.int64, device=vals_dev.device)
+    if k <= 0:
+        return out
+    work = torch.empty(_lib.load().qeb_cer_topk_global_workspace_bytes(n), dtype=torch.uint8, device=vals_dev.device)
+    _lib.call("qeb_cer_topk_global", vals_dev.data_ptr(), n, k, work.data_ptr(), out.data_ptr(), _lib.stream())
+    return out
+
+
 def _segmented(vals_list, ks, device, rands_list=None):
     """Run one launch over several segments. Returns list of int64 CPU index tensors."""
     n_seg = len(vals_list)
+    if rands_list is None and any(len(v) > _WARP_SEGMENT_MAX for v in vals_list):
+        # dataset-sized segments go through the sort kernel one by one, the minibatch-sized ones through the warp kernel
+        small = [i for i, v in enumerate(vals_list) if len(v) <= _WARP_SEGMENT_MAX]
+        res = [None] * n_seg
+        if small:
+            for i, r in zip(small, _segmented([vals_list[i] for i in small], [ks[i] for i in small], device)):
+                res[i] = r
+        for i, v in enumerate(vals_list):
+            if res[i] is None:
+                vd = torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=np.float32))).pin_memory().to(device, non_blocking=True)
+                res[i] = topk_global_device(vd, ks[i]).cpu()
+        return res
     sizes = np.array([len(v) for v in vals_list], dtype=np.int32)
     ks = np.array(ks, dtype=np.int32)
     seg_off = np.zeros(n_seg + 1, dtype=np.int32)

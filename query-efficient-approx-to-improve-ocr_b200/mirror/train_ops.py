@@ -54,7 +54,10 @@ class Adam(torch.optim.Optimizer):
         self._tables = {}
 
     def _table(self, gi, group, ps):
-        key = (gi, tuple(p.data_ptr() for p in ps), tuple(p.grad.data_ptr() for p in ps))
+        # the device table embeds raw pointers of the parameters, gradients AND moment buffers: all of them are part of the
+        # key, so optimizer.load_state_dict() (which replaces exp_avg / exp_avg_sq) rebuilds the table
+        key = (gi, tuple(p.data_ptr() for p in ps), tuple(p.grad.data_ptr() for p in ps),
+               tuple(self.state[p]["exp_avg"].data_ptr() for p in ps), tuple(self.state[p]["exp_avg_sq"].data_ptr() for p in ps))
         cached = self._tables.get(gi)
         if cached is not None and cached[0] == key:
             return cached[1], cached[2]
@@ -69,6 +72,14 @@ class Adam(torch.optim.Optimizer):
         dev = torch.from_numpy(host).pin_memory().to(ps[0].device, non_blocking=True)
         self._tables[gi] = (key, dev, chunk)
         return dev, chunk
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._tables = {}   # the moment tensors were replaced
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self._tables = {}
 
     @torch.no_grad()
     def step(self, closure=None):

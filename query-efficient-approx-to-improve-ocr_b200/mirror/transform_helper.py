@@ -12,18 +12,34 @@ import torch
 from .. import _lib
 
 
-def _launch(img2d, sigma, mean, coef, noise_in, seed, want_noise):
+def _launch(img2d, sigma, mean, coef, noise_in, seed, want_noise, out=None, seed_dev=None):
     n_img, hw = img2d.shape
-    out = torch.empty_like(img2d)
+    if out is None:
+        out = torch.empty_like(img2d)
     noise = torch.empty_like(img2d) if want_noise else None
-    _lib.call("qeb_gauss_jitter", img2d.data_ptr(), _lib.ptr(sigma), float(mean), float(coef), _lib.ptr(noise_in),
-              int(seed), n_img, hw, out.data_ptr(), _lib.ptr(noise), _lib.stream())
+    if seed_dev is not None:   # Philox key read from device memory when the kernel runs (CUDA-graph safe)
+        _lib.call("qeb_gauss_jitter_devseed", img2d.data_ptr(), _lib.ptr(sigma), float(mean), float(coef), seed_dev.data_ptr(),
+                  int(seed), n_img, hw, out.data_ptr(), _lib.ptr(noise), _lib.stream())
+    else:
+        _lib.call("qeb_gauss_jitter", img2d.data_ptr(), _lib.ptr(sigma), float(mean), float(coef), _lib.ptr(noise_in),
+                  int(seed), n_img, hw, out.data_ptr(), _lib.ptr(noise), _lib.stream())
     return out, noise
 
 
 def _check(images):
     if not images.is_cuda or images.dtype != torch.float32:
         raise _lib.QebError("qeb jitter needs CUDA fp32 images (no CPU fallback)")
+
+
+def _to_device(images):
+    """The reference trainers hand the noiser CPU tensors (`img_preds.detach().cpu()`, train_nn_area.py:225,236;
+    `text_crops.detach().cpu()`, train_nn_patch.py:260,270): move them to the current CUDA device for the kernel and
+    remember where the result has to go back to. No CPU arithmetic happens here - without a CUDA device this raises."""
+    if images.is_cuda:
+        return images, None
+    if not torch.cuda.is_available():
+        raise _lib.QebError("qeb jitter needs a CUDA device (no CPU fallback)")
+    return images.to(torch.device("cuda", torch.cuda.current_device()), torch.float32, non_blocking=True), images.device
 
 
 def apply_noise(images, noise, noise_coef=1):
@@ -35,9 +51,12 @@ def apply_noise(images, noise, noise_coef=1):
     return out.view_as(images)
 
 
-def jitter_batch(images, sigmas, mean=0.0, noise_coef=1, seed=None, return_noise=False):
+def jitter_batch(images, sigmas, mean=0.0, noise_coef=1, seed=None, return_noise=False, out=None, seed_dev=None):
     """images (N,...) CUDA fp32; sigmas (N) per-image std (host or device). One launch for the whole batch -
-    the fused form of the add_noise loops at train_nn_patch.py:187-191 / train_nn_area.py:184-191."""
+    the fused form of the add_noise loops at train_nn_patch.py:187-191 / train_nn_area.py:184-191.
+    out: optional preallocated result (same shape, contiguous). seed_dev: optional device tensor holding one uint64 (as
+    int64) Philox key that is read when the kernel RUNS (key = *seed_dev + seed): a captured CUDA graph then draws new
+    noise per replay once the caller updates that tensor; `seed` is an offset in that mode (default 0)."""
     _check(images)
     x = images.contiguous()
     n = x.shape[0]
@@ -45,8 +64,11 @@ def jitter_batch(images, sigmas, mean=0.0, noise_coef=1, seed=None, return_noise
     if not sg.is_cuda:
         sg = sg.pin_memory().to(x.device, non_blocking=True)
     if seed is None:
-        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
-    out, noise = _launch(x.view(n, -1), sg.contiguous(), mean, noise_coef, None, seed, return_noise)
+        seed = 0 if seed_dev is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+    if out is not None and (out.shape != images.shape or not out.is_contiguous() or out.device != x.device):
+        raise _lib.QebError("jitter_batch: `out` must be a contiguous tensor of the input's shape on its device")
+    out, noise = _launch(x.view(n, -1), sg.contiguous(), mean, noise_coef, None, seed, return_noise,
+                         None if out is None else out.view(n, -1), seed_dev)
     out = out.view_as(images)
     return (out, noise.view_as(images)) if return_noise else out
 
@@ -66,15 +88,23 @@ class AddGaussianNoice(object):
         return (r + 0.0000000000001).to(torch.float32)
 
     def __call__(self, image, noise_coef=1):
-        """One image (C,H,W) like the reference call."""
+        """One image (C,H,W) like the reference call; a CPU image (what the unmodified trainers pass) is processed on the
+        device and handed back on the CPU."""
+        image, home = _to_device(image)
         out = jitter_batch(image.unsqueeze(0), self._sigmas(1), self.mean, noise_coef, return_noise=self.return_noise)
         if self.return_noise:
-            return out[0].squeeze(0), out[1].squeeze(0)
-        return out.squeeze(0)
+            img, noise = out[0].squeeze(0), out[1].squeeze(0)
+            return (img, noise) if home is None else (img.to(home), noise.to(home))
+        out = out.squeeze(0)
+        return out if home is None else out.to(home)
 
     def batch(self, images, noise_coef=1):
         """Whole batch (N,C,H,W), one sigma per image, one launch."""
-        return jitter_batch(images, self._sigmas(images.shape[0]), self.mean, noise_coef, return_noise=self.return_noise)
+        images, home = _to_device(images)
+        out = jitter_batch(images, self._sigmas(images.shape[0]), self.mean, noise_coef, return_noise=self.return_noise)
+        if home is None:
+            return out
+        return tuple(o.to(home) for o in out) if self.return_noise else out.to(home)
 
 
 def add_noise(imgs, noiser, noise_coef=1):

@@ -412,6 +412,11 @@ def test_ocr_handoff_uint8_pixels_and_ring(m):
     assert np.array_equal(oh.to_uint8(xd).cpu().numpy().reshape(37, 32, 128), want)
     odd = torch.rand(3, 1, 5, 7, generator=g)                    # 105 elements: scalar tail path
     assert np.array_equal(oh.to_uint8(odd.to(DEV)).cpu().numpy(), odd.mul(255).byte().numpy())
+    # more pixels than one capped grid covers in a single pass (1184 blocks x 256 threads x 16 pixels = 4.85 M), and a count
+    # that is not a multiple of 16: every output byte must be written
+    big = torch.rand(5_300_003, generator=g)
+    got = oh.to_uint8(big.to(DEV).view(1, -1)).cpu().numpy().reshape(-1)
+    assert np.array_equal(got, big.mul(255).byte().numpy())
     ring = oh.OcrHandoff(depth=2)
     t0 = ring.submit(xd)
     t1 = ring.submit(1.0 - xd)
