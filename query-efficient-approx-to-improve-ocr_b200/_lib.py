@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqeb_sm100.so")
+# QEB_LIB: another build of the same ABI (same-box A/B measurements of a kernel change against the previous build)
+LIB_PATH = os.environ.get("QEB_LIB") or os.path.join(_HERE, "libqeb_sm100.so")
 
 P = ctypes.c_void_p
 I = ctypes.c_int

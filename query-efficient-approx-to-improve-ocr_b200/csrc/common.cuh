@@ -92,6 +92,28 @@ inline cudaError_t qeb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 #ifdef __CUDACC__
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// ---- tf32 operands, rounded where they are PRODUCED ---------------------------------------------------------------------
+// tcgen05.mma.kind::tf32 reads fp32 words from shared memory and TRUNCATES them to tf32 (10 mantissa bits): a bias of half an
+// ulp per operand that the backward pass of the random-init networks amplifies (weight gradients 1-2e-2 off the fp32 oracle,
+// profiles/r1_notes.md 7 / 21). TMA moves the bytes untouched, so the only place to round is the kernel that WRITES a tensor
+// which a tf32 contraction will read: it stores round-to-nearest(tf32) - an fp32 word whose low 13 mantissa bits are zero, so
+// the tensor core's truncation is exact. Same 11-bit significand as the fp16 operand copies of the forward pass, full fp32
+// range, no extra bytes. Applies to: activations kept for the weight gradients, every gradient tensor that feeds a dgrad /
+// wgrad contraction, the packed dgrad weights. QEB_TF32_RN=0 at compile time restores plain stores.
+#ifndef QEB_TF32_RN
+#define QEB_TF32_RN 1
+#endif
+__device__ __forceinline__ float qeb_tf32r(float x) {
+#if QEB_TF32_RN
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+#else
+  return x;
+#endif
+}
+__device__ __forceinline__ float4 qeb_tf32r4(float4 v) { return make_float4(qeb_tf32r(v.x), qeb_tf32r(v.y), qeb_tf32r(v.z), qeb_tf32r(v.w)); }
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));

@@ -113,6 +113,7 @@ struct FpropParams {
   const float* bn_scsh;      // non-NULL: `mask` holds z of the layer below; mask = z*scale + shift > 0, second sum = g*xhat
   int kblk;                  // operand elements per K block: 32 (tf32, or fp16 in 64-byte rows) or 64 (fp16 in 128-byte rows)
   __half* out16;             // optional fp16 shadow of the output (same element layout as `out`): the next layer's operand
+  int round_out;             // 1: fp32 stores are rounded to tf32 (the tensor is a tf32 operand of a later contraction)
 };
 
 struct TmapArray4 {
@@ -202,6 +203,10 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
                    : "memory");
   } else if (lim == 32 && p.vec_ok) {
     float4* d4 = reinterpret_cast<float4*>(dst);
+    if (p.round_out && !p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = qeb_tf32r(v[j]);
+    }
     if (p.accumulate) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -215,7 +220,7 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j < lim) dst[j] = p.accumulate ? dst[j] + v[j] : v[j];
+      if (j < lim) dst[j] = p.accumulate ? dst[j] + v[j] : (p.round_out ? qeb_tf32r(v[j]) : v[j]);
   }
 }
 
@@ -292,7 +297,7 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
           const float4 a = *reinterpret_cast<const float4*>(d);
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
-        *reinterpret_cast<float4*>(d) = o;
+        *reinterpret_cast<float4*>(d) = p.round_out ? qeb_tf32r4(o) : o;
         if (p.out16) {   // fp16 shadow, same element offset
           // (saturating: a value beyond fp16's range becomes +-65504, not inf; the fp32 output keeps the exact value)
           const __half2 h0 = __floats2half2_rn(fminf(fmaxf(o.x, -65504.f), 65504.f), fminf(fmaxf(o.y, -65504.f), 65504.f));
@@ -586,6 +591,7 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   QEB_REQUIRE(!ep.out16 || (p.vec_ok && n_total % 32 == 0 && ((uintptr_t)ep.out16 & 7) == 0),
               "tc fprop: an fp16 output shadow needs 16-byte aligned output rows and a multiple of 32 channels");
   p.out16 = static_cast<__half*>(ep.out16);
+  p.round_out = ep.round_out;
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
   static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
@@ -596,7 +602,7 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   // Few pixels, long K (the deep UNet levels and their input gradients): narrowing the N tile to fill the SMs makes every
   // CTA stream the whole A operand for a sliver of MMA work and the per-SM L2 read rate becomes the limit. With a plain
   // epilogue the K range is split instead and the partial sums are reduced into a zero-filled output.
-  const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && mode == 0 && p.vec_ok && n_total % 32 == 0 &&
+  const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && !ep.round_out && mode == 0 && p.vec_ok && n_total % 32 == 0 &&
                      out.c == n_total && out.sw == n_total && img_flat(out);
   if (allow_split && plain && (long long)m_tiles * qeb_cdiv(n_total, bn_max) * 2 <= min_ctas && num_kb >= 16) {
     // round DOWN: tiles beyond one per SM would make a few CTAs walk two tiles while the rest idle
@@ -700,7 +706,7 @@ int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const 
   uint32_t box[4];
   fprop_box(x.h, x.w, box);
   TcEpilogue ep;
-  if (shadows) { ep.in16 = shadows->in16; ep.w16 = shadows->w16; ep.out16 = shadows->out16; }
+  if (shadows) { ep.in16 = shadows->in16; ep.w16 = shadows->w16; ep.out16 = shadows->out16; ep.round_out = shadows->round_out; }
   const bool f16 = ep.in16 && ep.w16 && strides_ok16(x);
   if (f16) box[0] = kblk16(x.c);
   int rc = f16 ? tmap_img16(&ta.m[0], x, ep.in16, box) : tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);

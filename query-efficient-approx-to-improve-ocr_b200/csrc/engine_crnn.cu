@@ -215,7 +215,9 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   TRY(maxpool_fwd(A2f, 2, 2, A2, st, h ? p.a2h : nullptr));
   ep.bias = params[P_C3B];
   shadows(ep, p.a2h, p.wp3h, p.a3h);
+  ep.round_out = 1;   // A3 is the A operand of conv4's weight gradient
   TRY(tc_conv_fprop(A2, p.wp3, 256, 3, 3, 1, 1, A3, ep, st));
+  ep.round_out = 0;
   ep.bias = params[P_C4B];
   shadows(ep, p.a3h, p.wp4h, nullptr);
   TRY(tc_conv_fprop(A3, p.wp4, 256, 3, 3, 1, 1, A4f, ep, st));
@@ -240,7 +242,9 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     f.relu = 1;
     f.scale = p.scsh5; f.bias = p.scsh5 + 512;
     shadows(f, p.a4h, p.wp5h, p.a5h);
+    f.round_out = 1;   // A5 is the A operand of conv6's weight gradient
     TRY(tc_conv_fprop(A4, p.wp5, 512, 3, 3, 1, 1, A5, f, st));
+    f.round_out = 0;
     f.scale = p.scsh6; f.bias = p.scsh6 + 512;
     shadows(f, p.a5h, p.wp6h, nullptr);
     TRY(tc_conv_fprop(A5, p.wp6, 512, 3, 3, 1, 1, A6f, f, st));
@@ -252,6 +256,7 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   X0seq.p = p.x0; X0seq.n = B; X0seq.h = 1; X0seq.w = T; X0seq.c = 512; X0seq.sn = 512; X0seq.sh = 0; X0seq.sw = (long long)B * 512;
   TcEpilogue e7;
   e7.bias = params[P_C7B];
+  e7.round_out = 1;   // x0 is the A operand of the layer-0 W_ih weight gradient
   shadows(e7, p.a6h, p.wp7h, p.x0h);
   TRY(tc_conv_fprop(A6, p.wp7, 512, 2, 2, 0, 0, X0seq, e7, st));
 
@@ -271,7 +276,7 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
     eg.bias = bias;
     shadows(eg, xin16, l ? p.wih1h : p.wih0h, nullptr);
     TRY(tc_conv_fprop(img_nhwc(xin, 1, 1, TB, 512), wih, 2048, 1, 1, 0, 0, img_nhwc(g, 1, 1, TB, 2048), eg, st));
-    TRY(lstm_layer_fwd(g, lp[1], lp[5], c, y, T, B, st, h ? y16 : nullptr));
+    TRY(lstm_layer_fwd(g, lp[1], lp[5], c, y, T, B, st, h ? y16 : nullptr, 1));
     xin = y;
     xin16 = y16;
   }
@@ -305,6 +310,8 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   Img D4f = img_nhwc(p.d4f, B, 8, p.W4, 256), D4 = img_nhwc(p.d4, B, 4, p.W4, 256);
   Img D5 = img_nhwc(p.d5, B, 4, p.W4, 512), D6f = img_nhwc(p.d6f, B, 4, p.W4, 512), D6 = img_nhwc(p.d6, B, 2, p.W4, 512);
   const TcEpilogue plain;
+  TcEpilogue chained;   // the output is the operand of the next contraction(s) without an elementwise kernel in between
+  chained.round_out = 1;
   SideStream ss;  // weight / bias gradients run beside the input-gradient chain
   TRY(ss.init(st));
 
@@ -350,7 +357,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
     float* y = l ? p.y1 : p.y0;
     const float* dy = l ? p.dy1 : p.dy0;
     const Img Xin = l ? Y0 : X0;
-    TRY(lstm_layer_bwd(g, c, dy, lp[1], lp[5], T, B, st));  // g now holds d(pre-activations), (T,B,2,1024)
+    TRY(lstm_layer_bwd(g, c, dy, lp[1], lp[5], T, B, st, 1));  // g now holds d(pre-activations), (T,B,2,1024)
     TRY(ss.fork());
     for (int d = 0; d < 2; ++d) {
       Img DG = img_nhwc(g + d * 1024, 1, 1, TB, 1024, 2048);
@@ -368,7 +375,10 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
       else if (lg[d * 4 + 3]) TRY(colsum_acc(DG, lg[d * 4 + 3], ss.s()));
     }
     // d(input) = dG * [W_ih_fwd ; W_ih_rev]
-    TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), l ? p.wihT1 : p.wihT0, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512), plain, st));
+    // layer 1 -> dy0 feeds the layer-0 recurrence (which rounds its own operands); layer 0 -> dx0 = dz7 feeds conv7's
+    // weight- and input-gradient contractions directly
+    TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), l ? p.wihT1 : p.wihT0, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512),
+                      l ? plain : chained, st));
   }
 
   // ---- conv7 (dz7 = dx0, sequence-major view of a (B,1,T,512) image)
@@ -408,6 +418,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   } else {
     TcEpilogue e;
     e.scale = p.scsh5; e.mask = &A5;  // dz5 = d(a5) * scale, zero where a5 == 0, fused into the dgrad epilogue
+    e.round_out = 1;
     TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
   }
   TRY(ss.fork());
@@ -423,6 +434,7 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   {
     TcEpilogue e;
     e.mask = &A3;  // ReLU of conv3 fused into the dgrad epilogue
+    e.round_out = 1;
     TRY(tc_conv_fprop(D4f, p.wpd4, 256, 3, 3, 1, 1, D3, e, st));
   }
   TRY(ss.fork());

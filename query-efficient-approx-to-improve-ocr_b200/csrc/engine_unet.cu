@@ -217,6 +217,7 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   if (!c.scsh_ready) TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
   TcEpilogue f;
   f.relu = 1; f.scale = scsh; f.bias = scsh + cout;
+  f.round_out = 1;   // the activation is the A operand of the next unit's weight gradient
   if (in16) { f.in16 = in16; f.w16 = c.p->wph[unit]; }
   f.out16 = out16;
   return tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, out, f, c.st);
@@ -249,7 +250,10 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   }
   if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.ss->s()));
   if (din) {
-    const TcEpilogue e = (which == 1 && z_lower) ? grad_into_unit(c, unit - 1, z_lower) : TcEpilogue();
+    TcEpilogue e = (which == 1 && z_lower) ? grad_into_unit(c, unit - 1, z_lower) : TcEpilogue();
+    // first unit of a decoder block: half of its input gradient (the up-convolution's output gradient) is the operand of the
+    // ConvTranspose weight- and input-gradient contractions with no elementwise kernel in between
+    if (which == 0 && block >= 5) e.round_out = 1;
     TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, e, c.st));
   }
   return QEB_OK;
@@ -341,6 +345,7 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
     Img upo = img_nhwc(p.cat[i], B, p.h[i], p.w[i], C, 2 * C);
     TcEpilogue sh;
     if (h16) { sh.in16 = below16; sh.w16 = p.wuph[up]; sh.out16 = p.cat_h[i]; }
+    sh.round_out = 1;   // the up-convolved half of the concat buffer is an A operand of dec conv1's weight gradient
     TRY(tc_convT_fprop(below, p.wup[up], params[P_UP + up * 2 + 1], upo, c.st, &sh));
     Img cat = img_nhwc(p.cat[i], B, p.h[i], p.w[i], 2 * C);
     Img z1 = img_nhwc(p.dz1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.da1[i], B, p.h[i], p.w[i], C);

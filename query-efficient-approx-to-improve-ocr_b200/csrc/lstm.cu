@@ -118,6 +118,8 @@ struct LstmArgs {
   __half* y16;          // optional fp16 shadow of y (operand of the next projection GEMM), forward only
   const float* dy;      // (T,B,512), backward only
   int T, B;
+  int round_io;         // 1 (the network engines): y (forward) / d(pre-activations) (backward) are stored rounded to tf32 - they are
+                        // operands of the projection / weight-gradient contractions that follow (common.cuh qeb_tf32r)
   long long* tl;        // debugging aid (qeb_debug_set_timeline): clock64 stamps of CTA 0, 8 per step
 };
 
@@ -271,7 +273,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       const int b = b0 + warp + 8 * p;
       if (b < a.B) {
         a.cells[(((long long)t * a.B + b) * 2 + dir) * kH + rank * kUnits + lane] = c[p];
-        a.y[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + lane] = hv[p];
+        a.y[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + lane] = a.round_io ? tf32_rn(hv[p]) : hv[p];
         if (a.y16) a.y16[((long long)t * a.B + b) * (2 * kH) + dir * kH + rank * kUnits + lane] = __float2half_rn(hv[p]);
       }
     }
@@ -390,7 +392,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
         const int b = b0 + warp + 8 * p;
         if (b < a.B) {
           float* g = a.gates + (((long long)t * a.B + b) * 2 + dir) * (4 * kH) + rank * kUnits + lane;
-          g[0] = dgv[p][0]; g[kH] = dgv[p][1]; g[2 * kH] = dgv[p][2]; g[3 * kH] = dgv[p][3];
+          // operands of the W_ih / W_hh weight-gradient and the d(input) contractions: rounded to tf32 here
+          if (a.round_io) {
+            g[0] = tf32_rn(dgv[p][0]); g[kH] = tf32_rn(dgv[p][1]); g[2 * kH] = tf32_rn(dgv[p][2]); g[3 * kH] = tf32_rn(dgv[p][3]);
+          } else {
+            g[0] = dgv[p][0]; g[kH] = dgv[p][1]; g[2 * kH] = dgv[p][2]; g[3 * kH] = dgv[p][3];
+          }
         }
       }
     };
@@ -485,7 +492,7 @@ int launch_cluster(const void* fn, size_t smem, int n_clusters, LstmArgs& args, 
 }  // namespace
 
 int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
-                   cudaStream_t st, void* y16) {
+                   cudaStream_t st, void* y16, int round_io) {
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && y && T > 0 && B > 0, "lstm_layer_fwd: bad arguments");
   static bool attr = false;
   if (!attr) {
@@ -495,12 +502,13 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
   LstmArgs a;
   a.gates = gates; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_rev; a.cells = cells; a.y = y; a.dy = nullptr; a.T = T; a.B = B;
   a.y16 = static_cast<__half*>(y16);
+  a.round_io = round_io;
   ProfScope prof("lstm_fwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
   return launch_cluster((const void*)lstm_fwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
 
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
-                   int B, cudaStream_t st) {
+                   int B, cudaStream_t st, int round_io) {
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && dy && T > 0 && B > 0, "lstm_layer_bwd: bad arguments");
   static bool attr = false;
   if (!attr) {
@@ -511,6 +519,7 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
   a.gates = gates; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_rev; a.cells = const_cast<float*>(cells); a.y = nullptr; a.dy = dy;
   a.y16 = nullptr;
   a.T = T; a.B = B;
+  a.round_io = round_io;
   ProfScope prof("lstm_bwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
   return launch_cluster((const void*)lstm_bwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
@@ -518,9 +527,9 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
 // C ABI (tests): one bidirectional layer of the recurrence
 QEB_API int qeb_lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
                                void* stream) {
-  return lstm_layer_fwd(gates, w_hh_fwd, w_hh_rev, cells, y, T, B, (cudaStream_t)stream, nullptr);
+  return lstm_layer_fwd(gates, w_hh_fwd, w_hh_rev, cells, y, T, B, (cudaStream_t)stream, nullptr, 0);
 }
 QEB_API int qeb_lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev,
                                int T, int B, void* stream) {
-  return lstm_layer_bwd(gates, cells, dy, w_hh_fwd, w_hh_rev, T, B, (cudaStream_t)stream);
+  return lstm_layer_bwd(gates, cells, dy, w_hh_fwd, w_hh_rev, T, B, (cudaStream_t)stream, 0);
 }

@@ -52,6 +52,10 @@ struct TcEpilogue {
   const void* in16 = nullptr;
   const void* w16 = nullptr;
   void* out16 = nullptr;
+  // 1: the fp32 output is itself a tf32 tensor-core operand later (an activation kept for a weight gradient, a gradient that
+  // feeds the next dgrad / wgrad directly): it is stored rounded to tf32 (common.cuh qeb_tf32r). Rules out split-K (partial
+  // sums cannot be rounded), so the tile is narrowed instead.
+  int round_out = 0;
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
@@ -200,10 +204,10 @@ long long* qeb_debug_timeline();  // conv_tc.cu: buffer set by qeb_debug_set_tim
 // i,f,g,o as torch), overwritten with the ACTIVATED gates; w_hh[dir]: torch layout (1024,256); cells: (T,B,2,256) c_t;
 // y: (T,B,512) [forward | reverse].
 int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, float* cells, float* y, int T, int B,
-                   cudaStream_t st, void* y16 = nullptr);
+                   cudaStream_t st, void* y16 = nullptr, int round_io = 0);   // round_io: y stored rounded to tf32 (see lstm.cu)
 // dy: (T,B,512). gates (activated) are overwritten with the gradients at the pre-activations (T,B,2,1024).
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
-                   int B, cudaStream_t st);
+                   int B, cudaStream_t st, int round_io = 0);
 
 // ---- side stream, abi.cu ----------------------------------------------------------------------------------------
 // Weight and bias gradients are off the backward's critical path (only the input gradients feed the next layer), so the

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_fwd_kernel(const float* __re
         m.z = (v.z > m.z || v.z != v.z) ? v.z : m.z;
         m.w = (v.w > m.w || v.w != v.w) ? v.w : m.w;
       }
-    st4(out + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, m);
+    st4(out + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, qeb_tf32r4(m));   // weight-gradient operand: rounded to tf32 here
     if (out16) st4h(out16 + n * go.sn + hv * go.sh + wv * go.sw + cq * 4, m);
   }
 }
@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
           const float4 q = ld4(add + n * ga.sn + (long long)(hv * PH + a) * ga.sh + (long long)(wv * PW + b) * ga.sw + cq * 4);
           o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w;
         }
-        st4(dx + off, make_float4(o[0], o[1], o[2], o[3]));
+        st4(dx + off, qeb_tf32r4(make_float4(o[0], o[1], o[2], o[3])));   // dgrad / wgrad operand: rounded to tf32 here
         if constexpr (RED) {
           const float4 zv = ld4(bn_z + n * gz.sn + (long long)(hv * PH + a) * gz.sh + (long long)(wv * PW + b) * gz.sw + cq * 4);
           const float4 gm = bn_masked_grad(zv, make_float4(o[0], o[1], o[2], o[3]), bsc, bsh, 1);
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float* __restr
     const float4 v = ld4(z + r * zs + cq * 4);
     float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    st4(out + r * os + cq * 4, o);
+    st4(out + r * os + cq * 4, qeb_tf32r4(o));   // weight-gradient operand: rounded to tf32 here
     if (out16) st4h(out16 + r * os + cq * 4, o);
   }
 }
@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
     const float4 v = ld4(z + r * zs + cq * 4);
     float4 o = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    st4(out + r * os + cq * 4, o);
+    st4(out + r * os + cq * 4, qeb_tf32r4(o));   // weight-gradient operand: rounded to tf32 here
     if (out16) st4h(out16 + r * os + cq * 4, o);
   }
 }
@@ -602,7 +602,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_pool_kernel(const flo
         const float4 o = make_float4(fmaxf(fmaf(v.x, sc[0], sh[0]), 0.f), fmaxf(fmaf(v.y, sc[1], sh[1]), 0.f),
                                      fmaxf(fmaf(v.z, sc[2], sh[2]), 0.f), fmaxf(fmaf(v.w, sc[3], sh[3]), 0.f));
         const long long oo = n * go.sn + (long long)(2 * hv + a) * go.sh + (long long)(2 * wv + b) * go.sw + cq * 4;
-        st4(out + oo, o);
+        st4(out + oo, qeb_tf32r4(o));
         if (out16) st4h(out16 + oo, o);
         if (a == 0 && b == 0) {
           m = o;
@@ -614,7 +614,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_pool_kernel(const flo
         }
       }
     const long long po = n * gp.sn + (long long)hv * gp.sh + (long long)wv * gp.sw + cq * 4;
-    st4(pool + po, m);
+    st4(pool + po, qeb_tf32r4(m));
     if (pool16) st4h(pool16 + po, m);
   }
 }
@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
       o.z = sc.z * (g.z - mg.z - (v.z - mu.z) * is.z * mx.z);
       o.w = sc.w * (g.w - mg.w - (v.w - mu.w) * is.w * mx.w);
     }
-    st4(dz + r * dzs + cq * 4, o);
+    st4(dz + r * dzs + cq * 4, qeb_tf32r4(o));   // dgrad / wgrad operand: rounded to tf32 here
   }
 }
 
@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(kThreads) pack_multi_kernel(const __grid_const
       continue;
     }
     float* d = j.dst + i0 * j.d0 + i1 * j.d1 + i2;
-    *d = accumulate ? *d + v : v;
+    *d = accumulate ? *d + v : qeb_tf32r(v);   // plain re-layouts are tensor-core operands: rounded to tf32 here
   }
 }
 
@@ -847,12 +847,12 @@ __global__ void __launch_bounds__(kThreads) conv_pack_kernel(const __grid_consta
       const int a = r / T, tap = r - a * T;
       const long long o = ((long long)(a0 + a) * T + tap) * j.B + b0 + lane;
       if (j.half_out) reinterpret_cast<__half*>(j.dst)[o] = __float2half_rn(tile[a * pitch + lane * T + tap]);
-      else j.dst[o] = tile[a * pitch + lane * T + tap];
+      else j.dst[o] = qeb_tf32r(tile[a * pitch + lane * T + tap]);
     }
   } else if (j.mode == 1) {
     for (int r = warp; r < 32 * T; r += nwarp) {
       const int b = r / T, ft = r - b * T;
-      j.dst[((long long)(b0 + b) * T + ft) * j.A + a0 + lane] = tile[lane * pitch + b * T + (T - 1 - ft)];
+      j.dst[((long long)(b0 + b) * T + ft) * j.A + a0 + lane] = qeb_tf32r(tile[lane * pitch + b * T + (T - 1 - ft)]);
     }
   } else {
     for (int a = warp; a < 32; a += nwarp) {

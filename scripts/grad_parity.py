@@ -1,0 +1,103 @@
+"""Per-tensor parity of every UNet / CRNN weight gradient against the fp32 oracle (oracle/nn_oracle.py on torch CPU).
+
+  python scripts/grad_parity.py [--batch 16] [--out gpurun_out/grad_parity.json]
+
+Phase B (train_nn_area.py:277-287): UNet train-mode BN -> CRNN (train(), BN frozen) -> CTC + MSE; gradients of the UNet.
+Phase A (train_nn_area.py:245-275): CRNN train mode -> CTC; gradients of the CRNN.
+Prints rel-L2 and cosine per tensor, worst first; the JSON feeds bench.py's `parity` block and DESIGN.md.
+"""
+import argparse
+import copy
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def cos(a, b):
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+def measure(batch=16, seed=0):
+    import qeb_b200  # noqa: F401
+    from bench import CHAR_SET, encode, synth_batch
+    from oracle import nn_oracle
+    from qeb_b200.mirror import ctc as qctc
+    from qeb_b200.mirror import train_ops
+    from qeb_b200.mirror.models.model_crnn import CRNN
+    from qeb_b200.mirror.models.model_unet import UNet
+    from qeb_b200.mirror.utils import set_bn_eval
+
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(seed)
+    V = len(CHAR_SET)
+    crnn_cpu, unet_cpu = CRNN(V, False), UNet()
+    crnn, unet = copy.deepcopy(crnn_cpu).to(dev), copy.deepcopy(unet_cpu).to(dev)
+    x, labels = synth_batch(batch, 11)
+    c2i = {c: i for i, c in enumerate(CHAR_SET)}
+    y, y_size = encode(labels, c2i)
+    il = torch.full((batch,), 31, dtype=torch.int32)
+    out = {}
+
+    # ---- phase B
+    for m in (crnn_cpu, unet_cpu, crnn, unet):
+        m.train()
+    crnn_cpu.apply(set_bn_eval); crnn.apply(set_bn_eval)
+    img = unet(x.to(dev)); scores = crnn(img)
+    loss = qctc.CTCLoss()(scores, y, il, y_size) + train_ops.mse_to_ones(img)
+    loss.backward()
+    img_r = nn_oracle.unet_forward(unet_cpu, x); scores_r = nn_oracle.crnn_forward(crnn_cpu, img_r)
+    loss_r = torch.nn.CTCLoss()(scores_r, y, il, y_size) + torch.nn.MSELoss()(img_r, torch.ones_like(img_r))
+    loss_r.backward()
+    rows = {}
+    for (n, p), (_, pr) in zip(unet.named_parameters(), unet_cpu.named_parameters()):
+        rows["unet." + n] = [rel(p.grad, pr.grad), cos(p.grad, pr.grad)]
+    out["phase_b"] = {"loss_rel": abs(float(loss) - float(loss_r)) / abs(float(loss_r)), "img_rel": rel(img, img_r),
+                      "scores_rel": rel(scores, scores_r), "grads": rows}
+
+    # ---- phase A
+    for m in (crnn_cpu, crnn):
+        m.zero_grad(); m.train()
+    xa = x.to(dev)
+    scores = crnn(xa)
+    loss = qctc.CTCLoss()(scores, y, il, y_size)
+    loss.backward()
+    scores_r = nn_oracle.crnn_forward(crnn_cpu, x)
+    loss_r = torch.nn.CTCLoss()(scores_r, y, il, y_size)
+    loss_r.backward()
+    rows = {}
+    for (n, p), (_, pr) in zip(crnn.named_parameters(), crnn_cpu.named_parameters()):
+        rows["crnn." + n] = [rel(p.grad, pr.grad), cos(p.grad, pr.grad)]
+    out["phase_a"] = {"loss_rel": abs(float(loss) - float(loss_r)) / abs(float(loss_r)), "scores_rel": rel(scores, scores_r), "grads": rows}
+    for ph in ("phase_a", "phase_b"):
+        g = out[ph]["grads"]
+        worst = max(g, key=lambda k: g[k][0])
+        out[ph]["worst_tensor"] = worst
+        out[ph]["worst_rel_l2"] = g[worst][0]
+        out[ph]["min_cos"] = min(v[1] for v in g.values())
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--out", default=None)
+    a = ap.parse_args()
+    res = measure(a.batch)
+    for ph in ("phase_b", "phase_a"):
+        r = res[ph]
+        print(f"== {ph}: loss rel {r['loss_rel']:.2e}, scores rel {r['scores_rel']:.2e}, worst {r['worst_tensor']} {r['worst_rel_l2']:.2e}, min cos {r['min_cos']:.6f}")
+        for k, v in sorted(r["grads"].items(), key=lambda kv: -kv[1][0])[:12]:
+            print(f"   {k:44s} rel {v[0]:.2e} cos {v[1]:.6f}")
+    if a.out:
+        json.dump(res, open(a.out, "w"), indent=1)

@@ -147,7 +147,7 @@ AREA_FLAGS = ["--batch_size", "8", "--lr_crnn", "0.0001", "--scalar", "1", "--lr
 PATCH_FLAGS = ["--lr_crnn", "0.0001", "--scalar", "1", "--lr_prep", "0.00005", "--epoch", "1", "--random_seed", "42", "--std", "5",
                "--inner_limit", "2", "--inner_limit_skip", "--ocr", "fake", "--random_std", "--minibatch_subset", "topKCER",
                "--minibatch_subset_prop", "0.5", "--start_epoch", "0", "--exp_name", "dropin", "--exp_id", "7", "--warmup_epochs", "0",
-               "--weight_decay", "0.0005", "--window_size", "2", "--weightgen_method", "levenshtein", "--decay_factor", "0.7",
+               "--weight_decay", "0.0005", "--window_size", "2", "--weightgen_method", "decaying", "--decay_factor", "0.7",
                "--discount_factor", "1", "--query_dim", "8", "--emb_dim", "8", "--attn_activation", "softmax"]
 
 
@@ -206,6 +206,7 @@ def main():
                                                        "instead of constructing TrainNNPrep directly")
     ap.add_argument("--no-train", action="store_true", help="with --cli: TrainNNPrep.train becomes a no-op (flag parsing + construction)")
     a = ap.parse_args()
+    a.out = os.path.abspath(a.out)   # the run changes into its own scratch directory
 
     os.environ["WANDB_MODE"] = "disabled"      # before wandb is imported: the CLIs call wandb.init(project=...) themselves
     import torch

@@ -60,9 +60,13 @@ def _close(a, b, rel):
     return abs(a - b) <= rel * max(1.0, abs(b))
 
 
-def _compare_epoch(q, r, first_rel=3e-3, later_rel=3e-2):
+ZERO_GRAD = ("convo.conv5.bias", "convo.conv6.bias")   # conv bias before a train-mode BatchNorm: the true gradient is zero, Adam
+                                                       # integrates each implementation's own rounding noise
+
+
+def _compare_epoch(q, r, first_rel=2e-4, later_rel=2e-3):
     assert q["device"].startswith("cuda") and r["device"] == "cpu"
-    assert q["launches"] > 1000, "the CUDA path did not run"
+    assert q["launches"] > 300, "the CUDA path did not run"
     assert q["state_keys"] == r["state_keys"]
     assert len(q["phase_a_loss"]) == len(r["phase_a_loss"]) and len(q["phase_b_loss"]) == len(r["phase_b_loss"])
     # first phase-A and phase-B values: same weights, same inputs -> kernel tolerance; later ones also carry one Adam step
@@ -75,12 +79,15 @@ def _compare_epoch(q, r, first_rel=3e-3, later_rel=3e-2):
     assert list(q["cers"].keys()) == list(r["cers"].keys()) and q["all_cers"].keys() == r["all_cers"].keys()
     same = sum(q["cers"][k] == r["cers"][k] for k in r["cers"])
     assert same >= 0.9 * len(r["cers"]), (same, len(r["cers"]))  # CER of an untrained surrogate's decode: equal strings
-    assert q["ocr_calls"] == r["ocr_calls"] and q["ckpts"] == r["ckpts"] and q["exp_files"] == r["exp_files"]
+    # checkpoint names carry the validation accuracy of the (fake) OCR, which depends on the validation order and so on how many
+    # host-RNG draws the jitter made (the reference draws its noise from the host generator, the kernel from Philox)
+    strip = lambda names: sorted(n.rsplit("_", 1)[0] if n.startswith("Prep_model_0") else n for n in names if n != "Prep_model_best")
+    assert q["ocr_calls"] == r["ocr_calls"] and strip(q["ckpts"]) == strip(r["ckpts"]) and q["exp_files"] == r["exp_files"]
     assert q["tracked_labels"] == r["tracked_labels"]
     assert q["reloaded_class"] == "qeb_b200.mirror.models.model_unet.UNet"
     for net in ("crnn_digest", "prep_digest"):                  # after the epoch: every tensor moved the same way
         for k, (shape, norm) in r[net].items():
-            assert q[net][k][0] == shape and _close(q[net][k][1], norm, 2e-3), (net, k, q[net][k], norm)
+            assert q[net][k][0] == shape and (k in ZERO_GRAD or _close(q[net][k][1], norm, 1e-3)), (net, k, q[net][k], norm)
 
 
 @needs_ref
