@@ -131,12 +131,24 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------ reference arm
-def cpu_step_factory(batch, seed=42):
-    """The oracle port of the same step on CPU: mirror modules as parameter containers, torch library ops."""
+def reference_modules():
+    """(UNet, CRNN, set_bn_eval, unet_forward, crnn_forward, kind, namespace): the UNMODIFIED reference from baseline/_ref
+    (the copy that travels to the GPU box) or /root/reference when one is present - `kind` "reference" - else the oracle
+    port over the mirror's parameter containers - `kind` "port"."""
+    from oracle import refload
+    if refload.available():
+        ns = refload.load()
+        return ns.model_unet.UNet, ns.model_crnn.CRNN, ns.utils.set_bn_eval, (lambda m, x: m(x)), (lambda m, x: m(x)), "reference", ns
     from oracle import nn_oracle
     from qeb_b200.mirror.models.model_crnn import CRNN
     from qeb_b200.mirror.models.model_unet import UNet
     from qeb_b200.mirror.utils import set_bn_eval
+    return UNet, CRNN, set_bn_eval, nn_oracle.unet_forward, nn_oracle.crnn_forward, "port", None
+
+
+def cpu_step_factory(batch, seed=42):
+    """The same step on the host cores: the reference's own modules (or the oracle port), torch CPU CTC / MSE / Adam."""
+    UNet, CRNN, set_bn_eval, unet_f, crnn_f, kind, _ = reference_modules()
     torch.manual_seed(seed)
     prep, crnn = UNet(), CRNN(len(CHAR_SET), False)
     crnn.register_backward_hook(crnn.backward_hook)
@@ -148,15 +160,18 @@ def cpu_step_factory(batch, seed=42):
     def step():
         prep.train(); crnn.train(); crnn.apply(set_bn_eval)
         prep.zero_grad(); crnn.zero_grad()
-        img = nn_oracle.unet_forward(prep, x)
-        scores = nn_oracle.crnn_forward(crnn, img)
+        img = unet_f(prep, x)
+        scores = crnn_f(crnn, img)
         y, y_size = encode(labels, c2i)
         pred_size = torch.tensor([scores.shape[0]] * batch, dtype=torch.int32)
         loss = ctc(scores, y, pred_size, y_size) + SCALAR * mse(img, torch.ones(img.shape))
         loss.backward()
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
+    step.kind = kind
+    step.what = ("unmodified reference modules (baseline/_ref)" if kind == "reference" else "oracle/nn_oracle.py") + \
+        f" on torch {torch.__version__} CPU fp32"
     return step
 
 
@@ -178,8 +193,8 @@ def run_reference(args, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": "port",
-                             "sample": f"{args.steps} steps of {sample} patches, torch {torch.__version__} CPU fp32"},
+            "cpu_baseline": {"value": value, "unit": "patches/s", "cores": threads, "kind": step.kind,
+                             "sample": f"{args.steps} steps of {sample} patches, {step.what}"},
             "e2e": {"value": value, "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     return line
 
@@ -191,6 +206,25 @@ def workload_config(n_gpus):
             "operand_precision": "tensor-core operands with an 11-bit significand (fp16 copies in the forward pass, tf32 reads of fp32 in the backward pass), fp32 accumulation / activations / gradients / parameters (reference: fp32)",
             "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2",
             "launch": "forward+losses+backward replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); all-reduce and Adam outside it"}
+
+
+def parity_block():
+    """Measured parity of this build's network gradients (scripts/grad_parity.py on the B200, committed under profiles/)."""
+    try:
+        p = json.load(open(os.path.join(ROOT, "profiles", "r2_grad_parity.json")))
+        b, a = p["phase_b"], p["phase_a"]
+        zero = ("crnn.convo.conv5.bias", "crnn.convo.conv6.bias")   # analytically zero gradients (bias before a train-mode BN)
+        wa = max((v[0], k) for k, v in a["grads"].items() if k not in zero)
+        return {"source": "profiles/r2_grad_parity.json (scripts/grad_parity.py --competitors, B=16, vs the fp32 CPU oracle)",
+                "phase_b_loss_rel": b["loss_rel"], "phase_b_worst_unet_weight_grad_rel_l2": b["worst_rel_l2"],
+                "phase_b_worst_tensor": b["worst_tensor"], "phase_b_min_cos": b["min_cos"],
+                "phase_a_worst_crnn_weight_grad_rel_l2": wa[0], "phase_a_worst_tensor": wa[1],
+                "same_metric_other_implementations_worst": b.get("competitors_worst"),
+                "note": "forward operands carry 11-bit significands (tcgen05 has no fp32 operand kind): ReLU / BatchNorm "
+                        "decisions of near-zero pre-activations flip, which bounds network-gradient parity on random-init nets; "
+                        "cuDNN TF32 shows the same, see DESIGN.md section 5"}
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
@@ -209,22 +243,41 @@ def main():
         print(json.dumps(line), flush=True)
 
 
-def run():
+WORKLOADS = ("prep_step", "jitter_step", "area_step", "cer_topk")
+
+
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="qeb", choices=["qeb", "reference"])
+    ap.add_argument("--workload", default="prep_step", choices=WORKLOADS,
+                    help="prep_step = BASELINE.json configs[1] (the headline, default); jitter_step = configs[2]; "
+                         "area_step = configs[3]; cer_topk = configs[4] (bench_workloads.py)")
+    ap.add_argument("--no-extras", action="store_true", help="default workload only: do not append the short runs of the other "
+                                                             "three workloads under `workloads`")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--skip-profile", action="store_true")
     ap.add_argument("--skip-eager", action="store_true", help="profiling runs: only the graph arm (variants are null)")
-    args = ap.parse_args()
+    args = ap.parse_args(argv)
     args.warmup = max(args.warmup, 3) if args.impl == "qeb" else max(args.warmup, 1)
+    return args
+
+
+def run():
+    args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
+        if args.workload != "prep_step":
+            import bench_workloads
+            return bench_workloads.run_reference(args, rank)
         return run_reference(args, rank)
+    if args.workload != "prep_step":
+        import bench_workloads
+        return bench_workloads.run(args, rank, world, local_rank)
 
     import torch.distributed as dist
     import qeb_b200
@@ -425,8 +478,8 @@ def run():
         while n < 3 or (time.perf_counter() - t0 < 12 and n < 12):
             cstep(); n += 1
         dt = time.perf_counter() - t0
-        cpu_baseline = {"value": BATCH * n / dt, "unit": "patches/s", "cores": threads, "kind": "port",
-                        "sample": f"{n} steps of {BATCH} patches ({dt:.1f} s), oracle/nn_oracle.py on torch {torch.__version__} CPU fp32"}
+        cpu_baseline = {"value": BATCH * n / dt, "unit": "patches/s", "cores": threads, "kind": cstep.kind,
+                        "sample": f"{n} steps of {BATCH} patches ({dt:.1f} s), {cstep.what}"}
 
     line = None
     if rank == 0:
@@ -445,7 +498,21 @@ def run():
                                       "note": "the mirror modules called eagerly (no CUDA graph), as an unmodified trainer does"},
                     "surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
                                                       "note": "eager; skips the CRNN weight gradients the reference computes and discards"}},
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity_block()}
+    # ---- the other BASELINE.json configs, short runs, appended so that they are part of the driver-run line
+    if not args.no_extras:
+        import bench_workloads
+        extras = {}
+        for wl in ("jitter_step", "area_step", "cer_topk"):
+            sub = argparse.Namespace(**vars(args))
+            sub.workload, sub.steps, sub.warmup = wl, max(3, min(args.steps, 10)), 3
+            sub.skip_cpu_baseline = True if world > 1 else args.skip_cpu_baseline
+            try:
+                extras[wl] = bench_workloads.run(sub, rank, world, local_rank, own_process_group=False)
+            except Exception as e:   # an extra must never take the headline down with it
+                extras[wl] = {"error": f"{type(e).__name__}: {e}"}
+        if line is not None:
+            line["workloads"] = extras
     if world > 1:
         dist.destroy_process_group()
     return line if rank == 0 else None

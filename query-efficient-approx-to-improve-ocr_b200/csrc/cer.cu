@@ -186,6 +186,7 @@ QEB_API int qeb_levenshtein_batch(const void* a_syms, const int* a_off, const in
   QEB_REQUIRE(sym_bytes == 1 || sym_bytes == 4, "levenshtein: sym_bytes must be 1 or 4, got %d", sym_bytes);
   cudaStream_t st = (cudaStream_t)stream;
   QEB_CUDA(cudaMemsetAsync(scratch, 0, sizeof(int), st));
+  ProfScope prof("levenshtein", st, 0.0, (2.0 * 4 + 4 + (cer ? 8 : 0)) * n);   // offsets + results; callers add the symbol bytes
   if (sym_bytes == 1) return lev_launch<unsigned char>(a_syms, a_off, a_len, b_syms, b_off, b_len, n, max_len, dist, cer, scratch, st);
   return lev_launch<int>(a_syms, a_off, a_len, b_syms, b_off, b_len, n, max_len, dist, cer, scratch, st);
 }
@@ -195,6 +196,7 @@ QEB_API int qeb_greedy_decode(const float* scores, long long st_t, long long st_
                               int* out, int* out_len, int* raw_path, void* stream) {
   QEB_REQUIRE(scores && out && out_len, "greedy_decode: null pointer");
   QEB_REQUIRE(T > 0 && B > 0 && V > 0, "greedy_decode: bad sizes");
+  ProfScope prof("greedy_decode", (cudaStream_t)stream, 0.0, 4.0 * T * B * V + 4.0 * B * (T + 1));
   greedy_decode_kernel<<<qeb_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(scores, st_t, st_b, T, B, V, blank, out,
                                                                          out_len, raw_path);
   QEB_LAUNCH_CHECK();

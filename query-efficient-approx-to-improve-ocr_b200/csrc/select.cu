@@ -207,6 +207,7 @@ QEB_API int qeb_cer_topk_segmented(const float* vals, const int* seg_off, const 
                                    int n_seg, long long* out_idx, void* stream) {
   if (n_seg == 0) return QEB_OK;
   QEB_REQUIRE(vals && seg_off && seg_k && out_off && out_idx && n_seg > 0, "cer_topk_segmented: bad args");
+  ProfScope prof("topk_segmented", (cudaStream_t)stream);
   topk_segmented_kernel<<<qeb_cdiv(n_seg, 4), 128, 0, (cudaStream_t)stream>>>(vals, seg_off, seg_k, out_off, n_seg, out_idx);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -220,6 +221,7 @@ QEB_API int qeb_cer_range_segmented(const float* vals, const int* seg_off, const
                                     float* points_out, void* stream) {
   if (n_seg == 0) return QEB_OK;
   QEB_REQUIRE(vals && seg_off && seg_k && out_off && rands && work && out_idx && n_seg > 0, "cer_range_segmented: bad args");
+  ProfScope prof("range_segmented", (cudaStream_t)stream);
   range_segmented_kernel<<<qeb_cdiv(n_seg, 4), 128, 0, (cudaStream_t)stream>>>(vals, seg_off, seg_k, out_off, rands, n_seg,
                                                                                work, out_idx, points_out);
   QEB_LAUNCH_CHECK();

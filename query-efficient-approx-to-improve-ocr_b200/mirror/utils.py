@@ -71,10 +71,13 @@ def pred_to_string(scores, labels, index_to_char, show_text=False):
 # ---------------------------------------------------------------------------------------------------------------
 # Levenshtein / CER
 def _encode_csr(strings):
+    """list[str] -> (int32 code points, int32 offsets[n+1]). One C-level UTF-32 encode of the joined strings instead of a
+    Python loop over the characters (1 M strings: ~0.1 s instead of seconds); `surrogatepass` keeps lone surrogates as
+    their code points, which is what ord() gives."""
     offs = np.zeros(len(strings) + 1, dtype=np.int32)
     if len(strings):
-        np.cumsum([len(s) for s in strings], out=offs[1:])
-    flat = np.fromiter((ord(c) for s in strings for c in s), dtype=np.int32, count=int(offs[-1]))
+        np.cumsum(np.fromiter(map(len, strings), dtype=np.int64, count=len(strings)), out=offs[1:])
+    flat = np.frombuffer(bytearray("".join(strings).encode("utf-32-le", "surrogatepass")), dtype="<i4")   # writable for torch
     return flat, offs
 
 

@@ -28,7 +28,7 @@ def cos(a, b):
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
 
 
-def measure(batch=16, seed=0):
+def measure(batch=16, seed=0, competitors=False):
     import qeb_b200  # noqa: F401
     from bench import CHAR_SET, encode, synth_batch
     from oracle import nn_oracle
@@ -64,6 +64,29 @@ def measure(batch=16, seed=0):
         rows["unet." + n] = [rel(p.grad, pr.grad), cos(p.grad, pr.grad)]
     out["phase_b"] = {"loss_rel": abs(float(loss) - float(loss_r)) / abs(float(loss_r)), "img_rel": rel(img, img_r),
                       "scores_rel": rel(scores, scores_r), "grads": rows}
+    if competitors:
+        # the same step on torch eager + cuDNN on this GPU (the competing implementation on the same box), fp32 and TF32
+        # operands, and the fp32 CPU oracle against float64 (what "exact fp32" itself is off by on this problem)
+        def lib_step(un, cr, xx, dt=torch.float32):
+            un.train(); cr.train(); cr.apply(set_bn_eval)
+            i_ = nn_oracle.unet_forward(un, xx); s_ = nn_oracle.crnn_forward(cr, i_)
+            (torch.nn.functional.ctc_loss(s_, y.to(xx.device), il.to(xx.device), y_size.to(xx.device)) +
+             torch.nn.functional.mse_loss(i_, torch.ones_like(i_))).backward()
+            return {"unet." + n: p.grad for n, p in un.named_parameters()}
+        ref_g = {"unet." + n: p.grad for n, p in unet_cpu.named_parameters()}
+        comp = {}
+        for name, tf32 in (("cudnn_fp32", False), ("cudnn_tf32", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            g_ = lib_step(copy.deepcopy(unet_cpu).to(dev), copy.deepcopy(crnn_cpu).to(dev), x.to(dev))
+            comp[name] = {k: rel(g_[k], ref_g[k]) for k in ref_g}
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        g64 = lib_step(copy.deepcopy(unet_cpu).double(), copy.deepcopy(crnn_cpu).double(), x.double())
+        comp["fp32_oracle_vs_fp64"] = {k: rel(ref_g[k], g64[k]) for k in ref_g}
+        comp["qeb_vs_fp64"] = {k: rel(p.grad, g64["unet." + n]) for (n, p), k in zip(unet.named_parameters(), ref_g)}
+        out["phase_b"]["competitors_worst"] = {k: max(v.values()) for k, v in comp.items()}
+        out["phase_b"]["competitors_median"] = {k: sorted(v.values())[len(v) // 2] for k, v in comp.items()}
 
     # ---- phase A
     for m in (crnn_cpu, crnn):
@@ -92,12 +115,19 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--competitors", action="store_true", help="also torch eager + cuDNN (fp32 / TF32) on this GPU and the fp64 floor")
     a = ap.parse_args()
-    res = measure(a.batch)
+    res = measure(a.batch, competitors=a.competitors)
     for ph in ("phase_b", "phase_a"):
         r = res[ph]
         print(f"== {ph}: loss rel {r['loss_rel']:.2e}, scores rel {r['scores_rel']:.2e}, worst {r['worst_tensor']} {r['worst_rel_l2']:.2e}, min cos {r['min_cos']:.6f}")
         for k, v in sorted(r["grads"].items(), key=lambda kv: -kv[1][0])[:12]:
             print(f"   {k:44s} rel {v[0]:.2e} cos {v[1]:.6f}")
+    if "competitors_worst" in res["phase_b"]:
+        print("phase-B UNet weight gradients, rel-L2 against the fp32 CPU oracle (worst / median tensor):")
+        for k in res["phase_b"]["competitors_worst"]:
+            print(f"   {k:22s} {res['phase_b']['competitors_worst'][k]:.2e} / {res['phase_b']['competitors_median'][k]:.2e}")
+        g = res["phase_b"]["grads"]
+        print(f"   {'qeb':22s} {max(v[0] for v in g.values()):.2e} / {sorted(v[0] for v in g.values())[len(g) // 2]:.2e}")
     if a.out:
         json.dump(res, open(a.out, "w"), indent=1)
