@@ -234,7 +234,7 @@ def jitter_config(world):
             "operand_precision": "tensor-core operands with an 11-bit significand (fp16 forward copies, tf32 rounded-to-nearest "
                                  "backward), fp32 accumulation / activations / gradients / parameters",
             "l2": "no explicit flush: one copy streams ~0.6 GB of activations, > 126 MB L2",
-            "launch": "jitter + forward + CTC + backward of the rank's copies replayed as one CUDA graph; all-reduce and Adam outside it"}
+            "launch": "forward (jitter fused into conv1's input load, log-softmax into the head's epilogue) + CTC + backward of the rank's copies replayed as one CUDA graph; all-reduce and Adam outside it"}
 
 
 def run_jitter(env):
@@ -277,8 +277,10 @@ def run_jitter(env):
     def fwd_bwd():
         total = None
         for j, c in enumerate(copies):
-            img = th.jitter_batch(base_static, sig[c], seed=j, seed_dev=seed_dev, out=noisy[j])   # one launch per copy
-            loss = ctc_loss(crnn(img), tgs[j])
+            # add_noise + _call_model (train_nn_patch.py:289-292) in one pass: the jitter rides conv1's input load, the noisy
+            # batch is still materialised (noisy[j]) for the OCR hand-off
+            scores, _ = crnn.forward_jittered(base_static, sig[c], seed=j, seed_dev=seed_dev, out=noisy[j])
+            loss = ctc_loss(scores, tgs[j])
             loss.backward()                                               # inside the loop: gradients accumulate (:301-303)
             total = loss.detach() if total is None else total + loss.detach()
         return total

@@ -76,6 +76,10 @@ int qeb_levenshtein_batch(const void* a_syms, const int* a_off, const int* a_len
  * raw_path (B,T) optional per-timestep arg-max. First maximal index wins (torch.argmax). */
 int qeb_greedy_decode(const float* scores, long long st_t, long long st_b, int T, int B, int V, int blank, int* out,
                       int* out_len, int* raw_path, void* stream);
+/* The collapse half of pred_to_string (utils.py:84-89) on a per-frame arg-max path already on the device (the fused CRNN
+ * head writes one): frame t of sample b at path[t*st_t + b*st_b]; out / out_len as qeb_greedy_decode. */
+int qeb_greedy_collapse(const int* path, long long st_t, long long st_b, int T, int B, int blank, int* out, int* out_len,
+                        void* stream);
 
 /* ---- minibatch-subset selection ---------------------------------------------------------------------------------
  * TopKCERSampler.query selection_utils.py:144-151: per segment the indices of the k largest fp32 CERs, descending,
@@ -139,6 +143,17 @@ size_t qeb_crnn_workspace_bytes(int B, int W, int V);
 int qeb_crnn_num_params(void);
 int qeb_crnn_forward(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
                      void* ws, float* logits, void* stream);
+/* The same forward with the two fusions north_star names, selected per argument. log_softmax = 1: `out` (T,B,V) receives
+ * fn.log_softmax(self.linear(x), 2) (models/model_crnn.py:20) from the Linear GEMM's epilogue and argmax_path (T*B ints, frame
+ * t of sample b at [t*B + b], nullable) the per-frame arg-max pred_to_string takes (utils.py:78-89; see qeb_greedy_collapse).
+ * jit_sigma != NULL (B floats): x is the CLEAN batch and the network sees clamp(x - jit_coef*N(jit_mean, jit_sigma[b]), 0, 1)
+ * (AddGaussianNoice, transform_helper.py:33-45; add_noise, train_nn_patch.py:187-191) generated inside conv1's input load
+ * with the Philox stream of qeb_gauss_jitter (key jit_seed + *jit_seed_dev); noisy_out (B,1,32,W, required then) receives
+ * that image - hand it to the OCR engine and pass it as `x` to qeb_crnn_backward - and noise_out (nullable) the noise. */
+int qeb_crnn_forward_fused(const float* x, int B, int W, int V, const float* const* params, void* const* buffers,
+                           int bn_train, void* ws, float* out, int log_softmax, int* argmax_path, const float* jit_sigma,
+                           float jit_mean, float jit_coef, unsigned long long jit_seed,
+                           const unsigned long long* jit_seed_dev, float* noisy_out, float* noise_out, void* stream);
 int qeb_crnn_backward(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
                       const float* dlogits, float* const* grads, float* dx, void* stream);
 

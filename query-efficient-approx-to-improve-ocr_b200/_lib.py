@@ -27,6 +27,7 @@ SIGNATURES = {
     "qeb_log_softmax_bwd": (I, [P, P, P, LL, I, P]),
     "qeb_levenshtein_batch": (I, [P, P, P, P, P, P, I, I, I, P, P, P, P]),
     "qeb_greedy_decode": (I, [P, LL, LL, I, I, I, I, P, P, P, P]),
+    "qeb_greedy_collapse": (I, [P, LL, LL, I, I, I, P, P, P]),
     "qeb_cer_topk_segmented": (I, [P, P, P, P, I, P, P]),
     "qeb_cer_topk_global_workspace_bytes": (SZ, [LL]),
     "qeb_cer_topk_global": (I, [P, LL, LL, P, P, P]),
@@ -57,6 +58,7 @@ SIGNATURES = {
     "qeb_crnn_workspace_bytes": (SZ, [I, I, I]),
     "qeb_crnn_num_params": (I, []),
     "qeb_crnn_forward": (I, [P, I, I, I, P, P, I, P, P, P]),
+    "qeb_crnn_forward_fused": (I, [P, I, I, I, P, P, I, P, P, I, P, P, F, F, ULL, P, P, P, P]),
     "qeb_crnn_backward": (I, [P, I, I, I, P, I, P, P, P, P, P]),
     "qeb_unet_workspace_bytes": (SZ, [I, I, I]),
     "qeb_unet_num_params": (I, []),

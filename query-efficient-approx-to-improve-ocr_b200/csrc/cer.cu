@@ -173,6 +173,23 @@ __global__ void greedy_decode_kernel(const float* __restrict__ scores, long long
   }
 }
 
+// the collapse half of pred_to_string (utils.py:84-89) on a per-frame arg-max path that the CRNN head's epilogue already
+// produced (conv_tc.cu lsm_epilogue): drop blanks, collapse repeats. One thread per sample; frame t of sample b at
+// path[t * st_t + b * st_b] (coalesced over b for the (T,B) layout the head writes).
+__global__ void greedy_collapse_kernel(const int* __restrict__ path, long long st_t, long long st_b, int T, int B, int blank,
+                                       int* __restrict__ out, int* __restrict__ out_len) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int prev = -1, n = 0;
+  for (int t = 0; t < T; ++t) {
+    const int bi = path[t * st_t + b * st_b];
+    if (bi != blank && bi != prev) out[(long long)b * T + n++] = bi;
+    prev = bi;
+  }
+  out_len[b] = n;
+  for (int i = n; i < T; ++i) out[(long long)b * T + i] = -1;
+}
+
 }  // namespace
 
 // symbols: sym_bytes = 1 (uint8 char-set indices) or 4 (int32 code points). a = labels (CER denominator),
@@ -199,6 +216,18 @@ QEB_API int qeb_greedy_decode(const float* scores, long long st_t, long long st_
   ProfScope prof("greedy_decode", (cudaStream_t)stream, 0.0, 4.0 * T * B * V + 4.0 * B * (T + 1));
   greedy_decode_kernel<<<qeb_cdiv(B, 4), 128, 0, (cudaStream_t)stream>>>(scores, st_t, st_b, T, B, V, blank, out,
                                                                          out_len, raw_path);
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+// path: per-frame arg-max classes, frame t of sample b at path[t*st_t + b*st_b] -> the same out / out_len as qeb_greedy_decode.
+QEB_API int qeb_greedy_collapse(const int* path, long long st_t, long long st_b, int T, int B, int blank, int* out, int* out_len,
+                                void* stream) {
+  QEB_REQUIRE(path && out && out_len, "greedy_collapse: null pointer");
+  QEB_REQUIRE(T > 0 && B > 0, "greedy_collapse: bad sizes");
+  ProfScope prof("greedy_decode", (cudaStream_t)stream, 0.0, 4.0 * T * B + 4.0 * B * (T + 1));
+  greedy_collapse_kernel<<<qeb_cdiv(B, 128), 128, 0, (cudaStream_t)stream>>>(path, st_t, st_b, T, B, blank, out, out_len);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;

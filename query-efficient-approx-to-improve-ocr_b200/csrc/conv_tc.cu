@@ -114,6 +114,7 @@ struct FpropParams {
   int kblk;                  // operand elements per K block: 32 (tf32, or fp16 in 64-byte rows) or 64 (fp16 in 128-byte rows)
   __half* out16;             // optional fp16 shadow of the output (same element layout as `out`): the next layer's operand
   int round_out;             // 1: fp32 stores are rounded to tf32 (the tensor is a tf32 operand of a later contraction)
+  int* amax;                 // LSM kernels only (fused log-softmax head): arg-max class per output row, nullable
 };
 
 struct TmapArray4 {
@@ -332,7 +333,57 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   __syncwarp();
 }
 
-template <int BLOCK_N, int ROWB, bool F16>
+// torch.argmax ordering: NaN counts as the largest value, the first maximal index wins (cer.cu greedy_decode_kernel)
+__device__ __forceinline__ bool lsm_gt(float a, float b) { return (a > b) || ((a != a) && !(b != b)); }
+
+// Fused head of the CRNN (models/model_crnn.py:20, fn.log_softmax(self.linear(x), 2); utils.py:78-89, the per-frame arg-max
+// of pred_to_string): all n_total <= BLOCK_N classes of an output row are columns of ONE accumulator row, i.e. they sit in
+// one TMEM lane = one epilogue thread, so the row's max, log-sum-exp and arg-max need no cross-thread reduction. Three
+// passes over the lane's columns (TMEM reads, no shared or global traffic): max of the logits, sum of exp, then
+// lp = (logit - max) - log(sum) stored and its first arg-max recorded. The logits themselves never reach HBM.
+template <int BLOCK_N>
+__device__ __forceinline__ void lsm_epilogue(const FpropParams& p, uint32_t taddr, bool valid, int n, int h, int w) {
+  float m = -INFINITY;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N && c0 < p.n_total; c0 += 32) {
+    float v[32];
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < p.n_total) m = fmaxf(m, v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f));
+  }
+  float s = 0.f;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N && c0 < p.n_total; c0 += 32) {
+    float v[32];
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < p.n_total) s += expf(v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - m);
+  }
+  const float ls = logf(s);
+  float best = 0.f;
+  int bi = -1;
+  float* dst = p.out + n * p.osn + h * p.osh + w * p.osw;
+#pragma unroll 1
+  for (int c0 = 0; c0 < BLOCK_N && c0 < p.n_total; c0 += 32) {
+    float v[32];
+    tmem_ld32(taddr + (uint32_t)c0, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c0 + j < p.n_total) {
+        const float lp = v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - m - ls;
+        if (bi < 0 || lsm_gt(lp, best)) { best = lp; bi = c0 + j; }
+        if (valid) dst[c0 + j] = lp;
+      }
+  }
+  if (valid && p.amax) p.amax[((long long)n * p.h_out + h) * p.w_out + w] = bi;
+}
+
+template <int BLOCK_N, int ROWB, bool F16, bool LSM = false>
 __global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
 conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const FpropParams p) {
@@ -482,16 +533,20 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       if (tl && threadIdx.x == 64 && n_done == 0) tl[4] = clock64();
       tc_fence_after();
+      if constexpr (LSM) {
+        lsm_epilogue<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), valid, n, h, w);
+      } else {
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
-        tmem_ld_wait();
-        long long* tle = (tl && threadIdx.x == 64 && n_done == 0 && c0 == 0) ? tl : nullptr;
-        if (tle) tle[8] = clock64();
-        const int ncol = tile_n * BLOCK_N + c0;  // first GEMM-N column of this chunk
-        if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle, p.stats ? cta_stats : nullptr, c0);
-        if (tle) tle[10] = clock64();
+        for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + c0), v);
+          tmem_ld_wait();
+          long long* tle = (tl && threadIdx.x == 64 && n_done == 0 && c0 == 0) ? tl : nullptr;
+          if (tle) tle[8] = clock64();
+          const int ncol = tile_n * BLOCK_N + c0;  // first GEMM-N column of this chunk
+          if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle, p.stats ? cta_stats : nullptr, c0);
+          if (tle) tle[10] = clock64();
+        }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
@@ -508,13 +563,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
 
-template <int BLOCK_N, int ROWB, bool F16>
+template <int BLOCK_N, int ROWB, bool F16, bool LSM = false>
 int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p_in, int m_tiles, int n_tiles, int splits,
                  cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N, ROWB>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, LSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
   FpropParams p = p_in;
@@ -525,7 +580,7 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams&
   ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16>, grid, kThreads, Cfg::smem_bytes(p.stages), st, ta, tb, p));
+  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, LSM>, grid, kThreads, Cfg::smem_bytes(p.stages), st, ta, tb, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -592,6 +647,12 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
               "tc fprop: an fp16 output shadow needs 16-byte aligned output rows and a multiple of 32 channels");
   p.out16 = static_cast<__half*>(ep.out16);
   p.round_out = ep.round_out;
+  p.amax = ep.argmax;
+  if (ep.log_softmax) {
+    QEB_REQUIRE(n_total <= 128 && mode == 0 && !ep.scale && !ep.relu && !ep.mask && !ep.accumulate && !ep.out16 && !ep.bn_stats && !ep.bn_red,
+                "tc fprop: the fused log-softmax head needs <= 128 classes and a plain bias epilogue");
+    QEB_REQUIRE(!f16 || kblk == 64, "tc fprop: the fused log-softmax head needs a multiple of 64 input channels in fp16 mode");
+  }
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
   static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
@@ -609,7 +670,9 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     splits = min(num_kb / 8, min_ctas / (m_tiles * qeb_cdiv(n_total, bn_max)));
     if (splits < 1) splits = 1;
   }
-  if (splits == 1) {
+  if (ep.log_softmax) {
+    bn = 128; splits = 1;   // every class of a row in ONE accumulator row
+  } else if (splits == 1) {
     while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < min_ctas) bn >>= 1;
   }
   p.kb_per_split = qeb_cdiv(num_kb, splits);
@@ -641,7 +704,10 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     if (rc) return rc;
   }
   int rc;
-  if (!f16) {
+  if (ep.log_softmax) {
+    rc = f16 ? launch_fprop<128, 128, true, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st)
+             : launch_fprop<128, 128, false, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
+  } else if (!f16) {
     switch (bn) {
       case 32: rc = launch_fprop<32, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
       case 64: rc = launch_fprop<64, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;

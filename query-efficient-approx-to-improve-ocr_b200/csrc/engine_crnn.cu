@@ -140,8 +140,50 @@ QEB_API int qeb_crnn_num_params(void) { return P_COUNT; }
 // x: (B,1,32,W) fp32. params: P_COUNT device pointers in state_dict order; buffers: BN running_mean/var (fp32) and
 // num_batches_tracked (int64) for batchnorm1, batchnorm2. bn_train: 1 = batch statistics (+ running-stat update),
 // 0 = running statistics. logits: (T,B,V) dense. ws: qeb_crnn_workspace_bytes(), kept untouched until the backward.
+namespace {
+struct CrnnFwdOpts {
+  const JitterArgs* jitter = nullptr;   // non-NULL: x is the CLEAN image, the Gaussian jitter rides the conv1 input load
+  int log_softmax = 0;                  // 1: `logits` receives log_softmax(logits) straight from the Linear epilogue
+  int* argmax = nullptr;                // (T,B) per-frame arg-max of the log-probs (with log_softmax), nullable
+};
+int crnn_forward_impl(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
+                      void* ws, float* logits, const CrnnFwdOpts& opt, void* stream);
+}  // namespace
+
 QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* const* params, void* const* buffers,
                              int bn_train, void* ws, float* logits, void* stream) {
+  return crnn_forward_impl(x, B, W, V, params, buffers, bn_train, ws, logits, CrnnFwdOpts(), stream);
+}
+
+// The same forward with the two north_star fusions switched on per argument:
+//  - log_softmax = 1: `out` receives fn.log_softmax(self.linear(x), 2) (models/model_crnn.py:20) computed in the Linear
+//    GEMM's epilogue (no logits round trip, no separate launch); argmax_path (T*B ints, nullable) receives the per-frame
+//    arg-max class that pred_to_string takes (utils.py:78-89) - qeb_greedy_collapse turns it into strings' class indices;
+//  - jit_sigma != NULL: x is the CLEAN (B,1,32,W) batch and the network sees clamp(x - jit_coef * N(jit_mean, jit_sigma[b]),
+//    0, 1) (AddGaussianNoice, transform_helper.py:33-45), generated inside conv1's input load with the Philox stream of
+//    qeb_gauss_jitter (key = jit_seed + *jit_seed_dev). noisy_out (B,1,32,W, required) receives that image - the OCR engine
+//    and conv1's weight gradient need it: pass IT as `x` to qeb_crnn_backward - noise_out (nullable) the noise.
+QEB_API int qeb_crnn_forward_fused(const float* x, int B, int W, int V, const float* const* params, void* const* buffers,
+                                   int bn_train, void* ws, float* out, int log_softmax, int* argmax_path,
+                                   const float* jit_sigma, float jit_mean, float jit_coef, unsigned long long jit_seed,
+                                   const unsigned long long* jit_seed_dev, float* noisy_out, float* noise_out, void* stream) {
+  CrnnFwdOpts opt;
+  JitterArgs j;
+  if (jit_sigma) {
+    QEB_REQUIRE(noisy_out, "crnn_forward_fused: noisy_out is required with jitter (the backward pass reads it)");
+    j.sigma = jit_sigma; j.mean = jit_mean; j.coef = jit_coef; j.seed = jit_seed; j.seed_dev = jit_seed_dev;
+    j.noisy_out = noisy_out; j.noise_out = noise_out;
+    opt.jitter = &j;
+  }
+  opt.log_softmax = log_softmax;
+  opt.argmax = argmax_path;
+  QEB_REQUIRE(log_softmax || !argmax_path, "crnn_forward_fused: argmax_path needs log_softmax = 1");
+  return crnn_forward_impl(x, B, W, V, params, buffers, bn_train, ws, out, opt, stream);
+}
+
+namespace {
+int crnn_forward_impl(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
+                      void* ws, float* logits, const CrnnFwdOpts& opt, void* stream) {
   QEB_REQUIRE(x && params && buffers && ws && logits, "crnn_forward: null pointer");
   QEB_REQUIRE(B > 0 && W >= 8 && W % 4 == 0 && V > 0 && V <= 96, "crnn_forward: B=%d W=%d V=%d unsupported", B, W, V);
   QEB_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)x & 15) == 0, "crnn_forward: workspace/input alignment");
@@ -204,7 +246,8 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   auto shadows = [&](TcEpilogue& e, const void* in16, const void* w16, void* out16) {
     e.in16 = h ? in16 : nullptr; e.w16 = h ? w16 : nullptr; e.out16 = h ? out16 : nullptr;
   };
-  TRY(c1_conv_fwd(X, params[P_C1W], params[P_C1B], 1, A1f, st));
+  if (opt.jitter) TRY(c1_conv_fwd_jitter(x, B, 32, W, *opt.jitter, params[P_C1W], params[P_C1B], 1, A1f, st));
+  else TRY(c1_conv_fwd(X, params[P_C1W], params[P_C1B], 1, A1f, st));
   TRY(maxpool_fwd(A1f, 2, 2, A1, st, h ? p.a1h : nullptr));
   TRY(ss.wait_mark());
   TcEpilogue ep;
@@ -282,10 +325,13 @@ QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* c
   }
   TcEpilogue el;
   el.bias = params[P_LINB];
+  el.log_softmax = opt.log_softmax;
+  el.argmax = opt.argmax;
   shadows(el, p.y1h, p.wlinh, nullptr);
   TRY(tc_conv_fprop(img_nhwc(p.y1, 1, 1, TB, 512), params[P_LINW], V, 1, 1, 0, 0, img_nhwc(logits, 1, 1, TB, V), el, st));
   return QEB_OK;
 }
+}  // namespace
 
 // dlogits: (T,B,V) dense. grads: P_COUNT pointers (entries may be NULL, all NULL-able: that gradient is skipped);
 // every non-NULL gradient is ACCUMULATED into (zero it for a plain gradient). dx: (B,1,32,W) or NULL.

@@ -56,6 +56,11 @@ struct TcEpilogue {
   // feeds the next dgrad / wgrad directly): it is stored rounded to tf32 (common.cuh qeb_tf32r). Rules out split-K (partial
   // sums cannot be rounded), so the tile is narrowed instead.
   int round_out = 0;
+  // Fused CRNN head (models/model_crnn.py:20): the stored values are log_softmax(acc + bias) over the n_total <= 128 output
+  // channels of every pixel; argmax (optional, one int per output pixel): first index of the row's largest log-prob
+  // (torch.argmax order), what pred_to_string (utils.py:78-89) takes per frame. Plain bias epilogue only.
+  int log_softmax = 0;
+  int* argmax = nullptr;
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
@@ -146,6 +151,18 @@ int pack_flush(PackBatch& b, cudaStream_t st);
 // ---- direct (SIMT) kernels, nn_ops.cu ---------------------------------------------------------------------------
 // 3x3 pad-1 convolution with ONE input channel: x (n,h,w,1) -> out (n,h,w,cout); w torch layout (cout,1,3,3).
 int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const Img& out, cudaStream_t st);
+// Gaussian jitter fused into the input load (nn_ops.cu c1_jitter_fwd_kernel): x (n,h,w) contiguous is the CLEAN image; the
+// convolution sees clamp(x - coef * N(mean, sigma[n]), 0, 1), which is also written to noisy_out (and the noise to noise_out)
+struct JitterArgs {
+  const float* sigma = nullptr;                 // one std per image (device)
+  float mean = 0.f, coef = 1.f;
+  unsigned long long seed = 0;
+  const unsigned long long* seed_dev = nullptr;  // optional device-resident key added to `seed` when the kernel runs
+  float* noisy_out = nullptr;                   // (n,h,w): the jittered image (OCR hand-off, conv1 weight gradient)
+  float* noise_out = nullptr;                   // (n,h,w) or NULL
+};
+int c1_conv_fwd_jitter(const float* x, int n_img, int h, int w, const JitterArgs& j, const float* wgt, const float* bias, int relu,
+                       const Img& out, cudaStream_t st);
 int c1_conv_wgrad(const Img& x, const Img& dy, float* dw, float* dbias, cudaStream_t st);  // accumulates
 int c1_conv_dgrad(const Img& dy, const float* w, const Img& dx, cudaStream_t st);          // overwrites dx
 // 1x1 convolution to ONE output channel + sigmoid: y = sigmoid(sum_c x*w[c] + b)

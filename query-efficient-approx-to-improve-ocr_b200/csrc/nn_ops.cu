@@ -11,6 +11,7 @@
 #include <mutex>
 #include <unordered_map>
 #include "nn.cuh"
+#include "philox.cuh"
 #include <cuda_fp16.h>
 
 namespace {
@@ -100,6 +101,86 @@ __global__ void __launch_bounds__(kThreads) c1_fwd_kernel(const float* __restric
     float xv[3][6];
     load_window(x + (long long)qp.n * gx.sn, gx, qp.hv, qp.w0, xv);
     float* ob = out + (long long)qp.n * go.sn + (long long)qp.hv * go.sh + (long long)qp.w0 * go.sw + cq * 4;
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      float acc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = br[j];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) a = fmaf(xv[ky][px + kx], wr[j][ky * 3 + kx], a);
+        acc[j] = relu ? fmaxf(a, 0.f) : a;
+      }
+      st4(ob + (long long)px * go.sw, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+  }
+}
+
+// Gaussian jitter FUSED into the conv1 input load (north_star; transform_helper.py:33-45 -> models/model_crnn.py:47-48).
+// One block = one image x one band of kJitRows rows. Phase 1: the band plus one halo row above and below is jittered ONCE
+// per pixel into shared memory (same Philox counters as jitter_kernel, so the image is bit-identical to what the standalone
+// kernel writes); the band's own rows are also stored to `noisy_out` - the reference hands the noisy image to the OCR engine
+// (train_nn_patch.py:290-291) and the weight gradient of conv1 reads it - and the noise to `noise_out` when asked for
+// (AddGaussianNoice(return_noise=True)). Phase 2: the 3x3 convolution + bias + ReLU of c1_fwd_kernel out of shared memory.
+// The separate jitter launch and its 16 KB-in / 16 KB-out pass per patch disappear; the base image is read once.
+constexpr int kJitRows = 8;
+template <int COUT>
+__global__ void __launch_bounds__(kThreads) c1_jitter_fwd_kernel(const float* __restrict__ x, int h, int w,
+                                                                 const float* __restrict__ sigma, float mean, float coef,
+                                                                 unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                                                                 float* __restrict__ noisy_out, float* __restrict__ noise_out,
+                                                                 const float* __restrict__ wgt, const float* __restrict__ bias, int relu,
+                                                                 float* __restrict__ out, Geo go) {
+  qeb_pdl_sync();
+  extern __shared__ float tile[];   // (kJitRows + 2) rows x (w + 8) floats; pixel (r, c) at tile[(r - h0 + 1) * ts + c + 4]
+  if (seed_dev) seed += *seed_dev;
+  const int bands = (h + kJitRows - 1) / kJitRows;
+  const int n = blockIdx.x / bands, h0 = (blockIdx.x - n * bands) * kJitRows;
+  const int ts = w + 8, wq = w >> 2;
+  const float* xb = x + (long long)n * h * w;
+  const float sg = __ldg(sigma + n);
+  for (int i = threadIdx.x; i < (kJitRows + 2) * wq; i += kThreads) {
+    const int rr = i / wq, g = i - rr * wq, row = h0 - 1 + rr;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row >= 0 && row < h) {
+      const unsigned int grp = (unsigned int)(row * wq + g);
+      const float4 z = qebrng::noise4(grp, n, seed, mean, sg);
+      const float4 p = __ldg(reinterpret_cast<const float4*>(xb + (long long)row * w) + g);
+      v = make_float4(qebrng::jitter1(p.x, z.x, coef), qebrng::jitter1(p.y, z.y, coef), qebrng::jitter1(p.z, z.z, coef),
+                      qebrng::jitter1(p.w, z.w, coef));
+      if (rr >= 1 && rr <= kJitRows) {
+        const long long o = ((long long)n * h + row) * w + 4 * g;
+        if (noisy_out) st4(noisy_out + o, v);
+        if (noise_out) st4(noise_out + o, z);
+      }
+    }
+    st4(tile + rr * ts + 4 + 4 * g, v);
+  }
+  for (int rr = threadIdx.x; rr < kJitRows + 2; rr += kThreads) {   // zero padding left and right of every row
+    tile[rr * ts + 3] = 0.f;
+    tile[rr * ts + 4 + w] = 0.f;
+  }
+  __syncthreads();
+  constexpr int CQ = COUT / 4;
+  const int cq = threadIdx.x % CQ;
+  float wr[4][9], br[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[j][t] = __ldg(wgt + (cq * 4 + j) * 9 + t);
+    br[j] = bias ? __ldg(bias + cq * 4 + j) : 0.f;
+  }
+  const int rows = min(kJitRows, h - h0);
+  for (int q = threadIdx.x / CQ; q < rows * wq; q += kThreads / CQ) {
+    const int rr = q / wq, w0 = (q - rr * wq) * 4;
+    float xv[3][6];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) xv[r][c] = tile[(rr + r) * ts + 3 + w0 + c];
+    float* ob = out + (long long)n * go.sn + (long long)(h0 + rr) * go.sh + (long long)w0 * go.sw + cq * 4;
 #pragma unroll
     for (int px = 0; px < 4; ++px) {
       float acc[4];
@@ -923,6 +1004,31 @@ int c1_conv_fwd(const Img& x, const float* w, const float* bias, int relu, const
   const int g = out.c == 32 ? RGRID(c1_fwd_kernel<32>, nthr) : RGRID(c1_fwd_kernel<64>, nthr);
   if (out.c == 32) QEB_CUDA(qeb_launch(c1_fwd_kernel<32>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_quads));
   else QEB_CUDA(qeb_launch(c1_fwd_kernel<64>, g, kThreads, 0, st, x.p, geo(x), w, bias, relu, out.p, geo(out), n_quads));
+  QEB_LAUNCH_CHECK();
+  qeb_count_launch();
+  return QEB_OK;
+}
+
+int c1_conv_fwd_jitter(const float* x, int n_img, int h, int w, const JitterArgs& j, const float* wgt, const float* bias, int relu,
+                       const Img& out, cudaStream_t st) {
+  ProfScope prof("c1_conv_fwd", st, 18.0 * (double)n_img * h * w * out.c, 4.0 * (double)n_img * h * w * (2 + out.c));
+  QEB_REQUIRE(x && j.sigma && (out.c == 32 || out.c == 64), "c1_conv_fwd_jitter: 1 -> 32/64 channels, sigma per image required");
+  QEB_REQUIRE(out.n == n_img && out.h == h && out.w == w && vec4_ok(out), "c1_conv_fwd_jitter: geometry/alignment");
+  QEB_REQUIRE(w % 4 == 0 && w <= 2048 && (long long)h * (w / 4) < (1ll << 31), "c1_conv_fwd_jitter: the width must be a multiple of 4, <= 2048");
+  QEB_REQUIRE((((uintptr_t)x | (uintptr_t)j.noisy_out | (uintptr_t)j.noise_out) & 15) == 0, "c1_conv_fwd_jitter: 16-byte aligned images");
+  const int bands = (h + kJitRows - 1) / kJitRows;
+  const size_t smem = (size_t)(kJitRows + 2) * (w + 8) * sizeof(float);
+  const long long grid = (long long)n_img * bands;
+  QEB_REQUIRE(grid < (1ll << 31), "c1_conv_fwd_jitter: too many images");
+  if (out.c == 32) {
+    if (smem > 48 * 1024) QEB_CUDA(cudaFuncSetAttribute(c1_jitter_fwd_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QEB_CUDA(qeb_launch(c1_jitter_fwd_kernel<32>, (int)grid, kThreads, smem, st, x, h, w, j.sigma, j.mean, j.coef, j.seed, j.seed_dev,
+                        j.noisy_out, j.noise_out, wgt, bias, relu, out.p, geo(out)));
+  } else {
+    if (smem > 48 * 1024) QEB_CUDA(cudaFuncSetAttribute(c1_jitter_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QEB_CUDA(qeb_launch(c1_jitter_fwd_kernel<64>, (int)grid, kThreads, smem, st, x, h, w, j.sigma, j.mean, j.coef, j.seed, j.seed_dev,
+                        j.noisy_out, j.noise_out, wgt, bias, relu, out.p, geo(out)));
+  }
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;

@@ -153,6 +153,30 @@ class _LogSoftmax(torch.autograd.Function):
         return dx
 
 
+class _LogSoftmaxDone(torch.autograd.Function):
+    """The log-softmax NODE for a tensor whose values the CRNN head's GEMM epilogue already turned into log-probs
+    (qeb_crnn_forward_fused, log_softmax = 1): forward is the identity, backward is log-softmax's (dx = dy - exp(y) sum dy),
+    so the autograd graph - and what CRNN.backward_hook sees (models/model_crnn.py:30-32) - is the unfused one."""
+
+    @staticmethod
+    def forward(ctx, y):
+        ctx.save_for_backward(y)
+        return y.view_as(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(y)
+        V = y.shape[-1]
+        _lib.call("qeb_log_softmax_bwd", y.data_ptr(), dy.data_ptr(), dx.data_ptr(), y.numel() // V, V, _lib.stream())
+        return dx
+
+
+def log_softmax_node(log_probs):
+    return _LogSoftmaxDone.apply(log_probs)
+
+
 def log_softmax(x):
     if not x.is_cuda or x.dtype != torch.float32:
         raise _lib.QebError("qeb log_softmax needs a CUDA fp32 tensor (no CPU fallback)")

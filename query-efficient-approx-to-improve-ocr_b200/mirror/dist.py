@@ -92,16 +92,16 @@ def global_topk(local_cers, k, group=None, local_topk=None):
     if not multi:
         return torch.from_numpy(idx)
     # shard sizes -> global offsets; candidates padded to k entries (count travels with them)
-    sizes = [torch.zeros(1, dtype=torch.long) for _ in range(world)]
-    dist.all_gather(sizes, torch.tensor([len(vals)], dtype=torch.long), group=group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    sizes = [torch.zeros(1, dtype=torch.long, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([len(vals)], dtype=torch.long, device=dev), group=group)
     offs = np.concatenate([[0], np.cumsum([int(s) for s in sizes])])
     cand_v = torch.full((k,), float("-inf"), dtype=torch.float32)
     cand_i = torch.full((k + 1,), -1, dtype=torch.long)
     cand_v[:kl] = torch.from_numpy(vals[idx])
     cand_i[:kl] = torch.from_numpy(idx + offs[rank])
     cand_i[k] = kl
-    backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
     all_v = [torch.empty(k, dtype=torch.float32, device=dev) for _ in range(world)]
     all_i = [torch.empty(k + 1, dtype=torch.long, device=dev) for _ in range(world)]
     dist.all_gather(all_v, cand_v.to(dev), group=group)

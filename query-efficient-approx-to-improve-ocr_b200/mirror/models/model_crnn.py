@@ -15,9 +15,12 @@ import torch
 import torch.nn as nn
 
 from ... import _lib
-from ..ctc import log_softmax
+from ..ctc import log_softmax, log_softmax_node
 
 _POISON = os.environ.get("QEB_POISON_WORKSPACE", "0") == "1"
+# 1 (default): CRNN.forward takes log_softmax (+ the per-frame arg-max pred_to_string needs) from the Linear GEMM's epilogue;
+# 0: logits from the GEMM, log-softmax as its own launch (same-box A/B, debugging)
+_FUSED_HEAD = os.environ.get("QEB_FUSED_HEAD", "1") != "0"
 
 
 class Convolutional(nn.Module):
@@ -60,10 +63,13 @@ def _alloc_grads(params, need):
 
 
 class _CRNNTrunk(torch.autograd.Function):
-    """x (B,1,32,W) + the 36 parameters -> logits (T,B,V)."""
+    """x (B,1,32,W) + the 36 parameters -> logits (T,B,V); with `opts` the fused variants of the C ABI
+    (qeb_crnn_forward_fused): opts["log_softmax"] -> the output already holds log_softmax(logits) and opts["path"] receives
+    the per-frame arg-max (T,B) int32; opts["jitter"] = dict(sigma, mean, coef, seed, seed_dev, return_noise) -> x is the
+    CLEAN batch, the Gaussian jitter rides conv1's input load, opts["noisy"] (and opts["noise"]) receive the jittered batch."""
 
     @staticmethod
-    def forward(ctx, x, bn_train, buffers, *params):
+    def forward(ctx, x, bn_train, buffers, opts, *params):
         lib = _lib.load()
         B, C, H, W = x.shape
         V = params[-1].shape[0]
@@ -75,11 +81,36 @@ class _CRNNTrunk(torch.autograd.Function):
             ws.view(torch.float32).fill_(float("nan"))
         T = W // 4 - 1
         logits = torch.empty((T, B, V), dtype=torch.float32, device=x.device)
-        _lib.call("qeb_crnn_forward", x.data_ptr(), B, W, V, _ptr_array(params), _ptr_array(buffers), int(bn_train),
-                  ws.data_ptr(), logits.data_ptr(), _lib.stream())
-        ctx.save_for_backward(x, *params)
+        x_saved = x
+        if not opts:
+            _lib.call("qeb_crnn_forward", x.data_ptr(), B, W, V, _ptr_array(params), _ptr_array(buffers), int(bn_train),
+                      ws.data_ptr(), logits.data_ptr(), _lib.stream())
+        else:
+            lsm = bool(opts.get("log_softmax"))
+            path = torch.empty((T, B), dtype=torch.int32, device=x.device) if lsm else None
+            jit = opts.get("jitter")
+            sigma = noisy = noise = seed_dev = None
+            mean, coef, seed = 0.0, 1.0, 0
+            if jit is not None:
+                sigma = jit["sigma"]
+                if sigma.numel() != B or not sigma.is_cuda or sigma.dtype != torch.float32 or not sigma.is_contiguous():
+                    raise _lib.QebError("qeb CRNN jitter: sigma must be a contiguous CUDA fp32 tensor with one value per image")
+                mean, coef, seed, seed_dev = float(jit.get("mean", 0.0)), float(jit.get("coef", 1.0)), int(jit.get("seed", 0)), jit.get("seed_dev")
+                noisy = jit.get("out")
+                if noisy is None:
+                    noisy = torch.empty_like(x)
+                elif noisy.shape != x.shape or not noisy.is_contiguous() or noisy.device != x.device or noisy.dtype != torch.float32:
+                    raise _lib.QebError("qeb CRNN jitter: `out` must be a contiguous fp32 tensor of the input's shape on its device")
+                noise = torch.empty_like(x) if jit.get("return_noise") else None
+                x_saved = noisy   # conv1's weight gradient reads the image the network saw
+            _lib.call("qeb_crnn_forward_fused", x.data_ptr(), B, W, V, _ptr_array(params), _ptr_array(buffers), int(bn_train),
+                      ws.data_ptr(), logits.data_ptr(), int(lsm), _lib.ptr(path), _lib.ptr(sigma), mean, coef, seed, _lib.ptr(seed_dev),
+                      _lib.ptr(noisy), _lib.ptr(noise), _lib.stream())
+            opts["path"], opts["noisy"], opts["noise"] = path, noisy, noise
+        ctx.save_for_backward(x_saved, *params)
         ctx.ws = ws
         ctx.cfg = (B, W, V, int(bn_train))
+        ctx.jittered = bool(opts) and opts.get("jitter") is not None
         return logits
 
     @staticmethod
@@ -87,12 +118,13 @@ class _CRNNTrunk(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         B, W, V, bn_train = ctx.cfg
         dlogits = dlogits.contiguous()
-        grads = _alloc_grads(params, ctx.needs_input_grad[3:])
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        grads = _alloc_grads(params, ctx.needs_input_grad[4:])
+        # a jittered input is not differentiated (the reference adds the noise to detached CPU copies, train_nn_area.py:227,260)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] and not ctx.jittered else None
         _lib.call("qeb_crnn_backward", x.data_ptr(), B, W, V, _ptr_array(params), bn_train, ctx.ws.data_ptr(),
                   dlogits.data_ptr(), _ptr_array(grads), _lib.ptr(dx), _lib.stream())
         ctx.ws = None
-        return (dx, None, None) + tuple(grads)
+        return (dx, None, None, None) + tuple(grads)
 
 
 class CRNN(nn.Module):
@@ -128,7 +160,7 @@ class CRNN(nn.Module):
         return [c.batchnorm1.running_mean, c.batchnorm1.running_var, c.batchnorm1.num_batches_tracked,
                 c.batchnorm2.running_mean, c.batchnorm2.running_var, c.batchnorm2.num_batches_tracked]
 
-    def forward_logits(self, x):
+    def _trunk(self, x, opts):
         if not x.is_cuda or x.dtype != torch.float32:
             raise _lib.QebError("qeb CRNN needs a CUDA fp32 input (no CPU fallback)")
         c = self._stack()
@@ -138,10 +170,35 @@ class CRNN(nn.Module):
         for p in params:
             if not p.is_contiguous() or p.device != x.device:
                 raise _lib.QebError("qeb CRNN: parameters must be contiguous and on the input's device")
-        return _CRNNTrunk.apply(x.contiguous(), c.batchnorm1.training, self.qeb_buffers(), *params)
+        return _CRNNTrunk.apply(x.contiguous(), c.batchnorm1.training, self.qeb_buffers(), opts, *params)
+
+    def forward_logits(self, x):
+        return self._trunk(x, None)
 
     def forward(self, x):
-        return log_softmax(self.forward_logits(x))
+        if not _FUSED_HEAD:
+            return log_softmax(self.forward_logits(x))
+        opts = {"log_softmax": True}
+        out = log_softmax_node(self._trunk(x, opts))     # its own autograd node: backward_hook sees the gradient at the logits
+        out._qeb_path = (opts["path"], out._version)     # pred_to_string collapses this instead of re-reading (T,B,V) scores
+        return out
+
+    def forward_jittered(self, images, sigmas, mean=0.0, noise_coef=1, seed=None, seed_dev=None, return_noise=False, out=None):
+        """`self(AddGaussianNoice(...)(images))` for a whole batch in ONE pass: the jitter of transform_helper.py:33-45 (one
+        sigma per image, `sigmas`: (B) host or device) rides conv1's input load. Returns (log_probs, noisy_images[, noise]);
+        noisy_images is what the OCR engine gets (train_nn_area.py:260-261) and is bit-identical to
+        transform_helper.jitter_batch(images, sigmas, mean, noise_coef, seed) under the same seed. `seed_dev`: device-resident
+        Philox key (CUDA-graph replays draw fresh noise), `out`: preallocated noisy batch. No gradient flows to `images`."""
+        sg = torch.as_tensor(sigmas, dtype=torch.float32)
+        if not sg.is_cuda:
+            sg = sg.pin_memory().to(images.device, non_blocking=True)
+        if seed is None:
+            seed = 0 if seed_dev is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        opts = {"log_softmax": True, "jitter": {"sigma": sg.contiguous(), "mean": mean, "coef": noise_coef, "seed": seed,
+                                                "seed_dev": seed_dev, "return_noise": return_noise, "out": out}}
+        lp = log_softmax_node(self._trunk(images, opts))
+        lp._qeb_path = (opts["path"], lp._version)
+        return (lp, opts["noisy"], opts["noise"]) if return_noise else (lp, opts["noisy"])
 
     def map_to_sequence(self, map):
         batch, channel, height, width = map.size()

@@ -107,6 +107,15 @@ class AddGaussianNoice(object):
         return tuple(o.to(home) for o in out) if self.return_noise else out.to(home)
 
 
+def crnn_on_noised(crnn_model, imgs, noiser, noise_coef=1, seed_dev=None, out=None):
+    """`scores = crnn_model(add_noise(imgs, noiser))` in one pass (CRNN.forward_jittered): the jitter is generated inside
+    conv1's input load. Returns (scores, noisy_imgs) or (scores, noisy_imgs, noise) with noiser.return_noise - the noisy batch
+    is still materialised for the OCR engine (train_nn_area.py:260-262, train_nn_patch.py:289-292)."""
+    _check(imgs)
+    return crnn_model.forward_jittered(imgs, noiser._sigmas(imgs.shape[0]), noiser.mean, noise_coef, seed_dev=seed_dev,
+                                       return_noise=noiser.return_noise, out=out)
+
+
 def add_noise(imgs, noiser, noise_coef=1):
     """TrainNNPrep.add_noise (train_nn_area.py:184-191 returns (imgs, noise); train_nn_patch.py:187-191 imgs only,
     selected by noiser.return_noise)."""

@@ -40,7 +40,18 @@ def _require_cuda():
 # ---------------------------------------------------------------------------------------------------------------
 # greedy decode
 def decode_batch(scores, blank=0, want_path=False):
-    """scores (T,B,V) CUDA fp32 -> (codes (B,T) int32 padded with -1, lengths (B) int32), both on device."""
+    """scores (T,B,V) CUDA fp32 -> (codes (B,T) int32 padded with -1, lengths (B) int32), both on device.
+    Scores that come straight out of the qeb CRNN carry the per-frame arg-max its head epilogue computed (`_qeb_path`, valid
+    while the tensor has not been modified in place): then only that (T,B) int path is collapsed, the scores are not re-read."""
+    attached = getattr(scores, "_qeb_path", None)
+    if attached is not None and not want_path and blank >= 0 and attached[1] == scores._version and attached[0].shape == scores.shape[:2]:
+        path = attached[0]
+        T, B = path.shape
+        codes = torch.empty((B, T), dtype=torch.int32, device=path.device)
+        lens = torch.empty(B, dtype=torch.int32, device=path.device)
+        _lib.call("qeb_greedy_collapse", path.data_ptr(), path.stride(0), path.stride(1), T, B, blank, codes.data_ptr(), lens.data_ptr(),
+                  _lib.stream())
+        return codes, lens
     if not scores.is_cuda:
         _require_cuda()
         scores = scores.cuda()
