@@ -338,53 +338,89 @@ __device__ __forceinline__ bool lsm_gt(float a, float b) { return (a > b) || ((a
 
 // Fused head of the CRNN (models/model_crnn.py:20, fn.log_softmax(self.linear(x), 2); utils.py:78-89, the per-frame arg-max
 // of pred_to_string): all n_total <= BLOCK_N classes of an output row are columns of ONE accumulator row, i.e. they sit in
-// one TMEM lane = one epilogue thread, so the row's max, log-sum-exp and arg-max need no cross-thread reduction. Three
-// passes over the lane's columns (TMEM reads, no shared or global traffic): max of the logits, sum of exp, then
-// lp = (logit - max) - log(sum) stored and its first arg-max recorded. The logits themselves never reach HBM.
+// one TMEM lane = one epilogue thread, so the row's max, log-sum-exp and arg-max need no cross-thread reduction: the row is
+// read from TMEM once into registers, lp = (logit - max) - log(sum exp) and its first arg-max are computed in place, and the
+// tile's log-probs - one contiguous block of the (T*B, V) output - leave through a shared-memory staging tile with full-width
+// coalesced stores (a thread storing its own row would touch 32 different lines per warp store). The logits never reach HBM.
+constexpr int kLsmPitch = 129;                                     // odd row pitch of the staging tile: conflict-free both ways
+constexpr int kLsmStageBytes = (kBlockM * kLsmPitch * 4 + 1023) & ~1023;
+// sbias: BLOCK_N floats of shared memory (the per-CTA statistics area, unused by this variant)
 template <int BLOCK_N>
-__device__ __forceinline__ void lsm_epilogue(const FpropParams& p, uint32_t taddr, bool valid, int n, int h, int w) {
-  float m = -INFINITY;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N && c0 < p.n_total; c0 += 32) {
-    float v[32];
-    tmem_ld32(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+__device__ __forceinline__ void lsm_epilogue(const FpropParams& p, uint32_t taddr, int row, int row0, float* stage, float* sbias) {
+  static_assert(BLOCK_N == 128, "the fused head keeps a whole row of <= 128 classes in registers");
+  const int nt = p.n_total;
+  // bias staged once per tile (-inf beyond the last class: those columns drop out of max, sum and arg-max by themselves);
+  // per-element `if (j < nt) v += __ldg(bias + j)` compiles to a branch and an exposed global load per class (measured:
+  // 48 k cycles per tile)
+  sbias[row] = row < nt ? (p.bias ? __ldg(p.bias + row) : 0.f) : -INFINITY;
+  float v[BLOCK_N];
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c0 + j < p.n_total) m = fmaxf(m, v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f));
-  }
-  float s = 0.f;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N && c0 < p.n_total; c0 += 32) {
-    float v[32];
-    tmem_ld32(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+  for (int c = 0; c < BLOCK_N / 32; ++c) tmem_ld32(taddr + (uint32_t)(32 * c), v + 32 * c);
+  tmem_ld_wait();
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  // four independent chains per reduction (a single running max / sum / arg-max is 128 dependent steps for the one warp
+  // per scheduler that runs here)
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c0 + j < p.n_total) s += expf(v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - m);
+  for (int j = 0; j < BLOCK_N; ++j) {
+    v[j] += sbias[j];
+    m4[j & 3] = fmaxf(m4[j & 3], v[j]);
   }
-  const float ls = logf(s);
-  float best = 0.f;
-  int bi = -1;
-  float* dst = p.out + n * p.osn + h * p.osh + w * p.osw;
-#pragma unroll 1
-  for (int c0 = 0; c0 < BLOCK_N && c0 < p.n_total; c0 += 32) {
-    float v[32];
-    tmem_ld32(taddr + (uint32_t)c0, v);
-    tmem_ld_wait();
+  const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (c0 + j < p.n_total) {
-        const float lp = v[j] + (p.bias ? __ldg(p.bias + c0 + j) : 0.f) - m - ls;
-        if (bi < 0 || lsm_gt(lp, best)) { best = lp; bi = c0 + j; }
-        if (valid) dst[c0 + j] = lp;
-      }
+  for (int j = 0; j < BLOCK_N; ++j) s4[j & 3] += __expf(v[j] - m);    // exp(-inf) = 0 for the padding columns
+  const float ls = logf((s4[0] + s4[1]) + (s4[2] + s4[3]));
+  float* srow = stage + row * kLsmPitch;
+  // arg-max of the stored log-probs, first maximal index: chain q scans the contiguous quarter [32q, 32q + 32), the
+  // quarters are merged in index order with a strict comparison
+  float b4[4];
+  int i4[4];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    b4[q4] = v[32 * q4] - m - ls;
+    i4[q4] = 32 * q4;
+    srow[32 * q4] = b4[q4];
   }
-  if (valid && p.amax) p.amax[((long long)n * p.h_out + h) * p.w_out + w] = bi;
+#pragma unroll
+  for (int jj = 1; jj < 32; ++jj) {
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      const int j = 32 * q4 + jj;
+      const float lp = v[j] - m - ls;
+      const bool gt = lsm_gt(lp, b4[q4]);                         // padding columns are -inf: they never win
+      b4[q4] = gt ? lp : b4[q4];
+      i4[q4] = gt ? j : i4[q4];
+      srow[j] = lp;
+    }
+  }
+  float best = b4[0];
+  int bi = i4[0];
+#pragma unroll
+  for (int q4 = 1; q4 < 4; ++q4) {
+    const bool gt = lsm_gt(b4[q4], best);
+    best = gt ? b4[q4] : best;
+    bi = gt ? i4[q4] : bi;
+  }
+  const int rows_here = min(kBlockM, p.w_out - row0);
+  if (row < rows_here && p.amax) p.amax[row0 + row] = min(bi, nt - 1);
+  // the tile's rows are one contiguous block of the (T*B, V) output: each warp copies whole rows with coalesced stores
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int wq = (threadIdx.x >> 5) - 2, lane = threadIdx.x & 31;
+  float* dst = p.out + (long long)row0 * nt;
+#pragma unroll 4
+  for (int r = wq; r < rows_here; r += 4) {
+    const float* sr = stage + r * kLsmPitch;
+    float* dr = dst + (long long)r * nt;
+#pragma unroll
+    for (int c = 0; c < BLOCK_N / 32; ++c)
+      if (lane + 32 * c < nt) dr[lane + 32 * c] = sr[lane + 32 * c];
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile and bias are free for the CTA's next tile
 }
 
 template <int BLOCK_N, int ROWB, bool F16, bool LSM = false>
-__global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
+__global__ void __launch_bounds__(kThreads, LSM ? 1 : FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
 conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const FpropParams p) {
   using Cfg = FpropCfg<BLOCK_N, ROWB>;
@@ -534,7 +570,8 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       if (tl && threadIdx.x == 64 && n_done == 0) tl[4] = clock64();
       tc_fence_after();
       if constexpr (LSM) {
-        lsm_epilogue<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), valid, n, h, w);
+        lsm_epilogue<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), r, tile_m * kBlockM,
+                              reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kStatBytes + 256), cta_stats);
       } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -575,12 +612,13 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams&
   FpropParams p = p_in;
   const long long total = (long long)m_tiles * n_tiles * splits;
   p.stages = Cfg::pick_stages(total);
+  if (LSM) p.stages = min(p.stages, (Cfg::kMaxSmem - Cfg::smem_bytes(0) - kLsmStageBytes) / Cfg::kStageBytes);
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits;
   const int grid = (int)(total < (long long)kNumSMs * Cfg::resident(total) ? total : (long long)kNumSMs * Cfg::resident(total));
-  ProfScope prof(p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
+  ProfScope prof(LSM ? "tc_head_logsoftmax" : p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, LSM>, grid, kThreads, Cfg::smem_bytes(p.stages), st, ta, tb, p));
+  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, LSM>, grid, kThreads, Cfg::smem_bytes(p.stages) + (LSM ? kLsmStageBytes : 0), st, ta, tb, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -652,6 +690,8 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     QEB_REQUIRE(n_total <= 128 && mode == 0 && !ep.scale && !ep.relu && !ep.mask && !ep.accumulate && !ep.out16 && !ep.bn_stats && !ep.bn_red,
                 "tc fprop: the fused log-softmax head needs <= 128 classes and a plain bias epilogue");
     QEB_REQUIRE(!f16 || kblk == 64, "tc fprop: the fused log-softmax head needs a multiple of 64 input channels in fp16 mode");
+    QEB_REQUIRE(x_geom.n == 1 && h_out == 1 && out.c == n_total && out.sw == n_total && ((uintptr_t)out.p & 15) == 0,
+                "tc fprop: the fused log-softmax head writes a dense (rows, classes) matrix");
   }
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
