@@ -180,6 +180,33 @@ int SideStream::wait_mark() {
   return QEB_OK;
 }
 
+namespace {
+std::vector<std::string> parse_skip() {
+  std::vector<std::string> v;
+  const char* e = getenv("QEB_DBG_SKIP");
+  if (!e) return v;
+  std::string s(e), cur;
+  for (char c : s) {
+    if (c == ',') { if (!cur.empty()) v.push_back(cur); cur.clear(); }
+    else cur.push_back(c);
+  }
+  if (!cur.empty()) v.push_back(cur);
+  return v;
+}
+const std::vector<std::string>& skip_list() {
+  static const std::vector<std::string> v = parse_skip();
+  return v;
+}
+thread_local int g_skip_flag = 0;
+}  // namespace
+bool qeb_dbg_skip_active() { return !skip_list().empty(); }
+bool qeb_dbg_skip_tag(const char* tag) {
+  for (const auto& p : skip_list())
+    if (strncmp(tag, p.c_str(), p.size()) == 0) return true;
+  return false;
+}
+int& qeb_skip_flag() { return g_skip_flag; }
+
 bool qeb_pdl_enabled() {
   static const bool on = !(getenv("QEB_PDL") && atoi(getenv("QEB_PDL")) == 0);
   return on;

@@ -53,14 +53,26 @@ void qeb_count_launch(int n = 1);
 int qeb_prof_on();
 int qeb_prof_begin(const char* tag, cudaStream_t st, double flops, double bytes);
 void qeb_prof_end(int idx, cudaStream_t st);
+// Ablation aid (abi.cu): QEB_DBG_SKIP="tag1,tag2" makes every kernel launched through qeb_launch inside a ProfScope whose
+// tag starts with one of the listed prefixes a no-op. Results are garbage; the step time that disappears is that kernel
+// family's true share of the critical path inside the CUDA-graph replay (which per-launch events cannot show). Unset: free.
+bool qeb_dbg_skip_active();
+bool qeb_dbg_skip_tag(const char* tag);
+int& qeb_skip_flag();
 struct ProfScope {
   int idx = -1;
+  int prev_skip = 0;
   cudaStream_t st;
   ProfScope(const char* tag, cudaStream_t s, double flops = 0.0, double bytes = 0.0) : st(s) {
     if (qeb_prof_on()) idx = qeb_prof_begin(tag, s, flops, bytes);
+    if (qeb_dbg_skip_active()) {
+      prev_skip = qeb_skip_flag();
+      if (qeb_dbg_skip_tag(tag)) qeb_skip_flag() = 1;
+    }
   }
   ~ProfScope() {
     if (idx >= 0) qeb_prof_end(idx, st);
+    if (qeb_dbg_skip_active()) qeb_skip_flag() = prev_skip;
   }
 };
 
@@ -85,6 +97,7 @@ inline cudaError_t qeb_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
   cfg.numAttrs = qeb_pdl_enabled() ? 1 : 0;
+  if (qeb_dbg_skip_active() && qeb_skip_flag()) return cudaSuccess;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

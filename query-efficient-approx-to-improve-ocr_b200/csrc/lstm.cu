@@ -484,6 +484,7 @@ int launch_cluster(const void* fn, size_t smem, int n_clusters, LstmArgs& args, 
   cfg.attrs = at;
   cfg.numAttrs = qeb_pdl_enabled() ? 1 : 0;
   void* kargs[] = {&args};
+  if (qeb_dbg_skip_active() && qeb_skip_flag()) return QEB_OK;
   QEB_CUDA(cudaLaunchKernelExC(&cfg, fn, kargs));
   qeb_count_launch();
   return QEB_OK;
