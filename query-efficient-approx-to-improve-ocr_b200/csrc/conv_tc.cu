@@ -21,6 +21,7 @@
 #include "nn.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace tc {
 
@@ -64,6 +65,13 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, int swizzle_32b_atom) {
   return make_tmap_any(out, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32,
                        swizzle_32b_atom ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
+// output tensor maps of the TMA-store epilogue: plain fp32 (128-byte rows of 32 channels) / fp16 (64-byte rows)
+int make_tmap_store(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool half) {
+  return make_tmap_any(out, base, rank, dims, strides_bytes, box, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                       half ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
 }
 
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -115,6 +123,14 @@ struct FpropParams {
   __half* out16;             // optional fp16 shadow of the output (same element layout as `out`): the next layer's operand
   int round_out;             // 1: fp32 stores are rounded to tf32 (the tensor is a tf32 operand of a later contraction)
   int* amax;                 // LSM kernels only (fused log-softmax head): arg-max class per output row, nullable
+  int tma_out;               // 1: the epilogue stages each 32 x 32 chunk in shared memory and a TMA store writes it (tmap_out /
+                             // tmap_out16 kernel parameters); bw / bh: the per-warp box {32 ch, bw, bh, 32 / (bw * bh)}
+  int bw, bh;
+  int epi_bytes;             // bytes of the epilogue staging area (FpropCfg::kEpiBytes, + kEpi16Bytes with an fp16 TMA store)
+};
+
+struct TmapOut {
+  CUtensorMap f32, f16;
 };
 
 struct TmapArray4 {
@@ -128,7 +144,8 @@ struct FpropCfg {
   static constexpr int kABytes = kBlockM * ROWB;
   static constexpr int kBBytes = BLOCK_N * ROWB;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kEpiBytes = 4 * 4096;   // per epilogue warp: 32 x 32 floats for the store transposition
+  static constexpr int kEpiBytes = 4 * 4096;              // per epilogue warp: 32 x 32 floats (store transposition / TMA-store staging)
+  static constexpr int kEpi16Bytes = 4 * 2048;            // + 32 x 32 halves when the kernel also writes an fp16 shadow through TMA
   // The kernel is persistent: a CTA walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with the TMA ring running
   // across tile boundaries and two TMEM accumulators, so that the epilogue of one tile overlaps the main loop of the
   // next. Narrow tiles (short main loops, epilogue-heavy) still run two CTAs per SM to double the epilogue warps.
@@ -138,16 +155,16 @@ struct FpropCfg {
   static constexpr int kMaxSmem = 227 * 1024;
   static constexpr int kSmBudget = 224 * 1024;   // what resident CTAs share: 228 KB per SM minus 1 KB reserved per CTA and slack
   static constexpr int kStatBytes = 2 * BLOCK_N * 4;   // per-CTA (sum, sum of squares) accumulators of the fused BN statistics
-  static constexpr int smem_bytes(int stages) {
-    return stages * kStageBytes + kEpiBytes + kStatBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int smem_bytes(int stages, int epi_bytes = kEpiBytes) {
+    return stages * kStageBytes + epi_bytes + kStatBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   }
   static int resident(long long n_tiles_total) {
     int r = (int)((n_tiles_total + kNumSMs - 1) / kNumSMs);
     return r > kCtasPerSm ? kCtasPerSm : (r < 1 ? 1 : r);
   }
   // every byte of shared memory the resident CTAs leave goes into ring stages
-  static int pick_stages(long long n_tiles_total) {
-    int stages = (kSmBudget / resident(n_tiles_total) - 1280 - kEpiBytes - kStatBytes) / kStageBytes;
+  static int pick_stages(long long n_tiles_total, int epi_bytes = kEpiBytes) {
+    int stages = (kSmBudget / resident(n_tiles_total) - 1280 - epi_bytes - kStatBytes) / kStageBytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
     return stages;
@@ -333,6 +350,114 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   __syncwarp();
 }
 
+// ---- TMA-store epilogue ----------------------------------------------------------------------------------------------------
+// A thread owns one accumulator row = 32 consecutive channels of one output pixel = one 128-byte row of the output tensor. The
+// warp's 32 x 32 chunk is written to shared memory exactly in the SWIZZLE_128B layout of a TMA box {32 ch, bw, bh, bn} (the
+// warp's 32 rows are such a box of the tile: rows run w-fastest) and ONE cp.async.bulk.tensor store per chunk writes it -
+// full lines, image edges clipped by the hardware. The fp16 operand shadow leaves the same way (64-byte rows, SWIZZLE_64B).
+// Against the transposing epilogue (fprop_epilogue_warp: 8 x {ld.shared, 4 shuffles, st.global} per chunk, measured
+// 3.0-3.4 k cycles per chunk) this is 8 + 4 st.shared, one fence and one instruction of one lane.
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// stg32 / stg16: this warp's staging areas (shared-window addresses, 4 KB / 2 KB, 1024-byte aligned). (w0, h0, n0): output
+// coordinates of the warp's first row. Lane 0 owns the warp's bulk-store group: it waits for the previous chunk's store to
+// have READ the staging area before anybody overwrites it.
+__device__ __forceinline__ void fprop_epilogue_tma(const FpropParams& p, const TmapOut& to, float (&v)[32], bool valid, int n, int h,
+                                                   int w, int w0, int h0, int n0, int ncol, uint32_t stg32, uint32_t stg16, int lane,
+                                                   float* cta_stats, int c0_local) {
+  if (p.scale) {
+    const float sv = __ldg(p.scale + ncol + lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= __shfl_sync(FULL_MASK, sv, j);
+  }
+  if (p.bias) {
+    const float bv = __ldg(p.bias + ncol + lane);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(FULL_MASK, bv, j);
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (p.mask) {
+    if (valid) {   // ReLU-backward mask of the layer below: this pixel's 32 channels are one 128-byte row of the mask tensor
+      const float4* mk = reinterpret_cast<const float4*>(p.mask + n * p.msn + h * p.msh + w * p.msw + ncol);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 q4 = __ldg(mk + j);
+        v[4 * j] = q4.x > 0.f ? v[4 * j] : 0.f;
+        v[4 * j + 1] = q4.y > 0.f ? v[4 * j + 1] : 0.f;
+        v[4 * j + 2] = q4.z > 0.f ? v[4 * j + 2] : 0.f;
+        v[4 * j + 3] = q4.w > 0.f ? v[4 * j + 3] : 0.f;
+      }
+    }
+  }
+  if (p.round_out) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = qeb_tf32r(v[j]);
+  }
+  if (cta_stats && !valid) {   // rows outside the image are clipped by the store but must not reach the statistics
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  if (lane == 0) tma_store_wait_read();
+  __syncwarp();
+  const uint32_t row32 = stg32 + (uint32_t)lane * 128u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) st_shared_v4(row32 + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  if (p.out16) {
+    const uint32_t row16 = stg16 + (uint32_t)lane * 64u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      st_shared_v4u(row16 + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4), pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
+                    pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+  }
+  fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_4d(&to.f32, stg32, ncol, w0, h0, n0);
+    if (p.out16) tma_store_4d(&to.f16, stg16, ncol, w0, h0, n0);
+    tma_store_commit();
+  }
+  if (cta_stats) {
+    // fused BatchNorm statistics: lane c sums column c of the staged chunk (conflict-free: a row's 32 words are distinct banks)
+    float s1 = 0.f, s2 = 0.f;
+    const uint32_t cw = (uint32_t)(lane & 3) << 2, cs = (uint32_t)(lane >> 2);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float x = ld_shared_f32(stg32 + (uint32_t)i * 128u + ((cs ^ (uint32_t)(i & 7)) << 4) + cw);
+      s1 += x;
+      s2 = fmaf(x, x, s2);
+    }
+    float* a = cta_stats + 2 * (c0_local + lane);
+    atomicAdd(a, s1);
+    atomicAdd(a + 1, s2);
+  }
+}
+
 // torch.argmax ordering: NaN counts as the largest value, the first maximal index wins (cer.cu greedy_decode_kernel)
 __device__ __forceinline__ bool lsm_gt(float a, float b) { return (a > b) || ((a != a) && !(b != b)); }
 
@@ -419,16 +544,20 @@ __device__ __forceinline__ void lsm_epilogue(const FpropParams& p, uint32_t tadd
   asm volatile("bar.sync 1, 128;" ::: "memory");   // staging tile and bias are free for the CTA's next tile
 }
 
-template <int BLOCK_N, int ROWB, bool F16, bool LSM = false>
-__global__ void __launch_bounds__(kThreads, LSM ? 1 : FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
+// EPI: which epilogue this instance carries (one per instance keeps the kernels small: the transposing epilogue alone is
+// ~1000 instructions per variant branch) - kEpiLegacy: transposition through shared memory, every epilogue feature;
+// kEpiTma: TMA-store epilogue; kEpiLsm: fused log-softmax head
+enum { kEpiLegacy = 0, kEpiTma = 1, kEpiLsm = 2 };
+template <int BLOCK_N, int ROWB, bool F16, int EPI = kEpiLegacy>
+__global__ void __launch_bounds__(kThreads, EPI == kEpiLsm ? 1 : FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
 conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
-                     const FpropParams p) {
+                     const __grid_constant__ TmapOut tmaps_o, const FpropParams p) {
   using Cfg = FpropCfg<BLOCK_N, ROWB>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* epi_stage = reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes);
-  float* cta_stats = epi_stage + Cfg::kEpiBytes / 4;   // [BLOCK_N][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kStatBytes);
+  float* cta_stats = epi_stage + p.epi_bytes / 4;   // [BLOCK_N][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes + p.epi_bytes + Cfg::kStatBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]: accumulator a holds a finished tile
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]: the epilogue has read accumulator a
@@ -444,6 +573,10 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < (p.a_map_per_tap ? 4 : 1); ++i) prefetch_tmap(&tmaps_a.m[i]);
     prefetch_tmap(&tmap_b);
+    if (EPI == kEpiTma) {
+      prefetch_tmap(&tmaps_o.f32);
+      if (p.out16) prefetch_tmap(&tmaps_o.f16);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -569,9 +702,9 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       if (tl && threadIdx.x == 64 && n_done == 0) tl[4] = clock64();
       tc_fence_after();
-      if constexpr (LSM) {
+      if constexpr (EPI == kEpiLsm) {
         lsm_epilogue<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), r, tile_m * kBlockM,
-                              reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes + Cfg::kEpiBytes + Cfg::kStatBytes + 256), cta_stats);
+                              reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes + p.epi_bytes + Cfg::kStatBytes + 256), cta_stats);
       } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -581,7 +714,17 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
           long long* tle = (tl && threadIdx.x == 64 && n_done == 0 && c0 == 0) ? tl : nullptr;
           if (tle) tle[8] = clock64();
           const int ncol = tile_n * BLOCK_N + c0;  // first GEMM-N column of this chunk
-          if (ncol < p.n_total) fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle, p.stats ? cta_stats : nullptr, c0);
+          if (ncol < p.n_total) {
+            if constexpr (EPI == kEpiTma) {
+              // first row of this warp's 32-row box: tile row 32 q
+              const int r0 = q * 32;
+              fprop_epilogue_tma(p, tmaps_o, v, valid, n, h, w, tw * p.wt + r0 % p.wt, th * p.ht + (r0 / p.wt) % p.ht,
+                                 tn * p.nt + r0 / (p.wt * p.ht), ncol, smem_u32(epi_stage) + (uint32_t)q * 4096u,
+                                 smem_u32(epi_stage) + 16384u + (uint32_t)q * 2048u, lane, p.stats ? cta_stats : nullptr, c0);
+            } else {
+              fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle, p.stats ? cta_stats : nullptr, c0);
+            }
+          }
           if (tle) tle[10] = clock64();
         }
       }
@@ -592,6 +735,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       if (acc == 0) acc_phase ^= 1;
     }
     if (p.stats && stat_n >= 0) flush_stats(stat_n);
+    if (EPI == kEpiTma && lane == 0) tma_store_wait_all();   // the staging areas must outlive the stores that read them
     if (tl && threadIdx.x == 64) tl[3] = n_done;
   }
   tc_fence_before();
@@ -600,25 +744,27 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
 
-template <int BLOCK_N, int ROWB, bool F16, bool LSM = false>
-int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const FpropParams& p_in, int m_tiles, int n_tiles, int splits,
-                 cudaStream_t st) {
+template <int BLOCK_N, int ROWB, bool F16, int EPI = kEpiLegacy>
+int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const TmapOut& to, const FpropParams& p_in, int m_tiles, int n_tiles,
+                 int splits, cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N, ROWB>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, LSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
   FpropParams p = p_in;
   const long long total = (long long)m_tiles * n_tiles * splits;
-  p.stages = Cfg::pick_stages(total);
+  p.epi_bytes = Cfg::kEpiBytes + ((p.tma_out && p.out16) ? Cfg::kEpi16Bytes : 0);
+  p.stages = Cfg::pick_stages(total, p.epi_bytes);
+  constexpr bool LSM = EPI == kEpiLsm;
   if (LSM) p.stages = min(p.stages, (Cfg::kMaxSmem - Cfg::smem_bytes(0) - kLsmStageBytes) / Cfg::kStageBytes);
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits;
   const int grid = (int)(total < (long long)kNumSMs * Cfg::resident(total) ? total : (long long)kNumSMs * Cfg::resident(total));
   ProfScope prof(LSM ? "tc_head_logsoftmax" : p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, LSM>, grid, kThreads, Cfg::smem_bytes(p.stages) + (LSM ? kLsmStageBytes : 0), st, ta, tb, p));
+  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI>, grid, kThreads, Cfg::smem_bytes(p.stages, p.epi_bytes) + (LSM ? kLsmStageBytes : 0), st, ta, tb, to, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -743,30 +889,54 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     int rc = f16 ? make_tmap_16(&tb, ep.w16, 2, dims, str, box, kblk * 2) : make_tmap_f32(&tb, wpacked, 2, dims, str, box);
     if (rc) return rc;
   }
+  // TMA-store epilogue for plain NHWC outputs with full 32-channel chunks (not: pixel shuffle, split-K reductions, +=, the
+  // fused BatchNorm-backward reductions, ragged / unaligned rows, the log-softmax head)
+  static const int allow_tma_out = getenv("QEB_TMA_STORE") ? atoi(getenv("QEB_TMA_STORE")) : 1;
+  TmapOut to;
+  memset(&to, 0, sizeof(to));
+  p.tma_out = 0; p.bw = p.bh = 1;
+  if (allow_tma_out && mode == 0 && splits == 1 && !ep.accumulate && !p.bn_scsh && p.vec_ok && n_total % 32 == 0 && !ep.log_softmax &&
+      out.sw % 4 == 0 && (!ep.out16 || out.sw % 8 == 0)) {
+    p.bw = min(p.wt, 32);
+    p.bh = min(p.ht, 32 / p.bw);
+    const int bnn = 32 / (p.bw * p.bh);
+    // a dimension of extent 1 may carry any stride in the Img (e.g. sh = 0 of the sequence-major conv7 output): give the
+    // tensor map a legal one
+    const uint64_t sw = (uint64_t)out.sw, sh = h_out > 1 ? (uint64_t)out.sh : sw * (uint64_t)w_out,
+                   sn = x_geom.n > 1 ? (uint64_t)out.sn : sh * (uint64_t)h_out;
+    const uint64_t dims[4] = {(uint64_t)n_total, (uint64_t)w_out, (uint64_t)h_out, (uint64_t)x_geom.n};
+    const uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)bnn};
+    const uint64_t str32[3] = {sw * 4, sh * 4, sn * 4};
+    const uint64_t str16[3] = {sw * 2, sh * 2, sn * 2};
+    const bool ok = sh % 4 == 0 && sn % 4 == 0 && (!ep.out16 || (sh % 8 == 0 && sn % 8 == 0));
+    if (ok && make_tmap_store(&to.f32, out.p, 4, dims, str32, box, false) == QEB_OK &&
+        (!ep.out16 || make_tmap_store(&to.f16, ep.out16, 4, dims, str16, box, true) == QEB_OK))
+      p.tma_out = 1;
+  }
   int rc;
   if (ep.log_softmax) {
-    rc = f16 ? launch_fprop<128, 128, true, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st)
-             : launch_fprop<128, 128, false, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st);
+    rc = f16 ? launch_fprop<128, 128, true, kEpiLsm>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st)
+             : launch_fprop<128, 128, false, kEpiLsm>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st);
   } else if (!f16) {
     switch (bn) {
-      case 32: rc = launch_fprop<32, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      case 64: rc = launch_fprop<64, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      case 128: rc = launch_fprop<128, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      default: rc = launch_fprop<256, 128, false>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 32: rc = p.tma_out ? launch_fprop<32, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<32, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 64: rc = p.tma_out ? launch_fprop<64, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<64, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 128: rc = p.tma_out ? launch_fprop<128, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<128, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      default: rc = p.tma_out ? launch_fprop<256, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<256, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
     }
   } else if (kblk == 64) {
     switch (bn) {
-      case 32: rc = launch_fprop<32, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      case 64: rc = launch_fprop<64, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      case 128: rc = launch_fprop<128, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      default: rc = launch_fprop<256, 128, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 32: rc = p.tma_out ? launch_fprop<32, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<32, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 64: rc = p.tma_out ? launch_fprop<64, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<64, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 128: rc = p.tma_out ? launch_fprop<128, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<128, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      default: rc = p.tma_out ? launch_fprop<256, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<256, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
     }
   } else {
     switch (bn) {
-      case 32: rc = launch_fprop<32, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      case 64: rc = launch_fprop<64, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      case 128: rc = launch_fprop<128, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
-      default: rc = launch_fprop<256, 64, true>(ta_in, tb, p, m_tiles, n_tiles, splits, st); break;
+      case 32: rc = p.tma_out ? launch_fprop<32, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<32, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 64: rc = p.tma_out ? launch_fprop<64, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<64, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 128: rc = p.tma_out ? launch_fprop<128, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<128, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      default: rc = p.tma_out ? launch_fprop<256, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<256, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
     }
   }
   if (rc == QEB_OK && ep.bn_stats && !stats_fused) rc = bn_train_stats(out, ep.bn_stats, st);   // separate pass over the output

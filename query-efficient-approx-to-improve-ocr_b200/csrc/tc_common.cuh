@@ -152,5 +152,8 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 // the same for 2-byte elements (fp16 / bf16 share the encoding): row_bytes = 128 (SWIZZLE_128B) or 64 (SWIZZLE_64B)
 int make_tmap_16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                  const uint32_t* box, int row_bytes);
+// store-side map of an fp32 (SWIZZLE_128B, 128-byte inner box) or fp16 (SWIZZLE_64B, 64-byte inner box) NHWC tensor
+int make_tmap_store(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, bool half);
 
 }  // namespace tc
