@@ -92,6 +92,7 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 32;                     // fp32 elements = 128 bytes = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 4;  // 16 KB
 constexpr int kThreads = 192;
+constexpr int kBarBytes = 512;   // mbarrier area: full / empty per stage, full / empty per accumulator, weights, TMEM slot
 
 struct FpropParams {
   int n_img, h_out, w_out;
@@ -126,6 +127,7 @@ struct FpropParams {
   int tma_out;               // 1: the epilogue stages each 32 x 32 chunk in shared memory and a TMA store writes it (tmap_out /
                              // tmap_out16 kernel parameters); bw / bh: the per-warp box {32 ch, bw, bh, 32 / (bw * bh)}
   int bw, bh;
+  int win_bytes, w_bytes;    // WIN kernels: bytes of one window stage (180 operand rows, 1 KB aligned) / of the resident weight area
   int epi_bytes;             // bytes of the epilogue staging area (FpropCfg::kEpiBytes, + kEpi16Bytes with an fp16 TMA store)
 };
 
@@ -156,7 +158,7 @@ struct FpropCfg {
   static constexpr int kSmBudget = 224 * 1024;   // what resident CTAs share: 228 KB per SM minus 1 KB reserved per CTA and slack
   static constexpr int kStatBytes = 2 * BLOCK_N * 4;   // per-CTA (sum, sum of squares) accumulators of the fused BN statistics
   static constexpr int smem_bytes(int stages, int epi_bytes = kEpiBytes) {
-    return stages * kStageBytes + epi_bytes + kStatBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    return stages * kStageBytes + epi_bytes + kStatBytes + 1024 /*align slack*/ + kBarBytes;
   }
   static int resident(long long n_tiles_total) {
     int r = (int)((n_tiles_total + kNumSMs - 1) / kNumSMs);
@@ -548,20 +550,52 @@ __device__ __forceinline__ void lsm_epilogue(const FpropParams& p, uint32_t tadd
 // ~1000 instructions per variant branch) - kEpiLegacy: transposition through shared memory, every epilogue feature;
 // kEpiTma: TMA-store epilogue; kEpiLsm: fused log-softmax head
 enum { kEpiLegacy = 0, kEpiTma = 1, kEpiLsm = 2 };
-template <int BLOCK_N, int ROWB, bool F16, int EPI = kEpiLegacy>
-__global__ void __launch_bounds__(kThreads, EPI == kEpiLsm ? 1 : FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
+// WIN ("window" variant, 3x3 pad-1 convolutions on images of at least 16 rows): the kernel above loads the tap-shifted
+// 128-pixel tile once per filter tap, i.e. 9 x 128 operand rows per tile and channel slice - and the TMA unit retires a box
+// at ~3.4 cycles per ROW whatever its width (measured: 32 -> 32 and 64 -> 32 channels at 32 x 128 take the same 29 us of
+// main loop with half / all of the bytes), so the few-channel full-resolution layers are bound by TMA rows, not by bytes,
+// L2 or the tensor pipe. Here a tile is 8 x 16 output pixels and ONE box {channels, 8 + 2, 16 + 2} - the tile with its halo,
+// zero padding by TMA's out-of-bounds fill - lands per channel slice: 180 rows instead of 1152. A tap (dy, dx) is the same
+// window read from row (dy + 1) * 10 + (dx + 1) on: tile row hh (8 pixels = one 8-row core-matrix group) starts 10 window
+// rows after tile row hh - 1, which is exactly what the shared-memory descriptor's stride-byte-offset expresses (SBO =
+// 10 rows instead of 8), and the swizzle is a function of absolute shared-memory address bits, so a descriptor may start at
+// any row. The nine weight tiles of every channel slice stay RESIDENT in shared memory for all tiles of a CTA.
+constexpr int kWinW = 8, kWinH = 16, kWinRows = (kWinW + 2) * (kWinH + 2);
+
+// WIN kernels run one CTA per SM and are epilogue-bound on the few-channel layers (measured 1.3-1.8 k cycles of epilogue per
+// 128 x 32 tile against ~1 k of everything else): they carry TWO epilogue warpgroups, group g draining accumulator g, i.e.
+// every other tile, with its own staging and statistics areas.
+template <bool WIN>
+constexpr int fprop_threads() { return WIN ? 64 + 2 * 128 : kThreads; }
+// Accumulators of a WIN kernel: kAccs of BLOCK_N columns, the MMA warp works on kAccs / 2 tiles at a time, tap by tap across
+// the batch (independent accumulators back to back, one shared weight descriptor). Measured with 8 accumulators / batches
+// of 4: no gain (32 -> 32 at 32 x 128: 21.7 -> 22.8 us) - the narrow tiles are bound by the tensor core's shared-memory
+// operand reads (every 128 x 32 x 16 MMA re-reads 4 KB of the window for 16 cycles of tensor work), not by the latency of
+// dependent accumulations - so the default is the plain double buffer (2 accumulators, batches of 1).
+template <int BLOCK_N>
+constexpr int win_accs() { return 2; }
+
+template <int BLOCK_N, int ROWB, bool F16, int EPI = kEpiLegacy, bool WIN = false>
+__global__ void __launch_bounds__(fprop_threads<WIN>(), (EPI == kEpiLsm || WIN) ? 1 : FpropCfg<BLOCK_N, ROWB>::kCtasPerSm)
 conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ TmapOut tmaps_o, const FpropParams p) {
   using Cfg = FpropCfg<BLOCK_N, ROWB>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* epi_stage = reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes);
-  float* cta_stats = epi_stage + p.epi_bytes / 4;   // [BLOCK_N][2]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes + p.epi_bytes + Cfg::kStatBytes);
+  uint8_t* smem_all = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_all + (WIN ? p.w_bytes : 0);   // the operand ring; WIN: the resident weight tiles come first
+  const int stage_bytes = WIN ? p.win_bytes : Cfg::kStageBytes;
+  constexpr int kGroups = WIN ? 2 : 1;              // epilogue warpgroups
+  float* epi_stage = reinterpret_cast<float*>(smem + p.stages * stage_bytes);   // kGroups areas of p.epi_bytes
+  float* cta_stats = epi_stage + kGroups * p.epi_bytes / 4;   // kGroups x [BLOCK_N][2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes + kGroups * (p.epi_bytes + Cfg::kStatBytes));
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]: accumulator a holds a finished tile
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]: the epilogue has read accumulator a
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  constexpr int kAccs = WIN ? win_accs<BLOCK_N>() : 2;   // TMEM accumulators of BLOCK_N columns
+  constexpr int kBatch = kAccs / 2;                      // WIN: tiles the MMA warp interleaves
+  uint64_t* tmem_full_bar = empty_bar + p.stages;        // [kAccs]: accumulator a holds a finished tile
+  uint64_t* tmem_empty_bar = tmem_full_bar + kAccs;      // [kAccs]: the epilogue has read accumulator a
+  uint64_t* w_full_bar = tmem_empty_bar + kAccs;         // WIN: the weight tiles of the current N tile have landed
+  uint64_t* w_empty_bar = w_full_bar + 1;           // WIN: every MMA that reads the current weight tiles has completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_empty_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.kh * p.kw * p.kchunks;
@@ -581,14 +615,16 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kAccs; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);   // every epilogue thread arrives
+      mbar_init(&tmem_empty_bar[a], 128);   // every epilogue thread of the group that drains it arrives
     }
+    mbar_init(w_full_bar, 1);
+    mbar_init(w_empty_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, Cfg::kTmemCols);
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kThreads) cta_stats[i] = 0.f;
+  if (warp == 1) tmem_alloc(tmem_slot, kAccs * BLOCK_N);
+  for (int i = threadIdx.x; i < (WIN ? 4 : 2) * BLOCK_N; i += fprop_threads<WIN>()) cta_stats[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -602,6 +638,44 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     // every TMA / MMA instruction in an ELECT + R2UR + BRA.U.ANY lane loop (~60 cycles per instruction) =====
     int stage = 0;
     uint32_t phase = 0;
+    if constexpr (WIN) {
+      int cur_n = -1;
+      uint32_t w_phase = 0;
+      const int G = min(kBatch, p.stages);
+      int t = blockIdx.x;
+      while (t < total_tiles) {
+        // a batch: up to G consecutive tiles of this CTA that share the N tile (= the resident weights)
+        const int tile_n = t / p.m_tiles;
+        int nb = 1;
+        while (nb < G && t + nb * (int)gridDim.x < total_tiles && (t + nb * (int)gridDim.x) / p.m_tiles == tile_n) ++nb;
+        if (tile_n != cur_n) {   // (re)load the 9 x kchunks weight tiles of this N tile
+          if (cur_n >= 0) { mbar_wait(w_empty_bar, w_phase); w_phase ^= 1; }
+          if (elect_one()) {
+            mbar_expect_tx(w_full_bar, (uint32_t)(9 * p.kchunks * BLOCK_N * ROWB));
+            for (int i = 0; i < 9 * p.kchunks; ++i) {
+              const int kc = i / 9, tap = i - kc * 9;
+              tma_load_2d(smem_all + (size_t)i * BLOCK_N * ROWB, &tmap_b, w_full_bar, tap * p.cin + kc * p.kblk, tile_n * BLOCK_N);
+            }
+          }
+          __syncwarp();
+          cur_n = tile_n;
+        }
+        for (int kc = 0; kc < p.kchunks; ++kc) {      // channel slice by channel slice across the batch (the MMA warp's order)
+          for (int g = 0; g < nb; ++g) {
+            const int tile_m = t + g * (int)gridDim.x - tile_n * p.m_tiles;
+            const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (elect_one()) {
+              mbar_expect_tx(&full_bar[stage], (uint32_t)(kWinRows * ROWB));
+              tma_load_4d(smem + stage * stage_bytes, &tmaps_a.m[0], &full_bar[stage], kc * p.kblk, tw * kWinW - 1, th * kWinH - 1, tn);
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        t += nb * (int)gridDim.x;
+      }
+    } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int z = t / mn_tiles, r = t - z * mn_tiles;
       const int tile_n = r / p.m_tiles, tile_m = r - tile_n * p.m_tiles;
@@ -635,6 +709,82 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     constexpr uint32_t idesc = F16 ? instr_desc_f16(kBlockM, BLOCK_N, 0, 0) : instr_desc_tf32(kBlockM, BLOCK_N, 0, 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
+    if constexpr (WIN) {
+      int cur_n = -1;
+      uint32_t w_phase = 0;
+      constexpr uint64_t kSwz = ROWB == 128 ? (2ull << 61) : (4ull << 61);
+      // window operand: 8-row groups (one tile row) 10 operand rows apart; weight tiles: dense 8-row groups
+      constexpr uint64_t kDescA = (1ull << 16) | ((uint64_t)((10 * ROWB) >> 4) << 32) | (1ull << 46) | kSwz;
+      constexpr uint64_t kDescB = (1ull << 16) | ((uint64_t)((8 * ROWB) >> 4) << 32) | (1ull << 46) | kSwz;
+      const int G = min(kBatch, p.stages);
+      const uint32_t wbase = smem_u32(smem_all);
+      int t = blockIdx.x, i_tile = 0;   // i_tile: running tile index of this CTA -> accumulator i_tile % kAccs
+      while (t < total_tiles) {
+        const int tile_n = t / p.m_tiles;
+        int nb = 1;
+        while (nb < G && t + nb * (int)gridDim.x < total_tiles && (t + nb * (int)gridDim.x) / p.m_tiles == tile_n) ++nb;
+        if (tile_n != cur_n) { mbar_wait(w_full_bar, w_phase); w_phase ^= 1; cur_n = tile_n; }
+        long long c0 = tl ? clock64() : 0;
+        uint32_t td[kBatch];
+#pragma unroll
+        for (int g = 0; g < kBatch; ++g) {
+          const int it = i_tile + g, a = it % kAccs;
+          td[g] = tmem_base + (uint32_t)(a * BLOCK_N);
+          if (g < nb) mbar_wait(&tmem_empty_bar[a], (uint32_t)(((it / kAccs) & 1) ^ 1));   // drained kAccs tiles ago
+        }
+        if (tl && lane == 0) tl[14] += clock64() - c0;     // waiting for the epilogue to drain accumulators
+        tc_fence_after();
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          uint32_t sa[kBatch];
+          int st_idx[kBatch];
+          c0 = tl ? clock64() : 0;
+#pragma unroll
+          for (int g = 0; g < kBatch; ++g) {
+            st_idx[g] = stage;
+            sa[g] = smem_u32(smem + stage * stage_bytes);
+            if (g < nb) {
+              mbar_wait(&full_bar[stage], phase);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+          }
+          if (tl && lane == 0) tl[13] += clock64() - c0;   // waiting for windows to land
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t aoff = (uint32_t)((tap / 3) * (kWinW + 2) + tap % 3) * ROWB;
+              const uint64_t bdesc = kDescB | (uint64_t)(((wbase + (uint32_t)((kc * 9 + tap) * BLOCK_N * ROWB)) >> 4) & 0x3FFF);
+#pragma unroll
+              for (int k = 0; k < ROWB / 32; ++k) {
+#pragma unroll
+                for (int g = 0; g < kBatch; ++g) {
+                  if (g < nb) {
+                    const uint64_t adesc = kDescA | (uint64_t)(((sa[g] + aoff) >> 4) & 0x3FFF);
+                    if (F16) mma_f16_ss(td[g], adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
+                    else mma_tf32_ss(td[g], adesc + 2 * k, bdesc + 2 * k, idesc, (kc | tap | k) != 0);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < kBatch; ++g)
+              if (g < nb) mma_commit(&empty_bar[st_idx[g]]);
+          }
+          __syncwarp();
+        }
+        const int t_next = t + nb * (int)gridDim.x;
+        if (elect_one()) {
+#pragma unroll
+          for (int g = 0; g < kBatch; ++g)
+            if (g < nb) mma_commit(&tmem_full_bar[(i_tile + g) % kAccs]);
+          // the weight tiles may be replaced once these MMAs have retired
+          if (t_next < total_tiles && t_next / p.m_tiles != tile_n) mma_commit(w_empty_bar);
+        }
+        __syncwarp();
+        i_tile += nb;
+        t = t_next;
+      }
+    } else
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int z = t / mn_tiles;
       const int kb_begin = z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
@@ -666,30 +816,40 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       if (acc == 0) acc_phase ^= 1;
     }
   } else {
-    // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+    // ===== epilogue: warps 2..5 (WIN: and 6..9, group 1), TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
+    const int grp = WIN ? (warp - 2) >> 2 : 0;   // group g drains accumulator g = the tiles with (index within the CTA) % 2 == g
+    float* const epi_stage_g = epi_stage + grp * (p.epi_bytes / 4);
+    float* const cta_stats_g = cta_stats + grp * 2 * BLOCK_N;
+    const int gtid = (int)threadIdx.x - 64 - grp * 128;   // 0..127 inside the group
     const int r = q * 32 + lane;  // row of the tile = TMEM lane
     const int ww = r % p.wt, hh = (r / p.wt) % p.ht, nn = r / (p.wt * p.ht);
     int acc = 0;
     uint32_t acc_phase = 0;
-    int n_done = 0;
+    int n_done = 0, n_seen = 0;
     // fused BatchNorm statistics: the four epilogue warps add into shared-memory accumulators; they are flushed to global
     // memory (one double atomic per channel and CTA) when the CTA moves to another N tile and at the end
     int stat_n = -1;
+    auto group_sync = [&]() {
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      else asm volatile("bar.sync 2, 128;" ::: "memory");
+    };
     auto flush_stats = [&](int tn) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) {
+      group_sync();
+      for (int c = gtid; c < BLOCK_N; c += 128) {
         const int col = tn * BLOCK_N + c;
         if (col < p.n_total) {
-          atomicAdd(p.stats + col, (double)cta_stats[2 * c]);
-          atomicAdd(p.stats + p.n_total + col, (double)cta_stats[2 * c + 1]);
+          atomicAdd(p.stats + col, (double)cta_stats_g[2 * c]);
+          atomicAdd(p.stats + p.n_total + col, (double)cta_stats_g[2 * c + 1]);
         }
-        cta_stats[2 * c] = 0.f;
-        cta_stats[2 * c + 1] = 0.f;
+        cta_stats_g[2 * c] = 0.f;
+        cta_stats_g[2 * c + 1] = 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      group_sync();
     };
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_done) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_seen) {
+      if (WIN && (n_seen & 1) != grp) continue;   // the other group's tile
+      if (WIN) { acc = n_seen % kAccs; acc_phase = (uint32_t)((n_seen / kAccs) & 1); }
       const int z = t / mn_tiles, rr = t - z * mn_tiles;
       const int tile_n = rr / p.m_tiles, tile_m = rr - tile_n * p.m_tiles;
       if (p.stats && tile_n != stat_n) {
@@ -699,12 +859,15 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
       const int w = tw * p.wt + ww, h = th * p.ht + hh, n = tn * p.nt + nn;
       const bool valid = (w < p.w_out) && (h < p.h_out) && (n < p.n_img);
+      const long long e0 = tl ? clock64() : 0;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
+      const long long e1 = tl ? clock64() : 0;
+      if (tl && threadIdx.x == 64) tl[11] += e1 - e0;       // epilogue warp waiting for a finished accumulator
       if (tl && threadIdx.x == 64 && n_done == 0) tl[4] = clock64();
       tc_fence_after();
       if constexpr (EPI == kEpiLsm) {
         lsm_epilogue<BLOCK_N>(p, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N), r, tile_m * kBlockM,
-                              reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes + p.epi_bytes + Cfg::kStatBytes + 256), cta_stats);
+                              reinterpret_cast<float*>(smem + p.stages * Cfg::kStageBytes + p.epi_bytes + Cfg::kStatBytes + kBarBytes), cta_stats);
       } else {
 #pragma unroll 1
         for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -719,10 +882,10 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
               // first row of this warp's 32-row box: tile row 32 q
               const int r0 = q * 32;
               fprop_epilogue_tma(p, tmaps_o, v, valid, n, h, w, tw * p.wt + r0 % p.wt, th * p.ht + (r0 / p.wt) % p.ht,
-                                 tn * p.nt + r0 / (p.wt * p.ht), ncol, smem_u32(epi_stage) + (uint32_t)q * 4096u,
-                                 smem_u32(epi_stage) + 16384u + (uint32_t)q * 2048u, lane, p.stats ? cta_stats : nullptr, c0);
+                                 tn * p.nt + r0 / (p.wt * p.ht), ncol, smem_u32(epi_stage_g) + (uint32_t)q * 4096u,
+                                 smem_u32(epi_stage_g) + 16384u + (uint32_t)q * 2048u, lane, p.stats ? cta_stats_g : nullptr, c0);
             } else {
-              fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage + q * 1024, lane, tle, p.stats ? cta_stats : nullptr, c0);
+              fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage_g + q * 1024, lane, tle, p.stats ? cta_stats_g : nullptr, c0);
             }
           }
           if (tle) tle[10] = clock64();
@@ -730,9 +893,13 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[acc]);
+      if (tl && threadIdx.x == 64) tl[12] += clock64() - e1;   // epilogue body
       if (tl && threadIdx.x == 64 && n_done == 0) tl[5] = clock64();
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      ++n_done;
+      if (!WIN) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
     if (p.stats && stat_n >= 0) flush_stats(stat_n);
     if (EPI == kEpiTma && lane == 0) tma_store_wait_all();   // the staging areas must outlive the stores that read them
@@ -740,17 +907,17 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, kAccs * BLOCK_N);
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
 
-template <int BLOCK_N, int ROWB, bool F16, int EPI = kEpiLegacy>
+template <int BLOCK_N, int ROWB, bool F16, int EPI = kEpiLegacy, bool WIN = false>
 int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const TmapOut& to, const FpropParams& p_in, int m_tiles, int n_tiles,
                  int splits, cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N, ROWB>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    QEB_CUDA(cudaFuncSetAttribute(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI, WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
   FpropParams p = p_in;
@@ -759,12 +926,23 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const TmapOut& to,
   p.stages = Cfg::pick_stages(total, p.epi_bytes);
   constexpr bool LSM = EPI == kEpiLsm;
   if (LSM) p.stages = min(p.stages, (Cfg::kMaxSmem - Cfg::smem_bytes(0) - kLsmStageBytes) / Cfg::kStageBytes);
+  int smem_total = Cfg::smem_bytes(p.stages, p.epi_bytes) + (LSM ? kLsmStageBytes : 0);
+  int resident = Cfg::resident(total);
+  if (WIN) {   // one CTA per SM: resident weights + as many window stages as fit (<= 8)
+    p.win_bytes = (kWinRows * ROWB + 1023) & ~1023;
+    p.w_bytes = 9 * p.kchunks * BLOCK_N * ROWB;
+    const int fixed = p.w_bytes + 2 * (p.epi_bytes + Cfg::kStatBytes) + 1024 + kBarBytes;   // two epilogue groups
+    p.stages = min(8, (Cfg::kMaxSmem - fixed) / p.win_bytes);
+    QEB_REQUIRE(p.stages >= 2, "tc fprop (window): weights of %d bytes leave no room for two window stages", p.w_bytes);
+    smem_total = fixed + p.stages * p.win_bytes;
+    resident = 1;
+  }
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits;
-  const int grid = (int)(total < (long long)kNumSMs * Cfg::resident(total) ? total : (long long)kNumSMs * Cfg::resident(total));
+  const int grid = (int)(total < (long long)kNumSMs * resident ? total : (long long)kNumSMs * resident);
   ProfScope prof(LSM ? "tc_head_logsoftmax" : p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI>, grid, kThreads, Cfg::smem_bytes(p.stages, p.epi_bytes) + (LSM ? kLsmStageBytes : 0), st, ta, tb, to, p));
+  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI, WIN>, grid, fprop_threads<WIN>(), smem_total, st, ta, tb, to, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -795,16 +973,36 @@ int tmap_img16(CUtensorMap* out, const Img& a, const void* base16, const uint32_
 inline int kblk16(int cin) { return cin % 64 == 0 ? 64 : 32; }
 inline bool strides_ok16(const Img& a) { return a.sn % 8 == 0 && a.sh % 8 == 0 && a.sw % 8 == 0; }
 
+// window variant (conv_fprop_tc_kernel<..., WIN>): bytes the resident weight tiles may take so that three window stages, the
+// epilogue staging and the barriers still fit into one CTA's shared memory
+inline int win_weight_budget(int rowb) {
+  const int win_bytes = (kWinRows * rowb + 1023) & ~1023;
+  return 227 * 1024 - 4 * win_bytes - 2 * (4 * 4096 + 4 * 2048) - 2 * 2 * 128 * 4 - 1024 - kBarBytes;
+}
+// 3x3 pad-1 convolution on an image of >= 16 rows whose weights fit (at the narrowest N tile)
+// ... and with enough 8 x 16 tiles for the one-CTA-per-SM grid to balance (>= 7 per CTA). Measured in the step (per launch,
+// window vs per-tap loads): 32 x 128 images 36.0 -> 28.8 us (32 -> 32 channels), 40.7 -> 34.1 us (64 -> 32); 16 x 64 images (512
+// tiles, 3.5 per CTA) 30.2 -> 34.3 us: those stay on the per-tap kernel. QEB_WIN=0 switches the variant off, =2 drops the
+// tile-count condition.
+inline bool win_eligible(int kh, int kw, int ph, int pw, int n_img, int h_out, int w_out, int cin, int kblk, int rowb) {
+  static const int allow = getenv("QEB_WIN") ? atoi(getenv("QEB_WIN")) : 1;
+  const long long tiles = (long long)n_img * qeb_cdiv(h_out, kWinH) * qeb_cdiv(w_out, kWinW);
+  return allow && kh == 3 && kw == 3 && ph == 1 && pw == 1 && h_out >= kWinH && w_out >= kWinW &&
+         (allow == 2 || tiles >= 7 * kNumSMs) && 9 * (cin / kblk) * 32 * rowb <= win_weight_budget(rowb);
+}
+
 // shared driver of the three K-major entry points. a_maps: number of A tensor maps already encoded in ta (1 or 4).
 // f16: the A maps in ta_in describe the fp16 shadow (K block = kblk16(cin) elements) and ep.w16 holds the fp16 weights
 int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const float* wpacked, int n_total, int kh,
                  int kw, int ph, int pw, int cin, const Img& out, int h_out, int w_out, const TcEpilogue& ep, int mode,
-                 int up_c, const float* bias, cudaStream_t st, bool f16 = false) {
+                 int up_c, const float* bias, cudaStream_t st, bool f16 = false, bool win = false) {
   FpropParams p;
   p.n_img = x_geom.n; p.h_out = h_out; p.w_out = w_out;
   p.wt = min(pow2_ceil(w_out), kBlockM);
   p.ht = min(pow2_ceil(h_out), kBlockM / p.wt);
   p.nt = kBlockM / (p.wt * p.ht);
+  if (win) { p.wt = kWinW; p.ht = kWinH; p.nt = 1; }   // window variant: 8 x 16 pixel tiles (the A map's box is the tile + halo)
+  p.win_bytes = p.w_bytes = 0;
   p.tiles_w = qeb_cdiv(w_out, p.wt);
   p.tiles_h = qeb_cdiv(h_out, p.ht);
   const int m_tiles = p.tiles_w * p.tiles_h * qeb_cdiv(x_geom.n, p.nt);
@@ -851,12 +1049,18 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   // epilogue the K range is split instead and the partial sums are reduced into a zero-filled output.
   const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && !ep.round_out && mode == 0 && p.vec_ok && n_total % 32 == 0 &&
                      out.c == n_total && out.sw == n_total && img_flat(out);
-  if (allow_split && plain && (long long)m_tiles * qeb_cdiv(n_total, bn_max) * 2 <= min_ctas && num_kb >= 16) {
+  if (allow_split && !win && plain && (long long)m_tiles * qeb_cdiv(n_total, bn_max) * 2 <= min_ctas && num_kb >= 16) {
     // round DOWN: tiles beyond one per SM would make a few CTAs walk two tiles while the rest idle
     splits = min(num_kb / 8, min_ctas / (m_tiles * qeb_cdiv(n_total, bn_max)));
     if (splits < 1) splits = 1;
   }
-  if (ep.log_softmax) {
+  if (win) {
+    // widest N tile whose nine weight tiles per channel slice stay resident beside >= 3 window stages, narrowed to fill the SMs
+    splits = 1;
+    const int rowb = kblk * (f16 ? 2 : 4);
+    bn = min(128, bn_max);
+    while (bn > 32 && (9 * (cin / kblk) * bn * rowb > win_weight_budget(rowb) || (long long)m_tiles * qeb_cdiv(n_total, bn) < min_ctas)) bn >>= 1;
+  } else if (ep.log_softmax) {
     bn = 128; splits = 1;   // every class of a row in ONE accumulator row
   } else if (splits == 1) {
     while (bn > 32 && (long long)m_tiles * qeb_cdiv(n_total, bn) < min_ctas) bn >>= 1;
@@ -914,31 +1118,41 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
       p.tma_out = 1;
   }
   int rc;
+#define QEB_FPROP_CASE(BN, RB, F)                                                                                                      \
+  rc = win ? (p.tma_out ? launch_fprop<BN, RB, F, kEpiTma, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st)                        \
+                        : launch_fprop<BN, RB, F, kEpiLegacy, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st))                    \
+           : (p.tma_out ? launch_fprop<BN, RB, F, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st)                              \
+                        : launch_fprop<BN, RB, F>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st))
+#define QEB_FPROP_CASE_NOWIN(BN, RB, F)                                                                                                \
+  rc = p.tma_out ? launch_fprop<BN, RB, F, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st)                                     \
+                 : launch_fprop<BN, RB, F>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st)
   if (ep.log_softmax) {
     rc = f16 ? launch_fprop<128, 128, true, kEpiLsm>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st)
              : launch_fprop<128, 128, false, kEpiLsm>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st);
   } else if (!f16) {
     switch (bn) {
-      case 32: rc = p.tma_out ? launch_fprop<32, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<32, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      case 64: rc = p.tma_out ? launch_fprop<64, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<64, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      case 128: rc = p.tma_out ? launch_fprop<128, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<128, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      default: rc = p.tma_out ? launch_fprop<256, 128, false, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<256, 128, false>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 32: QEB_FPROP_CASE(32, 128, false); break;
+      case 64: QEB_FPROP_CASE(64, 128, false); break;
+      case 128: QEB_FPROP_CASE(128, 128, false); break;
+      default: QEB_FPROP_CASE_NOWIN(256, 128, false); break;
     }
   } else if (kblk == 64) {
     switch (bn) {
-      case 32: rc = p.tma_out ? launch_fprop<32, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<32, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      case 64: rc = p.tma_out ? launch_fprop<64, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<64, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      case 128: rc = p.tma_out ? launch_fprop<128, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<128, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      default: rc = p.tma_out ? launch_fprop<256, 128, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<256, 128, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 32: QEB_FPROP_CASE(32, 128, true); break;
+      case 64: QEB_FPROP_CASE(64, 128, true); break;
+      case 128: QEB_FPROP_CASE(128, 128, true); break;
+      default: QEB_FPROP_CASE_NOWIN(256, 128, true); break;
     }
   } else {
     switch (bn) {
-      case 32: rc = p.tma_out ? launch_fprop<32, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<32, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      case 64: rc = p.tma_out ? launch_fprop<64, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<64, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      case 128: rc = p.tma_out ? launch_fprop<128, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<128, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
-      default: rc = p.tma_out ? launch_fprop<256, 64, true, kEpiTma>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st) : launch_fprop<256, 64, true>(ta_in, tb, to, p, m_tiles, n_tiles, splits, st); break;
+      case 32: QEB_FPROP_CASE(32, 64, true); break;
+      case 64: QEB_FPROP_CASE(64, 64, true); break;
+      case 128: QEB_FPROP_CASE(128, 64, true); break;
+      default: QEB_FPROP_CASE_NOWIN(256, 64, true); break;
     }
   }
+#undef QEB_FPROP_CASE
+#undef QEB_FPROP_CASE_NOWIN
   if (rc == QEB_OK && ep.bn_stats && !stats_fused) rc = bn_train_stats(out, ep.bn_stats, st);   // separate pass over the output
   return rc;
 }
@@ -967,9 +1181,11 @@ int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int k
   fprop_box(out.h, out.w, box);
   const bool f16 = ep.in16 && ep.w16 && strides_ok16(x);
   if (f16) box[0] = kblk16(x.c);
+  const bool win = !ep.log_softmax && win_eligible(kh, kw, ph, pw, x.n, out.h, out.w, x.c, (int)box[0], (int)box[0] * (f16 ? 2 : 4));
+  if (win) { box[1] = kWinW + 2; box[2] = kWinH + 2; box[3] = 1; }   // the tile with its halo
   int rc = f16 ? tmap_img16(&ta.m[0], x, ep.in16, box) : tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
   if (rc) return rc;
-  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st, f16);
+  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st, f16, win);
 }
 
 int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st,

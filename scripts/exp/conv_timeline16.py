@@ -37,4 +37,4 @@ for (N, H, W, Cin, Cout) in SHAPES:
         tot = t[:, 6] - t[:, 0]
         print(f"{N}x{H}x{W} {Cin}->{Cout} {name:22s} {us:7.1f} us {gf/us*1e-3*1e3:7.1f} TF/s | CTAs {len(t):4d} tiles/CTA {t[:,3].mean():5.1f} "
               f"setup {np.mean(t[:,1]-t[:,0]):6.0f} first-stage {np.mean(t[:,2]-t[:,1]):6.0f} tile0: mainloop {np.mean(t[:,4]-t[:,2]):6.0f} epilogue {np.mean(t[:,5]-t[:,4]):6.0f} "
-              f"(ld {np.mean(t[:,8]-t[:,4]):5.0f} st.sh {np.mean(t[:,9]-t[:,8]):5.0f} out {np.mean(t[:,10]-t[:,9]):5.0f}) CTA total {tot.mean():7.0f} cyc/tile {np.mean(tot/np.maximum(t[:,3],1)):6.0f}")
+              f"(ld {np.mean(t[:,8]-t[:,4]):5.0f} st.sh {np.mean(t[:,9]-t[:,8]):5.0f} out {np.mean(t[:,10]-t[:,9]):5.0f}) CTA total {tot.mean():7.0f} cyc/tile {np.mean(tot/np.maximum(t[:,3],1)):6.0f} | per CTA: epi-wait {t[:,11].mean():7.0f} epi-body {t[:,12].mean():7.0f} mma-wait-window {t[:,13].mean():7.0f} mma-wait-acc {t[:,14].mean():7.0f}")

@@ -72,6 +72,8 @@ def st():
     (12, 32, 128, 64, 32, 3, 1, 0),     # two channel slices, 65-wide N overhang none
     (40, 16, 64, 32, 64, 3, 1, 1),      # two N tiles, W = 64
     (70, 10, 40, 64, 64, 3, 1, 0),      # odd geometry (last tile of every image is partial)
+    (64, 32, 128, 32, 32, 3, 1, 1),     # UNet level 1 at the bench batch: the WINDOW variant (>= 7 tiles of 8 x 16 per SM)
+    (2, 200, 520, 64, 32, 3, 1, 0),     # window variant, partial tiles at the bottom edge, two channel-slice weight sets
 ])
 def test_conv_fprop_dgrad_wgrad_tc(q, N, H, W, Cin, Cout, k, p, relu):
     g = torch.Generator(device=DEV).manual_seed(N * 1000 + Cin + Cout)
@@ -579,6 +581,9 @@ def test_validation_batch_matches_reference_loop(q):
     (2, 2, 31, 512, 512, 2, 0, 0),      # conv7 geometry (2x2, no padding)
     (1, 1, 1984, 512, 2048, 1, 0, 0),   # LSTM input projection
     (3, 5, 7, 96, 64, 3, 1, 1),         # 96 channels: not a multiple of 64 -> 32-element K blocks; ragged tiles
+    (64, 32, 128, 32, 32, 3, 1, 1),     # window variant, 64-byte operand rows (SWIZZLE_64B window)
+    (64, 32, 128, 64, 32, 3, 1, 0),     # window variant, 128-byte operand rows
+    (1, 400, 512, 32, 64, 3, 1, 1),     # window variant on a document-sized image, two N tiles... one CTA walks both
 ])
 def test_conv_fprop_fp16_operands(q, N, H, W, Cin, Cout, k, p, relu):
     """kind::f16 operand path of the fprop kernel (forward pass): exact on fp16-representable inputs up to fp32 accumulation
@@ -615,3 +620,15 @@ def test_fp16_shadow_saturates(q):
                out.data_ptr(), C, out16.data_ptr(), st())
     assert torch.allclose(out, torch.full_like(out, 1.92e6))
     assert torch.isfinite(out16).all() and float(out16.max()) == 65504.0
+
+
+def test_window_variant_on_every_conv_shape():
+    """The window variant of the conv kernel is chosen only for images with many 8 x 16 tiles; QEB_WIN=2 drops that
+    condition, so that every 3x3 pad-1 shape of the parametrised conv tests above (small batches, ragged tiles, N tile
+    changes inside a CTA, channel slices of wider buffers) runs through it. The switch is read once per process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, QEB_WIN="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
+                        "conv_fprop or channel_slices or unet_vs_oracle or crnn_vs_oracle"], env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
