@@ -208,6 +208,49 @@ def workload_config(n_gpus):
             "launch": "forward+losses+backward replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); all-reduce and Adam outside it"}
 
 
+def tensor_peaks():
+    """Measured dense peaks per operand kind: MEASURED_PEAKS.json (driver-written: bf16 burst / sustained) and, when present,
+    profiles/r2_tensor_peaks.json (scripts/measure_peaks.py on the same pool: fp16 and TF32 by the same cuBLAS method)."""
+    pk = {}
+    for f in (os.path.join(ROOT, "profiles", "r2_tensor_peaks.json"), os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        try:
+            pk.update(json.load(open(f)))
+        except (OSError, ValueError):
+            pass
+    return pk
+
+
+def fold_kinds(rep):
+    """Profile tags carry the operand kind of a tensor-core launch ("tc_conv_fprop.f16" / ".tf32"): returns the report with the
+    kinds folded into their family, and {family: {kind: record}}."""
+    fam, kinds = {}, {}
+    for k, v in rep.items():
+        base, _, kind = k.partition(".")
+        a = fam.setdefault(base, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for f in a:
+            a[f] += v[f]
+        if kind:
+            kinds.setdefault(base, {})[kind] = v
+    return fam, kinds
+
+
+def by_operand_kind(kinds, peaks):
+    """Each operand kind of a family against ITS measured dense peak (TF32: profiles/r2_tensor_peaks.json, else half the bf16 figure)."""
+    out = {}
+    for kind, v in kinds.items():
+        if kind == "tf32":
+            peak, src = peaks.get("tf32_tflops"), "measured TF32 cuBLAS burst (profiles/r2_tensor_peaks.json)"
+            if not peak:
+                peak, src = peaks.get("bf16_tflops", 1590.0) / 2, "half the measured bf16 burst (no TF32 measurement on file)"
+        else:
+            peak, src = peaks.get("fp16_tflops"), "measured fp16 cuBLAS burst (profiles/r2_tensor_peaks.json)"
+            if not peak:
+                peak, src = peaks.get("bf16_tflops", 1590.0), "measured bf16 burst (MEASURED_PEAKS.json)"
+        ach = v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0.0
+        out[kind] = {"achieved": ach, "peak": peak, "frac": ach / peak, "unit": "TFLOP/s", "launches": v["launches"], "ms": v["ms"], "peak_source": src}
+    return out
+
+
 def parity_block():
     """Measured parity of this build's network gradients (scripts/grad_parity.py on the B200, committed under profiles/)."""
     try:
@@ -224,6 +267,15 @@ def parity_block():
                         "decisions of near-zero pre-activations flip, which bounds network-gradient parity on random-init nets; "
                         "cuDNN TF32 shows the same, see DESIGN.md section 5"}
     except (OSError, ValueError, KeyError):
+        return None
+
+
+def decode_gate_block():
+    """Observed counts of the north_star decode gate (tests/test_trained_decode_gpu.py on the B200, committed under profiles/)."""
+    try:
+        g = json.load(open(os.path.join(ROOT, "profiles", "r2_decode_gate.json")))
+        return {"source": "profiles/r2_decode_gate.json (tests/test_trained_decode_gpu.py)", **g}
+    except (OSError, ValueError):
         return None
 
 
@@ -391,7 +443,7 @@ def run():
         for _ in range(psteps):
             step_device()
         torch.cuda.synchronize()
-        rep = _lib.prof_report()
+        rep, kinds = fold_kinds(_lib.prof_report())
         _lib.prof_enable(False)
         total = sum(v["ms"] for v in rep.values())
         kernels = {k: {"launches_per_step": v["launches"] / psteps, "ms_per_step": v["ms"] / psteps, "share": v["ms"] / total,
@@ -421,6 +473,9 @@ def run():
             ach = v["bytes"] / v["ms"] / 1e6
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "traffic": traffic, "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6650"}
+        if top in kinds:
+            roofline["by_operand_kind"] = by_operand_kind({k: dict(r, launches=r["launches"] / psteps, ms=r["ms"] / psteps) for k, r in kinds[top].items()},
+                                                          tensor_peaks())
         roofline["share_of_step"] = v["ms"] / total
         roofline["launches_per_step"] = v["launches"] / psteps
         roofline["avg_launch_ms"] = v["ms"] / v["launches"]
@@ -498,7 +553,8 @@ def run():
                                       "note": "the mirror modules called eagerly (no CUDA graph), as an unmodified trainer does"},
                     "surrogate_requires_grad_false": {"value": BATCH * world / (ms_frozen / 1e3), "ms_per_step": ms_frozen,
                                                       "note": "eager; skips the CRNN weight gradients the reference computes and discards"}},
-                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity_block()}
+                "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity_block(),
+                "decode_gate": decode_gate_block()}
     # ---- the other BASELINE.json configs, short runs, appended so that they are part of the driver-run line
     if not args.no_extras:
         import bench_workloads

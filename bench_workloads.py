@@ -173,6 +173,7 @@ def roofline_of(rep, psteps, prefer=None, bytes_override=None):
     """The family with the largest share of the profiled step (or `prefer`) against the measured peak of its bound."""
     if not rep:
         return None, None
+    rep, kinds = BB.fold_kinds(rep)
     total = sum(v["ms"] for v in rep.values()) or 1e-9
     kernels = {k: {"launches_per_step": v["launches"] / psteps, "ms_per_step": v["ms"] / psteps, "share": v["ms"] / total,
                    "tflops": v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0.0,
@@ -186,9 +187,12 @@ def roofline_of(rep, psteps, prefer=None, bytes_override=None):
         nbytes = bytes_override * v["launches"] if bytes_override is not None else v["bytes"]
         peak, ach, unit, bound = pk.get("hbm_gbs", 6650.0), nbytes / v["ms"] / 1e6, "GB/s", "hbm"
         src = "measured copy bandwidth (MEASURED_PEAKS.json)" if pk else "fallback 6650"
+    extra = {"by_operand_kind": BB.by_operand_kind({k: dict(r, launches=r["launches"] / psteps, ms=r["ms"] / psteps) for k, r in kinds[top].items()},
+                                                  BB.tensor_peaks())} if top in kinds else {}
     rf = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
           "peak_source": src, "share_of_step": v["ms"] / total, "launches_per_step": v["launches"] / psteps,
           "avg_launch_ms": v["ms"] / v["launches"]}
+    rf.update(extra)
     return rf, kernels
 
 

@@ -939,7 +939,8 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const TmapOut& to,
   }
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits;
   const int grid = (int)(total < (long long)kNumSMs * resident ? total : (long long)kNumSMs * resident);
-  ProfScope prof(LSM ? "tc_head_logsoftmax" : p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : "tc_conv_fprop"), st,
+  // ".f16" / ".tf32": the operand kind, so that bench.py can rate each against its own measured dense peak
+  ProfScope prof(LSM ? "tc_head_logsoftmax" : p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : (F16 ? "tc_conv_fprop.f16" : "tc_conv_fprop.tf32")), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
   QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI, WIN>, grid, fprop_threads<WIN>(), smem_total, st, ta, tb, to, p));

@@ -59,8 +59,43 @@ def _subset_ctc(loss_fn, scores, target, pred_size, target_size, img_indices):
     return loss_fn(scores[:, img_indices, :], target, pred_size_subset, target_size)
 
 
+def _all_depths_one_launch(self, scores, pred_size, target_batches, loss_weights, num_losses):
+    """Every history depth in ONE CTC launch: the depths' subsets are concatenated into one batch of
+    (column index, target) rows over the same log-prob tensor (qeb_ctc_fwd `batch_index`), the per-sample losses come back with
+    reduction 'none' and the depths' means / weights become one coefficient per row:
+      decaying:      sum_i w_i * mean_b(nll_b / max(1, len_b))      -> coef = w_i / (n_i * max(1, len_b))   (CTCLoss 'mean')
+      per-sample:    sum_i mean_b(W[b, i] * nll_b)                  -> coef = W[b, i] / n_i
+    The backward is one launch too (the coefficients are the per-row grad_out)."""
+    dev = scores.device
+    tgts, sizes, idx, coef = [], [], [], []
+    for i in range(num_losses):
+        target, target_size, img_indices = target_batches[i]
+        n_i = len(img_indices)
+        ts = torch.as_tensor(target_size).to("cpu", torch.int32).reshape(-1)
+        tgts.append(torch.as_tensor(target).to("cpu", torch.int32).reshape(-1))
+        sizes.append(ts)
+        ii = torch.as_tensor(img_indices, dtype=torch.int64)
+        idx.append(ii)
+        if self.weightgen_method == "decaying":   # w_i / (n_i * max(1, len_b)): built where the weight lives, no host sync
+            w_i = torch.as_tensor(loss_weights[i], dtype=torch.float32).to(dev, non_blocking=True)
+            coef.append(w_i / (n_i * ts.clamp(min=1).to(torch.float32)).pin_memory().to(dev, non_blocking=True))
+        else:
+            lw = torch.as_tensor(loss_weights)
+            coef.append(lw[ii.to(lw.device), i].to(dev, torch.float32) / n_i)
+    idx = torch.cat(idx)
+    nll = qctc.ctc_loss(scores, torch.cat(tgts), torch.as_tensor(pred_size)[idx], torch.cat(sizes), self.primary_loss_fn.blank,
+                        "none", self.primary_loss_fn.zero_infinity, batch_index=idx)
+    return (nll * torch.cat(coef)).sum()
+
+
 def weighted_ctc_loss(self, scores, pred_size, target_batches, loss_weights):
     num_losses = min(len(target_batches), self.window_size)
+    sample_wise = self.weightgen_method != "decaying"
+    fused = isinstance(self.primary_loss_fn, qctc.CTCLoss) and scores.is_cuda and num_losses > 0 and \
+        (not sample_wise or isinstance(getattr(self, "primary_loss_fn_sample_wise", None), qctc.CTCLoss)) and \
+        self.primary_loss_fn.reduction == "mean"
+    if fused:
+        return _all_depths_one_launch(self, scores, pred_size, target_batches, loss_weights, num_losses)
     all_ctc_losses = list()
     for i in range(num_losses):
         target, target_size, img_indices = target_batches[i]
@@ -72,6 +107,20 @@ def weighted_ctc_loss(self, scores, pred_size, target_batches, loss_weights):
             loss_weights_subset = loss_weights[img_indices, i]
             ctc_losses = _subset_ctc(self.primary_loss_fn_sample_wise, scores, target, pred_size, target_size, img_indices)
             all_ctc_losses.append(torch.mean(loss_weights_subset * ctc_losses))
+    return sum(all_ctc_losses)
+
+
+def weighted_ctc_loss_per_depth(self, scores, pred_size, target_batches, loss_weights):
+    """The reference's loop, one CTC call per history depth (kept for tests / A-B against the one-launch form)."""
+    num_losses = min(len(target_batches), self.window_size)
+    all_ctc_losses = list()
+    for i in range(num_losses):
+        target, target_size, img_indices = target_batches[i]
+        if self.weightgen_method == "decaying":
+            all_ctc_losses.append(loss_weights[i] * _subset_ctc(self.primary_loss_fn, scores, target, pred_size, target_size, img_indices))
+        else:
+            ctc_losses = _subset_ctc(self.primary_loss_fn_sample_wise, scores, target, pred_size, target_size, img_indices)
+            all_ctc_losses.append(torch.mean(loss_weights[img_indices, i] * ctc_losses))
     return sum(all_ctc_losses)
 
 

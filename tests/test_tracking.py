@@ -71,11 +71,23 @@ def test_weighted_ctc_loss_matches_reference(mode):
     pred_size = torch.tensor([scores.shape[0]] * B, dtype=torch.int)
     tb = tu.generate_ctc_target_batches(obj, j["names"][:B])
     lw = torch.from_numpy(g["lev_weights"]).cuda()[:B, 1:] if mode == "levenshtein" else torch.from_numpy(g["decay_weights"]).cuda()
-    loss = tu.weighted_ctc_loss(obj, scores, pred_size, tb, lw)
+    from qeb_b200 import _lib
+    n0 = _lib.launch_count()
+    loss = tu.weighted_ctc_loss(obj, scores, pred_size, tb, lw)          # every history depth in ONE CTC launch
+    n_fwd = _lib.launch_count() - n0
     loss.backward()
     ref_loss, ref_grad = float(g[f"loss_{mode}"]), torch.from_numpy(g[f"grad_{mode}"])
     assert abs(float(loss) - ref_loss) <= 1e-4 * abs(ref_loss)          # north_star: CTC within 1e-3 relative
     err = float((scores.grad.cpu() - ref_grad).norm() / ref_grad.norm())
     assert err < 1e-3, err
+    # the reference's loop (one CTC call per depth) gives the same value and gradient with len(tb) times the launches
+    s2 = scores.detach().clone().requires_grad_(True)
+    n0 = _lib.launch_count()
+    loss2 = tu.weighted_ctc_loss_per_depth(obj, s2, pred_size, tb, lw)
+    n_loop = _lib.launch_count() - n0
+    loss2.backward()
+    assert len(tb) > 1 and n_loop == len(tb) * n_fwd
+    assert abs(float(loss) - float(loss2)) <= 2e-6 * abs(float(loss2))
+    assert float((scores.grad - s2.grad).abs().max()) <= 1e-6 * float(s2.grad.abs().max()) + 1e-9
     # columns of images without a label at some history depth receive no gradient from that depth (scatter, not overwrite)
     assert torch.isfinite(scores.grad).all()

@@ -1,12 +1,18 @@
 """north_star gate: greedy-decoded strings identical to the fp32 reference graph on >= 99.9 % of patches.
 
 The gate is ill-conditioned on random-init weights (near-flat log-probs), so the surrogate is first
-TRAINED - through the qeb path itself (jitter-free phase-A steps: CRNN train mode -> CTC -> backward -> Adam, all
-sm_100a kernels) - on procedurally rendered glyph strips until it reads them, and the comparison is made on 4096 fresh
-patches in eval mode against oracle/nn_oracle.py (same weights, torch fp32, TF32 disabled). This also is the
-end-to-end proof that the backward pass trains: accuracy against the true labels goes from 0 to > 90 %.
+TRAINED on procedurally rendered glyph strips until it reads them, and the comparison is made on fresh patches in eval
+mode against oracle/nn_oracle.py (same weights, torch fp32, TF32 disabled):
+  - `reference`: trained by the REFERENCE path (the oracle graph on torch eager / cuDNN fp32, torch CTCLoss and Adam -
+    none of the qeb kernels), gate on 10,240 patches (SURVEY.md H1 asks for >= 10 k);
+  - `qeb`: trained through the qeb path itself (CRNN train mode -> CTC -> backward -> Adam, all sm_100a kernels), gate on
+    4,096 patches - also the end-to-end proof that the backward pass trains (accuracy goes from 0 to > 90 %).
+The 35 MB of trained weights are not committed as a fixture (the recipe is seeded: same weights on every run); the observed
+counts are written to gpurun_out/decode_gate.json (copied to profiles/ and quoted by bench.py's `parity` block).
 """
 import copy
+import json
+import os
 
 import pytest
 import torch
@@ -37,8 +43,9 @@ def render(bank, n, gen, max_len=8):
     return (x + 0.03 * torch.randn(x.shape, generator=gen)).clamp_(0, 1), labels
 
 
-@pytest.mark.timeout(300)
-def test_trained_surrogate_decode_parity():
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("trainer,n_eval", [("reference", 10240), ("qeb", 4096)])
+def test_trained_surrogate_decode_parity(trainer, n_eval):
     import qeb_b200  # noqa: F401
     from qeb_b200.mirror import ctc as qctc, train_ops, utils
     from qeb_b200.mirror.models.model_crnn import CRNN
@@ -50,9 +57,15 @@ def test_trained_surrogate_decode_parity():
     torch.manual_seed(0)
     m = CRNN(95, False).to(DEV)
     m.train()
-    m.register_backward_hook(m.backward_hook)
-    opt = train_ops.Adam(m.parameters(), lr=5e-4)
-    loss_fn = qctc.CTCLoss()
+    if trainer == "qeb":
+        m.register_backward_hook(m.backward_hook)
+        opt = train_ops.Adam(m.parameters(), lr=5e-4)
+        loss_fn = qctc.CTCLoss()
+        forward = m
+    else:   # the reference's graph and library ops only
+        opt = torch.optim.Adam(m.parameters(), lr=5e-4)
+        loss_fn = torch.nn.CTCLoss()
+        forward = lambda x: nn_oracle.crnn_forward(m, x)
     il = torch.full((64,), 31, dtype=torch.int32)
     first = last = None
     for it in range(2600):
@@ -63,7 +76,10 @@ def test_trained_surrogate_decode_parity():
         y = torch.cat(labels)
         ylen = torch.tensor([len(l) for l in labels], dtype=torch.int32)
         m.zero_grad(set_to_none=True)
-        loss = loss_fn(m(x.to(DEV)), y, il, ylen)
+        if trainer == "qeb":
+            loss = loss_fn(forward(x.to(DEV)), y, il, ylen)
+        else:
+            loss = loss_fn(forward(x.to(DEV)), y.to(DEV), il.to(DEV), ylen.to(DEV))
         loss.backward()
         opt.step()
         if it == 0:
@@ -74,15 +90,23 @@ def test_trained_surrogate_decode_parity():
     mr = copy.deepcopy(m)
     same = correct = total = 0
     with torch.no_grad():
-        for _ in range(16):
+        for _ in range(n_eval // 256):
             x, labels = render(bank, 256, gen)
             lp, lpr = m(x.to(DEV)), nn_oracle.crnn_forward(mr, x.to(DEV))
-            ca, la = utils.decode_batch(lp)
+            ca, la = utils.decode_batch(lp)                     # rides the head's arg-max path
             cb, lb = utils.decode_batch(lpr.contiguous())
             same += int(((ca == cb).all(dim=1) & (la == lb)).sum())
             total += 256
             ca, la = ca.cpu(), la.cpu()
             correct += sum(int(int(la[i]) == len(l) and torch.equal(ca[i, :len(l)], l)) for i, l in enumerate(labels))
-    print(f"trained surrogate: {same}/{total} strings identical to the fp32 graph, {correct}/{total} read correctly")
+    print(f"surrogate trained by the {trainer} path: {same}/{total} strings identical to the fp32 graph, {correct}/{total} read correctly")
+    try:   # observed counts for profiles/ (never fails the test)
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "decode_gate.json")
+        rec = json.load(open(out)) if os.path.exists(out) else {}
+        rec[trainer] = {"patches": total, "identical_to_fp32_graph": same, "read_correctly": correct, "required_identical": 0.999}
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        json.dump(rec, open(out, "w"), indent=1)
+    except OSError:
+        pass
     assert correct >= 0.9 * total
     assert same >= 0.999 * total        # north_star: >= 99.9 % identical greedy decodes

@@ -235,3 +235,51 @@ def test_area_minibatch_phases_a_b_c_vs_oracle():
     assert cer.tolist() == want_cers                                          # fp64, bit-exact
     sampler.update_cer(cer.tolist(), names)
     assert sampler.cers == dict(zip(names, want_cers)) and all(sampler.all_cers[n] == [c] for n, c in zip(names, want_cers))
+
+
+@pytest.mark.gpu
+def test_crnn_warmup_loop_matches_reference_loop():
+    """configs[0] / train_crnn.py:154-183 packaged as mirror/train_crnn.train_epoch + validate: three training steps and one
+    validation pass against the same statements on the oracle graph (torch CTCLoss / Adam, pred_to_string + compare_labels of
+    the oracle)."""
+    import qeb_b200  # noqa: F401
+    from qeb_b200.mirror import train_crnn as tc, train_ops
+    from qeb_b200.mirror.models.model_crnn import CRNN
+    torch.manual_seed(8)
+    m = CRNN(95, False).to(DEV)
+    mr = copy.deepcopy(m)
+    c2i = {c: i for i, c in enumerate(BB.CHAR_SET)}
+    i2c = {i: c for i, c in enumerate(BB.CHAR_SET)}
+    batches = []
+    for s in range(3):
+        x, labels = BB.synth_batch(16, 20 + s)
+        batches.append((x, labels))                               # CPU images, as a DataLoader hands them over
+    opt = train_ops.Adam(m.parameters(), lr=1e-4)
+    optr = torch.optim.Adam(mr.parameters(), lr=1e-4)
+    total, steps = tc.train_epoch(m, batches, opt, c2i, DEV)
+    assert steps == 3
+    mr.train()
+    ref_total = 0.0
+    for x, labels in batches:
+        mr.zero_grad()
+        scores = nn_oracle.crnn_forward(mr, x.to(DEV))
+        y, ys = BB.encode(labels, c2i)
+        loss = torch.nn.CTCLoss()(scores, y.to(DEV), torch.tensor([31] * 16, dtype=torch.int32, device=DEV), ys.to(DEV))
+        loss.backward(); optr.step()
+        ref_total += loss.item()
+    assert abs(total - ref_total) < 1e-3 * abs(ref_total)
+    for (n, p), (_, r) in zip(m.named_parameters(), mr.named_parameters()):
+        assert float((p - r).abs().max()) <= 3 * 2.1e-4, n           # three Adam steps of ~lr each
+    vloss, crt, cer, nb = tc.validate(m, batches[:2], c2i, i2c, DEV)
+    assert nb == 2 and not m.training
+    with torch.no_grad():
+        want_crt, want_cer, want_loss = 0, 0, 0.0
+        for x, labels in batches[:2]:
+            scores = m(x.to(DEV))                                     # same weights: decode / CER parity is exact
+            preds = po.pred_to_string(scores.cpu().numpy(), i2c)
+            c, e = po.compare_labels(preds, labels)
+            want_crt += c; want_cer += e
+            y, ys = BB.encode(labels, c2i)
+            want_loss += float(torch.nn.functional.ctc_loss(scores, y.to(DEV), torch.tensor([31] * 16, dtype=torch.int32, device=DEV), ys.to(DEV)))
+    assert (crt, cer) == (want_crt, want_cer)
+    assert abs(vloss - want_loss) < 1e-4 * abs(want_loss)
