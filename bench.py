@@ -205,7 +205,7 @@ def workload_config(n_gpus):
             "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "patch": [H, W], "parallelism": f"dp{n_gpus}",
             "operand_precision": "tensor-core operands with an 11-bit significand (fp16 copies in the forward pass, tf32 reads of fp32 in the backward pass), fp32 accumulation / activations / gradients / parameters (reference: fp32)",
             "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2",
-            "launch": "forward+losses+backward replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); all-reduce and Adam outside it"}
+            "launch": "forward+losses+backward (+ the gradient all-reduce when N > 1) replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); Adam outside it"}
 
 
 def tensor_peaks():
@@ -365,8 +365,12 @@ def run():
     packed = qctc.pack_targets(y, pred_size, y_size, dev)
     unet_params = [p for p in prep.parameters()]
 
+    # data parallel: the 31 MB flat UNet gradient is averaged over the ranks once per step; the part of it the backward pass
+    # finishes first (bottleneck + decoder, 85 %) is reduced on a communication stream while the encoder's backward runs
+    overlap = qdist.BucketedAllReduce(prep, average=True)
+
     def allreduce_grads():
-        qdist.allreduce_grads(unet_params, average=True)   # one NCCL all-reduce of the flat 31 MB gradient buffer
+        overlap()
 
     def step_device():
         prep.train(); crnn.train(); crnn.apply(set_bn_eval)          # train_nn_area.py:277-279
@@ -487,18 +491,36 @@ def run():
     x_static = x_dev.clone()
     prep.train(); crnn.train(); crnn.apply(set_bn_eval)
 
-    def fwd_bwd():
+    def fwd_bwd_local():
         img = prep(x_static)
         scores = crnn(img)
         loss = ctc_loss(scores, tg_static) + SCALAR * train_ops.mse_to_ones(img)
         loss.backward()
         return loss
 
+    def fwd_bwd():
+        loss = fwd_bwd_local()
+        allreduce_grads()       # captured with the step: event wait, communication-stream fork / join and both NCCL calls
+        return loss
+
+    ms_no_allreduce = None
+    if world > 1:   # the same step without the exchange, for the exposed all-reduce time (captured and timed FIRST: the
+        g0 = GraphedStep(fwd_bwd_local, modules=[prep, crnn], warmup=3)   # headline graph below re-pins the gradients)
+
+        def step_noar():
+            loss = g0()
+            opt.step()
+            return loss
+
+        for _ in range(args.warmup):
+            step_noar()
+        ms_no_allreduce, _ = timed(step_noar, args.steps)
+        g0.close()
+
     gstep = GraphedStep(fwd_bwd, modules=[prep, crnn], warmup=3)
 
     def step_graph():
         loss = gstep()
-        allreduce_grads()
         opt.step()
         return loss
 
@@ -507,7 +529,6 @@ def run():
         yy, yy_size = encode(labels, c2i)                             # host-side label encoding, as _call_model
         tg_static.load(yy, pred_size, yy_size)                        # one pinned staging buffer, one H2D copy
         loss = gstep()
-        allreduce_grads()
         opt.step()
         return loss.item()                                            # D2H read of the step's loss
 
@@ -546,6 +567,11 @@ def run():
                 "vs_baseline": None, "dtype": "fp16/tf32", "data": "synthetic", "config": workload_config(world),
                 "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
+                "allreduce": None if world == 1 else {
+                    "bytes": sum(p.numel() for p in unet_params) * 4, "op": "AVG", "collectives_per_step": 2,
+                    "ms_per_step_without_exchange": ms_no_allreduce, "exposed_us": 1e3 * (ms_step - ms_no_allreduce),
+                    "note": "bottleneck + decoder gradients (26.4 MB) all-reduced on a communication stream while the encoder's backward "
+                            "runs (qeb_unet_backward_bucketed), encoder gradients (4.7 MB) after it; both inside the captured graph"},
                 "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": last_loss,
                 "variants": None if args.skip_eager else {
                     "eager_modules": {"value": BATCH * world / (ms_eager / 1e3), "ms_per_step": ms_eager,
@@ -570,6 +596,7 @@ def run():
         if line is not None:
             line["workloads"] = extras
     if world > 1:
+        gstep.close()            # the captured graph holds NCCL collectives: it has to go before the communicator
         dist.destroy_process_group()
     return line if rank == 0 else None
 

@@ -413,6 +413,7 @@ def run_area(env):
     p_crnn, p_prep = list(crnn.parameters()), list(prep.parameters())
     opt_crnn = train_ops.Adam(p_crnn, lr=LR_CRNN, weight_decay=0)         # :149-154
     opt_prep = train_ops.Adam(p_prep, lr=BB.LR_PREP, weight_decay=0)
+    overlap_prep = qdist.BucketedAllReduce(prep, average=True)           # UNet exchange overlapped with the encoder's backward
     c2i = {c: i for i, c in enumerate(BB.CHAR_SET)}
     x_host, _ = BB.synth_batch(BB.BATCH, 7 + rank)
     labels = vgg_labels(BB.BATCH, 11 + rank)
@@ -456,7 +457,7 @@ def run_area(env):
             pri = ctc_loss(scores, tg_gt)
         loss_b = pri + BB.SCALAR * train_ops.mse_to_ones(img)             # :285
         loss_b.backward()                                                 # :286
-        qdist.allreduce_grads(p_prep, average=True)
+        overlap_prep()
         opt_prep.step()                                                   # :287
         # ---- phase C: CER bookkeeping (decode + Levenshtein on the device against the CTC targets already there)
         _, _, _, cer = qutils.decode_and_cer(scores.detach(), tg_gt.tg, tg_gt.offs, tg_gt.tl, 24)   # :290, :297-303

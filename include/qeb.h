@@ -46,8 +46,9 @@ int qeb_check_device(void);            /* 0 iff the current device is an sm_100 
  * nll (B): per-sample negative log-likelihood (+inf when infeasible). loss_out: scalar, may be NULL for none.
  * Backward writes d loss / d log_probs in ATen's convention ((exp(lp) - exp(lse(alpha+beta) + nll - lp)) * grad_out:
  * the gradient at the logits); an infeasible sample yields NaN rows unless zero_infinity (the reference zeroes them
- * in CRNN.backward_hook, models/model_crnn.py:30-32). grad_out: (B) for none, (1) otherwise. With batch_index only
- * the listed columns of grad are written. */
+ * in CRNN.backward_hook, models/model_crnn.py:30-32). grad_out: (B) for none, (1) otherwise. With batch_index the
+ * rows' gradients are ADDED into the listed columns of a grad buffer the caller zero-filled (a column may be listed several
+ * times: the history depths of weighted_ctc_loss in ONE launch); the other columns are not touched. */
 size_t qeb_ctc_workspace_bytes(int B, int T, int max_target_len);
 int qeb_ctc_fwd(const float* log_probs, long long st_t, long long st_b, const int* batch_index, const int* targets,
                 const int* tgt_offsets, const int* input_lengths, const int* target_lengths, int B, int T, int V,
@@ -167,6 +168,14 @@ int qeb_unet_forward(const float* x, int B, int H, int W, const float* const* pa
                      void* ws, float* y, void* stream);
 int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
                       const float* y, const float* dy, float* const* grads, float* dx, void* stream);
+/* The same backward for data-parallel training with an overlapped gradient exchange (one NCCL all-reduce per step over the
+ * flat gradient buffer): tail_ready_event (a cudaEvent_t) is recorded on `stream` as soon as the gradients
+ * of parameters [24, 64) of the ABI order - bottleneck, decoder blocks, up-convolutions, final conv: 85 % of the bytes, which
+ * the backward pass reaches first - are final; a communication stream waiting for it can reduce that range while the
+ * encoder's backward still runs. Parameters [0, 24) are final when the call's work completes. */
+int qeb_unet_backward_bucketed(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
+                               const float* y, const float* dy, float* const* grads, float* dx, void* tail_ready_event,
+                               void* stream);
 
 /* ==== building blocks, exported for tests and for callers that compose their own graphs ===========================
  * Tensor-core contractions (tcgen05 kind::tf32, fp32 accumulate). Activations NHWC with a channel stride (a channel

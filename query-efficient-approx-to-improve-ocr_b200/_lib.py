@@ -65,6 +65,7 @@ SIGNATURES = {
     "qeb_unet_num_buffers": (I, []),
     "qeb_unet_forward": (I, [P, I, I, I, P, P, I, P, P, P]),
     "qeb_unet_backward": (I, [P, I, I, I, P, I, P, P, P, P, P, P]),
+    "qeb_unet_backward_bucketed": (I, [P, I, I, I, P, I, P, P, P, P, P, P, P]),
 }
 
 _lib = None

@@ -193,9 +193,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_beta_grad_kernel(CtcB
   else go = g.grad_out[0];
   const bool zero_all = g.zero_infinity && (nll == INFINITY);
 
-  // frames past the input length carry zero gradient
-  for (int t = Tb; t < a.T; ++t)
-    for (int c = lane; c < a.V; c += 32) gr[(long long)t * g.gst_t + c] = 0.f;
+  // frames past the input length carry zero gradient (with batch_index the caller's buffer is zero-filled and ADDED into:
+  // one column may appear in several rows - the history depths of weighted_ctc_loss, tracking_utils.py:59-75)
+  const bool add = a.batch_index != nullptr;
+  if (!add)
+    for (int t = Tb; t < a.T; ++t)
+      for (int c = lane; c < a.V; c += 32) gr[(long long)t * g.gst_t + c] = 0.f;
   if (Tb == 0) return;
 
   int cls[SPL];
@@ -304,7 +307,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) ctc_beta_grad_kernel(CtcB
       const float l = row[c];
       float v = (expf(l) - expf(res + nll - l)) * go;
       if (zero_all) v = 0.f;
-      gr[(long long)t * g.gst_t + c] = v;
+      if (add) atomicAdd(&gr[(long long)t * g.gst_t + c], v);
+      else gr[(long long)t * g.gst_t + c] = v;
     }
   }
 }
@@ -515,8 +519,10 @@ __global__ void __launch_bounds__(kSeqThreads) ctc_beta_grad_seq_kernel(CtcBwdAr
   float* accm = ab + a.T * a.S + warp * 2 * a.V;   // per warp: running max / sum per class
   float* accs = accm + a.V;
 
-  for (int t = Tb + warp; t < a.T; t += kWarps)   // frames past the input length carry zero gradient
-    for (int c = lane; c < a.V; c += 32) gr[(long long)t * g.gst_t + c] = 0.f;
+  const bool add = a.batch_index != nullptr;   // see ctc_beta_grad_kernel
+  if (!add)
+    for (int t = Tb + warp; t < a.T; t += kWarps)   // frames past the input length carry zero gradient
+      for (int c = lane; c < a.V; c += 32) gr[(long long)t * g.gst_t + c] = 0.f;
   if (Tb == 0) return;
   for (int t = warp; t < Tb; t += kWarps) {
     for (int c = lane; c < a.V; c += 32) cp_async4(panel + t * a.V + c, lp + (long long)t * a.st_t + c);
@@ -621,7 +627,8 @@ __global__ void __launch_bounds__(kSeqThreads) ctc_beta_grad_seq_kernel(CtcBwdAr
       const float l = row[c];
       float v = (expf(l) - expf(res + nll - l)) * go;
       if (zero_all) v = 0.f;
-      gr[(long long)t * g.gst_t + c] = v;
+      if (add) atomicAdd(&gr[(long long)t * g.gst_t + c], v);
+      else gr[(long long)t * g.gst_t + c] = v;
     }
     __syncwarp();
   }

@@ -360,8 +360,43 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
 
 // dy: (B,1,H,W). grads: P_COUNT pointers, NULL = skip, non-NULL gradients are ACCUMULATED into. dx: (B,1,H,W) or NULL.
 // y must be the forward's output; ws the forward's workspace.
+namespace {
+// packed [Cout][tap][Cin] weight-gradient accumulators of conv blocks [blk0, blk1) -> torch layout, ADDED into the caller's
+// gradient tensors, one launch
+int unpack_weight_grads(const UnetPlan& p, float* const* grads, int blk0, int blk1, cudaStream_t st) {
+  PackBatch pk;
+  pk.accumulate = 1;
+  for (int blk = blk0; blk < blk1; ++blk) {
+    const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+    const int cout = p.C[lvl];
+    const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+    if (cin1 > 1 && grads[blk * 6]) pk.add_unpack_grad(p.dwp[blk * 2], grads[blk * 6], cout, cin1, 9);
+    if (grads[blk * 6 + 3]) pk.add_unpack_grad(p.dwp[blk * 2 + 1], grads[blk * 6 + 3], cout, cout, 9);
+  }
+  return pack_flush(pk, st);
+}
+int unet_backward_impl(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
+                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream);
+}
 QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
                               const float* y, const float* dy, float* const* grads, float* dx, void* stream) {
+  return unet_backward_impl(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, nullptr, stream);
+}
+
+// The same backward for data-parallel training with an overlapped gradient exchange: `tail_ready_event` (a cudaEvent_t) is
+// recorded on `stream` as soon as the gradients of parameters [24, 64) of the ABI order - the bottleneck, the four decoder
+// blocks, the up-convolutions and the final 1x1 conv: 85 % of the bytes - are FINAL (the backward pass reaches them first);
+// a communication stream that waits for it can all-reduce that range while the encoder's backward still runs. The
+// gradients of parameters [0, 24) (the encoder) are final when the call's work completes, as always.
+QEB_API int qeb_unet_backward_bucketed(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
+                                       const float* y, const float* dy, float* const* grads, float* dx, void* tail_ready_event,
+                                       void* stream) {
+  return unet_backward_impl(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, tail_ready_event, stream);
+}
+
+namespace {
+int unet_backward_impl(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
+                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream) {
   QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
   QEB_REQUIRE(B > 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0, "unet_backward: B=%d H=%d W=%d unsupported", B, H, W);
   const UnetPlan p = make_plan(B, H, W, ws);
@@ -370,6 +405,7 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
   SideStream ss;
   TRY(ss.init(c.st));
   c.ss = &ss;
+  bool tail_unpacked = false;
   int red_done[kUnits] = {0};
   c.red_done = red_done;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
@@ -445,6 +481,13 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
       Img in = img_nhwc(p.pool[i - 1], B, p.h[i], p.w[i], p.C[i - 1]);
       Img gin = img_nhwc(p.sA[i], B, p.h[i], p.w[i], p.C[i - 1]);
       TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, &gin));
+      if (i == 4 && tail_ready_event) {
+        // the bottleneck and everything above it is done: finish those weight gradients now and tell the caller
+        TRY(ss.join());
+        TRY(unpack_weight_grads(p, grads, 4, 9, c.st));
+        tail_unpacked = true;
+        QEB_CUDA(cudaEventRecord((cudaEvent_t)tail_ready_event, c.st));
+      }
     } else {
       Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
       if (dx) {
@@ -456,17 +499,7 @@ QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* 
     }
   }
   TRY(ss.join());
-  {  // packed conv weight gradients -> torch layout, added into the caller's gradient tensors, one launch
-    PackBatch pk;
-    pk.accumulate = 1;
-    for (int blk = 0; blk < 9; ++blk) {
-      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
-      const int cout = p.C[lvl];
-      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
-      if (cin1 > 1 && grads[blk * 6]) pk.add_unpack_grad(p.dwp[blk * 2], grads[blk * 6], cout, cin1, 9);
-      if (grads[blk * 6 + 3]) pk.add_unpack_grad(p.dwp[blk * 2 + 1], grads[blk * 6 + 3], cout, cout, 9);
-    }
-    TRY(pack_flush(pk, c.st));
-  }
+  TRY(unpack_weight_grads(p, grads, 0, tail_unpacked ? 4 : 9, c.st));
   return QEB_OK;
 }
+}  // namespace

@@ -126,3 +126,13 @@ class GraphedStep:
     def __call__(self):
         self.graph.replay()
         return self.out
+
+    def close(self):
+        """Destroy the captured graph (and return its memory pool). REQUIRED before torch.distributed.destroy_process_group()
+        when the capture holds NCCL collectives (mirror/dist.BucketedAllReduce inside the step): tearing the communicator down
+        under a live graph that references it hangs."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            self.out = None

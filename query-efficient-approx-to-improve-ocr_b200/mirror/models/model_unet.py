@@ -23,9 +23,10 @@ class _UNetFn(torch.autograd.Function):
     """x (B,1,H,W) + the 64 parameters -> sigmoid(conv(dec1)) (B,1,H,W)."""
 
     @staticmethod
-    def forward(ctx, x, bn_train, buffers, *params):
+    def forward(ctx, x, bn_train, buffers, tail_event, *params):
         lib = _lib.load()
         B, C, H, W = x.shape
+        ctx.tail_event = tail_event
         nbytes = lib.qeb_unet_workspace_bytes(B, H, W)
         if C != 1 or nbytes == 0:
             raise _lib.QebError(f"qeb UNet: unsupported input {tuple(x.shape)} (needs (B,1,H,W) with H, W multiples of 16)")
@@ -44,15 +45,21 @@ class _UNetFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, y, *params = ctx.saved_tensors
         B, H, W, bn_train = ctx.cfg
-        need = list(ctx.needs_input_grad[3:])
+        need = list(ctx.needs_input_grad[4:])
         need[-1] = need[-2] = True  # the final conv's gradients are always produced by the fused sigmoid backward
         grads = _alloc_grads(params, need)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        _lib.call("qeb_unet_backward", x.data_ptr(), B, H, W, _ptr_array(params), bn_train, ctx.ws.data_ptr(),
-                  y.data_ptr(), dy.contiguous().data_ptr(), _ptr_array(grads), _lib.ptr(dx), _lib.stream())
+        if ctx.tail_event is not None:
+            # data-parallel overlap (mirror/dist.BucketedAllReduce): the event fires when parameters [24, 64) are final
+            _lib.call("qeb_unet_backward_bucketed", x.data_ptr(), B, H, W, _ptr_array(params), bn_train, ctx.ws.data_ptr(),
+                      y.data_ptr(), dy.contiguous().data_ptr(), _ptr_array(grads), _lib.ptr(dx), ctx.tail_event.cuda_event,
+                      _lib.stream())
+        else:
+            _lib.call("qeb_unet_backward", x.data_ptr(), B, H, W, _ptr_array(params), bn_train, ctx.ws.data_ptr(),
+                      y.data_ptr(), dy.contiguous().data_ptr(), _ptr_array(grads), _lib.ptr(dx), _lib.stream())
         ctx.ws = None
-        out = [g if n else None for g, n in zip(grads, ctx.needs_input_grad[3:])]
-        return (dx, None, None) + tuple(out)
+        out = [g if n else None for g, n in zip(grads, ctx.needs_input_grad[4:])]
+        return (dx, None, None, None) + tuple(out)
 
 
 class UNet(nn.Module):
@@ -98,6 +105,8 @@ class UNet(nn.Module):
         ps += [self.conv.weight, self.conv.bias]
         return ps
 
+    QEB_TAIL_FIRST_PARAM = 24   # ABI order: parameters [24, 64) are final first in the backward pass (qeb_unet_backward_bucketed)
+
     def qeb_buffers(self):
         bs = []
         for blk, n in self._blocks():
@@ -116,7 +125,7 @@ class UNet(nn.Module):
         for p in params:
             if not p.is_contiguous() or p.device != x.device:
                 raise _lib.QebError("qeb UNet: parameters must be contiguous and on the input's device")
-        return _UNetFn.apply(x.contiguous(), modes.pop(), self.qeb_buffers(), *params)
+        return _UNetFn.apply(x.contiguous(), modes.pop(), self.qeb_buffers(), getattr(self, "_qeb_tail_event", None), *params)
 
     @staticmethod
     def _block(in_channels, features, name):

@@ -86,7 +86,7 @@ def test_weighted_ctc_loss_matches_reference(mode):
     loss2 = tu.weighted_ctc_loss_per_depth(obj, s2, pred_size, tb, lw)
     n_loop = _lib.launch_count() - n0
     loss2.backward()
-    assert len(tb) > 1 and n_loop == len(tb) * n_fwd
+    assert len(tb) > 1 and n_fwd <= 2 and n_loop >= len(tb) * 1 and n_loop >= 2 * n_fwd   # one CTC launch (+ one reduction) against one set per depth
     assert abs(float(loss) - float(loss2)) <= 2e-6 * abs(float(loss2))
     assert float((scores.grad - s2.grad).abs().max()) <= 1e-6 * float(s2.grad.abs().max()) + 1e-9
     # columns of images without a label at some history depth receive no gradient from that depth (scatter, not overwrite)
