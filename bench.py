@@ -234,8 +234,9 @@ def fold_kinds(rep):
     return fam, kinds
 
 
-def by_operand_kind(kinds, peaks):
-    """Each operand kind of a family against ITS measured dense peak (TF32: profiles/r2_tensor_peaks.json, else half the bf16 figure)."""
+def by_operand_kind(kinds, peaks, psteps=1):
+    """Each operand kind of a family against ITS measured dense peak (TF32: profiles/r2_tensor_peaks.json, else half the bf16
+    figure). kinds: raw profile records over `psteps` profiled steps."""
     out = {}
     for kind, v in kinds.items():
         if kind == "tf32":
@@ -247,7 +248,8 @@ def by_operand_kind(kinds, peaks):
             if not peak:
                 peak, src = peaks.get("bf16_tflops", 1590.0), "measured bf16 burst (MEASURED_PEAKS.json)"
         ach = v["flops"] / v["ms"] / 1e9 if v["ms"] > 0 else 0.0
-        out[kind] = {"achieved": ach, "peak": peak, "frac": ach / peak, "unit": "TFLOP/s", "launches": v["launches"], "ms": v["ms"], "peak_source": src}
+        out[kind] = {"achieved": ach, "peak": peak, "frac": ach / peak, "unit": "TFLOP/s", "launches_per_step": v["launches"] / psteps,
+                     "ms_per_step": v["ms"] / psteps, "peak_source": src}
     return out
 
 
@@ -478,8 +480,7 @@ def run():
             roofline = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                         "traffic": traffic, "peak_source": "measured copy bandwidth (MEASURED_PEAKS.json)" if peaks else "fallback 6650"}
         if top in kinds:
-            roofline["by_operand_kind"] = by_operand_kind({k: dict(r, launches=r["launches"] / psteps, ms=r["ms"] / psteps) for k, r in kinds[top].items()},
-                                                          tensor_peaks())
+            roofline["by_operand_kind"] = by_operand_kind(kinds[top], tensor_peaks(), psteps)
         roofline["share_of_step"] = v["ms"] / total
         roofline["launches_per_step"] = v["launches"] / psteps
         roofline["avg_launch_ms"] = v["ms"] / v["launches"]

@@ -187,8 +187,7 @@ def roofline_of(rep, psteps, prefer=None, bytes_override=None):
         nbytes = bytes_override * v["launches"] if bytes_override is not None else v["bytes"]
         peak, ach, unit, bound = pk.get("hbm_gbs", 6650.0), nbytes / v["ms"] / 1e6, "GB/s", "hbm"
         src = "measured copy bandwidth (MEASURED_PEAKS.json)" if pk else "fallback 6650"
-    extra = {"by_operand_kind": BB.by_operand_kind({k: dict(r, launches=r["launches"] / psteps, ms=r["ms"] / psteps) for k, r in kinds[top].items()},
-                                                  BB.tensor_peaks())} if top in kinds else {}
+    extra = {"by_operand_kind": BB.by_operand_kind(kinds[top], BB.tensor_peaks(), psteps)} if top in kinds else {}
     rf = {"kernel": top, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
           "peak_source": src, "share_of_step": v["ms"] / total, "launches_per_step": v["launches"] / psteps,
           "avg_launch_ms": v["ms"] / v["launches"]}

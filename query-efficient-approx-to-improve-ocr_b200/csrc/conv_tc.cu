@@ -21,6 +21,7 @@
 #include "nn.cuh"
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <unordered_map>
 #include <string.h>
 
 namespace tc {
@@ -50,8 +51,47 @@ static int make_tmap_any(CUtensorMap* out, const void* base, int rank, const uin
     qeb_set_error("tensor map base %p not 16-byte aligned", base);
     return QEB_ERR_INVALID;
   }
+  // A step encodes ~250 tensor maps (operands and, with the TMA-store epilogue, outputs) and the workspace layout is a pure
+  // function of (B, H, W): the caching allocator hands the same addresses back step after step, so the encoded descriptors are
+  // kept per host thread, keyed on everything that goes into them. An eagerly launched step (the unmodified trainers) then
+  // pays a hash lookup instead of a driver call per map; a map is a pure function of its key, so a hit can never be stale.
+  struct Key {
+    uintptr_t base;
+    uint64_t d[5], s[4];
+    uint32_t b[5];
+    int rank, dtype, swz;
+  };
+  Key key;
+  memset(&key, 0, sizeof(key));
+  key.base = (uintptr_t)base; key.rank = rank; key.dtype = (int)dtype; key.swz = (int)swz;
+  for (int i = 0; i < rank; ++i) { key.d[i] = d[i]; key.b[i] = b[i]; }
+  for (int i = 0; i + 1 < rank; ++i) key.s[i] = s[i];
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      const unsigned char* p = reinterpret_cast<const unsigned char*>(&k);
+      uint64_t h = 1469598103934665603ull;
+      for (size_t i = 0; i < sizeof(Key); ++i) { h ^= p[i]; h *= 1099511628211ull; }
+      return (size_t)h;
+    }
+  };
+  struct KeyEq {
+    bool operator()(const Key& a, const Key& c) const { return memcmp(&a, &c, sizeof(Key)) == 0; }
+  };
+  static thread_local std::unordered_map<Key, CUtensorMap, KeyHash, KeyEq> cache;
+  static const bool use_cache = !(getenv("QEB_TMAP_CACHE") && atoi(getenv("QEB_TMAP_CACHE")) == 0);
+  if (use_cache) {
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return QEB_OK;
+    }
+  }
   CUresult r = encode(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS && use_cache) {
+    if (cache.size() >= 8192) cache.clear();
+    cache.emplace(key, *out);
+  }
   if (r != CUDA_SUCCESS) {
     qeb_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u", (int)r, rank,
                   (unsigned long long)d[0], (unsigned long long)(rank > 1 ? d[1] : 0), (unsigned long long)(rank > 2 ? d[2] : 0),

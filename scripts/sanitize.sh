@@ -1,17 +1,14 @@
 #!/bin/bash
-# compute-sanitizer over small runs of both networks (forward + backward, train and frozen BatchNorm, the window conv
-# variant forced on with QEB_WIN=2) and of the integer / fused kernels. Output: gpurun_out/sanitizer_*.log
-# (copy the summaries to profiles/). Each tool run is bounded by `timeout`.
-OUT=${1:-gpurun_out}
+# compute-sanitizer, ONE tool per gpurun call (B200_PROFILING.md): scripts/sanitize.sh memcheck|racecheck|synccheck|initcheck
+# over one small process that runs both networks (forward + backward, train and frozen BatchNorm, the window conv variant
+# forced on), the fused head / jittered forward and the integer kernels. Output: gpurun_out/sanitizer_<tool>.log (copy to
+# profiles/). Bounded by `timeout`.
+TOOL=${1:-memcheck}
+OUT=gpurun_out
 mkdir -p $OUT
 export QEB_WIN=2
-for tool in memcheck racecheck; do
-  for what in crnn unet aux; do
-    script=scripts/dev_san.py; arg=$what
-    if [ $what = aux ]; then script=scripts/dev_san_aux.py; arg=; fi
-    echo "=== compute-sanitizer --tool $tool $script $arg" | tee -a $OUT/sanitizer_$tool.log
-    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python $script $arg 2>&1 | grep -v "^\s*$" | tail -25 >> $OUT/sanitizer_$tool.log
-    echo "exit: ${PIPESTATUS[0]}" >> $OUT/sanitizer_$tool.log
-  done
-done
-tail -4 $OUT/sanitizer_memcheck.log $OUT/sanitizer_racecheck.log
+python scripts/dev_san_all.py > $OUT/sanitizer_plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/sanitizer_plain.log; exit 1; }
+echo "=== compute-sanitizer --tool $TOOL python scripts/dev_san_all.py (QEB_WIN=2)" > $OUT/sanitizer_$TOOL.log
+timeout 1200 compute-sanitizer --tool $TOOL --print-limit 20 python scripts/dev_san_all.py 2>&1 | grep -v "^\s*$" | grep -v "Warning\|warn" | tail -40 >> $OUT/sanitizer_$TOOL.log
+echo "exit: ${PIPESTATUS[0]}" >> $OUT/sanitizer_$TOOL.log
+tail -6 $OUT/sanitizer_$TOOL.log
