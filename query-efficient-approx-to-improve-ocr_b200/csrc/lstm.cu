@@ -26,6 +26,7 @@
 #include "nn.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -66,6 +67,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(taddr)
                : "memory");
 }
@@ -123,7 +131,13 @@ struct LstmArgs {
   long long* tl;        // debugging aid (qeb_debug_set_timeline): clock64 stamps of CTA 0, 8 per step
 };
 
+// RB: batch rows a cluster really serves (16, or 8: the MMA keeps N = kBC = 16 - M = 128 allows no narrower tile - with the
+// upper 8 operand rows zero; the gate / cell / store work per thread and the pushed bytes halve and twice as many clusters
+// run: 128 instead of 64 CTAs at B = 64. Chosen by the launcher when all clusters still fit one wave.)
+template <int RB>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) lstm_fwd_kernel(LstmArgs a) {
+  constexpr int RPT = RB / 2;    // batch rows per gate thread
+  constexpr int CPT = RB / 8;    // batch rows per cell thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Hs = smem;                                     // B operand, double-buffered: [2][8 K chunks][16 batch][128 B]
@@ -134,7 +148,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kCluster;
-  const int dir = cid & 1, b0 = (cid >> 1) * kBC;
+  const int dir = cid & 1, b0 = (cid >> 1) * RB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q = warp & 3, bh = warp >> 2;
 
@@ -172,18 +186,18 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   cluster.sync();
   tc_fence_after();
 
-  // roles. gate thread: gate q of unit `lane` for batch rows [8 bh, 8 bh + 8); cell thread: unit `lane`, batch rows warp, warp + 8
+  // roles. gate thread: gate q of unit `lane` for batch rows [RPT bh, RPT bh + RPT); cell thread: unit `lane`, batch rows warp (, warp + 8)
   float c[2] = {0.f, 0.f};
   constexpr uint32_t idesc = instr_desc_tf32(128, kBC, 0, 0);
   const long long gstride = 2 * 4 * kH;  // floats between consecutive batch rows of `gates`
 
   // x-projections of this thread's gate row for its 8 batch rows, loaded one step ahead
-  float gx[8];
-  auto load_gx = [&](int s, float (&dst)[8]) {   // array by reference: a pointer parameter would force gx into local memory
+  float gx[RPT];
+  auto load_gx = [&](int s, float (&dst)[RPT]) {   // array by reference: a pointer parameter would force gx into local memory
     const int t = dir ? a.T - 1 - s : s;
-    const float* g = a.gates + (((long long)t * a.B + b0 + bh * 8) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
+    const float* g = a.gates + (((long long)t * a.B + b0 + bh * RPT) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dst[j] = (b0 + bh * 8 + j < a.B) ? g[j * gstride] : 0.f;
+    for (int j = 0; j < RPT; ++j) dst[j] = (b0 + bh * RPT + j < a.B) ? g[j * gstride] : 0.f;
   };
   load_gx(0, gx);
 
@@ -211,30 +225,34 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       }
       __syncwarp();
     }
-    float gx_next[8];
+    float gx_next[RPT];
     if (s + 1 < a.T) load_gx(s + 1, gx_next);
     mbar_wait(mma_bar, s & 1);
     tc_fence_after();
     if (tl) tl[8 * s + 2] = clock64();
-    float pre[kChains][8];
+    float pre[kChains][RPT];
 #pragma unroll
-    for (int ch = 0; ch < kChains; ++ch) tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol + (uint32_t)(ch * kBC + bh * 8), pre[ch]);
+    for (int ch = 0; ch < kChains; ++ch) {
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + kAccCol + (uint32_t)(ch * kBC + bh * RPT);
+      if constexpr (RPT == 8) tmem_ld8(ta, pre[ch]);
+      else tmem_ld4(ta, pre[ch]);
+    }
     tmem_ld_wait();
     tc_fence_before();
-    float av[8];
+    float av[RPT];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < RPT; ++j) {
       float v = gx[j];
 #pragma unroll
       for (int ch = 0; ch < kChains; ++ch) v += pre[ch][j];
       av[j] = q == 2 ? fast_tanh(v) : fast_sigmoid(v);
-      act[(q * kBC + bh * 8 + j) * kUnits + lane] = av[j];
+      act[(q * kBC + bh * RPT + j) * kUnits + lane] = av[j];
     }
     __syncthreads();
     if (tl) tl[8 * s + 3] = clock64();
-    float hv[2];
+    float hv[2] = {0.f, 0.f};
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < CPT; ++p) {
       const int bl = warp + 8 * p;
       const float ig = act[(0 * kBC + bl) * kUnits + lane], fg = act[(1 * kBC + bl) * kUnits + lane];
       const float gg = act[(2 * kBC + bl) * kUnits + lane], og = act[(3 * kBC + bl) * kUnits + lane];
@@ -249,13 +267,15 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     if (tl) tl[8 * s + 4] = clock64();
     if (warp == 0 && s + 1 < a.T) {   // warp-uniform branch + elected lane: the copy instructions take uniform operands
       if (elect_one()) {
-        // push this CTA's K chunk (16 batch rows x 128 B) into the same place of the 7 peers; arm the own barrier for theirs
-        mbar_expect_tx(&full_bar[(s + 1) & 1], (kCluster - 1) * kBTile);
+        // push this CTA's K chunk (RB batch rows x 128 B: the first RB rows of the tile) into the same place of the 7 peers;
+        // arm the own barrier for theirs
+        constexpr uint32_t kPush = RB * 128;
+        mbar_expect_tx(&full_bar[(s + 1) & 1], (kCluster - 1) * kPush);
         const uint32_t src = smem_u32(hnext + rank * kBTile), bar = smem_u32(&full_bar[(s + 1) & 1]);
 #pragma unroll
         for (int r = 1; r < kCluster; ++r) {
           const uint32_t peer = (uint32_t)((rank + r) & (kCluster - 1));
-          bulk_copy_to_cluster(mapa_u32(src, peer), src, kBTile, mapa_u32(bar, peer));
+          bulk_copy_to_cluster(mapa_u32(src, peer), src, kPush, mapa_u32(bar, peer));
         }
       }
       __syncwarp();
@@ -263,13 +283,13 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     if (tl) tl[8 * s + 5] = clock64();
     // global stores last: a proxy fence waits for the thread's outstanding stores, these drain during the next step
     {
-      float* g = a.gates + (((long long)t * a.B + b0 + bh * 8) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
+      float* g = a.gates + (((long long)t * a.B + b0 + bh * RPT) * 2 + dir) * (4 * kH) + q * kH + rank * kUnits + lane;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (b0 + bh * 8 + j < a.B) g[j * gstride] = av[j];   // activated gates, saved for the backward pass
+      for (int j = 0; j < RPT; ++j)
+        if (b0 + bh * RPT + j < a.B) g[j * gstride] = av[j];   // activated gates, saved for the backward pass
     }
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < CPT; ++p) {
       const int b = b0 + warp + 8 * p;
       if (b < a.B) {
         a.cells[(((long long)t * a.B + b) * 2 + dir) * kH + rank * kUnits + lane] = c[p];
@@ -278,7 +298,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
       }
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gx[j] = gx_next[j];
+    for (int j = 0; j < RPT; ++j) gx[j] = gx_next[j];
     if (tl) tl[8 * s + 6] = clock64();
   }
   tc_fence_before();
@@ -286,7 +306,9 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+template <int RB>   // see lstm_fwd_kernel
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) lstm_bwd_kernel(LstmArgs a) {
+  constexpr int CPT = RB / 8;    // batch rows per cell thread
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Dg = smem;                                        // B operand d(gates): 4 K chunks (one per gate) x [16 batch][128 B]
@@ -298,9 +320,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   const int cid = blockIdx.x / kCluster;
-  const int dir = cid & 1, b0 = (cid >> 1) * kBC;
+  const int dir = cid & 1, b0 = (cid >> 1) * RB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
+  if (RB < kBC)   // operand rows [RB, 16) are never written: they must read as zero
+    for (int i = tid; i < 4 * kBTile / 16; i += kThreads) reinterpret_cast<float4*>(Dg)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (tid == 0) {
     mbar_init(mma_bar, 1);
     mbar_init(&full_bar[0], 1);
@@ -349,7 +373,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     }
     return v;
   };
-  Saved sv[2] = {load_saved(0, 0), load_saved(0, 1)};
+  Saved sv[2] = {load_saved(0, 0), CPT > 1 ? load_saved(0, 1) : Saved{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
 
   long long* tl = (a.tl && blockIdx.x == 0 && tid == 0) ? a.tl : nullptr;
   for (int s = 0; s < a.T; ++s) {
@@ -360,7 +384,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     if (tl) tl[8 * s + 1] = clock64();
     float dgv[2][4];
 #pragma unroll
-    for (int p = 0; p < 2; ++p) {
+    for (int p = 0; p < CPT; ++p) {
       const int bl = warp + 8 * p, b = b0 + bl;
       float d_i = 0.f, d_f = 0.f, d_g = 0.f, d_o = 0.f;
       if (b < a.B) {
@@ -388,7 +412,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     }
     auto store_dgates = [&]() {   // d(pre-activations) for the weight-gradient GEMMs; after the proxy fence (see forward)
 #pragma unroll
-      for (int p = 0; p < 2; ++p) {
+      for (int p = 0; p < CPT; ++p) {
         const int b = b0 + warp + 8 * p;
         if (b < a.B) {
           float* g = a.gates + (((long long)t * a.B + b) * 2 + dir) * (4 * kH) + rank * kUnits + lane;
@@ -409,7 +433,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     __syncthreads();
     if (tl) tl[8 * s + 2] = clock64();
     if (warp == 0) {
-      if (lane == 0) mbar_expect_tx(&full_bar[s & 1], kCluster * kBlk * sizeof(float));   // the 8 blocks the cluster pushes in this step
+      if (lane == 0) mbar_expect_tx(&full_bar[s & 1], kCluster * RB * kUnits * sizeof(float));   // the 8 blocks the cluster pushes in this step
       tc_fence_after();
       if (elect_one()) {
         const uint32_t db = smem_u32(Dg);
@@ -430,7 +454,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     }
     store_dgates();
     sv[0] = load_saved(s + 1, 0);
-    sv[1] = load_saved(s + 1, 1);
+    if (CPT > 1) sv[1] = load_saved(s + 1, 1);
     mbar_wait(mma_bar, s & 1);
     tc_fence_after();
     if (tl) tl[8 * s + 3] = clock64();
@@ -438,16 +462,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     // owns one k (one TMEM lane); the block is transposed through shared memory into the receiver's [batch][unit] layout and
     // pushed with one 2 KB bulk copy. The staging buffer is double-buffered: the copy of step s-2 has been consumed by the
     // time step s was allowed to start, the one of step s-1 possibly not.
-    float v[kBC];
+    float v[RB];
     {
-      float vc[kChains][kBC];
+      float vc[kChains][RB];
 #pragma unroll
-      for (int ch = 0; ch < kChains; ++ch)
-        tmem_ld16(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCol + (uint32_t)(((warp >> 2) * kChains + ch) * kBC), vc[ch]);
+      for (int ch = 0; ch < kChains; ++ch) {
+        const uint32_t ta = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kAccCol + (uint32_t)(((warp >> 2) * kChains + ch) * kBC);
+        if constexpr (RB == 16) tmem_ld16(ta, vc[ch]);
+        else tmem_ld8(ta, vc[ch]);
+      }
       tmem_ld_wait();
       tc_fence_before();
 #pragma unroll
-      for (int j = 0; j < kBC; ++j) {
+      for (int j = 0; j < RB; ++j) {
         v[j] = vc[0][j];
 #pragma unroll
         for (int ch = 1; ch < kChains; ++ch) v[j] += vc[ch][j];
@@ -456,12 +483,12 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
     {
       float* stg = stage + ((s & 1) * kCluster + warp) * kBlk;
 #pragma unroll
-      for (int j = 0; j < kBC; ++j) stg[j * kUnits + lane] = v[j];
+      for (int j = 0; j < RB; ++j) stg[j * kUnits + lane] = v[j];
       fence_proxy_async_all();
       __syncwarp();
       if (elect_one()) {
         const uint32_t dst = smem_u32(recv + ((s & 1) * kCluster + rank) * kBlk);
-        bulk_copy_to_cluster(mapa_u32(dst, warp), smem_u32(stg), kBlk * sizeof(float), mapa_u32(smem_u32(&full_bar[s & 1]), warp));
+        bulk_copy_to_cluster(mapa_u32(dst, warp), smem_u32(stg), RB * kUnits * sizeof(float), mapa_u32(smem_u32(&full_bar[s & 1]), warp));
       }
     }
     if (tl) tl[8 * s + 4] = clock64();
@@ -469,6 +496,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1) 
   tc_fence_before();
   cluster.sync();   // no CTA leaves while a peer may still read the block it pushed or write into this CTA
   if (warp == 0) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Batch rows per cluster: 16. The 8-row form (twice the clusters: 128 instead of 64 CTAs at B = 64, half the gate / cell /
+// store work per thread and step) is correct (tests) but SLOWER in the step - 3.49 -> 3.66 ms (phase B), 12.4 -> 13.8 ms (jitter
+// step): a step of the recurrence is a latency chain (MMA -> tcgen05.ld -> gates -> barrier -> cell -> proxy fence -> barrier ->
+// push -> the peers' wait), not per-thread arithmetic, and twice as many whole-SM CTAs take the SMs away from the weight-
+// gradient kernels that run beside it. Kept behind QEB_LSTM_ROWS=8 for measurements.
+int rows_per_cluster(int B) {
+  static const int forced = getenv("QEB_LSTM_ROWS") ? atoi(getenv("QEB_LSTM_ROWS")) : 0;
+  (void)B;
+  return forced == 8 ? 8 : 16;
 }
 
 int launch_cluster(const void* fn, size_t smem, int n_clusters, LstmArgs& args, cudaStream_t st) {
@@ -497,7 +535,8 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && y && T > 0 && B > 0, "lstm_layer_fwd: bad arguments");
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
+    QEB_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
+    QEB_CUDA(cudaFuncSetAttribute(lstm_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
     attr = true;
   }
   LstmArgs a;
@@ -505,7 +544,8 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
   a.y16 = static_cast<__half*>(y16);
   a.round_io = round_io;
   ProfScope prof("lstm_fwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
-  return launch_cluster((const void*)lstm_fwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
+  if (rows_per_cluster(B) == 8) return launch_cluster((const void*)lstm_fwd_kernel<8>, kSmemPad, 2 * qeb_cdiv(B, 8), a, st);
+  return launch_cluster((const void*)lstm_fwd_kernel<16>, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
 
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
@@ -513,7 +553,8 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
   QEB_REQUIRE(gates && w_hh_fwd && w_hh_rev && cells && dy && T > 0 && B > 0, "lstm_layer_bwd: bad arguments");
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
+    QEB_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
+    QEB_CUDA(cudaFuncSetAttribute(lstm_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemPad));
     attr = true;
   }
   LstmArgs a;
@@ -522,7 +563,8 @@ int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const floa
   a.T = T; a.B = B;
   a.round_io = round_io;
   ProfScope prof("lstm_bwd", st, 2.0 * T * B * 2 * 1024 * 256, 4.0 * T * B * (2 * 2048 + 512 + 512));
-  return launch_cluster((const void*)lstm_bwd_kernel, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
+  if (rows_per_cluster(B) == 8) return launch_cluster((const void*)lstm_bwd_kernel<8>, kSmemPad, 2 * qeb_cdiv(B, 8), a, st);
+  return launch_cluster((const void*)lstm_bwd_kernel<16>, kSmemPad, 2 * qeb_cdiv(B, kBC), a, st);
 }
 
 // C ABI (tests): one bidirectional layer of the recurrence
