@@ -583,7 +583,9 @@ def run():
                 "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "parity": parity_block(),
                 "decode_gate": decode_gate_block()}
     # ---- the other BASELINE.json configs, short runs, appended so that they are part of the driver-run line
-    if not args.no_extras:
+    # (single-GPU line only: at N > 1 an exception on one rank inside an extra would leave the others waiting in a collective;
+    # the multi-GPU forms of the workloads are run explicitly with --workload)
+    if not args.no_extras and world == 1:
         import bench_workloads
         extras = {}
         for wl in ("jitter_step", "area_step", "cer_topk"):
