@@ -1,7 +1,9 @@
 // C-ABI plumbing shared by every entry point: thread-local error string, launch counter, device probe.
 #include "nn.cuh"
 #include <atomic>
+#include <list>
 #include <map>
+#include <unordered_map>
 #include <mutex>
 #include <string>
 #include <stdlib.h>
@@ -25,6 +27,7 @@ QEB_API const char* qeb_last_error(void) { return g_err; }
 QEB_API int qeb_abi_version(void) { return 1; }
 
 QEB_API long long qeb_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+long long qeb_launch_count_now() { return g_launches.load(std::memory_order_relaxed); }
 
 QEB_API void qeb_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
 
@@ -177,6 +180,79 @@ int SideStream::wait_mark() {
   if (!enabled || !marked) return QEB_OK;
   QEB_CUDA(cudaStreamWaitEvent(main, mark_ev, 0));
   marked = false;
+  return QEB_OK;
+}
+
+// ---- per-call CUDA graphs (nn.cuh) -------------------------------------------------------------------------------------------
+namespace {
+struct CallGraph {
+  std::string key;
+  cudaGraphExec_t exec = nullptr;
+  long long launches = 0;
+};
+struct CallGraphCache {
+  std::list<CallGraph> lru;                                            // most recently used first
+  std::unordered_map<std::string, std::list<CallGraph>::iterator> index;
+  cudaStream_t capture_stream = nullptr;
+  int device = -1;
+  ~CallGraphCache() {}   // graphs live until the process ends (destroying them at thread exit would race with the CUDA teardown)
+};
+thread_local CallGraphCache g_calls;
+constexpr size_t kMaxCallGraphs = 24;
+}  // namespace
+
+int qeb_run_cached(const CallKey& key, cudaStream_t st, const std::function<int(cudaStream_t)>& body) {
+  static const int mode = getenv("QEB_CALL_GRAPHS") ? atoi(getenv("QEB_CALL_GRAPHS")) : 1;
+  if (!mode || qeb_prof_on() || qeb_dbg_skip_active() || qeb_debug_timeline() != nullptr) return body(st);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return body(st); }
+  if (cap != cudaStreamCaptureStatusNone) return body(st);             // already inside somebody's capture (GraphedStep)
+  int dev = 0;
+  QEB_CUDA(cudaGetDevice(&dev));
+  CallGraphCache& c = g_calls;
+  if (c.device != dev) {   // first use on this thread (or another device: start over)
+    c.lru.clear(); c.index.clear();
+    if (cudaStreamCreateWithFlags(&c.capture_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return body(st); }
+    c.device = dev;
+  }
+  std::string k = key.bytes;
+  k.append(reinterpret_cast<const char*>(&dev), sizeof(dev));
+  auto hit = c.index.find(k);
+  if (hit != c.index.end()) {
+    c.lru.splice(c.lru.begin(), c.lru, hit->second);
+    qeb_count_launch((int)hit->second->launches);
+    QEB_CUDA(cudaGraphLaunch(hit->second->exec, st));
+    return QEB_OK;
+  }
+  const long long n0 = qeb_launch_count_now();
+  if (cudaStreamBeginCapture(c.capture_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return body(st); }
+  const int rc = body(c.capture_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c.capture_stream, &graph);
+  if (rc != QEB_OK) {   // argument error inside the body: nothing ran, report it
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc;
+  }
+  if (e != cudaSuccess || !graph) {   // not capturable on this driver / configuration: run it plainly from now on
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return body(st);
+  }
+  CallGraph g;
+  g.key = k;
+  g.launches = qeb_launch_count_now() - n0;
+  const cudaError_t ei = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) { cudaGetLastError(); return body(st); }
+  if (c.lru.size() >= kMaxCallGraphs) {
+    cudaGraphExecDestroy(c.lru.back().exec);
+    c.index.erase(c.lru.back().key);
+    c.lru.pop_back();
+  }
+  c.lru.push_front(g);
+  c.index[k] = c.lru.begin();
+  QEB_CUDA(cudaGraphLaunch(c.lru.front().exec, st));
   return QEB_OK;
 }
 

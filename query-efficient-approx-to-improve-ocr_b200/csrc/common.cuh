@@ -48,6 +48,7 @@ static inline int qeb_grid(long long total, int threads, int blocks_per_sm = 8) 
 
 // launch-counter (bench.py reports gpu_launches from it)
 void qeb_count_launch(int n = 1);
+long long qeb_launch_count_now();
 
 // per-launch profiling scope (abi.cu): no-op unless qeb_prof_enable(1)
 int qeb_prof_on();

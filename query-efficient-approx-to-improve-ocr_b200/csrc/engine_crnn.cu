@@ -146,8 +146,27 @@ struct CrnnFwdOpts {
   int log_softmax = 0;                  // 1: `logits` receives log_softmax(logits) straight from the Linear epilogue
   int* argmax = nullptr;                // (T,B) per-frame arg-max of the log-probs (with log_softmax), nullable
 };
-int crnn_forward_impl(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
+int crnn_forward_body(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
                       void* ws, float* logits, const CrnnFwdOpts& opt, void* stream);
+// one captured graph per distinct argument set (nn.cuh qeb_run_cached); a host-seeded jitter changes its key every call: plain launches
+int crnn_forward_impl(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
+                      void* ws, float* logits, const CrnnFwdOpts& opt, void* stream) {
+  QEB_REQUIRE(x && params && buffers && ws && logits, "crnn_forward: null pointer");
+  if (opt.jitter && !opt.jitter->seed_dev)
+    return crnn_forward_body(x, B, W, V, params, buffers, bn_train, ws, logits, opt, stream);
+  CallKey key;
+  key.add(1).add(x).add(B).add(W).add(V).add(bn_train).add(ws).add(logits).add(opt.log_softmax).add(opt.argmax);
+  key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(buffers), B_COUNT);
+  if (opt.jitter) {
+    const JitterArgs& j = *opt.jitter;
+    key.add(j.sigma).add(j.mean).add(j.coef).add(j.seed).add(j.seed_dev).add(j.noisy_out).add(j.noise_out);
+  } else {
+    key.add(0);
+  }
+  return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
+    return crnn_forward_body(x, B, W, V, params, buffers, bn_train, ws, logits, opt, (void*)st);
+  });
+}
 }  // namespace
 
 QEB_API int qeb_crnn_forward(const float* x, int B, int W, int V, const float* const* params, void* const* buffers,
@@ -182,7 +201,7 @@ QEB_API int qeb_crnn_forward_fused(const float* x, int B, int W, int V, const fl
 }
 
 namespace {
-int crnn_forward_impl(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
+int crnn_forward_body(const float* x, int B, int W, int V, const float* const* params, void* const* buffers, int bn_train,
                       void* ws, float* logits, const CrnnFwdOpts& opt, void* stream) {
   QEB_REQUIRE(x && params && buffers && ws && logits, "crnn_forward: null pointer");
   QEB_REQUIRE(B > 0 && W >= 8 && W % 4 == 0 && V > 0 && V <= 96, "crnn_forward: B=%d W=%d V=%d unsupported", B, W, V);
@@ -336,8 +355,23 @@ int crnn_forward_impl(const float* x, int B, int W, int V, const float* const* p
 // dlogits: (T,B,V) dense. grads: P_COUNT pointers (entries may be NULL, all NULL-able: that gradient is skipped);
 // every non-NULL gradient is ACCUMULATED into (zero it for a plain gradient). dx: (B,1,32,W) or NULL.
 // The workspace must be the one the forward filled, with the same B, W, V, params and bn_train.
+namespace {
+int crnn_backward_body(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
+                       const float* dlogits, float* const* grads, float* dx, void* stream);
+}
 QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
                               const float* dlogits, float* const* grads, float* dx, void* stream) {
+  QEB_REQUIRE(x && params && ws && dlogits && grads, "crnn_backward: null pointer");
+  CallKey key;
+  key.add(2).add(x).add(B).add(W).add(V).add(bn_train).add(ws).add(dlogits).add(dx);
+  key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(grads), P_COUNT);
+  return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
+    return crnn_backward_body(x, B, W, V, params, bn_train, ws, dlogits, grads, dx, (void*)st);
+  });
+}
+namespace {
+int crnn_backward_body(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
+                       const float* dlogits, float* const* grads, float* dx, void* stream) {
   QEB_REQUIRE(x && params && ws && dlogits && grads, "crnn_backward: null pointer");
   QEB_REQUIRE(B > 0 && W >= 8 && W % 4 == 0 && V > 0 && V <= 96, "crnn_backward: B=%d W=%d V=%d unsupported", B, W, V);
   cudaStream_t st = (cudaStream_t)stream;
@@ -515,3 +549,4 @@ QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* 
   }
   return QEB_OK;
 }
+}  // namespace

@@ -270,8 +270,23 @@ QEB_API int qeb_unet_num_params(void) { return P_COUNT; }
 QEB_API int qeb_unet_num_buffers(void) { return B_COUNT; }
 
 // x: (B,1,H,W) fp32, H and W multiples of 16. y: (B,1,H,W) in (0,1). bn_train as in qeb_crnn_forward.
+namespace {
+int unet_forward_body(const float* x, int B, int H, int W, const float* const* params, void* const* buffers, int bn_train, void* ws,
+                      float* y, void* stream);
+}
 QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* const* params, void* const* buffers,
                              int bn_train, void* ws, float* y, void* stream) {
+  QEB_REQUIRE(x && params && buffers && ws && y, "unet_forward: null pointer");
+  CallKey key;   // one captured graph per distinct argument set (nn.cuh qeb_run_cached)
+  key.add(3).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y);
+  key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(buffers), 3 * kUnits);
+  return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
+    return unet_forward_body(x, B, H, W, params, buffers, bn_train, ws, y, (void*)st);
+  });
+}
+namespace {
+int unet_forward_body(const float* x, int B, int H, int W, const float* const* params, void* const* buffers, int bn_train, void* ws,
+                      float* y, void* stream) {
   QEB_REQUIRE(x && params && buffers && ws && y, "unet_forward: null pointer");
   QEB_REQUIRE(B > 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0, "unet_forward: B=%d H=%d W=%d unsupported", B, H, W);
   QEB_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)x & 15) == 0, "unet_forward: workspace/input alignment");
@@ -357,6 +372,7 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
   }
   return o1_conv_sigmoid_fwd(below, params[P_CONVW], params[P_CONVB], y, c.st);
 }
+}  // namespace
 
 // dy: (B,1,H,W). grads: P_COUNT pointers, NULL = skip, non-NULL gradients are ACCUMULATED into. dx: (B,1,H,W) or NULL.
 // y must be the forward's output; ws the forward's workspace.
@@ -395,7 +411,21 @@ QEB_API int qeb_unet_backward_bucketed(const float* x, int B, int H, int W, cons
 }
 
 namespace {
+int unet_backward_body(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
+                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream);
 int unet_backward_impl(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
+                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream) {
+  QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
+  // an event recorded inside a private capture could not be waited for by the caller's communication stream: plain launches
+  if (tail_ready_event) return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, tail_ready_event, stream);
+  CallKey key;
+  key.add(4).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y).add(dy).add(dx);
+  key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(grads), P_COUNT);
+  return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
+    return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, nullptr, (void*)st);
+  });
+}
+int unet_backward_body(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
                        const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream) {
   QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
   QEB_REQUIRE(B > 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0, "unet_backward: B=%d H=%d W=%d unsupported", B, H, W);

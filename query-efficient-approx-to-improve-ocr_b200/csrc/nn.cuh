@@ -3,6 +3,8 @@
 // sequence-major (T,B,C) tensors and channel slices are read and written in place.
 #pragma once
 #include "common.cuh"
+#include <functional>
+#include <string>
 
 struct Img {
   float* p;
@@ -225,6 +227,28 @@ int lstm_layer_fwd(float* gates, const float* w_hh_fwd, const float* w_hh_rev, f
 // dy: (T,B,512). gates (activated) are overwritten with the gradients at the pre-activations (T,B,2,1024).
 int lstm_layer_bwd(float* gates, const float* cells, const float* dy, const float* w_hh_fwd, const float* w_hh_rev, int T,
                    int B, cudaStream_t st, int round_io = 0);
+
+// ---- per-call CUDA graphs, abi.cu --------------------------------------------------------------------------------------
+// An engine call (one network forward or backward) is 30-90 kernel launches issued from one C call; at ~3 us of host time per
+// cudaLaunchKernelEx an eagerly launched training step is bound by the HOST (4.3 ms issued for 3.5 ms of GPU work). The
+// launch sequence of a call is a pure function of its arguments - shapes, flags and POINTERS, and the caching allocator hands
+// the same workspace / gradient / input blocks back step after step - so the call is captured once per distinct argument
+// set (on an internal stream: the caller's stream may be the legacy default stream, which cannot be captured) and later
+// calls with the same arguments replay the instantiated graph on the caller's stream: one cudaGraphLaunch. Bypassed while
+// the caller's stream is itself being captured (GraphedStep), under qeb_prof_enable / QEB_DBG_SKIP, and with
+// QEB_CALL_GRAPHS=0. `key` must hold EVERYTHING the body's launches depend on.
+struct CallKey {
+  std::string bytes;
+  void raw(const void* p, size_t n) { bytes.append(static_cast<const char*>(p), n); }
+  template <typename T>
+  CallKey& add(const T& v) { raw(&v, sizeof(T)); return *this; }
+  CallKey& ptrs(const void* const* a, int n) {   // the VALUES of an array of pointers (NULL array: nothing)
+    if (a) raw(a, sizeof(void*) * (size_t)n);
+    else add(n);
+    return *this;
+  }
+};
+int qeb_run_cached(const CallKey& key, cudaStream_t st, const std::function<int(cudaStream_t)>& body);
 
 // ---- side stream, abi.cu ----------------------------------------------------------------------------------------
 // Weight and bias gradients are off the backward's critical path (only the input gradients feed the next layer), so the
