@@ -368,7 +368,7 @@ def run():
     unet_params = [p for p in prep.parameters()]
 
     # data parallel: the 31 MB flat UNet gradient is averaged over the ranks once per step; the part of it the backward pass
-    # finishes first (bottleneck + decoder, 85 %) is reduced on a communication stream while the encoder's backward runs
+    # finishes first (decoder, then bottleneck + encoder 4: 96 %) is reduced on a communication stream meanwhile
     overlap = qdist.BucketedAllReduce(prep, average=True)
 
     def allreduce_grads():
@@ -569,10 +569,11 @@ def run():
                 "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
                 "allreduce": None if world == 1 else {
-                    "bytes": sum(p.numel() for p in unet_params) * 4, "op": "AVG", "collectives_per_step": 2,
+                    "bytes": sum(p.numel() for p in unet_params) * 4, "op": "AVG", "collectives_per_step": 3,
                     "ms_per_step_without_exchange": ms_no_allreduce, "exposed_us": 1e3 * (ms_step - ms_no_allreduce),
-                    "note": "bottleneck + decoder gradients (26.4 MB) all-reduced on a communication stream while the encoder's backward "
-                            "runs (qeb_unet_backward_bucketed), encoder gradients (4.7 MB) after it; both inside the captured graph"},
+                    "note": "decoder gradients (12.2 MB) and bottleneck + encoder-4 gradients (17.7 MB) all-reduced on a communication stream as soon as "
+                            "they are final, while the rest of the backward runs (qeb_unet_backward_bucketed); the last 1.1 MB after it; all "
+                            "inside the captured graph"},
                 "tflops_algorithmic": GFLOP_PER_PATCH * value / 1e3, "loss": last_loss,
                 "variants": None if args.skip_eager else {
                     "eager_modules": {"value": BATCH * world / (ms_eager / 1e3), "ms_per_step": ms_eager,

@@ -168,13 +168,14 @@ int qeb_unet_forward(const float* x, int B, int H, int W, const float* const* pa
                      void* ws, float* y, void* stream);
 int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
                       const float* y, const float* dy, float* const* grads, float* dx, void* stream);
-/* The same backward for data-parallel training with an overlapped gradient exchange (one NCCL all-reduce per step over the
- * flat gradient buffer): tail_ready_event (a cudaEvent_t) is recorded on `stream` as soon as the gradients
- * of parameters [24, 64) of the ABI order - bottleneck, decoder blocks, up-convolutions, final conv: 85 % of the bytes, which
- * the backward pass reaches first - are final; a communication stream waiting for it can reduce that range while the
- * encoder's backward still runs. Parameters [0, 24) are final when the call's work completes. */
+/* The same backward for data-parallel training with an overlapped gradient exchange (NCCL all-reduces over ranges of the flat
+ * gradient buffer, SURVEY.md 8(e): "bucketed in reverse-layer order and overlapped with the remaining wgrads"). Gradients
+ * become final last layer first, i.e. from the END of the ABI parameter order: bucket_events = two cudaEvent_t, recorded as soon
+ * as parameters [30, 64) (decoder blocks, up-convolutions, final conv: 12.2 MB) resp. [18, 30) (encoder block 4, bottleneck:
+ * 17.7 MB) are final; parameters [0, 18) (1.1 MB) are final when the call's work completes. A communication stream that waits
+ * for an event can reduce its range while the rest of the backward runs. */
 int qeb_unet_backward_bucketed(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
-                               const float* y, const float* dy, float* const* grads, float* dx, void* tail_ready_event,
+                               const float* y, const float* dy, float* const* grads, float* dx, void* const* bucket_events,
                                void* stream);
 
 /* ==== building blocks, exported for tests and for callers that compose their own graphs ===========================

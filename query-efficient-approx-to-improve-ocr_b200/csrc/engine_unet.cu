@@ -392,32 +392,36 @@ int unpack_weight_grads(const UnetPlan& p, float* const* grads, int blk0, int bl
   return pack_flush(pk, st);
 }
 int unet_backward_impl(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
-                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream);
+                       const float* dy, float* const* grads, float* dx, void* const* bucket_events, void* stream);
 }
 QEB_API int qeb_unet_backward(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
                               const float* y, const float* dy, float* const* grads, float* dx, void* stream) {
   return unet_backward_impl(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, nullptr, stream);
 }
 
-// The same backward for data-parallel training with an overlapped gradient exchange: `tail_ready_event` (a cudaEvent_t) is
-// recorded on `stream` as soon as the gradients of parameters [24, 64) of the ABI order - the bottleneck, the four decoder
-// blocks, the up-convolutions and the final 1x1 conv: 85 % of the bytes - are FINAL (the backward pass reaches them first);
-// a communication stream that waits for it can all-reduce that range while the encoder's backward still runs. The
-// gradients of parameters [0, 24) (the encoder) are final when the call's work completes, as always.
+// The same backward for data-parallel training with an overlapped gradient exchange. Gradients become final in the order the
+// backward pass (and, behind it, the weight-gradient stream) walks the network - last layer first - which is the flat gradient
+// buffer from its END: `bucket_events` = two cudaEvent_t, recorded on the library's side stream (which the call joins before it
+// returns) as soon as a range of the ABI parameter order is FINAL:
+//   bucket_events[0]: parameters [30, 64) - the four decoder blocks, the up-convolutions, the final conv (12.2 MB)
+//   bucket_events[1]: parameters [18, 30) - encoder block 4 and the bottleneck (17.7 MB)
+// and parameters [0, 18) - encoder blocks 1-3, 1.1 MB - when the call's work completes, as always. A communication stream that
+// waits for an event can all-reduce its range while the rest of the backward runs.
 QEB_API int qeb_unet_backward_bucketed(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws,
-                                       const float* y, const float* dy, float* const* grads, float* dx, void* tail_ready_event,
+                                       const float* y, const float* dy, float* const* grads, float* dx, void* const* bucket_events,
                                        void* stream) {
-  return unet_backward_impl(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, tail_ready_event, stream);
+  QEB_REQUIRE(bucket_events && bucket_events[0] && bucket_events[1], "unet_backward_bucketed: two events are required");
+  return unet_backward_impl(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, bucket_events, stream);
 }
 
 namespace {
 int unet_backward_body(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
-                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream);
+                       const float* dy, float* const* grads, float* dx, void* const* bucket_events, void* stream);
 int unet_backward_impl(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
-                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream) {
+                       const float* dy, float* const* grads, float* dx, void* const* bucket_events, void* stream) {
   QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
   // an event recorded inside a private capture could not be waited for by the caller's communication stream: plain launches
-  if (tail_ready_event) return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, tail_ready_event, stream);
+  if (bucket_events) return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, bucket_events, stream);
   CallKey key;
   key.add(4).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y).add(dy).add(dx);
   key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(grads), P_COUNT);
@@ -426,7 +430,7 @@ int unet_backward_impl(const float* x, int B, int H, int W, const float* const* 
   });
 }
 int unet_backward_body(const float* x, int B, int H, int W, const float* const* params, int bn_train, void* ws, const float* y,
-                       const float* dy, float* const* grads, float* dx, void* tail_ready_event, void* stream) {
+                       const float* dy, float* const* grads, float* dx, void* const* bucket_events, void* stream) {
   QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
   QEB_REQUIRE(B > 0 && H >= 16 && W >= 16 && H % 16 == 0 && W % 16 == 0, "unet_backward: B=%d H=%d W=%d unsupported", B, H, W);
   const UnetPlan p = make_plan(B, H, W, ws);
@@ -435,7 +439,6 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
   SideStream ss;
   TRY(ss.init(c.st));
   c.ss = &ss;
-  bool tail_unpacked = false;
   int red_done[kUnits] = {0};
   c.red_done = red_done;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
@@ -486,6 +489,16 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
     const TcEpilogue e = grad_into_unit(c, blk_below * 2 + 1, &z_below);
     TRY(tc_convT_dgrad(dU, p.wupd[up], gbelow, e, c.st));
   }
+  int unpacked_from = 9;   // conv blocks [unpacked_from, 9) already have their weight gradients in the caller's tensors
+  if (bucket_events) {
+    // the decoder is done on the main chain: the side stream (which holds its weight gradients, in order) waits for this point
+    // of the main stream - the BatchNorm gradients are produced there -, finishes the decoder's conv weight gradients and
+    // signals the caller
+    TRY(ss.fork());
+    TRY(unpack_weight_grads(p, grads, 5, 9, ss.s()));
+    unpacked_from = 5;
+    QEB_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[0], ss.s()));
+  }
   TRY(ss.join());  // the encoder phase re-uses the decoder phase's gradient buffers
   for (int i = 4; i >= 0; --i) {  // bottleneck, then encoder blocks
     const int C = p.C[i];
@@ -511,12 +524,11 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
       Img in = img_nhwc(p.pool[i - 1], B, p.h[i], p.w[i], p.C[i - 1]);
       Img gin = img_nhwc(p.sA[i], B, p.h[i], p.w[i], p.C[i - 1]);
       TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, &gin));
-      if (i == 4 && tail_ready_event) {
-        // the bottleneck and everything above it is done: finish those weight gradients now and tell the caller
-        TRY(ss.join());
-        TRY(unpack_weight_grads(p, grads, 4, 9, c.st));
-        tail_unpacked = true;
-        QEB_CUDA(cudaEventRecord((cudaEvent_t)tail_ready_event, c.st));
+      if (i == 3 && bucket_events) {   // the bottleneck and encoder block 4: the same on the side stream, the main chain goes on
+        TRY(ss.fork());
+        TRY(unpack_weight_grads(p, grads, 3, 5, ss.s()));
+        unpacked_from = 3;
+        QEB_CUDA(cudaEventRecord((cudaEvent_t)bucket_events[1], ss.s()));
       }
     } else {
       Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
@@ -529,7 +541,7 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
     }
   }
   TRY(ss.join());
-  TRY(unpack_weight_grads(p, grads, 0, tail_unpacked ? 4 : 9, c.st));
+  TRY(unpack_weight_grads(p, grads, 0, unpacked_from, c.st));
   return QEB_OK;
 }
 }  // namespace

@@ -64,30 +64,32 @@ class BucketedAllReduce:
     """The UNet gradient exchange of a data-parallel step, overlapped with the backward pass ("bucketed in
     reverse-layer order and overlapped with the remaining wgrads").
 
-    The backward pass reaches the decoder, the up-convolutions and the bottleneck first - 85 % of the 31 MB - and the encoder
-    last. `qeb_unet_backward_bucketed` records an event when that first range of the flat gradient buffer is final; this
-    object all-reduces it on a communication stream that waits for the event, i.e. while the encoder's backward still runs,
-    and the encoder's 4.7 MB on the caller's stream afterwards:
+    Gradients become final in the order the backward pass - and, behind it, the weight-gradient stream - walks the network: the
+    decoder first, then the bottleneck and encoder block 4, the full-resolution encoder blocks last; that is the flat gradient
+    buffer from its END. `qeb_unet_backward_bucketed` records an event when each of the first two ranges (12.2 MB, 17.7 MB) is
+    final; this object all-reduces them on a communication stream that waits for the events, i.e. while the rest of the
+    backward runs, and the remaining 1.1 MB on the caller's stream afterwards:
 
-        ar = BucketedAllReduce(prep_model)            # once; installs the event on the module
+        ar = BucketedAllReduce(prep_model)            # once; installs the events on the module
         loss.backward(); ar(); optimizer.step()       # every step (also inside a GraphedStep capture)
 
-    Works inside a CUDA-graph capture (the event record, the stream fork / join and both NCCL calls are captured)."""
+    Works inside a CUDA-graph capture (the event records, the stream fork / join and the NCCL calls are captured)."""
 
     def __init__(self, unet, average=True, group=None):
         self.unet, self.average, self.group = unet, average, group
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
-        self.event = self.comm = None
+        self.events = self.comm = None
         if self.active and next(unet.parameters()).is_cuda:
-            self.event = torch.cuda.Event()
-            self.event.record()        # torch creates the cudaEvent lazily at the first record: the C ABI needs the handle
-            if not self.event.cuda_event:
-                raise RuntimeError("BucketedAllReduce: could not create the CUDA event")
+            self.events = (torch.cuda.Event(), torch.cuda.Event())
+            for ev in self.events:
+                ev.record()            # torch creates the cudaEvent lazily at the first record: the C ABI needs the handle
+                if not ev.cuda_event:
+                    raise RuntimeError("BucketedAllReduce: could not create the CUDA event")
             self.comm = torch.cuda.Stream()
-            unet._qeb_tail_event = self.event
+            unet._qeb_tail_event = self.events
 
     def close(self):
-        if getattr(self.unet, "_qeb_tail_event", None) is self.event:
+        if getattr(self.unet, "_qeb_tail_event", None) is self.events:
             self.unet._qeb_tail_event = None
 
     def __call__(self):
@@ -95,21 +97,23 @@ class BucketedAllReduce:
             return 0
         params = self.unet.qeb_parameters()
         flat = flat_grad_buffer(params)
-        if flat is None or self.event is None:
+        if flat is None or self.events is None:
             return allreduce_grads(params, self.average, self.group)
-        first = params[self.unet.QEB_TAIL_FIRST_PARAM].grad
         lo = min(p.grad.storage_offset() for p in params)
-        cut = first.storage_offset() - lo
-        head, tail = flat[:cut], flat[cut:]
+        cuts = [params[i].grad.storage_offset() - lo for i in self.unet.QEB_BUCKET_STARTS]      # descending offsets
         op = dist.ReduceOp.AVG if self.average else dist.ReduceOp.SUM
         cur = torch.cuda.current_stream()
-        self.comm.wait_event(self.event)            # fires in the middle of the backward pass
-        with torch.cuda.stream(self.comm):
-            dist.all_reduce(tail, op=op, group=self.group)
-        tail.record_stream(self.comm)
-        dist.all_reduce(head, op=op, group=self.group)
+        end = flat.numel()
+        for ev, cut in zip(self.events, cuts):          # ranges in the order they become final
+            part = flat[cut:end]
+            self.comm.wait_event(ev)                    # fires in the middle of the backward pass
+            with torch.cuda.stream(self.comm):
+                dist.all_reduce(part, op=op, group=self.group)
+            part.record_stream(self.comm)
+            end = cut
+        dist.all_reduce(flat[:end], op=op, group=self.group)
         cur.wait_stream(self.comm)
-        return 2
+        return len(cuts) + 1
 
 
 def shard_batch(n, rank, world):

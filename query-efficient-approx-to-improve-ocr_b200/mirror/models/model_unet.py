@@ -7,6 +7,7 @@ csrc/engine_unet.cu).
 """
 from collections import OrderedDict
 
+import ctypes
 import os
 
 import torch
@@ -50,10 +51,10 @@ class _UNetFn(torch.autograd.Function):
         grads = _alloc_grads(params, need)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
         if ctx.tail_event is not None:
-            # data-parallel overlap (mirror/dist.BucketedAllReduce): the event fires when parameters [24, 64) are final
+            # data-parallel overlap (mirror/dist.BucketedAllReduce): two events, fired when parameters [30, 64) / [18, 30) are final
+            evs = (ctypes.c_void_p * 2)(ctx.tail_event[0].cuda_event, ctx.tail_event[1].cuda_event)
             _lib.call("qeb_unet_backward_bucketed", x.data_ptr(), B, H, W, _ptr_array(params), bn_train, ctx.ws.data_ptr(),
-                      y.data_ptr(), dy.contiguous().data_ptr(), _ptr_array(grads), _lib.ptr(dx), ctx.tail_event.cuda_event,
-                      _lib.stream())
+                      y.data_ptr(), dy.contiguous().data_ptr(), _ptr_array(grads), _lib.ptr(dx), evs, _lib.stream())
         else:
             _lib.call("qeb_unet_backward", x.data_ptr(), B, H, W, _ptr_array(params), bn_train, ctx.ws.data_ptr(),
                       y.data_ptr(), dy.contiguous().data_ptr(), _ptr_array(grads), _lib.ptr(dx), _lib.stream())
@@ -105,7 +106,7 @@ class UNet(nn.Module):
         ps += [self.conv.weight, self.conv.bias]
         return ps
 
-    QEB_TAIL_FIRST_PARAM = 24   # ABI order: parameters [24, 64) are final first in the backward pass (qeb_unet_backward_bucketed)
+    QEB_BUCKET_STARTS = (30, 18)   # ABI order: parameters [30, 64) are final first in the backward pass, then [18, 30), then [0, 18)
 
     def qeb_buffers(self):
         bs = []

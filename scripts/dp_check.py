@@ -61,7 +61,7 @@ want = []
 for g in local:                                   # the definition: mean over the ranks of the local gradients
     t = g.clone(); dist.all_reduce(t); want.append(t / world)
 n = ar()                                          # bucketed exchange on the gradients of THIS backward
-assert n == 2, n
+assert n == 3, n
 bucketed = grads()
 for p, g in zip(prep.qeb_parameters(), local):    # put the local gradients back (in place: the flat buffer stays)
     p.grad.copy_(g)
