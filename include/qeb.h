@@ -201,6 +201,12 @@ int qeb_conv_fprop_tc16(const void* x16, int n_img, int h_in, int w_in, int cin,
                         float* out, int out_cstride, void* out16, void* stream);
 int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, int w_in, const float* dy, int cout,
                       int dy_cstride, int n_img, int kh, int kw, int ph, int pw, float* dw, void* stream);
+/* fp16-operand variant of qeb_conv_wgrad_tc (backward pass): x16 / dy16 = fp16 shadows of x / dy with the same element layout
+ * (channel strides multiples of 8); dy16 holds dy * S for a power-of-two S and alpha_dev (device scalar, nullable) = 1 / S
+ * multiplies the accumulator. kind::f16 MN-major operands, fp32 accumulation; QEB_FP16_BWD=0 falls back to the tf32 reads. */
+int qeb_conv_wgrad_tc16(const float* x, const void* x16, int cin, int x_cstride, int h_in, int w_in, const float* dy,
+                        const void* dy16, int cout, int dy_cstride, int n_img, int kh, int kw, int ph, int pw,
+                        const float* alpha_dev, float* dw, void* stream);
 int qeb_convT2x2_fprop_tc(const float* x, int n_img, int h, int w, int cin, int x_cstride, const float* wpacked,
                           const float* bias, int cout, float* out, int out_cstride, void* stream);
 int qeb_convT2x2_dgrad_tc(const float* dy, int n_img, int h, int w, int cout, int dy_cstride, const float* wpacked,

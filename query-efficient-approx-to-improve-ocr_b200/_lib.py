@@ -43,6 +43,7 @@ SIGNATURES = {
     "qeb_conv_fprop_tc": (I, [P, I, I, I, I, I, P, I, I, I, I, I, P, P, I, P, I, I, P]),
     "qeb_conv_fprop_tc16": (I, [P, I, I, I, I, I, P, I, I, I, I, I, P, P, I, P, I, P, P]),
     "qeb_conv_wgrad_tc": (I, [P, I, I, I, I, P, I, I, I, I, I, I, I, P, P]),
+    "qeb_conv_wgrad_tc16": (I, [P, P, I, I, I, I, P, P, I, I, I, I, I, I, I, P, P, P]),
     "qeb_convT2x2_fprop_tc": (I, [P, I, I, I, I, I, P, P, I, P, I, P]),
     "qeb_convT2x2_dgrad_tc": (I, [P, I, I, I, I, I, P, I, P, I, P]),
     "qeb_convT2x2_wgrad_tc": (I, [P, I, I, I, I, P, I, I, I, P, P]),

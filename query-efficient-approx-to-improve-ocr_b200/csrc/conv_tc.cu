@@ -1300,14 +1300,28 @@ QEB_API int qeb_convT2x2_dgrad_tc(const float* dy, int n_img, int h, int w, int 
 namespace {
 
 constexpr int kWgPix = 32;                 // pixels (GEMM-K) per stage
-constexpr int kBoxBytes = kWgPix * 32 * 4;  // 4 KB: [32 px][32 ch]
+constexpr int kBoxBytes = kWgPix * 32 * 4;  // 4 KB: [32 px][32 ch] tf32
+
+// ROWB = 0: tf32 operands (fp32 tensors, boxes of 32 channels, SWIZZLE_128B_BASE32B). ROWB = 128 / 64: fp16 operand shadows
+// in MN-major SWIZZLE_128B / SWIZZLE_64B tiles - a box is [32 px][64 or 32 ch] and an MMA consumes 16 pixels. With 64-channel
+// rows the same 32 pixels of a 128 x BLOCK_N tile are (2 + BLOCK_N / 64) x 32 operand rows instead of (4 + BLOCK_N / 32) x 32: the
+// kernel is bound by TMA rows (~3.4 cycles each), so the fp16 form does the same contraction in about half the time.
+template <int ROWB>
+struct WgCfg {
+  static constexpr bool kF16 = ROWB != 0;
+  static constexpr int kRowBytes = kF16 ? ROWB : 128;
+  static constexpr int kCh = kF16 ? ROWB / 2 : 32;            // channels per box = per operand row
+  static constexpr int kBox = kWgPix * kRowBytes;             // bytes of one box
+  static constexpr int kABoxes = kBlockM / kCh;
+  static constexpr int kASide = kABoxes * kBox;
+};
 
 struct WgradParams {
   int n_img, h_out, w_out;
   int wt, ht, nt;  // pixel box shape, wt*ht*nt == 32
   int tiles_w, tiles_h, tiles_total;
   int kh, kw, ph, pw;
-  int a_groups;       // 32-channel groups on the A side per tap
+  int a_groups;       // channel groups (one box wide) on the A side per tap
   int row_blocks;     // taps * a_groups
   int n_total;        // B-side channels
   int per_split;      // pixel tiles per gridDim.z slice
@@ -1316,17 +1330,21 @@ struct WgradParams {
   float* out;
   long long s_rowc, s_kh, s_kw, s_col;  // element strides of the gradient tensor
   long long* timeline;  // debugging aid (qeb_debug_set_timeline), NULL in production
+  const float* alpha;   // device scalar or NULL: the accumulator is multiplied by *alpha (1 / scale of a scaled fp16 operand)
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int ROWB>
 __global__ void __launch_bounds__(kThreads, FpropCfg<BLOCK_N>::kCtasPerSm)
 conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_constant__ CUtensorMap tmap_b,
                      const WgradParams p) {
-  using Cfg = FpropCfg<BLOCK_N>;  // same stage geometry: 16 KB A side + BLOCK_N*128 B side
-  constexpr int kBBoxes = BLOCK_N / 32;
+  using Cfg = FpropCfg<BLOCK_N>;  // stage geometry of the tf32 form (16 KB A side + BLOCK_N*128 B side); the fp16 forms use half
+  using W = WgCfg<ROWB>;
+  constexpr int kBBoxes = BLOCK_N / W::kCh;
+  static_assert(kBBoxes >= 1, "tile narrower than a box");
+  constexpr int kStage = W::kF16 ? W::kASide + kBBoxes * W::kBox : Cfg::kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * Cfg::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * kStage);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -1335,8 +1353,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   const int tile_m = blockIdx.x, tile_n = blockIdx.y;
   const int t_begin = blockIdx.z * p.per_split;
   const int t_end = min(t_begin + p.per_split, p.tiles_total);
-  const int rb0 = tile_m * 4;
-  const int n_rb = min(4, p.row_blocks - rb0);
+  const int rb0 = tile_m * W::kABoxes;
+  const int n_rb = min(W::kABoxes, p.row_blocks - rb0);
   long long* tl = p.timeline ? p.timeline + 16 * ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) : nullptr;
   if (tl && threadIdx.x == 0) { tl[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
 
@@ -1360,16 +1378,16 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
 
   if (t_begin < t_end) {
     if (warp == 0) {
-      // ===== TMA producer: up to 4 A boxes + BLOCK_N/32 B boxes per stage. The per-box constants (tap shift, channel
+      // ===== TMA producer: up to kABoxes A boxes + kBBoxes B boxes per stage. The per-box constants (tap shift, channel
       // offset, tensor map) are computed once and the tile coordinates are carried as counters, so the steady-state loop
       // has no integer division; control flow is warp-uniform and one elected lane issues, which keeps all of it in
       // uniform registers (see conv_fprop_tc_kernel) =====
-      int ac0[4], asx[4], asy[4], amap[4];
+      int ac0[W::kABoxes], asx[W::kABoxes], asy[W::kABoxes], amap[W::kABoxes];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < W::kABoxes; ++j) {
         const int rb = rb0 + (j < n_rb ? j : 0);
         const int tap = rb / p.a_groups, cg = rb - tap * p.a_groups;
-        ac0[j] = cg * 32;
+        ac0[j] = cg * W::kCh;
         amap[j] = p.a_map_per_tap ? tap : 0;
         asy[j] = p.a_map_per_tap ? 0 : tap / p.kw - p.ph;
         asx[j] = p.a_map_per_tap ? 0 : tap % p.kw - p.pw;
@@ -1377,20 +1395,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       int tw = t_begin % p.tiles_w, th = (t_begin / p.tiles_w) % p.tiles_h, tn = t_begin / (p.tiles_w * p.tiles_h);
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t bytes = (uint32_t)(n_rb + kBBoxes) * kBoxBytes;
+      const uint32_t bytes = (uint32_t)(n_rb + kBBoxes) * W::kBox;
       for (int t = t_begin; t < t_end; ++t) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (elect_one()) {
-          uint8_t* sbase = smem + stage * Cfg::kStageBytes;
+          uint8_t* sbase = smem + stage * kStage;
           mbar_expect_tx(&full_bar[stage], bytes);
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < W::kABoxes; ++j)
             if (j < n_rb)
-              tma_load_4d(sbase + j * kBoxBytes, &tmaps_a.m[amap[j]], &full_bar[stage], ac0[j], tw * p.wt + asx[j], th * p.ht + asy[j],
+              tma_load_4d(sbase + j * W::kBox, &tmaps_a.m[amap[j]], &full_bar[stage], ac0[j], tw * p.wt + asx[j], th * p.ht + asy[j],
                           tn * p.nt);
 #pragma unroll
           for (int j = 0; j < kBBoxes; ++j)
-            tma_load_4d(sbase + kABytes + j * kBoxBytes, &tmap_b, &full_bar[stage], tile_n * BLOCK_N + j * 32, tw * p.wt, th * p.ht,
+            tma_load_4d(sbase + W::kASide + j * W::kBox, &tmap_b, &full_bar[stage], tile_n * BLOCK_N + j * W::kCh, tw * p.wt, th * p.ht,
                         tn * p.nt);
         }
         __syncwarp();
@@ -1402,7 +1420,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       }
     } else if (warp == 1) {
       // MMA issuer: warp-uniform loop, elected lane issues (see conv_fprop_tc_kernel)
-      constexpr uint32_t idesc = instr_desc_tf32(kBlockM, BLOCK_N, 1, 1);
+      constexpr uint32_t idesc = W::kF16 ? instr_desc_f16(kBlockM, BLOCK_N, 0, 0, 1, 1) : instr_desc_tf32(kBlockM, BLOCK_N, 1, 1);
       int stage = 0;
       uint32_t phase = 0;
       for (int t = t_begin; t < t_end; ++t) {
@@ -1410,14 +1428,24 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         tc_fence_after();
         if (tl && lane == 0 && t == t_begin) tl[2] = clock64();
         if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint32_t sa = smem_u32(smem + stage * kStage);
+          const uint32_t sb = sa + W::kASide;
+          if constexpr (W::kF16) {
 #pragma unroll
-          for (int k = 0; k < kWgPix / 8; ++k) {
-            // 8 pixels (one swizzle atom of K) per MMA: +1024 B inside every [32 px][32 ch] block
-            const uint64_t adesc = smem_desc_mnmajor_sw128_32b(sa + k * 1024, kBoxBytes, 512);
-            const uint64_t bdesc = smem_desc_mnmajor_sw128_32b(sb + k * 1024, kBoxBytes, 512);
-            mma_tf32_ss(tmem_base, adesc, bdesc, idesc, (t > t_begin) || (k != 0));
+            for (int k = 0; k < kWgPix / 16; ++k) {
+              // 16 pixels (two 8-row K groups) per MMA: +16 rows inside every [32 px][kCh ch] box
+              const uint64_t adesc = smem_desc_mnmajor_16<W::kRowBytes>(sa + k * 16 * W::kRowBytes, W::kBox, 8 * W::kRowBytes);
+              const uint64_t bdesc = smem_desc_mnmajor_16<W::kRowBytes>(sb + k * 16 * W::kRowBytes, W::kBox, 8 * W::kRowBytes);
+              mma_f16_ss(tmem_base, adesc, bdesc, idesc, (t > t_begin) || (k != 0));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kWgPix / 8; ++k) {
+              // 8 pixels (one swizzle atom of K) per MMA: +1024 B inside every [32 px][32 ch] block
+              const uint64_t adesc = smem_desc_mnmajor_sw128_32b(sa + k * 1024, kBoxBytes, 512);
+              const uint64_t bdesc = smem_desc_mnmajor_sw128_32b(sb + k * 1024, kBoxBytes, 512);
+              mma_tf32_ss(tmem_base, adesc, bdesc, idesc, (t > t_begin) || (k != 0));
+            }
           }
           mma_commit(&empty_bar[stage]);
         }
@@ -1429,11 +1457,12 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     } else {
       const int q = warp & 3;
       const int r = q * 32 + lane;
-      const int rb = rb0 + q;  // row block = TMEM lane quarter
+      const int rb = rb0 + r / W::kCh;  // row block of this TMEM lane
       const bool valid = rb < p.row_blocks;
       const int tap = valid ? rb / p.a_groups : 0, cg = valid ? rb - tap * p.a_groups : 0;
-      float* row_out = p.out + (long long)(cg * 32 + (r & 31)) * p.s_rowc + (long long)(tap / p.kw) * p.s_kh +
+      float* row_out = p.out + (long long)(cg * W::kCh + (r % W::kCh)) * p.s_rowc + (long long)(tap / p.kw) * p.s_kh +
                        (long long)(tap % p.kw) * p.s_kw;
+      const float alpha = p.alpha ? __ldg(p.alpha) : 1.f;
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
       if (tl && threadIdx.x == 64) tl[4] = clock64();
@@ -1446,7 +1475,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         if (valid) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (ncol + j < p.n_total) atomicAdd(row_out + (long long)(ncol + j) * p.s_col, v[j]);
+            if (ncol + j < p.n_total) atomicAdd(row_out + (long long)(ncol + j) * p.s_col, v[j] * alpha);
         }
       }
       if (tl && threadIdx.x == 64) tl[5] = clock64();
@@ -1458,19 +1487,25 @@ conv_wgrad_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   if (tl && threadIdx.x == 32) { tl[6] = clock64(); tl[3] = t_end - t_begin; }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int ROWB>
 int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams& p_in, dim3 grid, cudaStream_t st) {
   using Cfg = FpropCfg<BLOCK_N>;
+  using W = WgCfg<ROWB>;
   static bool attr = false;
   if (!attr) {
-    QEB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
+    QEB_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel<BLOCK_N, ROWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kMaxSmem));
     attr = true;
   }
   WgradParams p = p_in;
-  p.stages = Cfg::pick_stages((long long)grid.x * grid.y * grid.z);
-  ProfScope prof("tc_conv_wgrad", st, 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.row_blocks * 32,
-                 4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.a_groups * 32 + p.n_total) + (double)p.n_total * p.row_blocks * 32));
-  QEB_CUDA(qeb_launch(conv_wgrad_tc_kernel<BLOCK_N>, grid, kThreads, Cfg::smem_bytes(p.stages), st, ta, tb, p));
+  const int stage_bytes = W::kF16 ? W::kASide + (BLOCK_N / W::kCh) * W::kBox : Cfg::kStageBytes;
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  p.stages = (Cfg::kSmBudget / Cfg::resident(ctas) - 1280) / stage_bytes;
+  p.stages = max(2, min(p.stages, W::kF16 ? 12 : Cfg::kMaxStages));
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + kBarBytes;
+  ProfScope prof(W::kF16 ? "tc_conv_wgrad.f16" : "tc_conv_wgrad.tf32", st, 2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.row_blocks * W::kCh,
+                 (W::kF16 ? 2.0 : 4.0) * ((double)p.n_img * p.h_out * p.w_out * (p.a_groups * W::kCh + p.n_total)) +
+                     4.0 * (double)p.n_total * p.row_blocks * W::kCh);
+  QEB_CUDA(qeb_launch(conv_wgrad_tc_kernel<BLOCK_N, ROWB>, grid, kThreads, smem, st, ta, tb, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -1479,24 +1514,43 @@ int launch_wgrad(const TmapArray4& ta, const CUtensorMap& tb, const WgradParams&
 
 namespace {
 
-int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, int a_c, int b_c, cudaStream_t st) {
-  int bn = min(256, max(32, pow2_ceil(b_c)));
-  const int m_tiles = qeb_cdiv(p.row_blocks, 4), n_tiles = qeb_cdiv(b_c, bn);
+// rowb: 0 = tf32 operands, 128 / 64 = fp16 operand shadows in rows of that many bytes
+int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, int a_c, int b_c, cudaStream_t st, int rowb = 0) {
+  int bn = min(256, max(rowb == 128 ? 64 : 32, pow2_ceil(b_c)));
+  const int a_boxes = rowb == 128 ? 2 : 4;
+  const int m_tiles = qeb_cdiv(p.row_blocks, a_boxes), n_tiles = qeb_cdiv(b_c, bn);
   // split-K so that the grid is about ONE CTA per SM, at least 8 pixel tiles per CTA: every CTA ends with a red.global.add
   // epilogue that retires at ~13 B per clock and SM (10 k cycles for a 128 x 256 tile, scripts/exp/wgrad_timeline.py), so a
   // second wave of CTAs pays setup + epilogue twice (same-box A/B: 296 CTAs 3.68 ms per step, 148 CTAs 3.65 ms)
   static const int wg_ctas = getenv("QEB_WG_CTAS") ? atoi(getenv("QEB_WG_CTAS")) : kNumSMs;
+  static const int wg_model = getenv("QEB_WG_SPLIT_MODEL") ? atoi(getenv("QEB_WG_SPLIT_MODEL")) : 1;
   int splits = qeb_cdiv(wg_ctas, m_tiles * n_tiles);
   splits = max(1, min(splits, qeb_cdiv(p.tiles_total, 8)));
+  if (wg_model) {
+    // The rounded-up split count above overshoots the SM count (216, 180, 162, 150 CTAs ...): the kernel then lasts as long as
+    // the SMs that got TWO CTAs. Pick the split count from a cost model instead: rounds of CTAs per SM x (K steps x ~600 cycles
+    // + the reduction epilogue, ~40 cycles per accumulator column), minimised over the candidates.
+    const int tiles = m_tiles * n_tiles, max_splits = max(1, p.tiles_total / 4);
+    long long best = -1;
+    for (int s = 1; s <= max_splits && s <= 4 * wg_ctas; ++s) {
+      const long long rounds = qeb_cdiv((long long)tiles * s, wg_ctas);
+      const long long cost = rounds * ((long long)qeb_cdiv(p.tiles_total, s) * 600 + 40LL * bn + 3000);
+      if (best < 0 || cost < best) { best = cost; splits = s; }
+    }
+  }
   p.per_split = qeb_cdiv(p.tiles_total, splits);
   splits = qeb_cdiv(p.tiles_total, p.per_split);
   const dim3 grid(m_tiles, n_tiles, splits);
+#define QEB_WG_CASE(BN)                                                                       \
+  return rowb == 128 ? launch_wgrad<(BN < 64 ? 64 : BN), 128>(ta, tb, p, grid, st)            \
+                     : (rowb == 64 ? launch_wgrad<BN, 64>(ta, tb, p, grid, st) : launch_wgrad<BN, 0>(ta, tb, p, grid, st))
   switch (bn) {
-    case 32: return launch_wgrad<32>(ta, tb, p, grid, st);
-    case 64: return launch_wgrad<64>(ta, tb, p, grid, st);
-    case 128: return launch_wgrad<128>(ta, tb, p, grid, st);
-    default: return launch_wgrad<256>(ta, tb, p, grid, st);
+    case 32: QEB_WG_CASE(32);
+    case 64: QEB_WG_CASE(64);
+    case 128: QEB_WG_CASE(128);
+    default: QEB_WG_CASE(256);
   }
+#undef QEB_WG_CASE
 }
 
 void wgrad_geometry(WgradParams& p, int n_img, int h_out, int w_out, uint32_t* box) {
@@ -1510,10 +1564,19 @@ void wgrad_geometry(WgradParams& p, int n_img, int h_out, int w_out, uint32_t* b
   box[0] = 32; box[1] = p.wt; box[2] = p.ht; box[3] = p.nt;
 }
 
+// fp16 operand shadows usable: both given, strides 16-byte friendly; returns the row bytes (128 when both channel counts are
+// multiples of 64, else 64), 0 = stay on tf32
+int wgrad_rowb16(const Img& x, const Img& dy, const WgradShadows* sh) {
+  static const int allow = getenv("QEB_FP16_BWD") ? atoi(getenv("QEB_FP16_BWD")) : 1;
+  if (!allow || !sh || !sh->x16 || !sh->dy16 || !strides_ok16(x) || !strides_ok16(dy)) return 0;
+  if (((uintptr_t)sh->x16 & 15) || ((uintptr_t)sh->dy16 & 15)) return 0;
+  return (x.c % 64 == 0 && dy.c % 64 == 0) ? 128 : 64;
+}
+
 }  // namespace
 
 int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, float* dw, long long s_co, long long s_ci,
-                  long long s_kh, long long s_kw, cudaStream_t st) {
+                  long long s_kh, long long s_kw, cudaStream_t st, const WgradShadows* sh) {
   QEB_REQUIRE(x.p && dy.p && dw, "tc_conv_wgrad: null pointer");
   QEB_REQUIRE(x.c > 0 && x.c % 32 == 0, "tc_conv_wgrad: input channels %d must be a multiple of 32", x.c);
   QEB_REQUIRE(strides_ok(x) && strides_ok(dy), "tc_conv_wgrad: operands must be 16-byte aligned, strides multiples of 4");
@@ -1523,20 +1586,31 @@ int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, f
   uint32_t box[4];
   wgrad_geometry(p, dy.n, dy.h, dy.w, box);
   p.kh = kh; p.kw = kw; p.ph = ph; p.pw = pw;
-  p.a_groups = x.c / 32;
+  const int rowb = wgrad_rowb16(x, dy, sh);
+  const int ch = rowb ? rowb / 2 : 32;   // channels per operand row / box
+  p.a_groups = x.c / ch;
   p.row_blocks = kh * kw * p.a_groups;
   p.n_total = dy.c;
   p.a_map_per_tap = 0;
   p.out = dw;
   p.s_rowc = s_ci; p.s_kh = s_kh; p.s_kw = s_kw; p.s_col = s_co;
+  p.alpha = rowb ? sh->alpha : nullptr;
   TmapArray4 ta;
   CUtensorMap tb;
-  int rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 1);
+  int rc;
+  if (rowb) {
+    box[0] = (uint32_t)ch;
+    rc = tmap_img16(&ta.m[0], x, sh->x16, box);
+    if (rc) return rc;
+    rc = tmap_img16(&tb, dy, sh->dy16, box);
+  } else {
+    rc = tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 1);
+    if (rc) return rc;
+    rc = tmap_img(&tb, dy, dy.p, dy.c, dy.sn, dy.sh, dy.sw, dy.w, dy.h, box, 1);
+  }
   if (rc) return rc;
   ta.m[1] = ta.m[2] = ta.m[3] = ta.m[0];
-  rc = tmap_img(&tb, dy, dy.p, dy.c, dy.sn, dy.sh, dy.sw, dy.w, dy.h, box, 1);
-  if (rc) return rc;
-  return wgrad_common(ta, tb, p, x.c, dy.c, st);
+  return wgrad_common(ta, tb, p, x.c, dy.c, st, rowb);
 }
 
 int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
@@ -1555,6 +1629,7 @@ int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
   p.n_total = x.c;
   p.a_map_per_tap = 1;
   p.out = dw;
+  p.alpha = nullptr;
   p.s_rowc = 4; p.s_kh = 2; p.s_kw = 1; p.s_col = (long long)dy.c * 4;
   TmapArray4 ta;
   CUtensorMap tb;
@@ -1590,6 +1665,17 @@ QEB_API int qeb_conv_wgrad_tc(const float* x, int cin, int x_cstride, int h_in, 
   Img xi = img_nhwc(const_cast<float*>(x), n_img, h_in, w_in, cin, x_cstride);
   Img di = img_nhwc(const_cast<float*>(dy), n_img, h_in + 2 * ph - kh + 1, w_in + 2 * pw - kw + 1, cout, dy_cstride);
   return tc_conv_wgrad(xi, di, kh, kw, ph, pw, dw, (long long)cin * kh * kw, (long long)kh * kw, kw, 1, (cudaStream_t)stream);
+}
+
+// the same with fp16 operand shadows (x16 / dy16: same element layout as x / dy; dy16 holds dy * S, alpha_dev -> 1 / S or NULL)
+QEB_API int qeb_conv_wgrad_tc16(const float* x, const void* x16, int cin, int x_cstride, int h_in, int w_in, const float* dy,
+                                const void* dy16, int cout, int dy_cstride, int n_img, int kh, int kw, int ph, int pw,
+                                const float* alpha_dev, float* dw, void* stream) {
+  Img xi = img_nhwc(const_cast<float*>(x), n_img, h_in, w_in, cin, x_cstride);
+  Img di = img_nhwc(const_cast<float*>(dy), n_img, h_in + 2 * ph - kh + 1, w_in + 2 * pw - kw + 1, cout, dy_cstride);
+  WgradShadows sh;
+  sh.x16 = x16; sh.dy16 = dy16; sh.alpha = alpha_dev;
+  return tc_conv_wgrad(xi, di, kh, kw, ph, pw, dw, (long long)cin * kh * kw, (long long)kh * kw, kw, 1, (cudaStream_t)stream, &sh);
 }
 
 QEB_API int qeb_convT2x2_wgrad_tc(const float* x, int cin, int x_cstride, int h, int w, const float* dy, int cout,

@@ -73,8 +73,16 @@ int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const 
 // its input gradient: dy (n,2h,2w,cout) -> dx (n,h,w,cin). wpacked: [cin][(dh*2+dw)*cout + co].
 int tc_convT_dgrad(const Img& dy, const float* wpacked, const Img& dx, const TcEpilogue& ep, cudaStream_t st);
 // weight gradient, accumulated with atomics: dw[co*s_co + ci*s_ci + ky*s_kh + kx*s_kw] += sum_pix x(pix+tap, ci) dy(pix, co)
+// sh (optional): fp16 shadows of both operands (same element layout as x / dy; dy16 = dy * S for a power-of-two S, alpha -> 1 / S
+// on the device or NULL) - the contraction then runs with kind::f16 MN-major operands (half the TMA rows and bytes), same
+// 11-bit significand as the rounded tf32 reads. QEB_FP16_BWD=0 ignores the shadows.
+struct WgradShadows {
+  const void* x16 = nullptr;
+  const void* dy16 = nullptr;
+  const float* alpha = nullptr;
+};
 int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, float* dw, long long s_co, long long s_ci,
-                  long long s_kh, long long s_kw, cudaStream_t st);
+                  long long s_kh, long long s_kw, cudaStream_t st, const WgradShadows* sh = nullptr);
 // ConvTranspose2d 2x2 s2 weight gradient: dw[ci][co][dh][dw] (torch layout) += sum x(n,h,w,ci) dy(n,2h+dh,2w+dw,co)
 int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st);
 

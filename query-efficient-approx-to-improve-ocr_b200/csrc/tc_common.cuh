@@ -128,9 +128,19 @@ __host__ __device__ constexpr uint32_t instr_desc_tf32(int M, int N, int a_mn, i
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
-// kind::f16 (fp16 or bf16 operands, chosen per operand), fp32 accumulate, K-major operands
-__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N, int a_bf16, int b_bf16) {
-  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// kind::f16 (fp16 or bf16 operands, chosen per operand), fp32 accumulate; a_mn / b_mn = 1 for MN-major operands
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N, int a_bf16, int b_bf16, int a_mn = 0, int b_mn = 0) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major 16-bit operand tile (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): K-rows of ROWB bytes (64 fp16 along
+// M/N in SWIZZLE_128B, 32 in SWIZZLE_64B), 8-row K groups. lbo = byte stride between the ROWB-wide M/N groups, sbo = between
+// 8-row K groups.
+template <int ROWB>
+__device__ __forceinline__ uint64_t smem_desc_mnmajor_16(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  static_assert(ROWB == 128 || ROWB == 64, "row bytes");
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) | ((ROWB == 128 ? 2ull : 4ull) << 61);
 }
 // D[tmem] (+)= A[smem] * B[smem], kind::f16 (K = 16 per instruction), issued by one thread
 __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {

@@ -10,8 +10,14 @@ KS = int(sys.argv[6]) if len(sys.argv) > 6 else 3   # 3: 3x3 pad 1 (torch gradie
 x = torch.randn(N, H, W, Cin, device="cuda"); dy = torch.randn(N, H, W, Cout, device="cuda")
 dw = torch.zeros(Cout, KS * KS, Cin, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
+F16 = os.environ.get("WG_F16", "0") == "1"   # fp16 MN-major operand shadows instead of tf32 reads
+x16, dy16 = x.half(), dy.half()
 def run():
-    _lib.call("qeb_conv_wgrad_tc", x.data_ptr(), Cin, Cin, H, W, dy.data_ptr(), Cout, Cout, N, KS, KS, KS // 2, KS // 2, dw.data_ptr(), st)
+    if F16:
+        _lib.call("qeb_conv_wgrad_tc16", x.data_ptr(), x16.data_ptr(), Cin, Cin, H, W, dy.data_ptr(), dy16.data_ptr(), Cout, Cout, N, KS, KS,
+                  KS // 2, KS // 2, None, dw.data_ptr(), st)
+    else:
+        _lib.call("qeb_conv_wgrad_tc", x.data_ptr(), Cin, Cin, H, W, dy.data_ptr(), Cout, Cout, N, KS, KS, KS // 2, KS // 2, dw.data_ptr(), st)
 for _ in range(3): run()
 torch.cuda.synchronize()
 ts = []
@@ -22,7 +28,7 @@ print(f"shape N{N} {H}x{W} {Cin}->{Cout}: kernel time us (L2-warm) median {sorte
 buf = torch.zeros(16 * 16384, dtype=torch.int64, device="cuda")
 L.qeb_debug_set_timeline(buf.data_ptr()); run(); torch.cuda.synchronize(); L.qeb_debug_set_timeline(None)
 t = buf.cpu().numpy().reshape(-1, 16); t = t[t[:, 0] > 0]
-print("CTAs", len(t), "k-steps per CTA", t[:, 3].mean())
+print("CTAs", len(t), "k-steps per CTA", t[:, 3].mean(), "main-loop cycles per k-step", ((t[:, 4] - t[:, 2]) / np.maximum(t[:, 3], 1)).mean())
 names = ["setup (barriers, TMEM alloc, PDL wait)", "first stage landed (from setup)", "main loop (first stage -> accumulator ready)", "epilogue (TMEM -> red.global.add)", "tail", "total CTA"]
 d = [t[:, 1] - t[:, 0], t[:, 2] - t[:, 1], t[:, 4] - t[:, 2], t[:, 5] - t[:, 4], t[:, 6] - t[:, 5], t[:, 6] - t[:, 0]]
 for n_, v in zip(names, d):

@@ -632,3 +632,38 @@ def test_window_variant_on_every_conv_shape():
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-k",
                         "conv_fprop or channel_slices or unet_vs_oracle or crnn_vs_oracle"], env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------------------------------ fp16 backward operands
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,p", [
+    (8, 4, 32, 512, 512, 3, 1),      # CRNN conv6: 64-channel rows (SWIZZLE_128B), 256-wide N tiles
+    (4, 8, 32, 128, 256, 3, 1),      # CRNN conv3
+    (8, 2, 32, 512, 512, 2, 0),      # CRNN conv7 (2 x 2 taps, no padding)
+    (16, 32, 128, 32, 32, 3, 1),     # UNet level 1: 32-channel rows (SWIZZLE_64B)
+    (12, 32, 128, 64, 32, 3, 1),     # mixed: 64 input channels, 32 output channels -> 32-channel rows
+    (40, 16, 64, 32, 64, 3, 1),
+    (70, 10, 40, 64, 64, 3, 1),      # odd geometry (partial pixel boxes)
+    (1, 1, 1984, 512, 2048, 1, 0),   # LSTM W_ih gradient as a GEMM
+    (1, 1, 1984, 512, 96, 1, 0),     # Linear (padded to 96 classes): 32-channel rows, 3 boxes on the N side
+    (3, 5, 7, 64, 128, 3, 1),        # boxes larger than the image
+])
+def test_conv_wgrad_tc16(q, N, H, W, Cin, Cout, k, p):
+    """Weight gradient with fp16 MN-major operand shadows (x16; dy16 = dy * 2^s, alpha = 2^-s) against torch fp32."""
+    g = torch.Generator(device=DEV).manual_seed(N * 77 + Cin + Cout)
+    x = torch.randn(N, Cin, H, W, device=DEV, generator=g)
+    w = (torch.randn(Cout, Cin, k, k, device=DEV, generator=g) / (Cin * k * k) ** 0.5).requires_grad_(True)
+    lin = F.conv2d(x, w, None, padding=p)
+    dy = torch.randn(lin.shape, device=DEV, generator=g) * 1e-4     # gradient-sized values: need the scale
+    lin.backward(dy)
+    xn = x.permute(0, 2, 3, 1).contiguous()
+    dyn = dy.permute(0, 2, 3, 1).contiguous()
+    S = 2.0 ** 16
+    x16, dy16 = xn.half(), (dyn * S).half()
+    alpha = torch.tensor([1.0 / S], device=DEV)
+    dw = torch.zeros_like(w)
+    q.lib.call("qeb_conv_wgrad_tc16", xn.data_ptr(), x16.data_ptr(), Cin, Cin, H, W, dyn.data_ptr(), dy16.data_ptr(), Cout, Cout, N,
+               k, k, p, p, alpha.data_ptr(), dw.data_ptr(), st())
+    assert rel(dw, w.grad) < 3e-3
+    q.lib.call("qeb_conv_wgrad_tc16", xn.data_ptr(), x16.data_ptr(), Cin, Cin, H, W, dyn.data_ptr(), dy16.data_ptr(), Cout, Cout, N,
+               k, k, p, p, alpha.data_ptr(), dw.data_ptr(), st())
+    assert rel(dw, 2 * w.grad) < 3e-3  # accumulates
