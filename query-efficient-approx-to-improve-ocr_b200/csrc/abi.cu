@@ -287,3 +287,86 @@ bool qeb_pdl_enabled() {
   static const bool on = !(getenv("QEB_PDL") && atoi(getenv("QEB_PDL")) == 0);
   return on;
 }
+
+// ---- delayed scales of the fp16 gradient shadows (nn.cuh GradShadow / GradScales) ---------------------------------------------
+namespace {
+struct ScaleSet {
+  unsigned* dev = nullptr;   // [n] running maxima (fp32 bit patterns) | [n] scales | [n] reciprocal scales
+  int n = 0;
+  long long calls = 0;       // backward calls issued with these slots
+};
+std::mutex g_scale_mu;
+std::map<std::pair<int, const void*>, ScaleSet> g_scale_sets;
+
+// S = 2^(4 - ceil(log2(max))): the largest magnitude of the previous call lands in [8, 16] (2^12 below fp16's largest value). A maximum of 0, inf or NaN (nothing
+// recorded, or a diverged step) keeps the previous scale.
+__global__ void grad_scale_update_kernel(unsigned* amax, float* scale, float* inv, int n) {
+  qeb_pdl_sync();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float a = __uint_as_float(amax[i]);
+  float s = scale[i];
+  if (a > 0.f && a < INFINITY) {
+    int e;
+    frexpf(a, &e);                       // a = m * 2^e, m in [0.5, 1)
+    e = min(max(4 - e, -60), 100);
+    s = ldexpf(1.f, e);
+  }
+  if (!(s > 0.f)) s = 1.f;
+  scale[i] = s;
+  inv[i] = 1.f / s;
+  amax[i] = 0u;
+}
+}  // namespace
+
+int grad_scales_state(int net_kind, const void* key) {
+  std::lock_guard<std::mutex> lk(g_scale_mu);
+  auto it = g_scale_sets.find({net_kind, key});
+  if (it == g_scale_sets.end()) return -1;
+  return it->second.calls > 0 ? 1 : 0;
+}
+
+void grad_scales_commit(int net_kind, const void* key) {
+  std::lock_guard<std::mutex> lk(g_scale_mu);
+  auto it = g_scale_sets.find({net_kind, key});
+  if (it != g_scale_sets.end()) it->second.calls += 1;
+}
+
+// allocates the slots of (net_kind, key) on first use - unless `st` is being captured: allocation is not a stream operation
+void grad_scales_prepare(int net_kind, const void* key, int n, cudaStream_t st) {
+  static const bool allow = !(getenv("QEB_FP16_BWD") && atoi(getenv("QEB_FP16_BWD")) == 0);
+  if (!allow) return;
+  std::lock_guard<std::mutex> lk(g_scale_mu);
+  auto it = g_scale_sets.find({net_kind, key});
+  if (it != g_scale_sets.end()) return;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return; }
+  if (cap != cudaStreamCaptureStatusNone) return;
+  if (g_scale_sets.size() >= 256) return;   // a process that keeps creating networks: stay on the tf32 path
+  unsigned* dev = nullptr;
+  if (cudaMalloc(&dev, (size_t)3 * n * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); return; }
+  if (cudaMemset(dev, 0, (size_t)3 * n * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); cudaFree(dev); return; }
+  ScaleSet set;
+  set.dev = dev; set.n = n; set.calls = 0;
+  g_scale_sets[{net_kind, key}] = set;
+}
+
+int grad_scales_begin(int net_kind, const void* key, int n, cudaStream_t st, GradScales* out) {
+  *out = GradScales();
+  ScaleSet set;
+  {
+    std::lock_guard<std::mutex> lk(g_scale_mu);
+    auto it = g_scale_sets.find({net_kind, key});
+    if (it == g_scale_sets.end() || it->second.n != n) return QEB_OK;   // no slots: the tf32 path
+    set = it->second;
+  }
+  out->amax = set.dev;
+  out->scale = reinterpret_cast<float*>(set.dev + n);
+  out->inv = reinterpret_cast<float*>(set.dev + 2 * n);
+  out->n = n;
+  out->valid = set.calls > 0;
+  ProfScope prof("grad_scale", st);
+  QEB_CUDA(qeb_launch(grad_scale_update_kernel, qeb_cdiv(n, 64), 64, 0, st, out->amax, out->scale, out->inv, n));
+  qeb_count_launch();
+  return QEB_OK;
+}

@@ -169,6 +169,9 @@ struct FpropParams {
   int bw, bh;
   int win_bytes, w_bytes;    // WIN kernels: bytes of one window stage (180 operand rows, 1 KB aligned) / of the resident weight area
   int epi_bytes;             // bytes of the epilogue staging area (FpropCfg::kEpiBytes, + kEpi16Bytes with an fp16 TMA store)
+  const float* alpha;        // device scalar or NULL: the accumulator is multiplied by *alpha first (1 / scale of a scaled fp16 operand)
+  const float* out16_scale;  // device scalar or NULL: the fp16 shadow holds v * *out16_scale (nn.cuh GradShadow)
+  unsigned* gamax;           // device or NULL: running maximum of |v| over the stored values (fp32 bit pattern)
 };
 
 struct TmapOut {
@@ -226,6 +229,11 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
   }
   const int lim = min(32, p.n_total - ncol);
   const int pcol = p.mode == 1 ? ncol % p.up_c : ncol;  // per-channel vectors are indexed by the output channel
+  if (p.alpha) {
+    const float al = __ldg(p.alpha);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= al;
+  }
   if (p.scale) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= (j < lim) ? __ldg(p.scale + pcol + j) : 0.f;
@@ -297,6 +305,11 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
     return;
   }
   const int pcol = p.mode == 1 ? ncol % p.up_c : ncol;
+  if (p.alpha) {
+    const float al = __ldg(p.alpha);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= al;
+  }
   if (p.scale) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] *= __ldg(p.scale + pcol + j);
@@ -327,6 +340,8 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
   if (tle) tle[9] = clock64();
   const int rsub = lane >> 3, c16 = lane & 7;
   float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float s16 = p.out16_scale ? __ldg(p.out16_scale) : 1.f;
+  float gmax = 0.f;
   float4 bsc, bsh, bmu, bis;   // BatchNorm constants of this lane's four channels (fused backward reductions)
   if (p.bn_scsh) {
     const float* c4 = p.bn_scsh + ncol + c16 * 4;
@@ -358,10 +373,12 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         *reinterpret_cast<float4*>(d) = p.round_out ? qeb_tf32r4(o) : o;
+        gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
         if (p.out16) {   // fp16 shadow, same element offset
           // (saturating: a value beyond fp16's range becomes +-65504, not inf; the fp32 output keeps the exact value)
-          const __half2 h0 = __floats2half2_rn(fminf(fmaxf(o.x, -65504.f), 65504.f), fminf(fmaxf(o.y, -65504.f), 65504.f));
-          const __half2 h1 = __floats2half2_rn(fminf(fmaxf(o.z, -65504.f), 65504.f), fminf(fmaxf(o.w, -65504.f), 65504.f));
+          const float4 os = make_float4(o.x * s16, o.y * s16, o.z * s16, o.w * s16);
+          const __half2 h0 = __floats2half2_rn(fminf(fmaxf(os.x, -65504.f), 65504.f), fminf(fmaxf(os.y, -65504.f), 65504.f));
+          const __half2 h1 = __floats2half2_rn(fminf(fmaxf(os.z, -65504.f), 65504.f), fminf(fmaxf(os.w, -65504.f), 65504.f));
           uint2 pk;
           pk.x = *reinterpret_cast<const uint32_t*>(&h0);
           pk.y = *reinterpret_cast<const uint32_t*>(&h1);
@@ -388,6 +405,10 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
       atomicAdd(a + 0, ssum.x); atomicAdd(a + 1, ssq.x); atomicAdd(a + 2, ssum.y); atomicAdd(a + 3, ssq.y);
       atomicAdd(a + 4, ssum.z); atomicAdd(a + 5, ssq.z); atomicAdd(a + 6, ssum.w); atomicAdd(a + 7, ssq.w);
     }
+  }
+  if (p.gamax) {
+    gmax = warp_max(gmax);
+    if (lane == 0 && gmax > 0.f) atomicMax(p.gamax, __float_as_uint(gmax));
   }
   __syncwarp();
 }
@@ -430,6 +451,11 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 __device__ __forceinline__ void fprop_epilogue_tma(const FpropParams& p, const TmapOut& to, float (&v)[32], bool valid, int n, int h,
                                                    int w, int w0, int h0, int n0, int ncol, uint32_t stg32, uint32_t stg16, int lane,
                                                    float* cta_stats, int c0_local) {
+  if (p.alpha) {
+    const float al = __ldg(p.alpha);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= al;
+  }
   if (p.scale) {
     const float sv = __ldg(p.scale + ncol + lane);
 #pragma unroll
@@ -470,12 +496,23 @@ __device__ __forceinline__ void fprop_epilogue_tma(const FpropParams& p, const T
   const uint32_t row32 = stg32 + (uint32_t)lane * 128u;
 #pragma unroll
   for (int j = 0; j < 8; ++j) st_shared_v4(row32 + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  if (p.gamax) {   // running maximum of the stored gradient (rows outside the image are clipped by the store: not counted)
+    float m = 0.f;
+    if (valid) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(v[j]));
+    }
+    m = warp_max(m);
+    if (lane == 0 && m > 0.f) atomicMax(p.gamax, __float_as_uint(m));
+  }
   if (p.out16) {
     const uint32_t row16 = stg16 + (uint32_t)lane * 64u;
+    const float s16 = p.out16_scale ? __ldg(p.out16_scale) : 1.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      st_shared_v4u(row16 + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4), pack_half2(v[8 * j], v[8 * j + 1]), pack_half2(v[8 * j + 2], v[8 * j + 3]),
-                    pack_half2(v[8 * j + 4], v[8 * j + 5]), pack_half2(v[8 * j + 6], v[8 * j + 7]));
+      st_shared_v4u(row16 + (uint32_t)((j ^ ((lane >> 1) & 3)) << 4), pack_half2(v[8 * j] * s16, v[8 * j + 1] * s16),
+                    pack_half2(v[8 * j + 2] * s16, v[8 * j + 3] * s16), pack_half2(v[8 * j + 4] * s16, v[8 * j + 5] * s16),
+                    pack_half2(v[8 * j + 6] * s16, v[8 * j + 7] * s16));
   }
   fence_proxy_async();
   __syncwarp();
@@ -1069,6 +1106,19 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   QEB_REQUIRE(!ep.out16 || (p.vec_ok && n_total % 32 == 0 && ((uintptr_t)ep.out16 & 7) == 0),
               "tc fprop: an fp16 output shadow needs 16-byte aligned output rows and a multiple of 32 channels");
   p.out16 = static_cast<__half*>(ep.out16);
+  p.alpha = ep.alpha;
+  p.out16_scale = nullptr;
+  p.gamax = nullptr;
+  if (ep.gs.amax || ep.gs.out16) {
+    // gradient shadow / running maximum: the vector epilogues only (aligned full rows); the caller learns through gs_done
+    const bool ok = p.vec_ok && n_total % 32 == 0 && mode == 0 && !ep.accumulate && !ep.out16 &&
+                    (!ep.gs.out16 || (((uintptr_t)ep.gs.out16 & 7) == 0 && ep.gs.scale));
+    if (ok) {
+      p.gamax = ep.gs.amax;
+      if (ep.gs.out16) { p.out16 = static_cast<__half*>(ep.gs.out16); p.out16_scale = ep.gs.scale; }
+    }
+    if (ep.gs_done) *ep.gs_done = ok ? 1 : 0;
+  }
   p.round_out = ep.round_out;
   p.amax = ep.argmax;
   if (ep.log_softmax) {
@@ -1088,7 +1138,8 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   // Few pixels, long K (the deep UNet levels and their input gradients): narrowing the N tile to fill the SMs makes every
   // CTA stream the whole A operand for a sliver of MMA work and the per-SM L2 read rate becomes the limit. With a plain
   // epilogue the K range is split instead and the partial sums are reduced into a zero-filled output.
-  const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && !ep.round_out && mode == 0 && p.vec_ok && n_total % 32 == 0 &&
+  const bool plain = !ep.scale && !bias && !ep.relu && !ep.mask && !ep.accumulate && !ep.round_out && !ep.gs.out16 && !ep.gs.amax && mode == 0 && p.vec_ok &&
+                     n_total % 32 == 0 &&
                      out.c == n_total && out.sw == n_total && img_flat(out);
   if (allow_split && !win && plain && (long long)m_tiles * qeb_cdiv(n_total, bn_max) * 2 <= min_ctas && num_kb >= 16) {
     // round DOWN: tiles beyond one per SM would make a few CTAs walk two tiles while the rest idle
@@ -1141,7 +1192,7 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   memset(&to, 0, sizeof(to));
   p.tma_out = 0; p.bw = p.bh = 1;
   if (allow_tma_out && mode == 0 && splits == 1 && !ep.accumulate && !p.bn_scsh && p.vec_ok && n_total % 32 == 0 && !ep.log_softmax &&
-      out.sw % 4 == 0 && (!ep.out16 || out.sw % 8 == 0)) {
+      out.sw % 4 == 0 && (!p.out16 || out.sw % 8 == 0)) {
     p.bw = min(p.wt, 32);
     p.bh = min(p.ht, 32 / p.bw);
     const int bnn = 32 / (p.bw * p.bh);
@@ -1153,9 +1204,9 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
     const uint32_t box[4] = {32u, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)bnn};
     const uint64_t str32[3] = {sw * 4, sh * 4, sn * 4};
     const uint64_t str16[3] = {sw * 2, sh * 2, sn * 2};
-    const bool ok = sh % 4 == 0 && sn % 4 == 0 && (!ep.out16 || (sh % 8 == 0 && sn % 8 == 0));
+    const bool ok = sh % 4 == 0 && sn % 4 == 0 && (!p.out16 || (sh % 8 == 0 && sn % 8 == 0));
     if (ok && make_tmap_store(&to.f32, out.p, 4, dims, str32, box, false) == QEB_OK &&
-        (!ep.out16 || make_tmap_store(&to.f16, ep.out16, 4, dims, str16, box, true) == QEB_OK))
+        (!p.out16 || make_tmap_store(&to.f16, p.out16, 4, dims, str16, box, true) == QEB_OK))
       p.tma_out = 1;
   }
   int rc;
@@ -1255,12 +1306,21 @@ int tc_convT_dgrad(const Img& dy, const float* wpacked, const Img& dx, const TcE
   TmapArray4 ta;
   uint32_t box[4];
   fprop_box(dx.h, dx.w, box);
+  const bool f16 = ep.in16 && ep.w16 && strides_ok16(dy) && ((uintptr_t)ep.in16 & 15) == 0;
+  if (f16) box[0] = kblk16(dy.c);
   for (int t = 0; t < 4; ++t) {  // sub-lattice (dh,dw) of dy viewed as a dx-sized image
     const int dh = t >> 1, dw = t & 1;
-    int rc = tmap_img(&ta.m[t], dy, dy.p + dh * dy.sh + dw * dy.sw, dy.c, dy.sn, 2 * dy.sh, 2 * dy.sw, dx.w, dx.h, box, 0);
+    int rc;
+    if (f16) {
+      Img sub = dy;   // geometry of the sub-lattice: every second row / pixel
+      sub.w = dx.w; sub.h = dx.h; sub.sh = 2 * dy.sh; sub.sw = 2 * dy.sw;
+      rc = tmap_img16(&ta.m[t], sub, static_cast<const __half*>(ep.in16) + dh * dy.sh + dw * dy.sw, box);
+    } else {
+      rc = tmap_img(&ta.m[t], dy, dy.p + dh * dy.sh + dw * dy.sw, dy.c, dy.sn, 2 * dy.sh, 2 * dy.sw, dx.w, dx.h, box, 0);
+    }
     if (rc) return rc;
   }
-  return fprop_common(ta, true, dx, wpacked, dx.c, 2, 2, 0, 0, dy.c, dx, dx.h, dx.w, ep, 0, 0, ep.bias, st);
+  return fprop_common(ta, true, dx, wpacked, dx.c, 2, 2, 0, 0, dy.c, dx, dx.h, dx.w, ep, 0, 0, ep.bias, st, f16);
 }
 
 // C ABI (tests and external callers): contiguous NHWC with channel strides.
@@ -1613,7 +1673,7 @@ int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, f
   return wgrad_common(ta, tb, p, x.c, dy.c, st, rowb);
 }
 
-int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
+int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st, const WgradShadows* sh) {
   QEB_REQUIRE(x.p && dy.p && dw, "tc_convT_wgrad: null pointer");
   QEB_REQUIRE(x.c % 32 == 0 && dy.c % 32 == 0, "tc_convT_wgrad: channels must be multiples of 32");
   QEB_REQUIRE(strides_ok(x) && strides_ok(dy), "tc_convT_wgrad: operand alignment");
@@ -1624,23 +1684,33 @@ int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st) {
   uint32_t box[4];
   wgrad_geometry(p, x.n, x.h, x.w, box);
   p.kh = 2; p.kw = 2; p.ph = 0; p.pw = 0;
-  p.a_groups = dy.c / 32;
+  const int rowb = wgrad_rowb16(x, dy, sh);
+  const int ch = rowb ? rowb / 2 : 32;
+  p.a_groups = dy.c / ch;
   p.row_blocks = 4 * p.a_groups;
   p.n_total = x.c;
   p.a_map_per_tap = 1;
   p.out = dw;
-  p.alpha = nullptr;
+  p.alpha = rowb ? sh->alpha : nullptr;
   p.s_rowc = 4; p.s_kh = 2; p.s_kw = 1; p.s_col = (long long)dy.c * 4;
   TmapArray4 ta;
   CUtensorMap tb;
+  if (rowb) box[0] = (uint32_t)ch;
   for (int t = 0; t < 4; ++t) {
     const int dh = t >> 1, dwi = t & 1;
-    int rc = tmap_img(&ta.m[t], dy, dy.p + dh * dy.sh + dwi * dy.sw, dy.c, dy.sn, 2 * dy.sh, 2 * dy.sw, x.w, x.h, box, 1);
+    int rc;
+    if (rowb) {
+      Img sub = dy;
+      sub.w = x.w; sub.h = x.h; sub.sh = 2 * dy.sh; sub.sw = 2 * dy.sw;
+      rc = tmap_img16(&ta.m[t], sub, static_cast<const __half*>(sh->dy16) + dh * dy.sh + dwi * dy.sw, box);
+    } else {
+      rc = tmap_img(&ta.m[t], dy, dy.p + dh * dy.sh + dwi * dy.sw, dy.c, dy.sn, 2 * dy.sh, 2 * dy.sw, x.w, x.h, box, 1);
+    }
     if (rc) return rc;
   }
-  int rc = tmap_img(&tb, x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 1);
+  int rc = rowb ? tmap_img16(&tb, x, sh->x16, box) : tmap_img(&tb, x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 1);
   if (rc) return rc;
-  return wgrad_common(ta, tb, p, dy.c, x.c, st);
+  return wgrad_common(ta, tb, p, dy.c, x.c, st, rowb);
 }
 
 // the same contraction with fp16 operands (x16: NHWC fp16 image, w16: packed fp16 weights) and an optional fp16 shadow of

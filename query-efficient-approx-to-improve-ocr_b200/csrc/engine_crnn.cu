@@ -54,6 +54,9 @@ struct CrnnPlan {
   void *wp2h, *wp3h, *wp4h, *wp5h, *wp6h, *wp7h, *wih0h, *wih1h, *wlinh;
   float *dwp2, *dwp3, *dwp4, *dwp5, *dwp6, *dwp7;  // packed [Cout][tap][Cin] weight-gradient accumulators, contiguous
   size_t dwp_bytes;
+  // backward pass with scaled fp16 operands (nn.cuh GradShadow): shadows of the conv stack's gradient tensors, fp16 dgrad B operands
+  void *dx0h, *d6fh, *d5h, *d4fh, *d3h, *d2fh;
+  void *wpd2h, *wpd3h, *wpd4h, *wpd5h, *wpd6h, *wpd7h;
   size_t bytes;
 };
 
@@ -101,6 +104,10 @@ CrnnPlan make_plan(int B, int W, int V, void* base) {
     p.wp2h = half((size_t)128 * 9 * 64); p.wp3h = half((size_t)256 * 9 * 128); p.wp4h = half((size_t)256 * 9 * 256);
     p.wp5h = half((size_t)512 * 9 * 256); p.wp6h = half((size_t)512 * 9 * 512); p.wp7h = half((size_t)512 * 4 * 512);
     p.wih0h = half((size_t)2048 * 512); p.wih1h = half((size_t)2048 * 512); p.wlinh = half((size_t)96 * 512);
+    p.dx0h = half(tb * 512); p.d6fh = half(px4 * 512); p.d5h = half(px4 * 512); p.d4fh = half(px8 * 256); p.d3h = half(px8 * 256);
+    p.d2fh = half(px16 * 128);
+    p.wpd2h = half((size_t)128 * 9 * 64); p.wpd3h = half((size_t)256 * 9 * 128); p.wpd4h = half((size_t)256 * 9 * 256);
+    p.wpd5h = half((size_t)512 * 9 * 256); p.wpd6h = half((size_t)512 * 9 * 512); p.wpd7h = half((size_t)512 * 4 * 512);
   }
   p.bytes = a.off;
   return p;
@@ -356,14 +363,18 @@ int crnn_forward_body(const float* x, int B, int W, int V, const float* const* p
 // every non-NULL gradient is ACCUMULATED into (zero it for a plain gradient). dx: (B,1,32,W) or NULL.
 // The workspace must be the one the forward filled, with the same B, W, V, params and bn_train.
 namespace {
+// gradient tensors of the conv stack that are operands of a dgrad / wgrad contraction (slots of nn.cuh GradScales)
+enum { GS_DZ7 = 0, GS_D6F, GS_D5, GS_D4F, GS_D3, GS_D2F, kGradSlots };
+constexpr int kNetKindCrnn = 2;
 int crnn_backward_body(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
                        const float* dlogits, float* const* grads, float* dx, void* stream);
 }
 QEB_API int qeb_crnn_backward(const float* x, int B, int W, int V, const float* const* params, int bn_train, void* ws,
                               const float* dlogits, float* const* grads, float* dx, void* stream) {
   QEB_REQUIRE(x && params && ws && dlogits && grads, "crnn_backward: null pointer");
+  grad_scales_prepare(kNetKindCrnn, params[0], kGradSlots, (cudaStream_t)stream);
   CallKey key;
-  key.add(2).add(x).add(B).add(W).add(V).add(bn_train).add(ws).add(dlogits).add(dx);
+  key.add(2).add(x).add(B).add(W).add(V).add(bn_train).add(ws).add(dlogits).add(dx).add(grad_scales_state(kNetKindCrnn, params[0]));
   key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(grads), P_COUNT);
   return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
     return crnn_backward_body(x, B, W, V, params, bn_train, ws, dlogits, grads, dx, (void*)st);
@@ -394,6 +405,20 @@ int crnn_backward_body(const float* x, int B, int W, int V, const float* const* 
   chained.round_out = 1;
   SideStream ss;  // weight / bias gradients run beside the input-gradient chain
   TRY(ss.init(st));
+  // scaled fp16 operands for the conv stack's backward contractions: needs the fp16 activation shadows of the forward pass
+  GradScales gsc;
+  if (fp16_fwd()) TRY(grad_scales_begin(kNetKindCrnn, params[0], kGradSlots, st, &gsc));
+  const bool b16 = gsc.valid;
+  // operands(slot, x16, dy16): shadows of a weight gradient's operands; dgrad16(e, slot, dy16, w16): the same for an input gradient
+  WgradShadows wsh;
+  auto operands = [&](int slot, const void* x16, const void* dy16) -> const WgradShadows* {
+    if (!b16) return nullptr;
+    wsh.x16 = x16; wsh.dy16 = dy16; wsh.alpha = gsc.inv + slot;
+    return &wsh;
+  };
+  auto dgrad16 = [&](TcEpilogue& e, int slot, const void* dy16, const void* w16) {
+    if (b16) { e.in16 = dy16; e.w16 = w16; e.alpha = gsc.inv + slot; }
+  };
 
   // ---- Linear
   TRY(fill_zero(p.dlp, (size_t)TB * 96 * sizeof(float), st));
@@ -409,12 +434,21 @@ int crnn_backward_body(const float* x, int B, int W, int V, const float* const* 
   }
   {  // the conv stack's input-gradient operands are not needed before the LSTM layers are done: side stream
     PackBatch pk;
-    pk.add_dgrad(params[P_C7W], p.wpd7, 512, 512, 4);
-    pk.add_dgrad(params[P_C6W], p.wpd6, 512, 512, 9);
-    pk.add_dgrad(params[P_C5W], p.wpd5, 512, 256, 9);
-    pk.add_dgrad(params[P_C4W], p.wpd4, 256, 256, 9);
-    pk.add_dgrad(params[P_C3W], p.wpd3, 256, 128, 9);
-    pk.add_dgrad(params[P_C2W], p.wpd2, 128, 64, 9);
+    if (b16) {   // fp16 B operands; the fp32 packs are not read then
+      pk.add_dgrad16(params[P_C7W], p.wpd7h, 512, 512, 4);
+      pk.add_dgrad16(params[P_C6W], p.wpd6h, 512, 512, 9);
+      pk.add_dgrad16(params[P_C5W], p.wpd5h, 512, 256, 9);
+      pk.add_dgrad16(params[P_C4W], p.wpd4h, 256, 256, 9);
+      pk.add_dgrad16(params[P_C3W], p.wpd3h, 256, 128, 9);
+      pk.add_dgrad16(params[P_C2W], p.wpd2h, 128, 64, 9);
+    } else {
+      pk.add_dgrad(params[P_C7W], p.wpd7, 512, 512, 4);
+      pk.add_dgrad(params[P_C6W], p.wpd6, 512, 512, 9);
+      pk.add_dgrad(params[P_C5W], p.wpd5, 512, 256, 9);
+      pk.add_dgrad(params[P_C4W], p.wpd4, 256, 256, 9);
+      pk.add_dgrad(params[P_C3W], p.wpd3, 256, 128, 9);
+      pk.add_dgrad(params[P_C2W], p.wpd2, 128, 64, 9);
+    }
     TRY(ss.fork());
     TRY(fill_zero(p.dwp2, p.dwp_bytes, ss.s()));  // packed conv weight-gradient accumulators: only side-stream kernels add into them
     TRY(pack_flush(pk, ss.s()));
@@ -457,79 +491,113 @@ int crnn_backward_body(const float* x, int B, int W, int V, const float* const* 
     // d(input) = dG * [W_ih_fwd ; W_ih_rev]
     // layer 1 -> dy0 feeds the layer-0 recurrence (which rounds its own operands); layer 0 -> dx0 = dz7 feeds conv7's
     // weight- and input-gradient contractions directly
+    TcEpilogue eo = l ? plain : chained;
+    int dz7_done = 0;
+    if (l == 0) { eo.gs = gsc.slot(GS_DZ7, p.dx0h); eo.gs_done = &dz7_done; }
     TRY(tc_conv_fprop(img_nhwc(g, 1, 1, TB, 2048), l ? p.wihT1 : p.wihT0, 512, 1, 1, 0, 0, img_nhwc(l ? p.dy0 : p.dx0, 1, 1, TB, 512),
-                      l ? plain : chained, st));
+                      eo, st));
+    QEB_REQUIRE(l || !gsc.amax || dz7_done, "crnn_backward: the gradient shadow of conv7's output was not written");
   }
 
   // ---- conv7 (dz7 = dx0, sequence-major view of a (B,1,T,512) image)
   Img DZ7;
   DZ7.p = p.dx0; DZ7.n = B; DZ7.h = 1; DZ7.w = T; DZ7.c = 512; DZ7.sn = 512; DZ7.sh = 0; DZ7.sw = (long long)B * 512;
   TRY(ss.fork());
-  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, p.dwp7, 4 * 512, 1, 2 * 512, 512, ss.s()));
+  if (grads[P_C7W]) TRY(tc_conv_wgrad(A6, DZ7, 2, 2, 0, 0, p.dwp7, 4 * 512, 1, 2 * 512, 512, ss.s(), operands(GS_DZ7, p.a6h, p.dx0h)));
   if (grads[P_C7B]) TRY(colsum_acc(img_nhwc(p.dx0, 1, 1, TB, 512), grads[P_C7B], ss.s()));
   TRY(ss.wait_mark());
-  TRY(tc_conv_fprop(DZ7, p.wpd7, 512, 2, 2, 1, 1, D6, plain, st));
+  {
+    TcEpilogue e;
+    dgrad16(e, GS_DZ7, p.dx0h, p.wpd7h);
+    TRY(tc_conv_fprop(DZ7, p.wpd7, 512, 2, 2, 1, 1, D6, e, st));
+  }
 
   // ---- conv6 + BN2 + ReLU + pool(2,1), conv5 + BN1 + ReLU
   const bool bn_grads = grads[P_BN1W] || grads[P_BN2W];
   if (bn_train || bn_grads) TRY(fill_zero(p.bnred, 2 * 512 * 2 * sizeof(double), st));
+  const GradShadow gs6 = gsc.slot(GS_D6F, p.d6fh), gs5 = gsc.slot(GS_D5, p.d5h), gs4 = gsc.slot(GS_D4F, p.d4fh),
+                   gs3 = gsc.slot(GS_D3, p.d3h), gs2 = gsc.slot(GS_D2F, p.d2fh);
   if (bn_train) {
     TRY(maxpool_bwd(A6f, D6, 2, 1, 0, nullptr, nullptr, D6f, st));  // grad at relu(bn(z6)); the ReLU mask comes from z6
     TRY(bn_bwd_reduce(Z6, D6f, p.scsh6, 1, p.bnred, st));
-    TRY(bn_bwd_apply_train(Z6, D6f, p.scsh6, 1, p.bnred, params[P_BN2W], D6f, grads[P_BN2W], grads[P_BN2B], st));
+    TRY(bn_bwd_apply_train(Z6, D6f, p.scsh6, 1, p.bnred, params[P_BN2W], D6f, grads[P_BN2W], grads[P_BN2B], st, &gs6));
   } else if (bn_grads) {
     TRY(maxpool_bwd(A6f, D6, 2, 1, 1, nullptr, nullptr, D6f, st));  // g = routed grad * (a6f > 0)
     TRY(bn_bwd_reduce(A6f, D6f, p.scsh6, 2, p.bnred, st));
-    TRY(bn_bwd_apply_eval(A6f, D6f, p.scsh6, 2, p.bnred, D6f, grads[P_BN2W], grads[P_BN2B], st));
+    TRY(bn_bwd_apply_eval(A6f, D6f, p.scsh6, 2, p.bnred, D6f, grads[P_BN2W], grads[P_BN2B], st, &gs6));
   } else {
-    TRY(maxpool_bwd(A6f, D6, 2, 1, 1, p.scsh6, nullptr, D6f, st));  // dz6 = routed grad * (a6f > 0) * scale, one pass
+    TRY(maxpool_bwd(A6f, D6, 2, 1, 1, p.scsh6, nullptr, D6f, st, nullptr, nullptr, nullptr, &gs6));  // dz6 = routed grad * (a6f > 0) * scale, one pass
   }
   TRY(ss.fork());
-  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, p.dwp6, 9 * 512, 1, 3 * 512, 512, ss.s()));
+  if (grads[P_C6W]) TRY(tc_conv_wgrad(A5, D6f, 3, 3, 1, 1, p.dwp6, 9 * 512, 1, 3 * 512, 512, ss.s(), operands(GS_D6F, p.a5h, p.d6fh)));
   if (grads[P_C6B]) TRY(colsum_acc(D6f, grads[P_C6B], ss.s()));
   if (bn_train) {
-    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, plain, st));
+    TcEpilogue e;
+    dgrad16(e, GS_D6F, p.d6fh, p.wpd6h);
+    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
     TRY(bn_bwd_reduce(Z5, D5, p.scsh5, 1, p.bnred + 1024, st));
-    TRY(bn_bwd_apply_train(Z5, D5, p.scsh5, 1, p.bnred + 1024, params[P_BN1W], D5, grads[P_BN1W], grads[P_BN1B], st));
+    TRY(bn_bwd_apply_train(Z5, D5, p.scsh5, 1, p.bnred + 1024, params[P_BN1W], D5, grads[P_BN1W], grads[P_BN1B], st, &gs5));
   } else if (bn_grads) {
-    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, plain, st));
+    TcEpilogue e;
+    dgrad16(e, GS_D6F, p.d6fh, p.wpd6h);
+    TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
     TRY(bn_bwd_reduce(A5, D5, p.scsh5, 2, p.bnred + 1024, st));
-    TRY(bn_bwd_apply_eval(A5, D5, p.scsh5, 2, p.bnred + 1024, D5, grads[P_BN1W], grads[P_BN1B], st));
+    TRY(bn_bwd_apply_eval(A5, D5, p.scsh5, 2, p.bnred + 1024, D5, grads[P_BN1W], grads[P_BN1B], st, &gs5));
   } else {
     TcEpilogue e;
     e.scale = p.scsh5; e.mask = &A5;  // dz5 = d(a5) * scale, zero where a5 == 0, fused into the dgrad epilogue
     e.round_out = 1;
+    int done = 0;
+    e.gs = gs5; e.gs_done = &done;
+    dgrad16(e, GS_D6F, p.d6fh, p.wpd6h);
     TRY(tc_conv_fprop(D6f, p.wpd6, 512, 3, 3, 1, 1, D5, e, st));
+    QEB_REQUIRE(!gsc.amax || done, "crnn_backward: the gradient shadow of conv5's output was not written");
   }
   TRY(ss.fork());
-  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, p.dwp5, 9 * 256, 1, 3 * 256, 256, ss.s()));
+  if (grads[P_C5W]) TRY(tc_conv_wgrad(A4, D5, 3, 3, 1, 1, p.dwp5, 9 * 256, 1, 3 * 256, 256, ss.s(), operands(GS_D5, p.a4h, p.d5h)));
   if (grads[P_C5B]) TRY(colsum_acc(D5, grads[P_C5B], ss.s()));
-  TRY(tc_conv_fprop(D5, p.wpd5, 256, 3, 3, 1, 1, D4, plain, st));
+  {
+    TcEpilogue e;
+    dgrad16(e, GS_D5, p.d5h, p.wpd5h);
+    TRY(tc_conv_fprop(D5, p.wpd5, 256, 3, 3, 1, 1, D4, e, st));
+  }
 
   // ---- conv4 + ReLU + pool(2,1), conv3 + ReLU
-  TRY(maxpool_bwd(A4f, D4, 2, 1, 1, nullptr, nullptr, D4f, st));
+  TRY(maxpool_bwd(A4f, D4, 2, 1, 1, nullptr, nullptr, D4f, st, nullptr, nullptr, nullptr, &gs4));
   TRY(ss.fork());
-  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, p.dwp4, 9 * 256, 1, 3 * 256, 256, ss.s()));
+  if (grads[P_C4W]) TRY(tc_conv_wgrad(A3, D4f, 3, 3, 1, 1, p.dwp4, 9 * 256, 1, 3 * 256, 256, ss.s(), operands(GS_D4F, p.a3h, p.d4fh)));
   if (grads[P_C4B]) TRY(colsum_acc(D4f, grads[P_C4B], ss.s()));
   {
     TcEpilogue e;
     e.mask = &A3;  // ReLU of conv3 fused into the dgrad epilogue
     e.round_out = 1;
+    int done = 0;
+    e.gs = gs3; e.gs_done = &done;
+    dgrad16(e, GS_D4F, p.d4fh, p.wpd4h);
     TRY(tc_conv_fprop(D4f, p.wpd4, 256, 3, 3, 1, 1, D3, e, st));
+    QEB_REQUIRE(!gsc.amax || done, "crnn_backward: the gradient shadow of conv3's output was not written");
   }
   TRY(ss.fork());
-  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, p.dwp3, 9 * 128, 1, 3 * 128, 128, ss.s()));
+  if (grads[P_C3W]) TRY(tc_conv_wgrad(A2, D3, 3, 3, 1, 1, p.dwp3, 9 * 128, 1, 3 * 128, 128, ss.s(), operands(GS_D3, p.a2h, p.d3h)));
   if (grads[P_C3B]) TRY(colsum_acc(D3, grads[P_C3B], ss.s()));
-  TRY(tc_conv_fprop(D3, p.wpd3, 128, 3, 3, 1, 1, D2, plain, st));
+  {
+    TcEpilogue e;
+    dgrad16(e, GS_D3, p.d3h, p.wpd3h);
+    TRY(tc_conv_fprop(D3, p.wpd3, 128, 3, 3, 1, 1, D2, e, st));
+  }
 
   // ---- conv2 + ReLU + pool, conv1 + ReLU + pool
-  TRY(maxpool_bwd(A2f, D2, 2, 2, 1, nullptr, nullptr, D2f, st));
+  TRY(maxpool_bwd(A2f, D2, 2, 2, 1, nullptr, nullptr, D2f, st, nullptr, nullptr, nullptr, &gs2));
   TRY(ss.fork());
-  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, p.dwp2, 9 * 64, 1, 3 * 64, 64, ss.s()));
+  if (grads[P_C2W]) TRY(tc_conv_wgrad(A1, D2f, 3, 3, 1, 1, p.dwp2, 9 * 64, 1, 3 * 64, 64, ss.s(), operands(GS_D2F, p.a1h, p.d2fh)));
   if (grads[P_C2B]) TRY(colsum_acc(D2f, grads[P_C2B], ss.s()));
   const bool need_d1 = grads[P_C1W] || grads[P_C1B] || dx;
   if (need_d1) {
-      TRY(tc_conv_fprop(D2f, p.wpd2, 64, 3, 3, 1, 1, D1, plain, st));
+    {
+      TcEpilogue e;
+      dgrad16(e, GS_D2F, p.d2fh, p.wpd2h);
+      TRY(tc_conv_fprop(D2f, p.wpd2, 64, 3, 3, 1, 1, D1, e, st));
+    }
     TRY(maxpool_bwd(A1f, D1, 2, 2, 1, nullptr, nullptr, D1f, st));
     TRY(ss.fork());
     if (grads[P_C1W]) TRY(c1_conv_wgrad(X, D1f, grads[P_C1W], grads[P_C1B], ss.s()));
@@ -547,6 +615,7 @@ int crnn_backward_body(const float* x, int B, int W, int V, const float* const* 
     if (grads[P_C7W]) pk.add_unpack_grad(p.dwp7, grads[P_C7W], 512, 512, 4);
     TRY(pack_flush(pk, st));
   }
+  grad_scales_commit(kNetKindCrnn, params[0]);
   return QEB_OK;
 }
 }  // namespace

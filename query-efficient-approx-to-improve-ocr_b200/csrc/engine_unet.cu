@@ -53,6 +53,9 @@ struct UnetPlan {
   __half *ea1h[kLevels], *pool_h[kLevels - 1], *cat_h[kLevels - 1], *bott_h;
   __half *da1h[kLevels - 1], *dout_h[kLevels - 1];
   __half *wph[kUnits], *wuph[4];
+  // backward pass with scaled fp16 operands (nn.cuh GradShadow): shadows of the gradient buffers and fp16 dgrad B operands
+  __half *sA_h[kLevels], *sB_h[kLevels], *sC_h[kLevels];
+  __half *wpdh[kUnits], *wupdh[4];
   size_t bytes;
 };
 
@@ -119,6 +122,16 @@ UnetPlan make_plan(int B, int H, int W, void* base) {
       p.wph[blk * 2] = half((size_t)cout * 9 * cin1); p.wph[blk * 2 + 1] = half((size_t)cout * 9 * cout);
     }
     for (int up = 0; up < 4; ++up) p.wuph[up] = half((size_t)4 * p.C[3 - up] * 2 * p.C[3 - up]);
+    for (int i = 0; i < kLevels; ++i) {
+      p.sA_h[i] = half(p.M[i] * 2 * p.C[i]); p.sB_h[i] = half(p.M[i] * p.C[i]); p.sC_h[i] = half(p.M[i] * p.C[i]);
+    }
+    for (int blk = 0; blk < 9; ++blk) {
+      const int lvl = blk < 5 ? blk : 3 - (blk - 5);
+      const int cout = p.C[lvl];
+      const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      p.wpdh[blk * 2] = half((size_t)cout * 9 * cin1); p.wpdh[blk * 2 + 1] = half((size_t)cout * 9 * cout);
+    }
+    for (int up = 0; up < 4; ++up) p.wupdh[up] = half((size_t)4 * p.C[3 - up] * 2 * p.C[3 - up]);
   }
   p.bytes = a.off;
   return p;
@@ -147,7 +160,10 @@ struct Ctx {
   int* red_done;   // backward only, [kUnits]: 1 = the BatchNorm-backward reductions of that unit were produced by the kernel
                    // that wrote its output gradient (fused epilogue), the separate reduction pass is skipped
   bool scsh_ready = false;   // eval-mode forward: scale / shift of units 1.. were folded on the side stream beforehand
+  const GradScales* gs = nullptr;   // backward only: slots [0, 18) = dz of the conv units, [18, 22) = the up-convolutions' output gradients
 };
+constexpr int kGradSlots = kUnits + 4;
+constexpr int kNetKindUnet = 1;
 
 // epilogue of an input-gradient kernel whose output is the gradient at the OUTPUT of conv unit `unit` (train-mode BatchNorm):
 // mask with relu(bn(z)) > 0 and accumulate that unit's BatchNorm-backward reductions
@@ -227,20 +243,26 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
 // din: where the gradient at the unit's input goes (nullptr: not needed).
 // z_lower: z of the conv unit that produced `in` (NULL: `in` is not the output of a conv unit, e.g. a pooled or concatenated
 // tensor) - its BatchNorm-backward reductions are then fused into this unit's input-gradient kernel.
+// in16: fp16 shadow of `in` (forward pass), g16: where the scaled fp16 shadow of dz goes, din16 / *din16_ok: the same for the input
+// gradient of a decoder block's first unit (slot 18 + level) - all NULL-able: that contraction then reads tf32.
 int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const Img& g, const Img* din,
-             const Img* z_lower = nullptr) {
+             const Img* z_lower = nullptr, const __half* in16 = nullptr, __half* g16 = nullptr, __half* din16 = nullptr,
+             int din_slot = -1, int* din16_ok = nullptr) {
   const int unit = block * 2 + which;
   const float* w = c.params[block * 6 + which * 3];
   float* const* gr = c.grads + block * 6 + which * 3;
   const float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
+  static const GradScales no_slots;
+  const GradScales& gsc = c.gs ? *c.gs : no_slots;
+  const GradShadow gsh = gsc.slot(unit, in.c == 1 ? nullptr : g16);   // the one-channel layer's kernels read the fp32 gradient
   if (c.bn_train) {
     double* red = c.p->bnred + (size_t)unit * 1024;
     if (!(c.red_done && c.red_done[unit])) TRY(bn_bwd_reduce(z, g, scsh, 1, red, c.st));
-    TRY(bn_bwd_apply_train(z, g, scsh, 1, red, nullptr, g, gr[1], gr[2], c.st));
+    TRY(bn_bwd_apply_train(z, g, scsh, 1, red, nullptr, g, gr[1], gr[2], c.st, &gsh));
   } else {  // frozen statistics: the mask and xhat come from the layer output
     double* red = gr[1] ? c.p->bnred + (size_t)unit * 1024 : nullptr;
     if (red) TRY(bn_bwd_reduce(out, g, scsh, 2, red, c.st));
-    TRY(bn_bwd_apply_eval(out, g, scsh, 2, red, g, gr[1], gr[2], c.st));
+    TRY(bn_bwd_apply_eval(out, g, scsh, 2, red, g, gr[1], gr[2], c.st, &gsh));
   }
   TRY(c.ss->fork());
   if (in.c == 1) {
@@ -248,12 +270,22 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     if (din) TRY(c1_conv_dgrad(g, w, *din, c.st));
     return QEB_OK;
   }
-  if (gr[0]) TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.ss->s()));
+  const bool h16 = gsh.out16 != nullptr;   // dz has a scaled fp16 shadow: kind::f16 contractions, accumulators x 1 / S
+  if (gr[0]) {
+    WgradShadows sh;
+    sh.x16 = in16; sh.dy16 = g16; sh.alpha = h16 ? gsc.inv + unit : nullptr;
+    TRY(tc_conv_wgrad(in, g, 3, 3, 1, 1, c.p->dwp[unit], (long long)in.c * 9, 1, (long long)in.c * 3, in.c, c.ss->s(),
+                      (h16 && in16) ? &sh : nullptr));
+  }
   if (din) {
     TcEpilogue e = (which == 1 && z_lower) ? grad_into_unit(c, unit - 1, z_lower) : TcEpilogue();
     // first unit of a decoder block: half of its input gradient (the up-convolution's output gradient) is the operand of the
     // ConvTranspose weight- and input-gradient contractions with no elementwise kernel in between
-    if (which == 0 && block >= 5) e.round_out = 1;
+    if (which == 0 && block >= 5) {
+      e.round_out = 1;
+      if (din_slot >= 0) { e.gs = gsc.slot(din_slot, din16); e.gs_done = din16_ok; }
+    }
+    if (h16) { e.in16 = g16; e.w16 = c.p->wpdh[unit]; e.alpha = gsc.inv + unit; }
     TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, e, c.st));
   }
   return QEB_OK;
@@ -421,9 +453,13 @@ int unet_backward_impl(const float* x, int B, int H, int W, const float* const* 
                        const float* dy, float* const* grads, float* dx, void* const* bucket_events, void* stream) {
   QEB_REQUIRE(x && params && ws && y && dy && grads, "unet_backward: null pointer");
   // an event recorded inside a private capture could not be waited for by the caller's communication stream: plain launches
-  if (bucket_events) return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, bucket_events, stream);
+  if (bucket_events) {
+    grad_scales_prepare(kNetKindUnet, params[0], kGradSlots, (cudaStream_t)stream);
+    return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, bucket_events, stream);
+  }
+  grad_scales_prepare(kNetKindUnet, params[0], kGradSlots, (cudaStream_t)stream);
   CallKey key;
-  key.add(4).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y).add(dy).add(dx);
+  key.add(4).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y).add(dy).add(dx).add(grad_scales_state(kNetKindUnet, params[0]));
   key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(grads), P_COUNT);
   return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
     return unet_backward_body(x, B, H, W, params, bn_train, ws, y, dy, grads, dx, nullptr, (void*)st);
@@ -441,6 +477,11 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
   c.ss = &ss;
   int red_done[kUnits] = {0};
   c.red_done = red_done;
+  // scaled fp16 operands for the backward contractions (nn.cuh GradShadow): needs the fp16 activation shadows of the forward pass
+  GradScales gsc;
+  if (fp16_fwd()) TRY(grad_scales_begin(kNetKindUnet, params[0], kGradSlots, c.st, &gsc));
+  c.gs = &gsc;
+  const bool b16 = gsc.valid;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
   {
     PackBatch pk;
@@ -448,12 +489,21 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
       const int lvl = blk < 5 ? blk : 3 - (blk - 5);
       const int cout = p.C[lvl];
       const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
-      if (cin1 > 1) pk.add_dgrad(params[blk * 6], p.wpd[blk * 2], cout, cin1, 9);
-      pk.add_dgrad(params[blk * 6 + 3], p.wpd[blk * 2 + 1], cout, cout, 9);
+      if (b16) {   // fp16 B operands; the fp32 packs are not read then
+        if (cin1 > 1) pk.add_dgrad16(params[blk * 6], p.wpdh[blk * 2], cout, cin1, 9);
+        pk.add_dgrad16(params[blk * 6 + 3], p.wpdh[blk * 2 + 1], cout, cout, 9);
+      } else {
+        if (cin1 > 1) pk.add_dgrad(params[blk * 6], p.wpd[blk * 2], cout, cin1, 9);
+        pk.add_dgrad(params[blk * 6 + 3], p.wpd[blk * 2 + 1], cout, cout, 9);
+      }
     }
     for (int up = 0; up < 4; ++up) {  // dgrad B operand [2C][(dh*2+dw)*C + co] from the torch weight (2C, C, 2, 2)
       const int C = p.C[3 - up];
       pk.add(params[P_UP + up * 2], p.wupd[up], 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
+      if (b16) {
+        pk.add(params[P_UP + up * 2], reinterpret_cast<float*>(p.wupdh[up]), 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
+        pk.last_to_half();
+      }
     }
     TRY(ss.fork());   // beside the final 1x1 conv's backward kernel
     TRY(fill_zero(p.dwp[0], p.dwp_bytes, ss.s()));   // packed weight-gradient accumulators: only side-stream kernels add into them
@@ -474,19 +524,27 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
     Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
     Img g = img_nhwc(p.sC[i], B, p.h[i], p.w[i], C), ga1 = img_nhwc(p.sB[i], B, p.h[i], p.w[i], C);
     Img gcat = img_nhwc(p.sA[i], B, p.h[i], p.w[i], 2 * C);
-    TRY(unit_bwd(c, blk, 1, a1, z2, out, g, &ga1, &z1));
-    TRY(unit_bwd(c, blk, 0, cat, z1, a1, ga1, &gcat));
+    int du16 = 0;   // 1: the up-convolution's output gradient got its scaled fp16 shadow (slot 18 + i)
+    TRY(unit_bwd(c, blk, 1, a1, z2, out, g, &ga1, &z1, p.da1h[i], p.sC_h[i]));
+    TRY(unit_bwd(c, blk, 0, cat, z1, a1, ga1, &gcat, nullptr, p.cat_h[i], p.sB_h[i], p.sA_h[i], kUnits + i, &du16));
+    du16 = du16 && b16;
     // up-convolution: dU = gcat[:, :C]
     Img dU = img_slice(gcat, 0, C);
     Img below = i < 3 ? img_nhwc(p.dout[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C) : img_nhwc(p.bott, B, p.h[4], p.w[4], 2 * C);
+    const __half* below16 = i < 3 ? p.dout_h[i + 1] : p.bott_h;
     TRY(ss.fork());
     if (grads[P_UP + up * 2 + 1]) TRY(colsum_acc(dU, grads[P_UP + up * 2 + 1], ss.s()));
-    if (grads[P_UP + up * 2]) TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], ss.s()));
+    if (grads[P_UP + up * 2]) {
+      WgradShadows sh;
+      sh.x16 = below16; sh.dy16 = p.sA_h[i]; sh.alpha = gsc.inv + kUnits + i;
+      TRY(tc_convT_wgrad(below, dU, grads[P_UP + up * 2], ss.s(), du16 ? &sh : nullptr));
+    }
     Img gbelow = img_nhwc(p.sC[i + 1], B, p.h[i + 1], p.w[i + 1], 2 * C);
     // `below` is the output of the second conv unit of the block one level down: fuse its BatchNorm-backward reductions
     const int blk_below = i < 3 ? 5 + (3 - (i + 1)) : 4;
     const Img z_below = img_nhwc(i < 3 ? p.dz2[i + 1] : p.ez2[4], B, p.h[i + 1], p.w[i + 1], 2 * C);
-    const TcEpilogue e = grad_into_unit(c, blk_below * 2 + 1, &z_below);
+    TcEpilogue e = grad_into_unit(c, blk_below * 2 + 1, &z_below);
+    if (du16) { e.in16 = p.sA_h[i]; e.w16 = p.wupdh[up]; e.alpha = gsc.inv + kUnits + i; }
     TRY(tc_convT_dgrad(dU, p.wupd[up], gbelow, e, c.st));
   }
   int unpacked_from = 9;   // conv blocks [unpacked_from, 9) already have their weight gradients in the caller's tensors
@@ -519,11 +577,11 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
         TRY(maxpool_bwd(out, gpool, 2, 2, 0, nullptr, &skip, g, c.st));
       }
     }
-    TRY(unit_bwd(c, i, 1, a1, z2, out, g, &ga1, &z1));
+    TRY(unit_bwd(c, i, 1, a1, z2, out, g, &ga1, &z1, p.ea1h[i], p.sC_h[i]));
     if (i > 0) {
       Img in = img_nhwc(p.pool[i - 1], B, p.h[i], p.w[i], p.C[i - 1]);
       Img gin = img_nhwc(p.sA[i], B, p.h[i], p.w[i], p.C[i - 1]);
-      TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, &gin));
+      TRY(unit_bwd(c, i, 0, in, z1, a1, ga1, &gin, nullptr, p.pool_h[i - 1], p.sB_h[i]));
       if (i == 3 && bucket_events) {   // the bottleneck and encoder block 4: the same on the side stream, the main chain goes on
         TRY(ss.fork());
         TRY(unpack_weight_grads(p, grads, 3, 5, ss.s()));
@@ -542,6 +600,7 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
   }
   TRY(ss.join());
   TRY(unpack_weight_grads(p, grads, 0, unpacked_from, c.st));
+  grad_scales_commit(kNetKindUnet, params[0]);
   return QEB_OK;
 }
 }  // namespace

@@ -29,6 +29,40 @@ static inline long long img_pixels(const Img& a) { return (long long)a.n * a.h *
 // true when pixel index (n,h,w) -> offset is a single stride (rows/images packed back to back)
 static inline bool img_flat(const Img& a) { return a.sh == a.sw * a.w && a.sn == a.sh * a.h; }
 
+// ---- scaled fp16 shadows of gradient tensors (operands of the backward contractions) ------------------------------------------
+// A gradient tensor that feeds a dgrad / wgrad contraction is written twice by its producer: the fp32 tensor and an fp16 copy
+// of v * S (saturating) for the tensor core - kind::f16 runs at twice the kind::tf32 rate on half the operand bytes with the
+// same 11-bit significand. S is a power of two per tensor (exact scaling) taken from the running maximum the producers of the
+// PREVIOUS backward call recorded for that tensor ("delayed scaling": S * max ~ 2^4, i.e. 2^12 of headroom before the shadow
+// saturates and 2^18 before small values leave fp16's normal range; profiles/r1_notes.md: a scale up to 2^16 off the ideal one
+// costs no accuracy). The consumer multiplies its accumulator by 1 / S (TcEpilogue::alpha, WgradShadows::alpha).
+struct GradShadow {
+  void* out16 = nullptr;          // fp16 copy, same element layout as the fp32 tensor; NULL: not written
+  const float* scale = nullptr;   // device scalar S
+  unsigned* amax = nullptr;       // device: max |v| as an fp32 bit pattern (red.max.u32), NULL: not tracked
+};
+// One set of slots per network instance (keyed on a parameter pointer), living in the library: [amax | S | 1/S] x n.
+struct GradScales {
+  unsigned* amax = nullptr;
+  float* scale = nullptr;
+  float* inv = nullptr;
+  int n = 0;
+  bool valid = false;   // a previous backward call has recorded the maxima these scales come from
+  GradShadow slot(int i, void* out16) const {
+    GradShadow g;
+    if (amax) { g.amax = amax + i; if (valid && out16) { g.out16 = out16; g.scale = scale + i; } }
+    return g;
+  }
+};
+// prepare: allocates the slots of (net_kind, key) on first use, unless `st` is being captured (then: no slots = the tf32 path).
+// begin: looks them up and enqueues the kernel that turns the previous call's maxima into this call's scales and clears the
+// maxima (never allocates: it may run inside a stream capture).
+void grad_scales_prepare(int net_kind, const void* key, int n, cudaStream_t st);
+int grad_scales_begin(int net_kind, const void* key, int n, cudaStream_t st, GradScales* out);
+// host-side peek used for the call-graph key: have these slots seen a backward call yet? (-1: no slots)
+int grad_scales_state(int net_kind, const void* key);
+void grad_scales_commit(int net_kind, const void* key);   // after the call has been issued: the next call finds valid maxima
+
 // ---- tensor-core (tcgen05, kind::tf32) contractions, conv_tc.cu -------------------------------------------------
 struct TcEpilogue {
   const float* bias = nullptr;   // per output channel
@@ -63,6 +97,12 @@ struct TcEpilogue {
   // (torch.argmax order), what pred_to_string (utils.py:78-89) takes per frame. Plain bias epilogue only.
   int log_softmax = 0;
   int* argmax = nullptr;
+  // backward pass with scaled fp16 operands: alpha (device scalar, 1 / S of the in16 operand) multiplies the accumulator before
+  // anything else; gs: the OUTPUT is itself an operand of a later contraction - its scaled fp16 shadow / running maximum.
+  // *gs_done = 1 when the kernel honoured gs (vector epilogues only: aligned rows, multiples of 32 channels, no split-K)
+  const float* alpha = nullptr;
+  GradShadow gs;
+  int* gs_done = nullptr;
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
@@ -84,7 +124,7 @@ struct WgradShadows {
 int tc_conv_wgrad(const Img& x, const Img& dy, int kh, int kw, int ph, int pw, float* dw, long long s_co, long long s_ci,
                   long long s_kh, long long s_kw, cudaStream_t st, const WgradShadows* sh = nullptr);
 // ConvTranspose2d 2x2 s2 weight gradient: dw[ci][co][dh][dw] (torch layout) += sum x(n,h,w,ci) dy(n,2h+dh,2w+dw,co)
-int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st);
+int tc_convT_wgrad(const Img& x, const Img& dy, float* dw, cudaStream_t st, const WgradShadows* sh = nullptr);
 
 // ---- weight packing, layout.cu ------------------------------------------------------------------------------------
 // generic strided gather: dst[i0*d0 + i1*d1 + i2] = src[i0*s0 + i1*s1 + i2*s2] for i0<n0, i1<n1, i2<n2 (dst innermost
@@ -109,7 +149,7 @@ struct ConvPackJob {
                     // 1: dst[b][taps-1-tap][a] = src[a][b][tap]   dgrad B operand (flipped taps, channels transposed)
                     // 2: dst[a][b][tap] (+)= src[a][tap][b]   packed weight gradient -> torch layout
   int tile_start;   // first 32 x 32 tile of this job in the batch-wide numbering
-  int half_out;     // mode 0 only: dst is an fp16 buffer
+  int half_out;     // modes 0, 1: dst is an fp16 buffer
 };
 struct PackBatch {
   enum { kMax = 28 };
@@ -149,6 +189,12 @@ struct PackBatch {
     if (!add_conv(w, dst, cout, cin, taps, 1))
       add(w + (taps - 1), dst, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout);
   }
+  // the dgrad B operand as fp16 (dst16: a buffer of cin*taps*cout halves)
+  void add_dgrad16(const float* w, void* dst16, int cout, int cin, int taps) {
+    float* d = static_cast<float*>(dst16);
+    if (add_conv(w, d, cout, cin, taps, 1)) cjobs[nc - 1].half_out = 1;
+    else { add(w + (taps - 1), d, cin, taps, cout, taps, -1, (long long)cin * taps, (long long)taps * cout, cout); last_to_half(); }
+  }
   void add_copy(const float* src, float* dst, long long n) { add(src, dst, 1, 1, (int)n, 0, 0, 1, 0, 0); }
   // packed weight gradient [Cout][tap][Cin] (what the wgrad kernel accumulates into with coalesced atomics) -> torch
   // layout (Cout,Cin,taps)
@@ -187,7 +233,8 @@ int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, v
 // bn_z / bn_scsh / bn_red (all or none): dx is the gradient at the output of a train-mode conv + BN + ReLU unit with
 // pre-activation bn_z; that unit's BatchNorm-backward reductions are accumulated into bn_red[2C] in the same pass
 int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
-                const Img& dx, cudaStream_t st, const Img* bn_z = nullptr, const float* bn_scsh = nullptr, double* bn_red = nullptr);
+                const Img& dx, cudaStream_t st, const Img* bn_z = nullptr, const float* bn_scsh = nullptr, double* bn_red = nullptr,
+                const GradShadow* gs = nullptr);   // gs: dx is a dgrad / wgrad operand
 // batch norm over all pixels of z (train: batch statistics; eval: running statistics)
 struct BnParams {
   const float* gamma; const float* beta;
@@ -211,11 +258,11 @@ int bn_apply(const Img& z, const float* scsh, int relu, const Img& out, cudaStre
 int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, double* red, cudaStream_t st);
 // train: dz = gamma*invstd*(g - sum_g/M - xhat*sum_gx/M); dgamma += sum_gx, dbeta += sum_g (when given)
 int bn_bwd_apply_train(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const float* gamma,
-                       const Img& dz, float* dgamma, float* dbeta, cudaStream_t st);
+                       const Img& dz, float* dgamma, float* dbeta, cudaStream_t st, const GradShadow* gs = nullptr);
 // eval (frozen statistics): dz = g*scale; relu = 2: `z` is the layer's ReLU OUTPUT (the pre-activation is not kept)
 // red (from bn_bwd_reduce on the same tensors) is only needed for dgamma += sum g*xhat, dbeta += sum g.
 int bn_bwd_apply_eval(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const Img& dz,
-                      float* dgamma, float* dbeta, cudaStream_t st);
+                      float* dgamma, float* dbeta, cudaStream_t st, const GradShadow* gs = nullptr);
 // out[c] += sum over pixels of x(pix, c)   (bias gradients)
 int colsum_acc(const Img& x, float* out, cudaStream_t st, float* out2 = nullptr);   // out2: a second accumulator receiving the same sums
 // dx = dy * (a > 0)

@@ -41,6 +41,16 @@ __device__ __forceinline__ void st4h(__half* p, const float4 v) {
   *reinterpret_cast<uint2*>(p) = pk;
 }
 
+// scaled fp16 shadow of a gradient (nn.cuh GradShadow) and the running maximum of |v|
+__device__ __forceinline__ void st4h_scaled(__half* p, const float4 v, float s) { st4h(p, make_float4(v.x * s, v.y * s, v.z * s, v.w * s)); }
+__device__ __forceinline__ float amax4(float m, const float4 v) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+}
+__device__ __forceinline__ void amax_flush(unsigned* slot, float m) {   // whole warp; one reduction per warp
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(slot, __float_as_uint(m));
+}
+
 __device__ __forceinline__ long long pix_off(const Geo& g, long long pix) {
   const int w = (int)(pix % g.w);
   const long long t = pix / g.w;
@@ -420,8 +430,12 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
                                                                Geo gd, int relu_mask, const float* __restrict__ chan_scale,
                                                                const float* __restrict__ add, Geo ga, float* __restrict__ dx,
                                                                Geo gdx, int cq_n, long long total, const float* __restrict__ bn_z,
-                                                               Geo gz, const float* __restrict__ bn_scsh, double* __restrict__ bn_red) {
+                                                               Geo gz, const float* __restrict__ bn_scsh, double* __restrict__ bn_red,
+                                                               __half* __restrict__ dx16, const float* __restrict__ gscale,
+                                                               unsigned* __restrict__ gamax) {
   qeb_pdl_sync();
+  const float gs_s = dx16 ? __ldg(gscale) : 1.f;
+  float gs_m = 0.f;
   // bn_red != NULL: dx is the gradient at the output of a train-mode conv + BN + ReLU unit whose pre-activation is bn_z; its
   // BatchNorm-backward reductions (sum of masked g, sum of masked g * xhat) are accumulated here instead of in a separate
   // pass over (z, dx). kThreads is a multiple of cq_n (host check): a thread keeps its channel quad.
@@ -477,6 +491,8 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
           o[0] += q.x; o[1] += q.y; o[2] += q.z; o[3] += q.w;
         }
         st4(dx + off, qeb_tf32r4(make_float4(o[0], o[1], o[2], o[3])));   // dgrad / wgrad operand: rounded to tf32 here
+        if (dx16) st4h_scaled(dx16 + off, make_float4(o[0], o[1], o[2], o[3]), gs_s);
+        if (gamax) gs_m = amax4(gs_m, make_float4(o[0], o[1], o[2], o[3]));
         if constexpr (RED) {
           const float4 zv = ld4(bn_z + n * gz.sn + (long long)(hv * PH + a) * gz.sh + (long long)(wv * PW + b) * gz.sw + cq * 4);
           const float4 gm = bn_masked_grad(zv, make_float4(o[0], o[1], o[2], o[3]), bsc, bsh, 1);
@@ -486,6 +502,7 @@ __global__ void __launch_bounds__(kThreads) maxpool_bwd_kernel(const float* __re
         }
       }
   }
+  if (gamax) amax_flush(gamax, gs_m);
   if constexpr (RED) {   // block reduction over the row lanes of each channel, then one double atomic per channel and block
     extern __shared__ float sm[];
     const int C = cq_n * 4, rpb = kThreads / cq_n, cq = threadIdx.x % cq_n, rl = threadIdx.x / cq_n;
@@ -753,8 +770,11 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
                                                                 const float* __restrict__ scsh, int relu,
                                                                 const double* __restrict__ red, int mode,
                                                                 float* __restrict__ dz, long long dzs, float* __restrict__ dgamma,
-                                                                float* __restrict__ dbeta) {
+                                                                float* __restrict__ dbeta, __half* __restrict__ dz16,
+                                                                const float* __restrict__ gscale, unsigned* __restrict__ gamax) {
   qeb_pdl_sync();
+  const float gs_s = dz16 ? __ldg(gscale) : 1.f;
+  float gs_m = 0.f;
   const int cq_n = C / 4;
   if (blockIdx.x == 0 && dgamma) {
     for (int c = threadIdx.x; c < C; c += kThreads) {
@@ -789,7 +809,10 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
       o.w = sc.w * (g.w - mg.w - (v.w - mu.w) * is.w * mx.w);
     }
     st4(dz + r * dzs + cq * 4, qeb_tf32r4(o));   // dgrad / wgrad operand: rounded to tf32 here
+    if (dz16) st4h_scaled(dz16 + r * dzs + cq * 4, o, gs_s);
+    gs_m = amax4(gs_m, o);
   }
+  if (gamax) amax_flush(gamax, gs_m);
 }
 
 __global__ void __launch_bounds__(kThreads) colsum_kernel(const float* __restrict__ x, long long xs, long long M, int C,
@@ -933,7 +956,9 @@ __global__ void __launch_bounds__(kThreads) conv_pack_kernel(const __grid_consta
   } else if (j.mode == 1) {
     for (int r = warp; r < 32 * T; r += nwarp) {
       const int b = r / T, ft = r - b * T;
-      j.dst[((long long)(b0 + b) * T + ft) * j.A + a0 + lane] = qeb_tf32r(tile[lane * pitch + b * T + (T - 1 - ft)]);
+      const long long o = ((long long)(b0 + b) * T + ft) * j.A + a0 + lane;
+      if (j.half_out) reinterpret_cast<__half*>(j.dst)[o] = __float2half_rn(tile[lane * pitch + b * T + (T - 1 - ft)]);
+      else j.dst[o] = qeb_tf32r(tile[lane * pitch + b * T + (T - 1 - ft)]);
     }
   } else {
     for (int a = warp; a < 32; a += nwarp) {
@@ -1103,7 +1128,10 @@ int maxpool_fwd(const Img& x, int ph, int pw, const Img& out, cudaStream_t st, v
 }
 
 int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, const float* chan_scale, const Img* add,
-                const Img& dx, cudaStream_t st, const Img* bn_z, const float* bn_scsh, double* bn_red) {
+                const Img& dx, cudaStream_t st, const Img* bn_z, const float* bn_scsh, double* bn_red, const GradShadow* gs) {
+  __half* dx16 = gs && gs->out16 && gs->scale ? static_cast<__half*>(gs->out16) : nullptr;
+  const float* gsc = gs ? gs->scale : nullptr;
+  unsigned* gam = gs ? gs->amax : nullptr;
   ProfScope prof("maxpool_bwd", st, 0.0, 4.0 * x.c * (2 * (double)img_pixels(x) + (double)img_pixels(dy) + (add ? (double)img_pixels(x) : 0.0)));
   QEB_REQUIRE(vec4_ok(x) && vec4_ok(dy) && vec4_ok(dx) && x.c == dy.c && x.c == dx.c, "maxpool_bwd: channel count / alignment");
   QEB_REQUIRE(x.h == dy.h * ph && x.w == dy.w * pw && x.n == dy.n, "maxpool_bwd: input must be a multiple of the window");
@@ -1129,13 +1157,13 @@ int maxpool_bwd(const Img& x, const Img& dy, int ph, int pw, int relu_mask, cons
   QEB_REQUIRE(!red || (ph == 2 && pw == 2), "maxpool_bwd: fused BatchNorm reductions exist for the 2x2 window only");
   if (ph == 2 && pw == 2 && red)
     QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2, true>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx),
-                        cq_n, total, zp, gz, bn_scsh, bn_red));
+                        cq_n, total, zp, gz, bn_scsh, bn_red, dx16, gsc, gam));
   else if (ph == 2 && pw == 2)
     QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 2, false>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx),
-                        cq_n, total, zp, gz, bn_scsh, (double*)nullptr));
+                        cq_n, total, zp, gz, bn_scsh, (double*)nullptr, dx16, gsc, gam));
   else if (ph == 2 && pw == 1)
     QEB_CUDA(qeb_launch(maxpool_bwd_kernel<2, 1, false>, g, kThreads, smem, st, x.p, geo(x), dy.p, geo(dy), relu_mask, chan_scale, ap, ga, dx.p, geo(dx),
-                        cq_n, total, zp, gz, bn_scsh, (double*)nullptr));
+                        cq_n, total, zp, gz, bn_scsh, (double*)nullptr, dx16, gsc, gam));
   else QEB_REQUIRE(false, "maxpool_bwd: window %dx%d not supported", ph, pw);
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
@@ -1248,7 +1276,9 @@ int bn_bwd_reduce(const Img& z, const Img& dy, const float* scsh, int relu, doub
 }
 
 static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, int mode, const Img& dz,
-                        float* dgamma, float* dbeta, cudaStream_t st) {
+                        float* dgamma, float* dbeta, cudaStream_t st, const GradShadow* gs) {
+  __half* dz16 = gs && gs->out16 && gs->scale ? static_cast<__half*>(gs->out16) : nullptr;
+  QEB_REQUIRE(!dz16 || (((uintptr_t)dz16 & 7) == 0), "bn_bwd_apply: fp16 shadow alignment");
   ProfScope prof("bn_bwd_apply", st, 0.0, 12.0 * z.c * (double)img_pixels(z));
   REQ_FLAT(z, "bn_bwd_apply");
   REQ_FLAT(dy, "bn_bwd_apply");
@@ -1258,21 +1288,22 @@ static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu
   QEB_REQUIRE(kThreads % (z.c / 4) == 0, "bn_bwd_apply: C/4 must divide %d", kThreads);
   const long long M = img_pixels(z);
   QEB_CUDA(qeb_launch(bn_bwd_apply_kernel, RGRID(bn_bwd_apply_kernel, M * (z.c / 4)), kThreads, 0, st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
-                                                                             dz.p, dz.sw, dgamma, dbeta));
+                                                                             dz.p, dz.sw, dgamma, dbeta, dz16, gs ? gs->scale : nullptr,
+                                                                             gs ? gs->amax : nullptr));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
 }
 
 int bn_bwd_apply_train(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const float* gamma,
-                       const Img& dz, float* dgamma, float* dbeta, cudaStream_t st) {
+                       const Img& dz, float* dgamma, float* dbeta, cudaStream_t st, const GradShadow* gs) {
   (void)gamma;  // scale = gamma*invstd is already in scsh
-  return bn_bwd_apply(z, dy, scsh, relu, red, 0, dz, dgamma, dbeta, st);
+  return bn_bwd_apply(z, dy, scsh, relu, red, 0, dz, dgamma, dbeta, st, gs);
 }
 
 int bn_bwd_apply_eval(const Img& z, const Img& dy, const float* scsh, int relu, const double* red, const Img& dz,
-                      float* dgamma, float* dbeta, cudaStream_t st) {
-  return bn_bwd_apply(z, dy, scsh, relu, red, 1, dz, red ? dgamma : nullptr, red ? dbeta : nullptr, st);
+                      float* dgamma, float* dbeta, cudaStream_t st, const GradShadow* gs) {
+  return bn_bwd_apply(z, dy, scsh, relu, red, 1, dz, red ? dgamma : nullptr, red ? dbeta : nullptr, st, gs);
 }
 
 int colsum_acc(const Img& x, float* out, cudaStream_t st, float* out2) {

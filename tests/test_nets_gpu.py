@@ -277,8 +277,23 @@ def test_unet_golden_from_reference(q):
 
 
 # ------------------------------------------------------------------------------------------------ networks vs oracle
+def _fp16_backward_launches(rep):
+    return sum(v["launches"] for k, v in rep.items() if k in ("tc_conv_wgrad.f16",)), rep
+
+
 @pytest.mark.parametrize("B,W,mode", [(64, 128, "train"), (64, 128, "bneval"), (5, 256, "train"), (3, 64, "bneval")])
 def test_crnn_vs_oracle(q, B, W, mode):
+    _crnn_vs_oracle(q, B, W, mode, False)
+
+
+@pytest.mark.parametrize("B,W,mode", [(64, 128, "train"), (64, 128, "bneval"), (5, 256, "bneval")])
+def test_crnn_vs_oracle_fp16_backward(q, B, W, mode):
+    """The same comparison for the SECOND backward call of a network: the first records the gradient maxima (tf32 operands), from
+    then on the conv stack's dgrad / wgrad contractions read scaled fp16 shadows (nn.cuh GradShadow)."""
+    _crnn_vs_oracle(q, B, W, mode, True)
+
+
+def _crnn_vs_oracle(q, B, W, mode, prime):
     torch.manual_seed(B + W)
     m = q.CRNN(95, False).to(DEV)
     with torch.no_grad():
@@ -290,6 +305,14 @@ def test_crnn_vs_oracle(q, B, W, mode):
         if mode == "bneval":
             mm.apply(q.utils.set_bn_eval)
     x = torch.rand(B, 1, 32, W, device=DEV)
+    if prime:   # a backward call on another batch (a third of the loss: the scales must not depend on matching magnitudes)
+        bufs = copy.deepcopy(m.state_dict())
+        lp0 = m(torch.rand(B, 1, 32, W, device=DEV).requires_grad_(True))
+        yl0 = torch.randint(1, 9, (B,), dtype=torch.int32)
+        (q.ctc.CTCLoss()(lp0, torch.randint(1, 95, (int(yl0.sum()),), dtype=torch.int32), torch.full((B,), lp0.shape[0], dtype=torch.int32), yl0) / 3).backward()
+        m.zero_grad()
+        m.load_state_dict(bufs)   # BatchNorm running statistics as before the priming call
+        q.lib.prof_enable(True)
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     lp, lpr = m(xa), nn_oracle.crnn_forward(mr, xb)
     assert lp.shape == (W // 4 - 1, B, 95)
@@ -302,6 +325,10 @@ def test_crnn_vs_oracle(q, B, W, mode):
     lb = torch.nn.CTCLoss()(lpr, y.to(DEV), il.to(DEV), ylen.to(DEV))
     assert abs(float(la) - float(lb)) < 1e-3 * abs(float(lb))
     la.backward(); lb.backward()
+    if prime:
+        rep = q.lib.prof_report()
+        q.lib.prof_enable(False)
+        assert rep.get("tc_conv_wgrad.f16", {}).get("launches", 0) >= 6, rep.keys()   # conv2..conv7 weight gradients
     assert cos(xa.grad, xb.grad) > 0.99
     for (n, p), (_, r) in zip(m.named_parameters(), mr.named_parameters()):
         if mode == "train" and n in ("convo.conv5.bias", "convo.conv6.bias"):   # analytically zero (train-mode BN follows)
@@ -314,6 +341,16 @@ def test_crnn_vs_oracle(q, B, W, mode):
 
 @pytest.mark.parametrize("B,H,W,mode", [(64, 32, 128, "train"), (1, 400, 512, "train"), (2, 48, 80, "eval")])
 def test_unet_vs_oracle(q, B, H, W, mode):
+    _unet_vs_oracle(q, B, H, W, mode, False)
+
+
+@pytest.mark.parametrize("B,H,W,mode", [(64, 32, 128, "train"), (2, 48, 80, "train"), (2, 48, 80, "eval")])
+def test_unet_vs_oracle_fp16_backward(q, B, H, W, mode):
+    """Second backward call of the network: scaled fp16 operands in every tensor-core dgrad / wgrad (see the CRNN twin)."""
+    _unet_vs_oracle(q, B, H, W, mode, True)
+
+
+def _unet_vs_oracle(q, B, H, W, mode, prime):
     torch.manual_seed(H + W)
     m = q.UNet().to(DEV)
     with torch.no_grad():
@@ -324,11 +361,21 @@ def test_unet_vs_oracle(q, B, H, W, mode):
     for mm in (m, mr):
         mm.train() if mode == "train" else mm.eval()
     x = torch.rand(B, 1, H, W, device=DEV)
+    if prime:
+        bufs = copy.deepcopy(m.state_dict())
+        (q.train_ops.mse_to_ones(m(torch.rand(B, 1, H, W, device=DEV).requires_grad_(True))) / 3).backward()
+        m.zero_grad()
+        m.load_state_dict(bufs)
+        q.lib.prof_enable(True)
     xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
     y, yr = m(xa), nn_oracle.unet_forward(mr, xb)
     assert float((y - yr).abs().max()) < 3e-3
     (q.train_ops.mse_to_ones(y)).backward()
     torch.nn.MSELoss()(yr, torch.ones_like(yr)).backward()
+    if prime:
+        rep = q.lib.prof_report()
+        q.lib.prof_enable(False)
+        assert rep.get("tc_conv_wgrad.f16", {}).get("launches", 0) >= 17, rep.keys()   # 17 conv units + 4 up-convolutions
     assert cos(xa.grad, xb.grad) > 0.98
     for (n, p), (_, r) in zip(m.named_parameters(), mr.named_parameters()):
         assert cos(p.grad, r.grad) > 0.98, (n, cos(p.grad, r.grad))
