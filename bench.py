@@ -203,7 +203,7 @@ def workload_config(n_gpus):
     return {"workload": "configs[1]: train_nn_area phase B step - UNet(train BN) + CRNN surrogate (BN frozen) fwd/bwd + CTC(mean) + "
                         "1.0*MSE-to-white + Adam(lr 5e-5) on the UNet; 64 synthetic 32x128 patches per GPU, V=95, T=31",
             "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "patch": [H, W], "parallelism": f"dp{n_gpus}",
-            "operand_precision": "tensor-core operands with an 11-bit significand (fp16 copies in the forward pass, tf32 reads of fp32 in the backward pass), fp32 accumulation / activations / gradients / parameters (reference: fp32)",
+            "operand_precision": "tensor-core operands with an 11-bit significand: fp16 copies of the activations in the forward pass, fp16 copies of the gradients scaled by a power of two per tensor (from the previous step's maximum) in the conv backward passes, tf32 reads of fp32 in the LSTM / Linear backward and in a network's first backward call; fp32 accumulation / activations / gradients / parameters (reference: fp32)",
             "l2": "no explicit flush: a step streams ~1.4 GB of activations, > 126 MB L2",
             "launch": "forward+losses+backward (+ the gradient all-reduce when N > 1) replayed as one CUDA graph (qeb_b200.graphs.GraphedStep); Adam outside it"}
 
@@ -472,7 +472,7 @@ def run():
             ach = v["flops"] / v["ms"] / 1e9
             roofline = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                         "traffic": traffic, "peak_source": ("measured bf16 dense burst (MEASURED_PEAKS.json); the family is kind::f16 in the forward "
-                                                            "pass and kind::tf32 (nominally half the rate) in the backward pass"
+                                                            "pass and in the conv backward passes, kind::tf32 (nominally half the rate) in the LSTM / Linear backward"
                                                             if peaks else "fallback 1590 bf16")}
         else:
             peak = peaks.get("hbm_gbs", 6650.0)

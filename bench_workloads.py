@@ -234,8 +234,9 @@ def jitter_config(world):
                         "gradients summed over the copies, Adam(lr 1e-4, wd 5e-4) on the CRNN; V=95, T=31",
             "copies": INNER_LIMIT, "copies_per_gpu": INNER_LIMIT // world, "patches_per_step": BB.BATCH * INNER_LIMIT,
             "patch": [BB.H, BB.W], "parallelism": f"dp{world} over the noised copies, all-reduce SUM of the flat 35 MB CRNN gradient",
-            "operand_precision": "tensor-core operands with an 11-bit significand (fp16 forward copies, tf32 rounded-to-nearest "
-                                 "backward), fp32 accumulation / activations / gradients / parameters",
+            "operand_precision": "tensor-core operands with an 11-bit significand (fp16 forward copies, power-of-two-scaled fp16 gradient "
+                                 "copies in the conv backward, tf32 rounded-to-nearest in the LSTM / Linear backward), fp32 accumulation / "
+                                 "activations / gradients / parameters",
             "l2": "no explicit flush: one copy streams ~0.6 GB of activations, > 126 MB L2",
             "launch": "forward (jitter fused into conv1's input load, log-softmax into the head's epilogue) + CTC + backward of the rank's copies replayed as one CUDA graph; all-reduce and Adam outside it"}
 

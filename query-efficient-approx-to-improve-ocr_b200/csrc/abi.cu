@@ -121,7 +121,7 @@ namespace {
 struct SideRes {
   int device = -1;
   cudaStream_t side = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, mark_ev = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, mark_ev = nullptr, mark2_ev = nullptr;
 };
 thread_local SideRes g_side;
 }  // namespace
@@ -140,15 +140,17 @@ int SideStream::init(cudaStream_t main_stream) {
   if (g_side.device != dev) {
     if (g_side.side) {
       cudaStreamDestroy(g_side.side); cudaEventDestroy(g_side.fork_ev); cudaEventDestroy(g_side.join_ev); cudaEventDestroy(g_side.mark_ev);
+      cudaEventDestroy(g_side.mark2_ev);
     }
     g_side = SideRes();
     QEB_CUDA(cudaStreamCreateWithFlags(&g_side.side, cudaStreamNonBlocking));
     QEB_CUDA(cudaEventCreateWithFlags(&g_side.fork_ev, cudaEventDisableTiming));
     QEB_CUDA(cudaEventCreateWithFlags(&g_side.join_ev, cudaEventDisableTiming));
     QEB_CUDA(cudaEventCreateWithFlags(&g_side.mark_ev, cudaEventDisableTiming));
+    QEB_CUDA(cudaEventCreateWithFlags(&g_side.mark2_ev, cudaEventDisableTiming));
     g_side.device = dev;
   }
-  side = g_side.side; fork_ev = g_side.fork_ev; join_ev = g_side.join_ev; mark_ev = g_side.mark_ev;
+  side = g_side.side; fork_ev = g_side.fork_ev; join_ev = g_side.join_ev; mark_ev = g_side.mark_ev; mark2_ev = g_side.mark2_ev;
   enabled = true;
   return QEB_OK;
 }
@@ -180,6 +182,20 @@ int SideStream::wait_mark() {
   if (!enabled || !marked) return QEB_OK;
   QEB_CUDA(cudaStreamWaitEvent(main, mark_ev, 0));
   marked = false;
+  return QEB_OK;
+}
+
+int SideStream::mark2() {
+  if (!enabled) return QEB_OK;
+  QEB_CUDA(cudaEventRecord(mark2_ev, side));
+  marked2 = true;
+  return QEB_OK;
+}
+
+int SideStream::wait_mark2() {
+  if (!enabled || !marked2) return QEB_OK;
+  QEB_CUDA(cudaStreamWaitEvent(main, mark2_ev, 0));
+  marked2 = false;
   return QEB_OK;
 }
 

@@ -227,23 +227,28 @@ int crnn_forward_body(const float* x, int B, int W, int V, const float* const* p
   const bool h = fp16_fwd();
   SideStream ss;
   TRY(ss.init(st));
-  {  // every weight re-layout of this pass in one launch
+  // the weight re-layouts of this pass in two launches: conv2-conv4 (10 % of the bytes), needed at once, and the rest - first read
+  // by conv5, ~100 us into the pass - behind them (QEB_PACK_SPLIT=0: one launch, one wait)
+  static const bool split = !(getenv("QEB_PACK_SPLIT") && atoi(getenv("QEB_PACK_SPLIT")) == 0);
+  PackBatch pk2;
+  {
     PackBatch pk;
     if (h) {   // fp16 B operands; the fp32 packs are not needed by the forward pass then
+      PackBatch& late = split ? pk2 : pk;
       pk.add_fprop16(params[P_C2W], p.wp2h, 128, 64, 9);
       pk.add_fprop16(params[P_C3W], p.wp3h, 256, 128, 9);
       pk.add_fprop16(params[P_C4W], p.wp4h, 256, 256, 9);
-      pk.add_fprop16(params[P_C5W], p.wp5h, 512, 256, 9);
-      pk.add_fprop16(params[P_C6W], p.wp6h, 512, 512, 9);
-      pk.add_fprop16(params[P_C7W], p.wp7h, 512, 512, 4);
+      late.add_fprop16(params[P_C5W], p.wp5h, 512, 256, 9);
+      late.add_fprop16(params[P_C6W], p.wp6h, 512, 512, 9);
+      late.add_fprop16(params[P_C7W], p.wp7h, 512, 512, 4);
       for (int l = 0; l < 2; ++l)
         for (int d = 0; d < 2; ++d) {
           __half* dst = static_cast<__half*>(l ? p.wih1h : p.wih0h) + (size_t)d * 1024 * 512;
-          pk.add_copy(params[P_LSTM0 + l * 8 + d * 4], reinterpret_cast<float*>(dst), (long long)1024 * 512);
-          pk.last_to_half();
+          late.add_copy(params[P_LSTM0 + l * 8 + d * 4], reinterpret_cast<float*>(dst), (long long)1024 * 512);
+          late.last_to_half();
         }
-      pk.add_copy(params[P_LINW], static_cast<float*>(p.wlinh), (long long)V * 512);
-      pk.last_to_half();
+      late.add_copy(params[P_LINW], static_cast<float*>(p.wlinh), (long long)V * 512);
+      late.last_to_half();
     } else {
       pk.add_fprop(params[P_C2W], p.wp2, 128, 64, 9);
       pk.add_fprop(params[P_C3W], p.wp3, 256, 128, 9);
@@ -257,7 +262,10 @@ int crnn_forward_body(const float* x, int B, int W, int V, const float* const* p
     }
     TRY(ss.fork());   // beside conv1 (direct kernel, no packed weights) and its pooling
     TRY(pack_flush(pk, ss.s()));
+    if (pk2.n + pk2.nc > 0) TRY(ss.mark());
   }
+  const bool two_marks = pk2.n + pk2.nc > 0;
+  if (two_marks) TRY(pack_flush(pk2, ss.s()));
   // the other parameter-only preparations ride along: summed LSTM biases, folded frozen-BatchNorm scale / shift
   const BnParams bn1 = bn_of(params, buffers, P_BN1W, P_BN1B, B_BN1_MEAN), bn2 = bn_of(params, buffers, P_BN2W, P_BN2B, B_BN2_MEAN);
   for (int l = 0; l < 2; ++l)
@@ -267,7 +275,8 @@ int crnn_forward_body(const float* x, int B, int W, int V, const float* const* p
     TRY(bn_eval_scsh(512, bn1, params[P_C5B], p.scsh5, ss.s()));
     TRY(bn_eval_scsh(512, bn2, params[P_C6B], p.scsh6, ss.s()));
   }
-  TRY(ss.mark());
+  if (two_marks) TRY(ss.mark2());
+  else TRY(ss.mark());
   // shadows(in, w, out): the fp16 copies a contraction reads / writes in fp16 mode (nulls otherwise: tf32 path)
   auto shadows = [&](TcEpilogue& e, const void* in16, const void* w16, void* out16) {
     e.in16 = h ? in16 : nullptr; e.w16 = h ? w16 : nullptr; e.out16 = h ? out16 : nullptr;
@@ -291,6 +300,7 @@ int crnn_forward_body(const float* x, int B, int W, int V, const float* const* p
   shadows(ep, p.a3h, p.wp4h, nullptr);
   TRY(tc_conv_fprop(A3, p.wp4, 256, 3, 3, 1, 1, A4f, ep, st));
   TRY(maxpool_fwd(A4f, 2, 1, A4, st, h ? p.a4h : nullptr));
+  TRY(ss.wait_mark2());   // conv5 ... Linear operands, LSTM bias sums, folded BatchNorm constants
 
   if (bn_train) {
     TRY(fill_zero(p.bnstats, 2 * 2 * 512 * sizeof(double), st));
@@ -427,10 +437,18 @@ int crnn_backward_body(const float* x, int B, int W, int V, const float* const* 
     PackBatch pk;
     pk.add(dlogits, p.dlp, 1, TB, V, 0, V, 1, 0, 96);
     pk.add(params[P_LINW], p.wlinT, 1, 512, V, 0, 1, 512, 0, 96);  // wlinT[c][v] = W[v][c]
+    // the LSTM layers' d(input) operands are first read after the layer-1 recurrence: side stream, ahead of the conv stack's
+    PackBatch pkl;
+    static const bool split = !(getenv("QEB_PACK_SPLIT") && atoi(getenv("QEB_PACK_SPLIT")) == 0);
     for (int l = 0; l < 2; ++l)  // d(input) B operand [512][2048]: wihT[c][d*1024 + r] = W_ih_d[r][c]
       for (int d = 0; d < 2; ++d)
-        pk.add(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wihT1 : p.wihT0) + d * 1024, 1, 512, 1024, 0, 1, 512, 0, 2048);
+        (split ? pkl : pk).add(params[P_LSTM0 + l * 8 + d * 4], (l ? p.wihT1 : p.wihT0) + d * 1024, 1, 512, 1024, 0, 1, 512, 0, 2048);
     TRY(pack_flush(pk, st));
+    if (split) {
+      TRY(ss.fork());
+      TRY(pack_flush(pkl, ss.s()));
+      TRY(ss.mark2());
+    }
   }
   {  // the conv stack's input-gradient operands are not needed before the LSTM layers are done: side stream
     PackBatch pk;
@@ -472,6 +490,7 @@ int crnn_backward_body(const float* x, int B, int W, int V, const float* const* 
     const float* dy = l ? p.dy1 : p.dy0;
     const Img Xin = l ? Y0 : X0;
     TRY(lstm_layer_bwd(g, c, dy, lp[1], lp[5], T, B, st, 1));  // g now holds d(pre-activations), (T,B,2,1024)
+    TRY(ss.wait_mark2());   // the d(input) operands (first pass of the loop only)
     TRY(ss.fork());
     for (int d = 0; d < 2; ++d) {
       Img DG = img_nhwc(g + d * 1024, 1, 1, TB, 1024, 2048);

@@ -254,7 +254,11 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
   const float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
   static const GradScales no_slots;
   const GradScales& gsc = c.gs ? *c.gs : no_slots;
-  const GradShadow gsh = gsc.slot(unit, in.c == 1 ? nullptr : g16);   // the one-channel layer's kernels read the fp32 gradient
+  GradShadow gsh = gsc.slot(unit, in.c == 1 ? nullptr : g16);   // the one-channel layer's kernels read the fp32 gradient
+  // dz is read by this unit's weight- and input-gradient contractions only (the convolutions have no bias): with both on the
+  // fp16 shadow the fp32 copy is never read, so it is not written (QEB_DZ_ONLY16=0 keeps it)
+  static const bool only16 = !(getenv("QEB_DZ_ONLY16") && atoi(getenv("QEB_DZ_ONLY16")) == 0);
+  if (gsh.out16 && in16 && only16) gsh.only16 = 1;
   if (c.bn_train) {
     double* red = c.p->bnred + (size_t)unit * 1024;
     if (!(c.red_done && c.red_done[unit])) TRY(bn_bwd_reduce(z, g, scsh, 1, red, c.st));
@@ -331,29 +335,37 @@ int unet_forward_body(const float* x, int B, int H, int W, const float* const* p
   TRY(ss.init(c.st));
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
   const bool h16 = fp16_fwd();
-  {  // every weight re-layout of this pass in one launch
-    PackBatch pk;
+  {  // the weight re-layouts of this pass in two launches: encoder blocks 1-3 (3 % of the bytes), needed at once, and the rest
+     // - first read by encoder block 4, ~150 us into the pass - behind them (QEB_PACK_SPLIT=0: one launch, one wait)
+    static const bool split = !(getenv("QEB_PACK_SPLIT") && atoi(getenv("QEB_PACK_SPLIT")) == 0);
+    PackBatch pk, pk2;
     for (int blk = 0; blk < 9; ++blk) {
       const int lvl = blk < 5 ? blk : 3 - (blk - 5);
       const int cout = p.C[lvl];
       const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      PackBatch& b = (split && blk >= 3) ? pk2 : pk;
       if (h16) {   // fp16 B operands; the fp32 packs are not needed by the forward pass then
-        if (cin1 > 1) pk.add_fprop16(params[blk * 6], p.wph[blk * 2], cout, cin1, 9);
-        pk.add_fprop16(params[blk * 6 + 3], p.wph[blk * 2 + 1], cout, cout, 9);
+        if (cin1 > 1) b.add_fprop16(params[blk * 6], p.wph[blk * 2], cout, cin1, 9);
+        b.add_fprop16(params[blk * 6 + 3], p.wph[blk * 2 + 1], cout, cout, 9);
       } else {
-        if (cin1 > 1) pk.add_fprop(params[blk * 6], p.wp[blk * 2], cout, cin1, 9);
-        pk.add_fprop(params[blk * 6 + 3], p.wp[blk * 2 + 1], cout, cout, 9);
+        if (cin1 > 1) b.add_fprop(params[blk * 6], p.wp[blk * 2], cout, cin1, 9);
+        b.add_fprop(params[blk * 6 + 3], p.wp[blk * 2 + 1], cout, cout, 9);
       }
     }
     for (int up = 0; up < 4; ++up) {  // ConvTranspose weight (2C, C, 2, 2) -> B operand [(dh*2+dw)*C + co][2C]
       const int C = p.C[3 - up];
-      pk.add(params[P_UP + up * 2], h16 ? reinterpret_cast<float*>(p.wuph[up]) : p.wup[up], 4, C, 2 * C, 1, 4, (long long)C * 4,
-             (long long)C * 2 * C, 2 * C);
-      if (h16) pk.last_to_half();
+      PackBatch& b = split ? pk2 : pk;
+      b.add(params[P_UP + up * 2], h16 ? reinterpret_cast<float*>(p.wuph[up]) : p.wup[up], 4, C, 2 * C, 1, 4, (long long)C * 4,
+            (long long)C * 2 * C, 2 * C);
+      if (h16) b.last_to_half();
     }
     // beside the first (one-channel, direct) convolution unit, which reads no packed weights
     TRY(ss.fork());
     TRY(pack_flush(pk, ss.s()));
+    if (split) {
+      TRY(ss.mark());
+      TRY(pack_flush(pk2, ss.s()));
+    }
     if (!bn_train && ss.enabled) {   // frozen statistics: fold every unit's scale / shift here too (unit 0 is needed at once: main)
       for (int unit = 1; unit < kUnits; ++unit) {
         const int blk = unit / 2, lvl = blk < 5 ? blk : 3 - (blk - 5);
@@ -361,7 +373,8 @@ int unet_forward_body(const float* x, int B, int H, int W, const float* const* p
       }
       c.scsh_ready = true;
     }
-    TRY(ss.mark());
+    if (split) TRY(ss.mark2());
+    else TRY(ss.mark());
   }
 
   Img in = img_nhwc(const_cast<float*>(x), B, H, W, 1);
@@ -372,6 +385,7 @@ int unet_forward_body(const float* x, int B, int H, int W, const float* const* p
     Img z2 = img_nhwc(p.ez2[i], B, p.h[i], p.w[i], C);
     Img out = i < 4 ? img_nhwc(p.cat[i] + C, B, p.h[i], p.w[i], C, 2 * C) : img_nhwc(p.bott, B, p.h[i], p.w[i], C);
     __half* out16 = h16 ? (i < 4 ? p.cat_h[i] + C : p.bott_h) : nullptr;   // same channel slice of the fp16 concat buffer
+    if (i == 3 || (i == 0 && !bn_train)) TRY(ss.wait_mark2());   // the deep layers' weights (eval mode: every unit's folded scale / shift)
     TRY(unit_fwd(c, i, 0, in, z1, a1, in16, h16 ? p.ea1h[i] : nullptr));
     TRY(ss.wait_mark());   // the packed weights (first pass of the loop only)
     const bool pool_fused = i < 4 && bn_train && pool_fuse();   // train mode: BatchNorm + ReLU + 2x2 pooling in one pass over z2
@@ -484,31 +498,40 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
   const bool b16 = gsc.valid;
   TRY(fill_zero(p.bnred, (size_t)kUnits * 1024 * sizeof(double), c.st));
   {
-    PackBatch pk;
+    // two launches: the decoder blocks 1 and 2 with their up-convolutions and encoder blocks 1-3 (small), needed first, then the
+    // deep layers (decoder blocks 3 and 4, bottleneck, encoder block 4: most of the bytes), first read by decoder block 3
+    static const bool split = !(getenv("QEB_PACK_SPLIT") && atoi(getenv("QEB_PACK_SPLIT")) == 0);
+    PackBatch pk, pk2;
     for (int blk = 0; blk < 9; ++blk) {
       const int lvl = blk < 5 ? blk : 3 - (blk - 5);
       const int cout = p.C[lvl];
       const int cin1 = blk == 0 ? 1 : (blk < 5 ? p.C[lvl - 1] : 2 * cout);
+      PackBatch& b = (split && lvl >= 2) ? pk2 : pk;
       if (b16) {   // fp16 B operands; the fp32 packs are not read then
-        if (cin1 > 1) pk.add_dgrad16(params[blk * 6], p.wpdh[blk * 2], cout, cin1, 9);
-        pk.add_dgrad16(params[blk * 6 + 3], p.wpdh[blk * 2 + 1], cout, cout, 9);
+        if (cin1 > 1) b.add_dgrad16(params[blk * 6], p.wpdh[blk * 2], cout, cin1, 9);
+        b.add_dgrad16(params[blk * 6 + 3], p.wpdh[blk * 2 + 1], cout, cout, 9);
       } else {
-        if (cin1 > 1) pk.add_dgrad(params[blk * 6], p.wpd[blk * 2], cout, cin1, 9);
-        pk.add_dgrad(params[blk * 6 + 3], p.wpd[blk * 2 + 1], cout, cout, 9);
+        if (cin1 > 1) b.add_dgrad(params[blk * 6], p.wpd[blk * 2], cout, cin1, 9);
+        b.add_dgrad(params[blk * 6 + 3], p.wpd[blk * 2 + 1], cout, cout, 9);
       }
     }
     for (int up = 0; up < 4; ++up) {  // dgrad B operand [2C][(dh*2+dw)*C + co] from the torch weight (2C, C, 2, 2)
       const int C = p.C[3 - up];
-      pk.add(params[P_UP + up * 2], p.wupd[up], 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
+      PackBatch& b = (split && up < 2) ? pk2 : pk;
+      b.add(params[P_UP + up * 2], p.wupd[up], 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
       if (b16) {
-        pk.add(params[P_UP + up * 2], reinterpret_cast<float*>(p.wupdh[up]), 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
-        pk.last_to_half();
+        b.add(params[P_UP + up * 2], reinterpret_cast<float*>(p.wupdh[up]), 2 * C, 4, C, (long long)C * 4, 1, 4, (long long)4 * C, C);
+        b.last_to_half();
       }
     }
     TRY(ss.fork());   // beside the final 1x1 conv's backward kernel
     TRY(fill_zero(p.dwp[0], p.dwp_bytes, ss.s()));   // packed weight-gradient accumulators: only side-stream kernels add into them
     TRY(pack_flush(pk, ss.s()));
     TRY(ss.mark());
+    if (split) {
+      TRY(pack_flush(pk2, ss.s()));
+      TRY(ss.mark2());
+    }
   }
 
   // final 1x1 conv + sigmoid
@@ -524,6 +547,7 @@ int unet_backward_body(const float* x, int B, int H, int W, const float* const* 
     Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
     Img g = img_nhwc(p.sC[i], B, p.h[i], p.w[i], C), ga1 = img_nhwc(p.sB[i], B, p.h[i], p.w[i], C);
     Img gcat = img_nhwc(p.sA[i], B, p.h[i], p.w[i], 2 * C);
+    if (i == 2) TRY(ss.wait_mark2());   // the deep layers' operands (levels 2 and 3, bottleneck, encoder block 4)
     int du16 = 0;   // 1: the up-convolution's output gradient got its scaled fp16 shadow (slot 18 + i)
     TRY(unit_bwd(c, blk, 1, a1, z2, out, g, &ga1, &z1, p.da1h[i], p.sC_h[i]));
     TRY(unit_bwd(c, blk, 0, cat, z1, a1, ga1, &gcat, nullptr, p.cat_h[i], p.sB_h[i], p.sA_h[i], kUnits + i, &du16));

@@ -40,6 +40,7 @@ struct GradShadow {
   void* out16 = nullptr;          // fp16 copy, same element layout as the fp32 tensor; NULL: not written
   const float* scale = nullptr;   // device scalar S
   unsigned* amax = nullptr;       // device: max |v| as an fp32 bit pattern (red.max.u32), NULL: not tracked
+  int only16 = 0;                 // 1 (with out16): every reader takes the shadow - the fp32 store is dropped (bn_bwd_apply_* only)
 };
 // One set of slots per network instance (keyed on a parameter pointer), living in the library: [amax | S | 1/S] x n.
 struct GradScales {
@@ -313,8 +314,8 @@ int qeb_run_cached(const CallKey& key, cudaStream_t st, const std::function<int(
 // keeps everything on the caller's stream.
 struct SideStream {
   cudaStream_t main = nullptr, side = nullptr;
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, mark_ev = nullptr;
-  bool enabled = false, dirty = false, marked = false;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, mark_ev = nullptr, mark2_ev = nullptr;
+  bool enabled = false, dirty = false, marked = false, marked2 = false;
   int init(cudaStream_t main_stream);
   int fork();
   int join();
@@ -322,5 +323,9 @@ struct SideStream {
   // for side work queued after it). Used for the weight re-layouts, which run beside the first kernels of a pass.
   int mark();
   int wait_mark();
+  // a second, independent mark: the re-layouts of the weights a pass needs late (the deep layers - most of the bytes) are queued
+  // behind those it needs at once and waited for where they are first read
+  int mark2();
+  int wait_mark2();
   cudaStream_t s() const { return enabled ? side : main; }
 };

@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
                                                                 const double* __restrict__ red, int mode,
                                                                 float* __restrict__ dz, long long dzs, float* __restrict__ dgamma,
                                                                 float* __restrict__ dbeta, __half* __restrict__ dz16,
-                                                                const float* __restrict__ gscale, unsigned* __restrict__ gamax) {
+                                                                const float* __restrict__ gscale, unsigned* __restrict__ gamax, int only16) {
   qeb_pdl_sync();
   const float gs_s = dz16 ? __ldg(gscale) : 1.f;
   float gs_m = 0.f;
@@ -808,7 +808,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_apply_kernel(const float* __r
       o.z = sc.z * (g.z - mg.z - (v.z - mu.z) * is.z * mx.z);
       o.w = sc.w * (g.w - mg.w - (v.w - mu.w) * is.w * mx.w);
     }
-    st4(dz + r * dzs + cq * 4, qeb_tf32r4(o));   // dgrad / wgrad operand: rounded to tf32 here
+    if (!only16) st4(dz + r * dzs + cq * 4, qeb_tf32r4(o));   // dgrad / wgrad operand: rounded to tf32 here
     if (dz16) st4h_scaled(dz16 + r * dzs + cq * 4, o, gs_s);
     gs_m = amax4(gs_m, o);
   }
@@ -1289,7 +1289,7 @@ static int bn_bwd_apply(const Img& z, const Img& dy, const float* scsh, int relu
   const long long M = img_pixels(z);
   QEB_CUDA(qeb_launch(bn_bwd_apply_kernel, RGRID(bn_bwd_apply_kernel, M * (z.c / 4)), kThreads, 0, st, z.p, z.sw, dy.p, dy.sw, M, z.c, scsh, relu, red, mode,
                                                                              dz.p, dz.sw, dgamma, dbeta, dz16, gs ? gs->scale : nullptr,
-                                                                             gs ? gs->amax : nullptr));
+                                                                             gs ? gs->amax : nullptr, (dz16 && gs->only16) ? 1 : 0));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;

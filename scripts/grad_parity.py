@@ -28,7 +28,7 @@ def cos(a, b):
     return float((a @ b) / (a.norm() * b.norm()).clamp_min(1e-30))
 
 
-def measure(batch=16, seed=0, competitors=False):
+def measure(batch=16, seed=0, competitors=False, prime=False):
     import qeb_b200  # noqa: F401
     from bench import CHAR_SET, encode, synth_batch
     from oracle import nn_oracle
@@ -53,6 +53,15 @@ def measure(batch=16, seed=0, competitors=False):
     for m in (crnn_cpu, unet_cpu, crnn, unet):
         m.train()
     crnn_cpu.apply(set_bn_eval); crnn.apply(set_bn_eval)
+    if prime:
+        # a network's FIRST backward call reads tf32 operands and records the gradient maxima; from the second call on the conv
+        # backward contractions read scaled fp16 shadows (csrc/nn.cuh GradShadow). Measure that second call: one throw-away step on
+        # another batch, BatchNorm buffers restored.
+        keep = copy.deepcopy(unet.state_dict())
+        x0, _ = synth_batch(batch, 12)
+        img0 = unet(x0.to(dev)); sc0 = crnn(img0)
+        (qctc.CTCLoss()(sc0, y, il, y_size) + train_ops.mse_to_ones(img0)).backward()
+        unet.zero_grad(); crnn.zero_grad(); unet.load_state_dict(keep)
     img = unet(x.to(dev)); scores = crnn(img)
     loss = qctc.CTCLoss()(scores, y, il, y_size) + train_ops.mse_to_ones(img)
     loss.backward()
@@ -92,6 +101,11 @@ def measure(batch=16, seed=0, competitors=False):
     for m in (crnn_cpu, crnn):
         m.zero_grad(); m.train()
     xa = x.to(dev)
+    if prime:
+        keep = copy.deepcopy(crnn.state_dict())
+        x0, _ = synth_batch(batch, 12)
+        qctc.CTCLoss()(crnn(x0.to(dev)), y, il, y_size).backward()
+        crnn.zero_grad(); crnn.load_state_dict(keep)
     scores = crnn(xa)
     loss = qctc.CTCLoss()(scores, y, il, y_size)
     loss.backward()
@@ -116,8 +130,10 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=16)
     ap.add_argument("--out", default=None)
     ap.add_argument("--competitors", action="store_true", help="also torch eager + cuDNN (fp32 / TF32) on this GPU and the fp64 floor")
+    ap.add_argument("--prime", action="store_true", help="measure the SECOND backward call of each network (scaled fp16 gradient operands)")
     a = ap.parse_args()
-    res = measure(a.batch, competitors=a.competitors)
+    res = measure(a.batch, competitors=a.competitors, prime=a.prime)
+    res["primed"] = bool(a.prime)
     for ph in ("phase_b", "phase_a"):
         r = res[ph]
         print(f"== {ph}: loss rel {r['loss_rel']:.2e}, scores rel {r['scores_rel']:.2e}, worst {r['worst_tensor']} {r['worst_rel_l2']:.2e}, min cos {r['min_cos']:.6f}")
