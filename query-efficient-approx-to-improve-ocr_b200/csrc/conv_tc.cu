@@ -172,6 +172,7 @@ struct FpropParams {
   const float* alpha;        // device scalar or NULL: the accumulator is multiplied by *alpha first (1 / scale of a scaled fp16 operand)
   const float* out16_scale;  // device scalar or NULL: the fp16 shadow holds v * *out16_scale (nn.cuh GradShadow)
   unsigned* gamax;           // device or NULL: running maximum of |v| over the stored values (fp32 bit pattern)
+  int out16_cols;            // the fp16 shadow (and the running maximum) cover output channels [0, out16_cols) only
 };
 
 struct TmapOut {
@@ -298,7 +299,7 @@ __device__ __forceinline__ void fprop_epilogue_store(const FpropParams& p, float
 // instruction writes 4 complete 128-byte row segments. stg: this warp's staging area (the pipeline ring is idle by then).
 __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float (&v)[32], bool valid, int n, int h, int w,
                                                     int ncol, bool split, float* stg, int lane, long long* tle = nullptr,
-                                                    float* cta_stats = nullptr, int c0_local = 0) {
+                                                    float* cta_stats = nullptr, int c0_local = 0, float* gmax_run = nullptr) {
   const int lim = min(32, p.n_total - ncol);
   if (lim < 32 || !p.vec_ok) {  // ragged / unaligned rows (warp-uniform): per-thread path
     if (valid) fprop_epilogue_store(p, v, n, h, w, ncol, split);
@@ -373,8 +374,8 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
           o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         *reinterpret_cast<float4*>(d) = p.round_out ? qeb_tf32r4(o) : o;
-        gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
-        if (p.out16) {   // fp16 shadow, same element offset
+        if (ncol < p.out16_cols) gmax = fmaxf(fmaxf(gmax, fmaxf(fabsf(o.x), fabsf(o.y))), fmaxf(fabsf(o.z), fabsf(o.w)));
+        if (p.out16 && ncol < p.out16_cols) {   // fp16 shadow, same element offset
           // (saturating: a value beyond fp16's range becomes +-65504, not inf; the fp32 output keeps the exact value)
           const float4 os = make_float4(o.x * s16, o.y * s16, o.z * s16, o.w * s16);
           const __half2 h0 = __floats2half2_rn(fminf(fmaxf(os.x, -65504.f), 65504.f), fminf(fmaxf(os.y, -65504.f), 65504.f));
@@ -406,10 +407,7 @@ __device__ __forceinline__ void fprop_epilogue_warp(const FpropParams& p, float 
       atomicAdd(a + 4, ssum.z); atomicAdd(a + 5, ssq.z); atomicAdd(a + 6, ssum.w); atomicAdd(a + 7, ssq.w);
     }
   }
-  if (p.gamax) {
-    gmax = warp_max(gmax);
-    if (lane == 0 && gmax > 0.f) atomicMax(p.gamax, __float_as_uint(gmax));
-  }
+  if (gmax_run) *gmax_run = fmaxf(*gmax_run, gmax);   // folded over the CTA's tiles, one reduction per warp at the end of the kernel
   __syncwarp();
 }
 
@@ -450,7 +448,7 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 // have READ the staging area before anybody overwrites it.
 __device__ __forceinline__ void fprop_epilogue_tma(const FpropParams& p, const TmapOut& to, float (&v)[32], bool valid, int n, int h,
                                                    int w, int w0, int h0, int n0, int ncol, uint32_t stg32, uint32_t stg16, int lane,
-                                                   float* cta_stats, int c0_local) {
+                                                   float* cta_stats, int c0_local, float* gmax_run) {
   if (p.alpha) {
     const float al = __ldg(p.alpha);
 #pragma unroll
@@ -496,16 +494,14 @@ __device__ __forceinline__ void fprop_epilogue_tma(const FpropParams& p, const T
   const uint32_t row32 = stg32 + (uint32_t)lane * 128u;
 #pragma unroll
   for (int j = 0; j < 8; ++j) st_shared_v4(row32 + (uint32_t)((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  if (p.gamax) {   // running maximum of the stored gradient (rows outside the image are clipped by the store: not counted)
-    float m = 0.f;
-    if (valid) {
+  const bool shadow = p.out16 && ncol < p.out16_cols;
+  if (p.gamax && valid && ncol < p.out16_cols) {   // running maximum of the stored gradient (rows outside the image are clipped by the store: not counted);
+    float m = *gmax_run;     // folded over the CTA's tiles, one reduction per warp at the end of the kernel
 #pragma unroll
-      for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(v[j]));
-    }
-    m = warp_max(m);
-    if (lane == 0 && m > 0.f) atomicMax(p.gamax, __float_as_uint(m));
+    for (int j = 0; j < 32; ++j) m = fmaxf(m, fabsf(v[j]));
+    *gmax_run = m;
   }
-  if (p.out16) {
+  if (shadow) {
     const uint32_t row16 = stg16 + (uint32_t)lane * 64u;
     const float s16 = p.out16_scale ? __ldg(p.out16_scale) : 1.f;
 #pragma unroll
@@ -518,7 +514,7 @@ __device__ __forceinline__ void fprop_epilogue_tma(const FpropParams& p, const T
   __syncwarp();
   if (lane == 0) {
     tma_store_4d(&to.f32, stg32, ncol, w0, h0, n0);
-    if (p.out16) tma_store_4d(&to.f16, stg16, ncol, w0, h0, n0);
+    if (shadow) tma_store_4d(&to.f16, stg16, ncol, w0, h0, n0);
     tma_store_commit();
   }
   if (cta_stats) {
@@ -904,6 +900,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     int n_done = 0, n_seen = 0;
+    float gmax_run = 0.f;   // running maximum of |stored value| (FpropParams::gamax)
     // fused BatchNorm statistics: the four epilogue warps add into shared-memory accumulators; they are flushed to global
     // memory (one double atomic per channel and CTA) when the CTA moves to another N tile and at the end
     int stat_n = -1;
@@ -960,9 +957,10 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
               const int r0 = q * 32;
               fprop_epilogue_tma(p, tmaps_o, v, valid, n, h, w, tw * p.wt + r0 % p.wt, th * p.ht + (r0 / p.wt) % p.ht,
                                  tn * p.nt + r0 / (p.wt * p.ht), ncol, smem_u32(epi_stage_g) + (uint32_t)q * 4096u,
-                                 smem_u32(epi_stage_g) + 16384u + (uint32_t)q * 2048u, lane, p.stats ? cta_stats_g : nullptr, c0);
+                                 smem_u32(epi_stage_g) + 16384u + (uint32_t)q * 2048u, lane, p.stats ? cta_stats_g : nullptr, c0, &gmax_run);
             } else {
-              fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage_g + q * 1024, lane, tle, p.stats ? cta_stats_g : nullptr, c0);
+              fprop_epilogue_warp(p, v, valid, n, h, w, ncol, split, epi_stage_g + q * 1024, lane, tle, p.stats ? cta_stats_g : nullptr, c0,
+                                  p.gamax ? &gmax_run : nullptr);
             }
           }
           if (tle) tle[10] = clock64();
@@ -979,6 +977,10 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       }
     }
     if (p.stats && stat_n >= 0) flush_stats(stat_n);
+    if (EPI != kEpiLsm && p.gamax) {
+      gmax_run = warp_max(gmax_run);
+      if (lane == 0 && gmax_run > 0.f) atomicMax(p.gamax, __float_as_uint(gmax_run));
+    }
     if (EPI == kEpiTma && lane == 0) tma_store_wait_all();   // the staging areas must outlive the stores that read them
     if (tl && threadIdx.x == 64) tl[3] = n_done;
   }
@@ -1109,6 +1111,7 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   p.alpha = ep.alpha;
   p.out16_scale = nullptr;
   p.gamax = nullptr;
+  p.out16_cols = (ep.gs_cols > 0 && ep.gs_cols % 32 == 0) ? ep.gs_cols : n_total;
   if (ep.gs.amax || ep.gs.out16) {
     // gradient shadow / running maximum: the vector epilogues only (aligned full rows); the caller learns through gs_done
     const bool ok = p.vec_ok && n_total % 32 == 0 && mode == 0 && !ep.accumulate && !ep.out16 &&

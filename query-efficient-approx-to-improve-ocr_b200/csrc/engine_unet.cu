@@ -287,7 +287,7 @@ int unit_bwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     // ConvTranspose weight- and input-gradient contractions with no elementwise kernel in between
     if (which == 0 && block >= 5) {
       e.round_out = 1;
-      if (din_slot >= 0) { e.gs = gsc.slot(din_slot, din16); e.gs_done = din16_ok; }
+      if (din_slot >= 0) { e.gs = gsc.slot(din_slot, din16); e.gs_done = din16_ok; e.gs_cols = din->c / 2; }   // the up-convolved half
     }
     if (h16) { e.in16 = g16; e.w16 = c.p->wpdh[unit]; e.alpha = gsc.inv + unit; }
     TRY(tc_conv_fprop(g, c.p->wpd[unit], in.c, 3, 3, 1, 1, *din, e, c.st));

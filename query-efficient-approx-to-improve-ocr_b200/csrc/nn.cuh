@@ -104,6 +104,7 @@ struct TcEpilogue {
   const float* alpha = nullptr;
   GradShadow gs;
   int* gs_done = nullptr;
+  int gs_cols = 0;   // > 0 (a multiple of 32): only output channels [0, gs_cols) are an operand later - shadow / maximum of those
 };
 // stride-1 convolution / GEMM. wpacked: [n_total][kh*kw*x.c] (K-major). out.c >= n_total channels are written.
 int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int kw, int ph, int pw, const Img& out,
