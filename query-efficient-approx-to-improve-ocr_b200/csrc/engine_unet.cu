@@ -160,6 +160,8 @@ struct Ctx {
   int* red_done;   // backward only, [kUnits]: 1 = the BatchNorm-backward reductions of that unit were produced by the kernel
                    // that wrote its output gradient (fused epilogue), the separate reduction pass is skipped
   bool scsh_ready = false;   // eval-mode forward: scale / shift of units 1.. were folded on the side stream beforehand
+  bool act_only16 = false;   // train-mode forward of a network whose backward runs on fp16 operands: activations that only feed
+                             // contractions (the first unit's output of every block, decoder outputs) skip their fp32 copy
   const GradScales* gs = nullptr;   // backward only: slots [0, 18) = dz of the conv units, [18, 22) = the up-convolutions' output gradients
 };
 constexpr int kGradSlots = kUnits + 4;
@@ -206,7 +208,7 @@ BnParams bn_of(const Ctx& c, int block, int which) {
 // one conv3x3 (no bias) + BN + ReLU unit. z: raw conv output (train mode only), out: activation. in16 / out16: fp16 shadows
 // of `in` / `out` (NULL: tf32 operands from the fp32 tensors / no shadow wanted).
 int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, const Img& out, const __half* in16 = nullptr,
-             __half* out16 = nullptr, const Img* pool = nullptr, __half* pool16 = nullptr) {
+             __half* out16 = nullptr, const Img* pool = nullptr, __half* pool16 = nullptr, bool out_only16 = false) {
   const int unit = block * 2 + which;
   const float* w = c.params[block * 6 + which * 3];
   float* scsh = c.p->scsh + (size_t)unit * 4 * 512;
@@ -228,7 +230,8 @@ int unit_fwd(const Ctx& c, int block, int which, const Img& in, const Img& z, co
     if (in16) { raw.in16 = in16; raw.w16 = c.p->wph[unit]; }
     TRY(tc_conv_fprop(in, wp, cout, 3, 3, 1, 1, z, raw, c.st));
     if (pool) return bn_train_finalize_apply_pool(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, out, out16, *pool, pool16, c.st);
-    return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st, out16);
+    return bn_train_finalize_apply(z, c.p->bnstats + (size_t)unit * 1024, bn, scsh, 1, out, c.st, out16,
+                                   (out_only16 && c.act_only16 && in16) ? 1 : 0);
   }
   if (!c.scsh_ready) TRY(bn_eval_scsh(cout, bn, nullptr, scsh, c.st));
   TcEpilogue f;
@@ -314,7 +317,7 @@ QEB_API int qeb_unet_forward(const float* x, int B, int H, int W, const float* c
                              int bn_train, void* ws, float* y, void* stream) {
   QEB_REQUIRE(x && params && buffers && ws && y, "unet_forward: null pointer");
   CallKey key;   // one captured graph per distinct argument set (nn.cuh qeb_run_cached)
-  key.add(3).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y);
+  key.add(3).add(x).add(B).add(H).add(W).add(bn_train).add(ws).add(y).add(grad_scales_state(kNetKindUnet, params[0]));
   key.ptrs(reinterpret_cast<const void* const*>(params), P_COUNT).ptrs(reinterpret_cast<const void* const*>(buffers), 3 * kUnits);
   return qeb_run_cached(key, (cudaStream_t)stream, [&](cudaStream_t st) {
     return unet_forward_body(x, B, H, W, params, buffers, bn_train, ws, y, (void*)st);
@@ -335,6 +338,9 @@ int unet_forward_body(const float* x, int B, int H, int W, const float* const* p
   TRY(ss.init(c.st));
   if (bn_train) TRY(fill_zero(p.bnstats, (size_t)kUnits * 1024 * sizeof(double), c.st));
   const bool h16 = fp16_fwd();
+  // the network has been through a backward call: the next one reads fp16 operands only (QEB_ACT_ONLY16=0 keeps the fp32 copies)
+  static const bool act16 = !(getenv("QEB_ACT_ONLY16") && atoi(getenv("QEB_ACT_ONLY16")) == 0);
+  c.act_only16 = act16 && bn_train && h16 && grad_scales_state(kNetKindUnet, params[0]) == 1;
   {  // the weight re-layouts of this pass in two launches: encoder blocks 1-3 (3 % of the bytes), needed at once, and the rest
      // - first read by encoder block 4, ~150 us into the pass - behind them (QEB_PACK_SPLIT=0: one launch, one wait)
     static const bool split = !(getenv("QEB_PACK_SPLIT") && atoi(getenv("QEB_PACK_SPLIT")) == 0);
@@ -386,7 +392,7 @@ int unet_forward_body(const float* x, int B, int H, int W, const float* const* p
     Img out = i < 4 ? img_nhwc(p.cat[i] + C, B, p.h[i], p.w[i], C, 2 * C) : img_nhwc(p.bott, B, p.h[i], p.w[i], C);
     __half* out16 = h16 ? (i < 4 ? p.cat_h[i] + C : p.bott_h) : nullptr;   // same channel slice of the fp16 concat buffer
     if (i == 3 || (i == 0 && !bn_train)) TRY(ss.wait_mark2());   // the deep layers' weights (eval mode: every unit's folded scale / shift)
-    TRY(unit_fwd(c, i, 0, in, z1, a1, in16, h16 ? p.ea1h[i] : nullptr));
+    TRY(unit_fwd(c, i, 0, in, z1, a1, in16, h16 ? p.ea1h[i] : nullptr, nullptr, nullptr, true));
     TRY(ss.wait_mark());   // the packed weights (first pass of the loop only)
     const bool pool_fused = i < 4 && bn_train && pool_fuse();   // train mode: BatchNorm + ReLU + 2x2 pooling in one pass over z2
     Img pl_f = img_nhwc(p.pool[i < 4 ? i : 0], B, p.h[i < 4 ? i + 1 : 1], p.w[i < 4 ? i + 1 : 1], C);
@@ -411,8 +417,8 @@ int unet_forward_body(const float* x, int B, int H, int W, const float* const* p
     Img cat = img_nhwc(p.cat[i], B, p.h[i], p.w[i], 2 * C);
     Img z1 = img_nhwc(p.dz1[i], B, p.h[i], p.w[i], C), a1 = img_nhwc(p.da1[i], B, p.h[i], p.w[i], C);
     Img z2 = img_nhwc(p.dz2[i], B, p.h[i], p.w[i], C), out = img_nhwc(p.dout[i], B, p.h[i], p.w[i], C);
-    TRY(unit_fwd(c, blk, 0, cat, z1, a1, h16 ? p.cat_h[i] : nullptr, h16 ? p.da1h[i] : nullptr));
-    TRY(unit_fwd(c, blk, 1, a1, z2, out, h16 ? p.da1h[i] : nullptr, (h16 && i > 0) ? p.dout_h[i] : nullptr));
+    TRY(unit_fwd(c, blk, 0, cat, z1, a1, h16 ? p.cat_h[i] : nullptr, h16 ? p.da1h[i] : nullptr, nullptr, nullptr, true));
+    TRY(unit_fwd(c, blk, 1, a1, z2, out, h16 ? p.da1h[i] : nullptr, (h16 && i > 0) ? p.dout_h[i] : nullptr, nullptr, nullptr, i > 0));
     below = out;
     below16 = h16 ? p.dout_h[i] : nullptr;
   }

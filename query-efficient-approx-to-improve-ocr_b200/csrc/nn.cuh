@@ -248,8 +248,9 @@ struct BnParams {
 int bn_train_stats(const Img& z, double* stats, cudaStream_t st);
 int bn_train_finalize(const double* stats, long long count, int c, const BnParams& bn, float* scsh, cudaStream_t st);
 // finalize + apply fused (train mode): out = relu?(bn(z)) from the batch sums; writes scsh, updates the running statistics
+// only16 (with out16): every later reader takes the fp16 shadow - the fp32 store is dropped
 int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
-                            cudaStream_t st, void* out16 = nullptr);
+                            cudaStream_t st, void* out16 = nullptr, int only16 = 0);
 // the same (ReLU on) fused with the 2 x 2 max pooling of the unit's output: writes out (+ out16) and pool (+ pool16)
 int bn_train_finalize_apply_pool(const Img& z, const double* stats, const BnParams& bn, float* scsh, const Img& out, void* out16,
                                  const Img& pool, void* pool16, cudaStream_t st);   // out16: fp16 shadow of out (same element layout)

@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
                                                                   const float* __restrict__ beta, float* running_mean,
                                                                   float* running_var, long long* nbt, float eps, float momentum,
                                                                   float* __restrict__ scsh, int relu, float* __restrict__ out,
-                                                                  long long os, __half* __restrict__ out16) {
+                                                                  long long os, __half* __restrict__ out16, int only16) {
   qeb_pdl_sync();
   const int cq_n = C / 4;
   const int cq = threadIdx.x % cq_n;
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(kThreads) bn_apply_train_kernel(const float* _
     const float4 v = ld4(z + r * zs + cq * 4);
     float4 o = make_float4(fmaf(v.x, sc[0], sh[0]), fmaf(v.y, sc[1], sh[1]), fmaf(v.z, sc[2], sh[2]), fmaf(v.w, sc[3], sh[3]));
     if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-    st4(out + r * os + cq * 4, qeb_tf32r4(o));   // weight-gradient operand: rounded to tf32 here
+    if (!only16) st4(out + r * os + cq * 4, qeb_tf32r4(o));   // weight-gradient operand: rounded to tf32 here
     if (out16) st4h(out16 + r * os + cq * 4, o);
   }
 }
@@ -1223,7 +1223,7 @@ int bn_eval_scsh(int c, const BnParams& bn, const float* conv_bias, float* scsh,
 }
 
 int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& bn, float* scsh, int relu, const Img& out,
-                            cudaStream_t st, void* out16) {
+                            cudaStream_t st, void* out16, int only16) {
   ProfScope prof("bn_apply", st, 0.0, 8.0 * z.c * (double)img_pixels(z));
   REQ_FLAT(z, "bn_train_finalize_apply");
   REQ_FLAT(out, "bn_train_finalize_apply");
@@ -1233,7 +1233,8 @@ int bn_train_finalize_apply(const Img& z, const double* stats, const BnParams& b
   QEB_CUDA(qeb_launch(bn_apply_train_kernel, RGRID(bn_apply_train_kernel, M * (z.c / 4)), kThreads, 0, st, z.p, z.sw, M, z.c, stats, bn.gamma, bn.beta,
                                                                                bn.running_mean, bn.running_var,
                                                                                bn.num_batches_tracked, bn.eps, bn.momentum, scsh,
-                                                                               relu, out.p, out.sw, static_cast<__half*>(out16)));
+                                                                               relu, out.p, out.sw, static_cast<__half*>(out16),
+                                                                               (only16 && out16) ? 1 : 0));
   QEB_LAUNCH_CHECK();
   qeb_count_launch();
   return QEB_OK;
