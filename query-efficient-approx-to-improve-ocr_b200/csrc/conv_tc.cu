@@ -1133,8 +1133,15 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   }
 
   // widest tile that still yields about one wave of CTAs; never wider than the (padded) problem
-  static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : kNumSMs;
-  static const int allow_split = getenv("QEB_TC_SPLITK") ? atoi(getenv("QEB_TC_SPLITK")) : 1;
+  // 128, not the SM count: a layer with exactly 128 tiles at the wide N tile stays there instead of being narrowed to 256 tiles
+  // (same-box A/B with fp16 operands: 112 / 120 / 128 -> 2.993-2.999 ms per step, 136 / 144 / 148 -> 3.04-3.05 ms)
+  static const int min_ctas = getenv("QEB_TC_MIN_CTAS") ? atoi(getenv("QEB_TC_MIN_CTAS")) : 128;
+  // Split-K with global reductions was the round-1 answer for the deep layers (tf32 operands: a narrowed N tile made every CTA stream
+  // the whole fp32 A operand for a sliver of MMA work). With fp16 operands - forward AND backward since round 2 - the narrowed tile
+  // is never slower per layer (scripts/exp/cluster_splitk_time.py, QEB_TC_CLUSTER=0 columns) and keeps the fused statistics, the
+  // TMA-store epilogue and no zero-fill: same-box A/B of the step 3.206 -> 3.088 ms with split-K off. Off by default
+  // (QEB_TC_SPLITK=1 brings it back); forward and input gradients are then bit-reproducible run to run.
+  static const int allow_split = getenv("QEB_TC_SPLITK") ? atoi(getenv("QEB_TC_SPLITK")) : 0;
   const int num_kb = kh * kw * (cin / kblk);
   const int bn_max = min(256, max(32, pow2_ceil(n_total)));
   int bn = bn_max, splits = 1;
@@ -1585,7 +1592,9 @@ int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, in
   // split-K so that the grid is about ONE CTA per SM, at least 8 pixel tiles per CTA: every CTA ends with a red.global.add
   // epilogue that retires at ~13 B per clock and SM (10 k cycles for a 128 x 256 tile, scripts/exp/wgrad_timeline.py), so a
   // second wave of CTAs pays setup + epilogue twice (same-box A/B: 296 CTAs 3.68 ms per step, 148 CTAs 3.65 ms)
-  static const int wg_ctas = getenv("QEB_WG_CTAS") ? atoi(getenv("QEB_WG_CTAS")) : kNumSMs;
+  // CTA slots the cost model below fills per round: 168 (two CTAs per SM are resident for BLOCK_N < 256; same-box A/B of the step
+  // 148 -> 3.007 ms, 160-176 -> 2.978-2.991 ms, 192 -> 2.999, 222 -> 3.004)
+  static const int wg_ctas = getenv("QEB_WG_CTAS") ? atoi(getenv("QEB_WG_CTAS")) : 168;
   static const int wg_model = getenv("QEB_WG_SPLIT_MODEL") ? atoi(getenv("QEB_WG_SPLIT_MODEL")) : 1;
   int splits = qeb_cdiv(wg_ctas, m_tiles * n_tiles);
   splits = max(1, min(splits, qeb_cdiv(p.tiles_total, 8)));
