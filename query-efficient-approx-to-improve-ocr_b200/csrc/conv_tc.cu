@@ -1143,7 +1143,8 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   // (QEB_TC_SPLITK=1 brings it back); forward and input gradients are then bit-reproducible run to run.
   static const int allow_split = getenv("QEB_TC_SPLITK") ? atoi(getenv("QEB_TC_SPLITK")) : 0;
   const int num_kb = kh * kw * (cin / kblk);
-  const int bn_max = min(256, max(32, pow2_ceil(n_total)));
+  static const int bn_cap = getenv("QEB_TC_BN_MAX") ? atoi(getenv("QEB_TC_BN_MAX")) : 256;
+  const int bn_max = min(bn_cap, max(32, pow2_ceil(n_total)));
   int bn = bn_max, splits = 1;
   // Few pixels, long K (the deep UNet levels and their input gradients): narrowing the N tile to fill the SMs makes every
   // CTA stream the whole A operand for a sliver of MMA work and the per-SM L2 read rate becomes the limit. With a plain
@@ -1606,7 +1607,9 @@ int wgrad_common(const TmapArray4& ta, const CUtensorMap& tb, WgradParams& p, in
     long long best = -1;
     for (int s = 1; s <= max_splits && s <= 4 * wg_ctas; ++s) {
       const long long rounds = qeb_cdiv((long long)tiles * s, wg_ctas);
-      const long long cost = rounds * ((long long)qeb_cdiv(p.tiles_total, s) * 600 + 40LL * bn + 3000);
+      static const int c_k = getenv("QEB_WG_CK") ? atoi(getenv("QEB_WG_CK")) : 600;
+      static const int c_e = getenv("QEB_WG_CE") ? atoi(getenv("QEB_WG_CE")) : 40;
+      const long long cost = rounds * ((long long)qeb_cdiv(p.tiles_total, s) * c_k + (long long)c_e * bn + 3000);
       if (best < 0 || cost < best) { best = cost; splits = s; }
     }
   }
