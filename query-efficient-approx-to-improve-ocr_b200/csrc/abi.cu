@@ -312,7 +312,22 @@ struct ScaleSet {
   long long calls = 0;       // backward calls issued with these slots
 };
 std::mutex g_scale_mu;
-std::map<std::pair<int, const void*>, ScaleSet> g_scale_sets;
+// key: (network kind, current device, first parameter pointer) - the same pointer value may exist on two devices of a process
+struct ScaleKey {
+  int kind, device;
+  const void* ptr;
+  bool operator<(const ScaleKey& o) const {
+    if (kind != o.kind) return kind < o.kind;
+    if (device != o.device) return device < o.device;
+    return ptr < o.ptr;
+  }
+};
+std::map<ScaleKey, ScaleSet> g_scale_sets;
+ScaleKey scale_key(int kind, const void* ptr) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return ScaleKey{kind, dev, ptr};
+}
 
 // S = 2^(4 - ceil(log2(max))): the largest magnitude of the previous call lands in [8, 16] (2^12 below fp16's largest value). A maximum of 0, inf or NaN (nothing
 // recorded, or a diverged step) keeps the previous scale.
@@ -337,14 +352,14 @@ __global__ void grad_scale_update_kernel(unsigned* amax, float* scale, float* in
 
 int grad_scales_state(int net_kind, const void* key) {
   std::lock_guard<std::mutex> lk(g_scale_mu);
-  auto it = g_scale_sets.find({net_kind, key});
+  auto it = g_scale_sets.find(scale_key(net_kind, key));
   if (it == g_scale_sets.end()) return -1;
   return it->second.calls > 0 ? 1 : 0;
 }
 
 void grad_scales_commit(int net_kind, const void* key) {
   std::lock_guard<std::mutex> lk(g_scale_mu);
-  auto it = g_scale_sets.find({net_kind, key});
+  auto it = g_scale_sets.find(scale_key(net_kind, key));
   if (it != g_scale_sets.end()) it->second.calls += 1;
 }
 
@@ -353,7 +368,7 @@ void grad_scales_prepare(int net_kind, const void* key, int n, cudaStream_t st) 
   static const bool allow = !(getenv("QEB_FP16_BWD") && atoi(getenv("QEB_FP16_BWD")) == 0);
   if (!allow) return;
   std::lock_guard<std::mutex> lk(g_scale_mu);
-  auto it = g_scale_sets.find({net_kind, key});
+  auto it = g_scale_sets.find(scale_key(net_kind, key));
   if (it != g_scale_sets.end()) return;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); return; }
@@ -364,7 +379,7 @@ void grad_scales_prepare(int net_kind, const void* key, int n, cudaStream_t st) 
   if (cudaMemset(dev, 0, (size_t)3 * n * sizeof(unsigned)) != cudaSuccess) { cudaGetLastError(); cudaFree(dev); return; }
   ScaleSet set;
   set.dev = dev; set.n = n; set.calls = 0;
-  g_scale_sets[{net_kind, key}] = set;
+  g_scale_sets[scale_key(net_kind, key)] = set;
 }
 
 int grad_scales_begin(int net_kind, const void* key, int n, cudaStream_t st, GradScales* out) {
@@ -372,7 +387,7 @@ int grad_scales_begin(int net_kind, const void* key, int n, cudaStream_t st, Gra
   ScaleSet set;
   {
     std::lock_guard<std::mutex> lk(g_scale_mu);
-    auto it = g_scale_sets.find({net_kind, key});
+    auto it = g_scale_sets.find(scale_key(net_kind, key));
     if (it == g_scale_sets.end() || it->second.n != n) return QEB_OK;   // no slots: the tf32 path
     set = it->second;
   }
