@@ -173,6 +173,11 @@ struct FpropParams {
   const float* out16_scale;  // device scalar or NULL: the fp16 shadow holds v * *out16_scale (nn.cuh GradShadow)
   unsigned* gamax;           // device or NULL: running maximum of |v| over the stored values (fp32 bit pattern)
   int out16_cols;            // the fp16 shadow (and the running maximum) cover output channels [0, out16_cols) only
+  int mc_dim;                // > 0: A-tile multicast - the kernel runs as clusters of TWO CTAs that work on the two N tiles 2j, 2j + 1 of the
+                             // same pixel tile; each loads HALF of the shared A tile (tensor map m[1]: the box halved along box dimension
+                             // mc_dim, mc_half = half its extent) and multicasts it into both CTAs' rings, so the A operand crosses
+                             // L2 -> SM once per pair. The kernels are bound by that path (~43 B per clock and SM with all SMs streaming).
+  int mc_half;
 };
 
 struct TmapOut {
@@ -674,6 +679,15 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   const int num_kb = p.kh * p.kw * p.kchunks;
   const int mn_tiles = p.m_tiles * p.n_tiles, total_tiles = mn_tiles * p.splits;
   const bool split = p.splits > 1;
+  // A-tile multicast (FpropParams::mc_dim): cluster c of gridDim.x / 2 walks the tile PAIRS c, c + gridDim.x / 2, ...; pair i =
+  // pixel tile i % m_tiles, N tiles 2 (i / m_tiles) + {0, 1}. it_* describe the walk of this CTA, tile_of() maps a walk index to
+  // the tile number t the code below decomposes.
+  const bool mc = !WIN && p.mc_dim > 0;
+  const uint32_t crank = mc ? cluster_ctarank() : 0u;
+  const int it_first = mc ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+  const int it_step = mc ? (int)gridDim.x / 2 : (int)gridDim.x;
+  const int it_count = mc ? mn_tiles / 2 : total_tiles;
+  auto tile_of = [&](int it) { return mc ? ((it / p.m_tiles) * 2 + (int)crank) * p.m_tiles + it % p.m_tiles : it; };
   long long* tl = p.timeline ? p.timeline + 16 * blockIdx.x : nullptr;
   if (tl && threadIdx.x == 0) { tl[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
 
@@ -686,7 +700,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
     }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], (!WIN && p.mc_dim > 0) ? 2 : 1);   // multicast: a stage is free when BOTH CTAs' MMAs have read it
     }
     for (int a = 0; a < kAccs; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -702,6 +716,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (mc) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can arrive on them
   qeb_pdl_sync();   // everything above (tensor-map prefetch, barrier init, TMEM allocation) overlaps the previous grid's tail
   if (tl && threadIdx.x == 0) tl[1] = clock64();
 
@@ -749,11 +764,15 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         t += nb * (int)gridDim.x;
       }
     } else
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int it = it_first; it < it_count; it += it_step) {
+      const int t = tile_of(it);
       const int z = t / mn_tiles, r = t - z * mn_tiles;
       const int tile_n = r / p.m_tiles, tile_m = r - tile_n * p.m_tiles;
       const int tw = tile_m % p.tiles_w, th = (tile_m / p.tiles_w) % p.tiles_h, tn = tile_m / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.wt, h0 = th * p.ht, n0 = tn * p.nt;
+      // multicast: this CTA's half of the A box starts `crank * mc_half` further along box dimension mc_dim
+      const int mw = (mc && p.mc_dim == 1) ? (int)crank * p.mc_half : 0, mh = (mc && p.mc_dim == 2) ? (int)crank * p.mc_half : 0,
+                mn = (mc && p.mc_dim == 3) ? (int)crank * p.mc_half : 0;
       const int kb_begin = z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
       int tap = kb_begin / p.kchunks, kc = kb_begin - tap * p.kchunks;
       int dy = tap / p.kw - p.ph, dx = tap % p.kw - p.pw;
@@ -763,7 +782,8 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * p.kblk, w0, h0, n0);
+          if (mc) tma_load_4d_mc(sa + crank * (Cfg::kABytes / 2), &tmaps_a.m[1], &full_bar[stage], kc * p.kblk, w0 + dx + mw, h0 + dy + mh, n0 + mn, (uint16_t)3);
+          else if (p.a_map_per_tap) tma_load_4d(sa, &tmaps_a.m[tap], &full_bar[stage], kc * p.kblk, w0, h0, n0);
           else tma_load_4d(sa, &tmaps_a.m[0], &full_bar[stage], kc * p.kblk, w0 + dx, h0 + dy, n0);
           tma_load_2d(sb, &tmap_b, &full_bar[stage], tap * p.cin + kc * p.kblk, tile_n * BLOCK_N);
         }
@@ -858,7 +878,8 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
         t = t_next;
       }
     } else
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int it = it_first; it < it_count; it += it_step) {
+      const int t = tile_of(it);
       const int z = t / mn_tiles;
       const int kb_begin = z * p.kb_per_split, kb_end = min(kb_begin + p.kb_per_split, num_kb);
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);   // the epilogue has drained this accumulator (two tiles ago)
@@ -878,7 +899,8 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
             if (F16) mma_f16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
             else mma_tf32_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb != kb_begin) || (k != 0));
           }
-          mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (mc) mma_commit_mc(&empty_bar[stage], (uint16_t)3);   // ... in both CTAs: either may refill the stage's A half
+          else mma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -921,7 +943,8 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
       }
       group_sync();
     };
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++n_seen) {
+    for (int it = it_first; it < it_count; it += it_step, ++n_seen) {
+      const int t = tile_of(it);
       if (WIN && (n_seen & 1) != grp) continue;   // the other group's tile
       if (WIN) { acc = n_seen % kAccs; acc_phase = (uint32_t)((n_seen / kAccs) & 1); }
       const int z = t / mn_tiles, rr = t - z * mn_tiles;
@@ -986,6 +1009,7 @@ conv_fprop_tc_kernel(const __grid_constant__ TmapArray4 tmaps_a, const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if (mc) cluster_sync_all();   // the peer may multicast into this CTA's ring / arrive on its barriers until its own last tile is done
   if (warp == 1) tmem_dealloc(tmem_base, kAccs * BLOCK_N);
   if (tl && threadIdx.x == 32) tl[6] = clock64();
 }
@@ -1017,12 +1041,19 @@ int launch_fprop(const TmapArray4& ta, const CUtensorMap& tb, const TmapOut& to,
     resident = 1;
   }
   p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.splits = splits;
-  const int grid = (int)(total < (long long)kNumSMs * resident ? total : (long long)kNumSMs * resident);
+  int grid = (int)(total < (long long)kNumSMs * resident ? total : (long long)kNumSMs * resident);
+  if (p.mc_dim > 0) {
+    QEB_REQUIRE(!WIN && !LSM && splits == 1 && n_tiles % 2 == 0, "tc fprop: A-tile multicast needs an even number of N tiles and no split-K");
+    grid &= ~1;   // whole clusters of two
+  }
   // ".f16" / ".tf32": the operand kind, so that bench.py can rate each against its own measured dense peak
   ProfScope prof(LSM ? "tc_head_logsoftmax" : p.a_map_per_tap ? "tc_convT_dgrad" : (p.mode == 1 ? "tc_convT_fprop" : (F16 ? "tc_conv_fprop.f16" : "tc_conv_fprop.tf32")), st,
                  2.0 * p.n_img * p.h_out * p.w_out * (double)p.n_total * p.kh * p.kw * p.cin,
                  4.0 * ((double)p.n_img * p.h_out * p.w_out * (p.cin + p.n_total) + (double)p.n_total * p.kh * p.kw * p.cin));
-  QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI, WIN>, grid, fprop_threads<WIN>(), smem_total, st, ta, tb, to, p));
+  if (p.mc_dim > 0)
+    QEB_CUDA(qeb_launch_cluster(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI, WIN>, grid, fprop_threads<WIN>(), smem_total, st, 2, ta, tb, to, p));
+  else
+    QEB_CUDA(qeb_launch(conv_fprop_tc_kernel<BLOCK_N, ROWB, F16, EPI, WIN>, grid, fprop_threads<WIN>(), smem_total, st, ta, tb, to, p));
   qeb_count_launch();
   return QEB_OK;
 }
@@ -1075,7 +1106,7 @@ inline bool win_eligible(int kh, int kw, int ph, int pw, int n_img, int h_out, i
 // f16: the A maps in ta_in describe the fp16 shadow (K block = kblk16(cin) elements) and ep.w16 holds the fp16 weights
 int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const float* wpacked, int n_total, int kh,
                  int kw, int ph, int pw, int cin, const Img& out, int h_out, int w_out, const TcEpilogue& ep, int mode,
-                 int up_c, const float* bias, cudaStream_t st, bool f16 = false, bool win = false) {
+                 int up_c, const float* bias, cudaStream_t st, bool f16 = false, bool win = false, int mc_dim = 0, int mc_half = 0) {
   FpropParams p;
   p.n_img = x_geom.n; p.h_out = h_out; p.w_out = w_out;
   p.wt = min(pow2_ceil(w_out), kBlockM);
@@ -1186,6 +1217,10 @@ int fprop_common(const TmapArray4& ta_in, bool per_tap, const Img& x_geom, const
   if (mode == 1) while (bn > p.up_c) bn >>= 1;
   QEB_REQUIRE(mode == 0 || p.up_c % bn == 0, "tc fprop: tile width %d must divide the up-conv channels %d", bn, p.up_c);
   const int n_tiles = qeb_cdiv(n_total, bn);
+  // A-tile multicast between the two CTAs of a cluster (FpropParams::mc_dim): every layer with an even number of N tiles
+  static const int allow_mc = getenv("QEB_TC_MCAST") ? atoi(getenv("QEB_TC_MCAST")) : 1;
+  p.mc_dim = (allow_mc && mc_dim > 0 && !win && !ep.log_softmax && mode == 0 && !per_tap && splits == 1 && n_tiles % 2 == 0) ? mc_dim : 0;
+  p.mc_half = mc_half;
 
   CUtensorMap tb;
   {
@@ -1288,7 +1323,17 @@ int tc_conv_fprop(const Img& x, const float* wpacked, int n_total, int kh, int k
   if (win) { box[1] = kWinW + 2; box[2] = kWinH + 2; box[3] = 1; }   // the tile with its halo
   int rc = f16 ? tmap_img16(&ta.m[0], x, ep.in16, box) : tmap_img(&ta.m[0], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, box, 0);
   if (rc) return rc;
-  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st, f16, win);
+  // the A box halved along its outermost dimension of extent > 1 (rows 0-63 / 64-127 of the tile): the operand of the multicast form
+  int mc_dim = 0, mc_half = 0;
+  if (!win) {
+    uint32_t hb[4] = {box[0], box[1], box[2], box[3]};
+    mc_dim = box[3] > 1 ? 3 : (box[2] > 1 ? 2 : 1);
+    hb[mc_dim] /= 2;
+    mc_half = (int)hb[mc_dim];
+    rc = f16 ? tmap_img16(&ta.m[1], x, ep.in16, hb) : tmap_img(&ta.m[1], x, x.p, x.c, x.sn, x.sh, x.sw, x.w, x.h, hb, 0);
+    if (rc) return rc;
+  }
+  return fprop_common(ta, false, x, wpacked, n_total, kh, kw, ph, pw, x.c, out, out.h, out.w, ep, 0, 0, ep.bias, st, f16, win, mc_dim, mc_half);
 }
 
 int tc_convT_fprop(const Img& x, const float* wpacked, const float* bias, const Img& out, cudaStream_t st,
