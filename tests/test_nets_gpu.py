@@ -714,3 +714,30 @@ def test_conv_wgrad_tc16(q, N, H, W, Cin, Cout, k, p):
     q.lib.call("qeb_conv_wgrad_tc16", xn.data_ptr(), x16.data_ptr(), Cin, Cin, H, W, dyn.data_ptr(), dy16.data_ptr(), Cout, Cout, N,
                k, k, p, p, alpha.data_ptr(), dw.data_ptr(), st())
     assert rel(dw, 2 * w.grad) < 3e-3  # accumulates
+
+
+@pytest.mark.parametrize("factor", [256.0, 1.0 / 256.0, 3000.0])
+def test_unet_fp16_backward_scale_jump(q, factor):
+    """Delayed gradient scales (csrc/nn.cuh GradShadow): the operand copies of a backward call are scaled by the PREVIOUS call's
+    maxima with 2^12 of headroom above and 2^18 of normal range below. A loss that jumps by 256x / 3000x up or 256x down between
+    two calls must still give gradients that match the fp32 graph (direction and norm), and the call after it is scaled afresh."""
+    torch.manual_seed(11)
+    m = q.UNet().to(DEV)
+    mr = copy.deepcopy(m)
+    m.train(); mr.train()
+    x = torch.rand(8, 1, 32, 128, device=DEV)
+    bufs = copy.deepcopy(m.state_dict())
+    q.train_ops.mse_to_ones(m(x)).backward()                 # first call: tf32 reads, records the maxima at loss scale 1
+    m.zero_grad(); m.load_state_dict(bufs)
+    (factor * q.train_ops.mse_to_ones(m(x))).backward()      # second call: fp16 operands scaled for loss scale 1, gradients x factor
+    yr = nn_oracle.unet_forward(mr, x)
+    (factor * torch.nn.MSELoss()(yr, torch.ones_like(yr))).backward()
+    for (n, p), (_, r) in zip(m.named_parameters(), mr.named_parameters()):
+        assert torch.isfinite(p.grad).all(), n
+        assert cos(p.grad, r.grad) > 0.98, (n, cos(p.grad, r.grad))
+        assert abs(float(p.grad.double().norm()) / float(r.grad.double().norm()) - 1.0) < 0.2, n
+    g2 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad(); m.load_state_dict(bufs)
+    (factor * q.train_ops.mse_to_ones(m(x))).backward()      # third call: scales from the second call's maxima
+    for n, p in m.named_parameters():
+        assert cos(p.grad, g2[n]) > 0.995, n
