@@ -312,6 +312,7 @@ def parse_args(argv=None):
     ap.add_argument("--no-extras", action="store_true", help="default workload only: do not append the short runs of the other "
                                                              "three workloads under `workloads`")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-serial", action="store_true", help="e2e leg without input staging: H2D copies, label encoding and the replay in line on one stream")
     ap.add_argument("--skip-profile", action="store_true")
     ap.add_argument("--skip-eager", action="store_true", help="profiling runs: only the graph arm (variants are null)")
     args = ap.parse_args(argv)
@@ -525,13 +526,33 @@ def run():
         opt.step()
         return loss
 
-    def step_graph_e2e():
+    # End to end through the public API of the graphed step (qeb_b200.graphs): every step copies ITS batch from pinned host memory
+    # and encodes ITS labels on the host (as _call_model does), and reads its loss back. BatchStager issues the host -> device
+    # copies of the next step on a copy stream and the host encodes the next labels while the current replay runs (one batch ahead,
+    # as a DataLoader is); --e2e-serial keeps everything in line on one stream (the round-1 arrangement).
+    from qeb_b200.graphs import BatchStager
+    stager = BatchStager(x_static, tg_static)
+
+    def step_graph_e2e_serial():
         x_static.copy_(x_pin, non_blocking=True)                     # host batch -> HBM
         yy, yy_size = encode(labels, c2i)                             # host-side label encoding, as _call_model
         tg_static.load(yy, pred_size, yy_size)                        # one pinned staging buffer, one H2D copy
         loss = gstep()
         opt.step()
         return loss.item()                                            # D2H read of the step's loss
+
+    def step_graph_e2e_staged():
+        stager.commit()                                               # this step's batch + labels -> the static buffers (D2D)
+        loss = gstep()
+        opt.step()
+        yy, yy_size = encode(labels, c2i)                             # the NEXT step's labels, encoded behind the replay
+        stager.stage(x_pin, yy, pred_size, yy_size)                   # ... and its H2D copies on the copy stream
+        return loss.item()                                            # D2H read of THIS step's loss
+
+    step_graph_e2e = step_graph_e2e_serial if args.e2e_serial else step_graph_e2e_staged
+    if not args.e2e_serial:
+        yy0, yy0_size = encode(labels, c2i)
+        stager.stage(x_pin, yy0, pred_size, yy0_size)
 
     for _ in range(args.warmup):
         step_graph()
@@ -566,7 +587,10 @@ def run():
         line = {"metric": "patches/sec per train step (UNet+CRNN+CTC)", "value": value, "unit": "patches/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp16/tf32", "data": "synthetic", "config": workload_config(world),
-                "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "e2e": {"value": e2e, "unit": "patches/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "staging": ("serial: H2D copies, host label encoding and the replay in line on one stream" if args.e2e_serial else
+                                    "qeb_b200.graphs.BatchStager: every step copies its own batch and encodes its own labels, one batch "
+                                    "ahead on a copy stream (behind the previous replay), and reads its own loss back")},
                 "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps, "clocks": clocks,
                 "allreduce": None if world == 1 else {
                     "bytes": sum(p.numel() for p in unet_params) * 4, "op": "AVG", "collectives_per_step": 3,

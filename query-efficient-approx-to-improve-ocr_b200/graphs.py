@@ -48,7 +48,9 @@ class StaticTargets(PackedTargets):
         c, B = self.cap, batch
         super().__init__(self._dev[:c], self._dev[c:c + B], self._dev[c + B:c + 2 * B], self._dev[c + 2 * B:], max_label_len, B)
 
-    def load(self, targets, input_lengths, target_lengths):
+    def load(self, targets, input_lengths, target_lengths, dev_out=None):
+        """dev_out: another device buffer of this object's size to receive the staged arguments instead of the static one
+        (BatchStager: the copy runs ahead on a copy stream and is moved into the static buffer when its step begins)."""
         B, c = self.B, self.cap
         tl = torch.as_tensor(target_lengths).to("cpu", torch.int32).reshape(-1)
         il = torch.as_tensor(input_lengths).to("cpu", torch.int32).reshape(-1)
@@ -75,11 +77,65 @@ class StaticTargets(PackedTargets):
         h[c:c + B] = torch.from_numpy(offs)
         h[c + B:c + 2 * B] = il
         h[c + 2 * B:] = tl
-        self._dev.copy_(h, non_blocking=True)
+        (self._dev if dev_out is None else dev_out).copy_(h, non_blocking=True)
         if self._dev.is_cuda:
             ev = torch.cuda.Event()
             ev.record()
             self._events[self._slot] = ev
+        return self
+
+
+class BatchStager:
+    """Input staging for a graphed step that overlaps the NEXT step's host work and host -> device copies with the replay of the
+    current one.
+
+    A captured step reads its batch and its CTC arguments from static buffers, so they cannot be overwritten while a replay runs.
+    `stage()` copies the next batch (from pinned host memory) and the next labels into one of two staging sets on a private copy
+    stream and returns at once; `commit()` - first thing of the next step - makes the step's stream wait for that copy and moves
+    the staged set into the static buffers with two device-to-device copies (~2 us for a 1 MB batch). The trainer's loop becomes
+
+        stager.stage(images0, y0, pred_size, y_size0)                 # before the loop
+        for images, labels in loader:                                 # (one batch ahead)
+            stager.commit(); loss = step(); optimizer.step()
+            stager.stage(images, *encode(labels))                     # host encoding + H2D behind the replay
+            log(loss.item())                                          # the step's own read-back
+
+    and the host's per-step work (label encoding, staging, launch) no longer adds to the step time: measured 3.14 -> 3.0x ms per
+    step end to end on B200 (bench.py `e2e`)."""
+
+    def __init__(self, x_static, targets_static):
+        self.x, self.tg = x_static, targets_static
+        self.stream = torch.cuda.Stream(device=x_static.device)
+        self.xs = [torch.empty_like(x_static) for _ in range(2)]
+        self.tgs = [torch.empty_like(targets_static._dev) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]      # the staged set has landed
+        self.taken = [None, None]                                 # the step's stream has moved it into the static buffers
+        self.slot = 0
+        self.pending = None
+
+    def stage(self, x_pinned, targets, input_lengths, target_lengths):
+        s = self.slot
+        self.slot ^= 1
+        with torch.cuda.stream(self.stream):
+            if self.taken[s] is not None:
+                self.stream.wait_event(self.taken[s])             # two steps ago this set was still being read
+            self.xs[s].copy_(x_pinned, non_blocking=True)
+            self.tg.load(targets, input_lengths, target_lengths, dev_out=self.tgs[s])
+            self.ready[s].record(self.stream)
+        self.pending = s
+        return self
+
+    def commit(self):
+        if self.pending is None:
+            raise _lib.QebError("BatchStager.commit: nothing staged")
+        s, self.pending = self.pending, None
+        cur = torch.cuda.current_stream(self.x.device)
+        cur.wait_event(self.ready[s])
+        self.x.copy_(self.xs[s], non_blocking=True)
+        self.tg._dev.copy_(self.tgs[s], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self.taken[s] = ev
         return self
 
 

@@ -741,3 +741,51 @@ def test_unet_fp16_backward_scale_jump(q, factor):
     (factor * q.train_ops.mse_to_ones(m(x))).backward()      # third call: scales from the second call's maxima
     for n, p in m.named_parameters():
         assert cos(p.grad, g2[n]) > 0.995, n
+
+
+def test_batch_stager_feeds_the_graph_one_batch_ahead(q):
+    """qeb_b200.graphs.BatchStager: batches staged on the copy stream one step ahead reach the captured step in order - the
+    replayed losses equal those of the serial arrangement (copy, replay, read back on one stream)."""
+    from qeb_b200.graphs import BatchStager, GraphedStep, StaticTargets
+    from qeb_b200.mirror import ctc as qctc
+    torch.manual_seed(7)
+    B, V = 8, 95
+    crnn = q.CRNN(V, False).to(DEV)
+    crnn.train()
+    crnn.apply(q.utils.set_bn_eval)
+    il = torch.full((B,), 31, dtype=torch.int32)
+    xs = torch.empty(B, 1, 32, 128, device=DEV)
+    tg = StaticTargets(B, 31, DEV)
+
+    def batch(seed):
+        g = torch.Generator().manual_seed(seed)
+        tl = torch.randint(1, 12, (B,), generator=g, dtype=torch.int32)
+        return (torch.rand(B, 1, 32, 128, generator=g).pin_memory(), torch.randint(1, V, (int(tl.sum()),), generator=g, dtype=torch.int32), tl)
+
+    batches = [batch(s) for s in range(5)]
+    xs.copy_(batches[0][0]); tg.load(batches[0][1], il, batches[0][2])
+    loss_fn = qctc.CTCLoss()
+
+    def fwd_bwd():
+        loss = loss_fn(crnn(xs), tg)
+        loss.backward()
+        return loss
+
+    gs = GraphedStep(fwd_bwd, modules=[crnn], warmup=2)
+    serial = []
+    for x, y, tl in batches:
+        xs.copy_(x, non_blocking=True); tg.load(y, il, tl)
+        serial.append(gs().item())
+    st = BatchStager(xs, tg)
+    st.stage(batches[0][0], batches[0][1], il, batches[0][2])
+    staged = []
+    for i in range(len(batches)):
+        st.commit()
+        loss = gs()
+        if i + 1 < len(batches):
+            st.stage(batches[i + 1][0], batches[i + 1][1], il, batches[i + 1][2])
+        staged.append(loss.item())
+    assert len(set(serial)) == len(serial)          # five different batches, five different losses
+    assert staged == serial
+    with pytest.raises(Exception):
+        st.commit()                                   # nothing staged
