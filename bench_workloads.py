@@ -318,15 +318,38 @@ def run_jitter(env):
         finish()
         return out
 
-    def step_e2e():
-        base_static.copy_(base_pin, non_blocking=True)                    # host crops -> HBM
-        for tg, c in zip(tgs, copies):
+    # every step copies its own crops from pinned memory and encodes its own OCR strings on the host; graphs.BatchStager issues
+    # those one step ahead on a copy stream, behind the running replay (bench.py --e2e-serial: in line on the step's stream)
+    from qeb_b200.graphs import BatchStager
+    stager = BatchStager(base_static, tgs)
+
+    def host_sets():
+        sets = []
+        for c in copies:
             yy, ys = BB.encode(ocr[c], c2i)                               # _call_model's host-side label encoding per copy
-            tg.load(yy, pred_size, ys)
+            sets.append((yy, pred_size, ys))
+        return sets
+
+    def step_e2e_serial():
+        base_static.copy_(base_pin, non_blocking=True)                    # host crops -> HBM
+        for tg, (yy, il_, ys) in zip(tgs, host_sets()):
+            tg.load(yy, il_, ys)
         seed_dev.add_(local)
         out = gstep()
         finish()
         return out.item()                                                 # temp_loss += loss.item()
+
+    def step_e2e_staged():
+        stager.commit()
+        seed_dev.add_(local)
+        out = gstep()
+        finish()
+        stager.stage(base_pin, host_sets())                               # the next step's crops and labels, behind the replay
+        return out.item()                                                 # temp_loss += loss.item()
+
+    step_e2e = step_e2e_serial if getattr(a, "e2e_serial", False) else step_e2e_staged
+    if step_e2e is step_e2e_staged:
+        stager.stage(base_pin, host_sets())
 
     for _ in range(a.warmup):
         step_graph()

@@ -104,23 +104,32 @@ class BatchStager:
     step end to end on B200 (bench.py `e2e`)."""
 
     def __init__(self, x_static, targets_static):
-        self.x, self.tg = x_static, targets_static
+        """targets_static: one StaticTargets or a list of them (a step with several CTC calls, e.g. one per noised copy)."""
+        self.x = x_static
+        self.many = isinstance(targets_static, (list, tuple))
+        self.tg = list(targets_static) if self.many else [targets_static]
         self.stream = torch.cuda.Stream(device=x_static.device)
         self.xs = [torch.empty_like(x_static) for _ in range(2)]
-        self.tgs = [torch.empty_like(targets_static._dev) for _ in range(2)]
+        self.tgs = [[torch.empty_like(t._dev) for t in self.tg] for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]      # the staged set has landed
         self.taken = [None, None]                                 # the step's stream has moved it into the static buffers
         self.slot = 0
         self.pending = None
 
-    def stage(self, x_pinned, targets, input_lengths, target_lengths):
+    def stage(self, x_pinned, targets, input_lengths=None, target_lengths=None):
+        """One target set: stage(x, targets, input_lengths, target_lengths). Several: stage(x, [(targets, input_lengths,
+        target_lengths), ...]) in the order of the StaticTargets given to the constructor."""
+        sets = targets if self.many else [(targets, input_lengths, target_lengths)]
+        if len(sets) != len(self.tg):
+            raise _lib.QebError(f"BatchStager.stage: {len(sets)} target sets for {len(self.tg)} static ones")
         s = self.slot
         self.slot ^= 1
         with torch.cuda.stream(self.stream):
             if self.taken[s] is not None:
                 self.stream.wait_event(self.taken[s])             # two steps ago this set was still being read
             self.xs[s].copy_(x_pinned, non_blocking=True)
-            self.tg.load(targets, input_lengths, target_lengths, dev_out=self.tgs[s])
+            for t, dst, (y, il, tl) in zip(self.tg, self.tgs[s], sets):
+                t.load(y, il, tl, dev_out=dst)
             self.ready[s].record(self.stream)
         self.pending = s
         return self
@@ -132,7 +141,8 @@ class BatchStager:
         cur = torch.cuda.current_stream(self.x.device)
         cur.wait_event(self.ready[s])
         self.x.copy_(self.xs[s], non_blocking=True)
-        self.tg._dev.copy_(self.tgs[s], non_blocking=True)
+        for t, src in zip(self.tg, self.tgs[s]):
+            t._dev.copy_(src, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(cur)
         self.taken[s] = ev
